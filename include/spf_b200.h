@@ -1,0 +1,164 @@
+/*
+ * spf_b200.h -- C ABI of libspf_b200.so, the B200-native TFHE bootstrapping engine that slots in
+ * under parasol_runtime's Evaluation / CircuitProcessor::exec_op.
+ *
+ * The reference (Sunscreen-tech/spf v0.9.0) has no FFI of its own: the seam is a set of plain
+ * Rust calls on `Evaluation` (parasol_runtime/src/crypto/evaluation.rs) dispatched one task at
+ * a time from CircuitProcessor::exec_op (parasol_runtime/src/circuit_processor/mod.rs:255-546).
+ * Each entry point below names the reference method it replaces.  Differences that are
+ * deliberate: every op is BATCHED (`batch` independent inputs, contiguous), because the GPU is
+ * fed from the runtime's ready-queue rather than one rayon task at a time.
+ *
+ * Conventions
+ *  - All buffers are caller-owned, contiguous, in the reference's own flat layouts
+ *    (sunscreen_tfhe/src/entities/, OverlaySize::size): element = u64 torus value or
+ *    Complex<f64> = (re, im) pair of doubles.  FFT-domain data (GGSW, keys) is in the
+ *    reference's natural bin order and scale (unnormalised forward DFT).
+ *  - Functions return 0 on success, a negative spf_status otherwise; they never throw or abort.
+ *    The reference panics on wrong sizes (dst.rs:520-523) -- here that is SPF_E_INVALID.
+ *    spf_b200_last_error() returns the message of the last failing call on that context (or of
+ *    the last failing spf_b200_create when ctx is NULL).
+ *  - `spf_b200_*`    : host pointers; the call copies in, computes on the GPU, copies out, and
+ *                      returns when the outputs are valid (what Evaluation's methods do).
+ *    `spf_b200_dev_*`: device pointers, asynchronous on `stream` (a cudaStream_t passed as
+ *                      void*, NULL = the context's own stream).  Device-resident FFT-domain
+ *                      ciphertexts (GGSW) carry a 2^-10 scale factor; they only
+ *                      ever travel between spf_b200_dev_* calls.
+ *  - A context is bound to one CUDA device and may be used from one thread at a time (the
+ *    reference allows only one dispatching thread as well: CircuitProcessor methods take
+ *    &mut self, circuit_processor/mod.rs:125-130).
+ *  - There is no CPU fallback: without a usable CUDA device spf_b200_create fails.
+ */
+#ifndef SPF_B200_H
+#define SPF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SPF_OK = 0,
+  SPF_E_INVALID = -1,     /* bad argument / size mismatch (reference: panic in assert_is_valid) */
+  SPF_E_UNSUPPORTED = -2, /* parameter set the sm_100a kernels are not specialised for */
+  SPF_E_CUDA = -3,        /* CUDA runtime error; message in spf_b200_last_error */
+  SPF_E_GRAPH = -4        /* malformed graph (reference: RuntimeError, runtime_error.rs:8) */
+} spf_status;
+
+/* RadixDecomposition (sunscreen_tfhe/src/params.rs) */
+typedef struct { uint32_t radix_log; uint32_t count; } spf_radix;
+
+/* Params (parasol_runtime/src/params.rs:59-91), flattened.  spf_b200_default_128 fills in
+ * DEFAULT_128 (params.rs:107-134). */
+typedef struct {
+  uint32_t lwe_n;    /* l0_params.dim                        637     */
+  double   lwe_std;  /* l0_params.std                        7.25e-5 */
+  uint32_t glwe_k;   /* l1_params.dim.size                   1       */
+  uint32_t glwe_n;   /* l1_params.dim.polynomial_degree      2048    */
+  double   glwe_std; /* l1_params.std                        7e-16   */
+  spf_radix cbs, pbs, ks, pfks, ss, tr;
+} spf_params;
+
+typedef struct spf_b200_ctx spf_b200_ctx;
+
+void spf_b200_default_128(spf_params *p);
+
+/* Entity sizes in elements (u64 or complex) for the given params; the OverlaySize::size
+ * functions of sunscreen_tfhe/src/entities. */
+size_t spf_b200_len_lwe_l0(const spf_params *p);   /* n+1                       638   */
+size_t spf_b200_len_lwe_l1(const spf_params *p);   /* kN+1                      2049  */
+size_t spf_b200_len_glwe_l1(const spf_params *p);  /* (k+1)N                    4096  */
+size_t spf_b200_len_glev_l1(const spf_params *p);  /* l_cbs (k+1) N             16384 */
+size_t spf_b200_len_ggsw_l1(const spf_params *p);  /* (k+1) l_cbs (k+1) N/2 c64 16384 */
+size_t spf_b200_len_bsk(const spf_params *p);      /* BootstrapKeyFft   (bootstrap_key.rs:122-124) */
+size_t spf_b200_len_ksk(const spf_params *p);      /* LweKeyswitchKey   (lwe_keyswitch_key.rs:27-36) */
+size_t spf_b200_len_ssk(const spf_params *p);      /* SchemeSwitchKeyFft */
+size_t spf_b200_len_ak(const spf_params *p);       /* AutomorphismKeyFft (automorphism_key_fft.rs:25-27) */
+
+/* Evaluation::new(Arc<ComputeKey>, &Params, &Encryption) (evaluation.rs:161-197): uploads the
+ * four arrays of ComputeKey {bs_key, ks_key, ss_key, auto_key} (crypto/keys.rs:306-318) to
+ * `device`.  Lengths are element counts and must equal spf_b200_len_*.  FFT keys are complex
+ * (re, im) pairs exactly as ComputeKey serialises them. */
+int spf_b200_create(const spf_params *params, const double *bsk_fft, size_t bsk_len, const uint64_t *ksk,
+                    size_t ksk_len, const double *ssk_fft, size_t ssk_len, const double *ak_fft, size_t ak_len,
+                    int device, spf_b200_ctx **out);
+/* Same, with the key arrays already resident on `device` in the reference layout (used after a
+ * one-time NCCL / peer broadcast of the compute key to every GPU of a box). */
+int spf_b200_create_from_device(const spf_params *params, const double *d_bsk_fft, size_t bsk_len,
+                                const uint64_t *d_ksk, size_t ksk_len, const double *d_ssk_fft, size_t ssk_len,
+                                const double *d_ak_fft, size_t ak_len, int device, spf_b200_ctx **out);
+void spf_b200_destroy(spf_b200_ctx *ctx);
+const char *spf_b200_last_error(const spf_b200_ctx *ctx);
+/* Number of CUDA kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t spf_b200_kernel_launches(const spf_b200_ctx *ctx);
+int spf_b200_device(const spf_b200_ctx *ctx);
+int spf_b200_synchronize(spf_b200_ctx *ctx);
+
+/* ---- host-pointer ops: one call == `batch` calls of the reference method ---------------- */
+
+/* Evaluation::circuit_bootstrap (evaluation.rs:211-225) ->
+ * circuit_bootstrap_via_trace_and_scheme_switch (circuit_bootstrapping.rs:342-384).
+ * lwe0_in [batch][n+1] u64 -> ggsw_out [batch][len_ggsw_l1] complex. */
+int spf_b200_circuit_bootstrap(spf_b200_ctx *ctx, double *ggsw_out, const uint64_t *lwe0_in, size_t batch);
+
+/* generalized_programmable_bootstrap (programmable_bootstrapping.rs:342-410).
+ * lut_glwe: one trivial-GLWE LUT [len_glwe_l1] shared by the batch. glwe_out [batch][len_glwe_l1]. */
+int spf_b200_programmable_bootstrap(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *lwe0_in,
+                                    const uint64_t *lut_glwe, uint32_t log_chi, uint32_t log_v, size_t batch);
+
+/* KeylessEvaluation::cmux (evaluation.rs:68-83): out = sel ? b : a.  sel [batch][len_ggsw_l1]. */
+int spf_b200_cmux(spf_b200_ctx *ctx, uint64_t *glwe_out, const double *sel_ggsw, const uint64_t *a,
+                  const uint64_t *b, size_t batch);
+/* KeylessEvaluation::glev_cmux (evaluation.rs:86-101); a, b, out are GLEVs [batch][len_glev_l1]. */
+int spf_b200_glev_cmux(spf_b200_ctx *ctx, uint64_t *glev_out, const double *sel_ggsw, const uint64_t *a,
+                       const uint64_t *b, size_t batch);
+/* KeylessEvaluation::multiply_glwe_ggsw (evaluation.rs:104-123). */
+int spf_b200_multiply_glwe_ggsw(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *glwe, const double *ggsw,
+                                size_t batch);
+/* Evaluation::keyswitch_lwe_l1_lwe_l0 (evaluation.rs:243-252). [batch][kN+1] -> [batch][n+1]. */
+int spf_b200_keyswitch_lwe_l1_lwe_l0(spf_b200_ctx *ctx, uint64_t *lwe0_out, const uint64_t *lwe1_in, size_t batch);
+/* KeylessEvaluation::sample_extract_l1 (evaluation.rs:126-133); idx[batch] or NULL with idx_all. */
+int spf_b200_sample_extract_l1(spf_b200_ctx *ctx, uint64_t *lwe1_out, const uint64_t *glwe_in, const uint32_t *idx,
+                               uint32_t idx_all, size_t batch);
+/* Evaluation::scheme_switch (evaluation.rs:231-240): GLEV [batch][len_glev_l1] -> GGSW-FFT. */
+int spf_b200_scheme_switch(spf_b200_ctx *ctx, double *ggsw_out, const uint64_t *glev_in, size_t batch);
+/* sunscreen_tfhe::ops::automorphisms::trace (automorphisms/mod.rs:53-85). */
+int spf_b200_trace(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *glwe_in, size_t batch);
+/* KeylessEvaluation::{not,xor,mul_xn} (evaluation.rs:48-65). */
+int spf_b200_not(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *glwe_in, size_t batch);
+int spf_b200_xor(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *a, const uint64_t *b, size_t batch);
+int spf_b200_mul_xn(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *glwe_in, uint32_t n, size_t batch);
+
+/* ---- device-pointer ops (asynchronous on `stream`) --------------------------------------- */
+
+/* scratch_glwe: device scratch of batch*len_glwe_l1 u64 for the PBS output (may be NULL: the
+ * context's own grow-only scratch is used).  ggsw_out is device-scale (2^-10) unless
+ * reference_scale != 0. */
+int spf_b200_dev_circuit_bootstrap(spf_b200_ctx *ctx, double *d_ggsw_out, const uint64_t *d_lwe0_in, size_t batch,
+                                   int reference_scale, void *stream);
+int spf_b200_dev_programmable_bootstrap(spf_b200_ctx *ctx, uint64_t *d_glwe_out, const uint64_t *d_lwe0_in,
+                                        const uint64_t *d_lut_glwe, uint32_t log_chi, uint32_t log_v, size_t batch,
+                                        void *stream);
+/* d_sel_ggsw is device-scale.  ggsw_stride: elements between consecutive selectors (0 = one
+ * selector shared by the whole batch). */
+int spf_b200_dev_cmux(spf_b200_ctx *ctx, uint64_t *d_glwe_out, const double *d_sel_ggsw, size_t ggsw_stride,
+                      const uint64_t *d_a, const uint64_t *d_b, size_t batch, void *stream);
+int spf_b200_dev_keyswitch_lwe_l1_lwe_l0(spf_b200_ctx *ctx, uint64_t *d_lwe0_out, const uint64_t *d_lwe1_in,
+                                         size_t batch, void *stream);
+int spf_b200_dev_sample_extract_l1(spf_b200_ctx *ctx, uint64_t *d_lwe1_out, const uint64_t *d_glwe_in,
+                                   const uint32_t *d_idx, uint32_t idx_all, size_t batch, void *stream);
+/* dst = src * 2^-10 (to_device != 0) or * 2^10: converts GGSW-FFT data between the reference
+ * scale and the device scale; n complex elements. */
+int spf_b200_dev_fft_rescale(spf_b200_ctx *ctx, double *d_dst, const double *d_src, size_t n, int to_device,
+                             void *stream);
+
+/* FP64 peak probe used by bench.py for the roofline denominator: runs a dependent-free DFMA
+ * loop on every SM and returns achieved TFLOP/s (2 flops per DFMA). */
+int spf_b200_fp64_peak(spf_b200_ctx *ctx, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,352 @@
+"""spf_b200 -- B200-native TFHE bootstrapping engine behind parasol_runtime's Evaluation boundary.
+
+This package is a thin ctypes mirror of the reference's `Evaluation` / `KeylessEvaluation`
+(parasol_runtime/src/crypto/evaluation.rs) over the C ABI of ``libspf_b200.so``
+(``include/spf_b200.h``).  All arithmetic runs in hand-written sm_100a CUDA kernels
+(``spf_b200/csrc``); there is NO CPU fallback -- if the library or a GPU is missing every
+entry point raises.  Nothing here imports the test oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspf_b200.so")
+
+
+class SpfError(RuntimeError):
+    """Mirrors parasol_runtime's RuntimeError(String) (runtime_error.rs:8) plus the panics of
+    assert_is_valid (dst.rs:520-523), surfaced as exceptions with the C ABI's status code."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"spf_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Radix(C.Structure):
+    _fields_ = [("radix_log", C.c_uint32), ("count", C.c_uint32)]
+
+
+class Params(C.Structure):
+    """parasol_runtime/src/params.rs:59-91 (spf_params)."""
+
+    _fields_ = [
+        ("lwe_n", C.c_uint32),
+        ("lwe_std", C.c_double),
+        ("glwe_k", C.c_uint32),
+        ("glwe_n", C.c_uint32),
+        ("glwe_std", C.c_double),
+        ("cbs", Radix),
+        ("pbs", Radix),
+        ("ks", Radix),
+        ("pfks", Radix),
+        ("ss", Radix),
+        ("tr", Radix),
+    ]
+
+
+_lib = None
+_vp = C.c_void_p
+_sz = C.c_size_t
+
+# name -> argtypes (restype int unless listed in _RESTYPES); this is the full export list of
+# include/spf_b200.h and is what tests/test_abi.py checks the .so against.
+ABI = {
+    "spf_b200_default_128": [C.POINTER(Params)],
+    "spf_b200_len_lwe_l0": [C.POINTER(Params)],
+    "spf_b200_len_lwe_l1": [C.POINTER(Params)],
+    "spf_b200_len_glwe_l1": [C.POINTER(Params)],
+    "spf_b200_len_glev_l1": [C.POINTER(Params)],
+    "spf_b200_len_ggsw_l1": [C.POINTER(Params)],
+    "spf_b200_len_bsk": [C.POINTER(Params)],
+    "spf_b200_len_ksk": [C.POINTER(Params)],
+    "spf_b200_len_ssk": [C.POINTER(Params)],
+    "spf_b200_len_ak": [C.POINTER(Params)],
+    "spf_b200_create": [C.POINTER(Params), _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, C.c_int, C.POINTER(_vp)],
+    "spf_b200_create_from_device": [C.POINTER(Params), _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, C.c_int, C.POINTER(_vp)],
+    "spf_b200_destroy": [_vp],
+    "spf_b200_last_error": [_vp],
+    "spf_b200_kernel_launches": [_vp],
+    "spf_b200_device": [_vp],
+    "spf_b200_synchronize": [_vp],
+    "spf_b200_circuit_bootstrap": [_vp, _vp, _vp, _sz],
+    "spf_b200_programmable_bootstrap": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _sz],
+    "spf_b200_cmux": [_vp, _vp, _vp, _vp, _vp, _sz],
+    "spf_b200_glev_cmux": [_vp, _vp, _vp, _vp, _vp, _sz],
+    "spf_b200_multiply_glwe_ggsw": [_vp, _vp, _vp, _vp, _sz],
+    "spf_b200_keyswitch_lwe_l1_lwe_l0": [_vp, _vp, _vp, _sz],
+    "spf_b200_sample_extract_l1": [_vp, _vp, _vp, _vp, C.c_uint32, _sz],
+    "spf_b200_scheme_switch": [_vp, _vp, _vp, _sz],
+    "spf_b200_trace": [_vp, _vp, _vp, _sz],
+    "spf_b200_not": [_vp, _vp, _vp, _sz],
+    "spf_b200_xor": [_vp, _vp, _vp, _vp, _sz],
+    "spf_b200_mul_xn": [_vp, _vp, _vp, C.c_uint32, _sz],
+    "spf_b200_dev_circuit_bootstrap": [_vp, _vp, _vp, _sz, C.c_int, _vp],
+    "spf_b200_dev_programmable_bootstrap": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _sz, _vp],
+    "spf_b200_dev_cmux": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp],
+    "spf_b200_dev_keyswitch_lwe_l1_lwe_l0": [_vp, _vp, _vp, _sz, _vp],
+    "spf_b200_dev_sample_extract_l1": [_vp, _vp, _vp, _vp, C.c_uint32, _sz, _vp],
+    "spf_b200_dev_fft_rescale": [_vp, _vp, _vp, _sz, C.c_int, _vp],
+    "spf_b200_fp64_peak": [_vp, C.POINTER(C.c_double)],
+}
+_RESTYPES = {
+    "spf_b200_default_128": None,
+    "spf_b200_destroy": None,
+    "spf_b200_last_error": C.c_char_p,
+    "spf_b200_kernel_launches": C.c_uint64,
+    **{n: _sz for n in ("spf_b200_len_lwe_l0", "spf_b200_len_lwe_l1", "spf_b200_len_glwe_l1", "spf_b200_len_glev_l1",
+                        "spf_b200_len_ggsw_l1", "spf_b200_len_bsk", "spf_b200_len_ksk", "spf_b200_len_ssk",
+                        "spf_b200_len_ak")},
+}
+
+
+def lib() -> C.CDLL:
+    """Load libspf_b200.so.  Fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()); "
+                "spf_b200 has no CPU fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, argtypes in ABI.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = l
+    return _lib
+
+
+def default_128() -> Params:
+    """DEFAULT_128 (parasol_runtime/src/params.rs:107-134)."""
+    p = Params()
+    lib().spf_b200_default_128(C.byref(p))
+    return p
+
+
+def _ptr(a) -> int:
+    """Host pointer of a C-contiguous numpy array, or a raw integer device pointer."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise SpfError(-1, "buffers must be C-contiguous")
+        return a.ctypes.data
+    return int(a)
+
+
+class Evaluation:
+    """`Evaluation` (+ the `KeylessEvaluation` it derefs to) of
+    parasol_runtime/src/crypto/evaluation.rs, batched.  Every method takes arrays whose leading
+    dimension is the batch; outputs are freshly allocated numpy arrays (the reference's
+    `enc.allocate_*` + `&mut` out-parameter pattern, circuit_processor/mod.rs:333-340)."""
+
+    def __init__(self, bsk_fft, ksk, ssk_fft, ak_fft, params: Params | None = None, device: int = 0,
+                 on_device: bool = False):
+        """Evaluation::new(Arc<ComputeKey>, &Params, &Encryption) (evaluation.rs:161-197).
+        Key arrays are ComputeKey's four fields in the reference layout; with on_device=True
+        they are raw device pointers (ints) to the same layout already on `device`."""
+        l = lib()
+        self.params = params if params is not None else default_128()
+        p = self.params
+        self._h = _vp()
+        lens = (l.spf_b200_len_bsk(C.byref(p)), l.spf_b200_len_ksk(C.byref(p)), l.spf_b200_len_ssk(C.byref(p)),
+                l.spf_b200_len_ak(C.byref(p)))
+        if on_device:
+            rc = l.spf_b200_create_from_device(C.byref(p), bsk_fft, lens[0], ksk, lens[1], ssk_fft, lens[2], ak_fft,
+                                               lens[3], device, C.byref(self._h))
+        else:
+            arrs = []
+            for a, dt, n, name in ((bsk_fft, np.complex128, lens[0], "bs_key"), (ksk, np.uint64, lens[1], "ks_key"),
+                                   (ssk_fft, np.complex128, lens[2], "ss_key"), (ak_fft, np.complex128, lens[3], "auto_key")):
+                a = np.ascontiguousarray(a, dtype=dt).reshape(-1)
+                if a.size != n:
+                    raise SpfError(-1, f"{name} has {a.size} elements, params require {n}")
+                arrs.append(a)
+            rc = l.spf_b200_create(C.byref(p), arrs[0].ctypes.data, lens[0], arrs[1].ctypes.data, lens[1],
+                                   arrs[2].ctypes.data, lens[2], arrs[3].ctypes.data, lens[3], device,
+                                   C.byref(self._h))
+        if rc != 0:
+            raise SpfError(rc, (l.spf_b200_last_error(None) or b"").decode())
+        self.len_lwe_l0 = l.spf_b200_len_lwe_l0(C.byref(p))
+        self.len_lwe_l1 = l.spf_b200_len_lwe_l1(C.byref(p))
+        self.len_glwe = l.spf_b200_len_glwe_l1(C.byref(p))
+        self.len_glev = l.spf_b200_len_glev_l1(C.byref(p))
+        self.len_ggsw = l.spf_b200_len_ggsw_l1(C.byref(p))
+
+    # -- plumbing --------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().spf_b200_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SpfError(rc, (lib().spf_b200_last_error(self._h) or b"").decode())
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().spf_b200_kernel_launches(self._h))
+
+    def synchronize(self):
+        self._check(lib().spf_b200_synchronize(self._h))
+
+    def fp64_peak_tflops(self) -> float:
+        out = C.c_double()
+        self._check(lib().spf_b200_fp64_peak(self._h, C.byref(out)))
+        return out.value
+
+    @staticmethod
+    def _in(a, dtype, width, name):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        if a.ndim != 2 or a.shape[1] != width:
+            raise SpfError(-1, f"{name}: expected [batch][{width}] {np.dtype(dtype).name}, got {a.shape}")
+        return a
+
+    # -- Evaluation ------------------------------------------------------------------------
+    def circuit_bootstrap(self, lwe0) -> np.ndarray:
+        """Evaluation::circuit_bootstrap (evaluation.rs:211-225): L0 LWE -> L1 GGSW (FFT)."""
+        x = self._in(lwe0, np.uint64, self.len_lwe_l0, "lwe0")
+        out = np.empty((x.shape[0], self.len_ggsw), dtype=np.complex128)
+        self._check(lib().spf_b200_circuit_bootstrap(self._h, out.ctypes.data, x.ctypes.data, x.shape[0]))
+        return out
+
+    def programmable_bootstrap(self, lwe0, lut_glwe, log_chi: int = 0, log_v: int = 0) -> np.ndarray:
+        """generalized_programmable_bootstrap (programmable_bootstrapping.rs:342-410)."""
+        x = self._in(lwe0, np.uint64, self.len_lwe_l0, "lwe0")
+        lut = self._in(lut_glwe, np.uint64, self.len_glwe, "lut")
+        out = np.empty((x.shape[0], self.len_glwe), dtype=np.uint64)
+        self._check(lib().spf_b200_programmable_bootstrap(self._h, out.ctypes.data, x.ctypes.data, lut.ctypes.data,
+                                                          log_chi, log_v, x.shape[0]))
+        return out
+
+    def keyswitch_lwe_l1_lwe_l0(self, lwe1) -> np.ndarray:
+        """Evaluation::keyswitch_lwe_l1_lwe_l0 (evaluation.rs:243-252)."""
+        x = self._in(lwe1, np.uint64, self.len_lwe_l1, "lwe1")
+        out = np.empty((x.shape[0], self.len_lwe_l0), dtype=np.uint64)
+        self._check(lib().spf_b200_keyswitch_lwe_l1_lwe_l0(self._h, out.ctypes.data, x.ctypes.data, x.shape[0]))
+        return out
+
+    def scheme_switch(self, glev) -> np.ndarray:
+        """Evaluation::scheme_switch (evaluation.rs:231-240)."""
+        x = self._in(glev, np.uint64, self.len_glev, "glev")
+        out = np.empty((x.shape[0], self.len_ggsw), dtype=np.complex128)
+        self._check(lib().spf_b200_scheme_switch(self._h, out.ctypes.data, x.ctypes.data, x.shape[0]))
+        return out
+
+    def trace(self, glwe) -> np.ndarray:
+        """ops::automorphisms::trace (automorphisms/mod.rs:53-85)."""
+        x = self._in(glwe, np.uint64, self.len_glwe, "glwe")
+        out = np.empty_like(x)
+        self._check(lib().spf_b200_trace(self._h, out.ctypes.data, x.ctypes.data, x.shape[0]))
+        return out
+
+    # -- KeylessEvaluation -----------------------------------------------------------------
+    def cmux(self, sel, a, b) -> np.ndarray:
+        """KeylessEvaluation::cmux(output, sel, a, b) (evaluation.rs:68-83): sel ? b : a."""
+        s = self._in(sel, np.complex128, self.len_ggsw, "sel")
+        a = self._in(a, np.uint64, self.len_glwe, "a")
+        b = self._in(b, np.uint64, self.len_glwe, "b")
+        if not (s.shape[0] == a.shape[0] == b.shape[0]):
+            raise SpfError(-1, "cmux: batch sizes differ")
+        out = np.empty_like(a)
+        self._check(lib().spf_b200_cmux(self._h, out.ctypes.data, s.ctypes.data, a.ctypes.data, b.ctypes.data, a.shape[0]))
+        return out
+
+    def glev_cmux(self, sel, a, b) -> np.ndarray:
+        """KeylessEvaluation::glev_cmux (evaluation.rs:86-101)."""
+        s = self._in(sel, np.complex128, self.len_ggsw, "sel")
+        a = self._in(a, np.uint64, self.len_glev, "a")
+        b = self._in(b, np.uint64, self.len_glev, "b")
+        if not (s.shape[0] == a.shape[0] == b.shape[0]):
+            raise SpfError(-1, "glev_cmux: batch sizes differ")
+        out = np.empty_like(a)
+        self._check(lib().spf_b200_glev_cmux(self._h, out.ctypes.data, s.ctypes.data, a.ctypes.data, b.ctypes.data, a.shape[0]))
+        return out
+
+    def multiply_glwe_ggsw(self, glwe, ggsw) -> np.ndarray:
+        """KeylessEvaluation::multiply_glwe_ggsw (evaluation.rs:104-123)."""
+        g = self._in(glwe, np.uint64, self.len_glwe, "glwe")
+        s = self._in(ggsw, np.complex128, self.len_ggsw, "ggsw")
+        if g.shape[0] != s.shape[0]:
+            raise SpfError(-1, "multiply_glwe_ggsw: batch sizes differ")
+        out = np.empty_like(g)
+        self._check(lib().spf_b200_multiply_glwe_ggsw(self._h, out.ctypes.data, g.ctypes.data, s.ctypes.data, g.shape[0]))
+        return out
+
+    def sample_extract_l1(self, glwe, idx) -> np.ndarray:
+        """KeylessEvaluation::sample_extract_l1 (evaluation.rs:126-133); idx scalar or [batch]."""
+        g = self._in(glwe, np.uint64, self.len_glwe, "glwe")
+        out = np.empty((g.shape[0], self.len_lwe_l1), dtype=np.uint64)
+        if np.isscalar(idx):
+            rc = lib().spf_b200_sample_extract_l1(self._h, out.ctypes.data, g.ctypes.data, None, int(idx), g.shape[0])
+        else:
+            ix = np.ascontiguousarray(idx, dtype=np.uint32)
+            if ix.shape != (g.shape[0],):
+                raise SpfError(-1, "sample_extract_l1: idx must have one entry per ciphertext")
+            rc = lib().spf_b200_sample_extract_l1(self._h, out.ctypes.data, g.ctypes.data, ix.ctypes.data, 0, g.shape[0])
+        self._check(rc)
+        return out
+
+    def not_(self, glwe) -> np.ndarray:
+        """KeylessEvaluation::not (evaluation.rs:48-50)."""
+        g = self._in(glwe, np.uint64, self.len_glwe, "glwe")
+        out = np.empty_like(g)
+        self._check(lib().spf_b200_not(self._h, out.ctypes.data, g.ctypes.data, g.shape[0]))
+        return out
+
+    def xor(self, a, b) -> np.ndarray:
+        """KeylessEvaluation::xor (evaluation.rs:53-55)."""
+        a = self._in(a, np.uint64, self.len_glwe, "a")
+        b = self._in(b, np.uint64, self.len_glwe, "b")
+        if a.shape != b.shape:
+            raise SpfError(-1, "xor: batch sizes differ")
+        out = np.empty_like(a)
+        self._check(lib().spf_b200_xor(self._h, out.ctypes.data, a.ctypes.data, b.ctypes.data, a.shape[0]))
+        return out
+
+    def mul_xn(self, glwe, n: int) -> np.ndarray:
+        """KeylessEvaluation::mul_xn (evaluation.rs:58-65)."""
+        g = self._in(glwe, np.uint64, self.len_glwe, "glwe")
+        out = np.empty_like(g)
+        self._check(lib().spf_b200_mul_xn(self._h, out.ctypes.data, g.ctypes.data, int(n), g.shape[0]))
+        return out
+
+    # -- device-pointer entry points (ints = CUdeviceptr), asynchronous on `stream` ----------
+    def dev_circuit_bootstrap(self, d_ggsw_out: int, d_lwe0_in: int, batch: int, reference_scale: bool = False,
+                              stream: int = 0):
+        self._check(lib().spf_b200_dev_circuit_bootstrap(self._h, d_ggsw_out, d_lwe0_in, batch,
+                                                         1 if reference_scale else 0, stream or None))
+
+    def dev_programmable_bootstrap(self, d_glwe_out: int, d_lwe0_in: int, d_lut: int, log_chi: int, log_v: int,
+                                   batch: int, stream: int = 0):
+        self._check(lib().spf_b200_dev_programmable_bootstrap(self._h, d_glwe_out, d_lwe0_in, d_lut, log_chi, log_v,
+                                                              batch, stream or None))
+
+    def dev_cmux(self, d_out: int, d_sel: int, ggsw_stride: int, d_a: int, d_b: int, batch: int, stream: int = 0):
+        self._check(lib().spf_b200_dev_cmux(self._h, d_out, d_sel, ggsw_stride, d_a, d_b, batch, stream or None))
+
+    def dev_keyswitch_lwe_l1_lwe_l0(self, d_out: int, d_in: int, batch: int, stream: int = 0):
+        self._check(lib().spf_b200_dev_keyswitch_lwe_l1_lwe_l0(self._h, d_out, d_in, batch, stream or None))
+
+    def dev_sample_extract_l1(self, d_out: int, d_glwe: int, d_idx: int, idx_all: int, batch: int, stream: int = 0):
+        self._check(lib().spf_b200_dev_sample_extract_l1(self._h, d_out, d_glwe, d_idx or None, idx_all, batch,
+                                                         stream or None))
+
+    def dev_fft_rescale(self, d_dst: int, d_src: int, n: int, to_device: bool, stream: int = 0):
+        self._check(lib().spf_b200_dev_fft_rescale(self._h, d_dst, d_src, n, 1 if to_device else 0, stream or None))

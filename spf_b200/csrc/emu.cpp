@@ -1,0 +1,141 @@
+// emu.cpp -- HOST EMULATOR of the device kernel bodies (team_ops.cuh / fft16.cuh).
+// Test infrastructure: runs the exact __host__ __device__ code of the CUDA kernels with one
+// host thread per virtual GPU thread (64 per team) and a pthread barrier in place of bar.sync,
+// so the FFT factorisation, the team layout and every index computation are checked against
+// the oracle on machines without a GPU.  Built by g++ into libspf_emu.so; never shipped on the
+// product path and never used as a fallback.
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cmath>
+#include <vector>
+
+#include "tables.h"
+#include "team_ops.cuh"
+
+using namespace spf;
+
+namespace {
+
+struct HostCx {
+  int u;
+  pthread_barrier_t* bar;
+  void sync() { pthread_barrier_wait(bar); }
+};
+
+template <class Body>
+struct Launch {
+  Body* body;
+  HostCx cx;
+  static void* run(void* p) {
+    Launch* l = (Launch*)p;
+    (*l->body)(l->cx);
+    return nullptr;
+  }
+};
+
+template <class Body>
+void run_team(Body body) {
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, kTeam);
+  std::vector<Launch<Body>> ls(kTeam);
+  std::vector<pthread_t> th(kTeam);
+  for (int u = 0; u < kTeam; u++) {
+    ls[u].body = &body;
+    ls[u].cx = HostCx{u, &bar};
+    pthread_create(&th[u], nullptr, Launch<Body>::run, &ls[u]);
+  }
+  for (int u = 0; u < kTeam; u++) pthread_join(th[u], nullptr);
+  pthread_barrier_destroy(&bar);
+}
+
+struct Tables {
+  std::vector<C2> T1, T2;
+  Tables() : T1(kT1Elems), T2(kT2Elems) { fill_twiddle_tables(T1.data(), T2.data()); }
+};
+const Tables& tables() {
+  static Tables t;
+  return t;
+}
+
+}  // namespace
+
+extern "C" {
+
+// reference-scale FFT-domain polys -> device scale (2^-10)
+void emu_import_fft(const C2* src, C2* dst, size_t npoly) {
+  for (size_t q = 0; q < npoly; q++) import_fft_poly(src + q * kM, dst + q * kM);
+}
+void emu_export_fft(const C2* src, C2* dst, size_t npoly) {
+  for (size_t q = 0; q < npoly; q++) export_fft_poly(src + q * kM, dst + q * kM);
+}
+
+// PolynomialRef::fft in the reference's (natural order, unscaled) convention, via the team code.
+void emu_poly_fft(const uint64_t* poly, C2* out_natural) {
+  const Tables& t = tables();
+  std::vector<C2> xbuf(kXBuf), dev(kM);
+  run_team([&](HostCx& cx) {
+    C2 v[16];
+    team_poly_fft(cx, v, [&](int j) { return poly[j]; }, xbuf.data(), t.T1.data(), t.T2.data());
+    for (int s = 0; s < 16; s++) dev[bin_of(cx.u, s)] = v[s];
+  });
+  export_fft_poly(dev.data(), out_natural);
+}
+
+// PolynomialFftRef::ifft (natural order, unscaled input) via the team code.
+void emu_poly_ifft(const C2* in_natural, uint64_t* poly) {
+  const Tables& t = tables();
+  std::vector<C2> xbuf(kXBuf), dev(kM);
+  import_fft_poly(in_natural, dev.data());
+  run_team([&](HostCx& cx) {
+    C2 v[16];
+    for (int s = 0; s < 16; s++) v[s] = dev[bin_of(cx.u, s)];
+    team_fft_inv(cx, v, xbuf.data(), t.T1.data(), t.T2.data());
+    for (int m = 0; m < 16; m++) {
+      poly[cx.u + 64 * m] = f64_to_torus(v[m].x);
+      poly[cx.u + 64 * m + kM] = f64_to_torus(v[m].y);
+    }
+  });
+}
+
+uint64_t emu_f64_to_torus(double x) { return f64_to_torus(x); }
+double emu_i32_to_f64(int32_t x) { return i32_to_f64(x); }
+
+// cmux with the GGSW given in team layout (2^-10 scaled); d0 may be null (external product)
+void emu_cmux(uint64_t* out, const uint64_t* d0, const uint64_t* d1, const C2* ggsw_dev, int radix_log,
+              int count) {
+  const Tables& t = tables();
+  std::vector<C2> xbuf(kXBuf);
+  std::vector<uint64_t> st(32 * 64);
+  run_team([&](HostCx& cx) {
+    cmux_team(cx, out, d0, d1, ggsw_dev, st.data(), xbuf.data(), t.T1.data(), t.T2.data(), radix_log, count);
+  });
+}
+
+// generalized PBS; bsk in team layout.  lut may be null (CBS mode).
+void emu_pbs(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, const C2* bsk_dev, int lwe_n,
+             int log_chi, int log_v, int cbs_radix_log, int cbs_count) {
+  const Tables& t = tables();
+  std::vector<C2> xbuf(kXBuf);
+  std::vector<uint64_t> acc(2 * kN);
+  std::vector<int16_t> stash(32 * 64);
+  PbsArgs A{lwe_in, lut, glwe_out, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count};
+  run_team([&](HostCx& cx) { pbs_team(cx, A, acc.data(), stash.data(), xbuf.data(), t.T1.data(), t.T2.data()); });
+}
+
+// trace / CBS tail for one level.  mode: 0 CBS pre-process + trace (+SS), 1 plain trace, 2 SS only.
+void emu_trace_ss(const uint64_t* glwe_in, uint64_t* glev_out, C2* ggsw_out_dev, const C2* ak_dev,
+                  const C2* ssk_dev, int level, int mode, int cbs_radix_log, int cbs_count, int tr_radix_log,
+                  int tr_count, int ss_radix_log, int ss_count) {
+  const Tables& t = tables();
+  std::vector<C2> xbuf(kXBuf);
+  std::vector<uint64_t> g(2 * kN), st(32 * 64);
+  uint32_t kinv[11];
+  fill_kinv(kinv);
+  TraceSsArgs A{glwe_in, glev_out, ggsw_out_dev, ak_dev, ssk_dev, kinv, level, mode, cbs_radix_log,
+                cbs_count, tr_radix_log, tr_count, ss_radix_log, ss_count, 1.0};
+  run_team([&](HostCx& cx) { trace_ss_team(cx, A, g.data(), st.data(), xbuf.data(), t.T1.data(), t.T2.data()); });
+}
+
+}  // extern "C"

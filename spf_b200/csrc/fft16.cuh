@@ -1,0 +1,279 @@
+// fft16.cuh -- the negacyclic f64 FFT of an N=2048 torus polynomial for one TEAM of 64 threads,
+// 16 complex points per thread held in registers.  Replaces TwistedFft::{forward,reverse}
+// (sunscreen_tfhe/src/math/fft/negacyclic/mod.rs:96-122) + complex_twist/untwist
+// (math/simd/scalar.rs:19-35) + the rustfft butterflies behind them.
+//
+// Everything here is __host__ __device__: the SAME index arithmetic is executed on the CPU
+// by csrc/emu.cpp (one loop iteration per virtual thread, phases split at the barriers) so the
+// factorisation is validated against the oracle without a GPU.
+//
+// Factorisation of the length-1024 complex DFT: 1024 = 16 x 16 x 4.
+//   n = a + 64 m           (a = thread, m = register)           time index
+//   k = k1 + 16 (k2 + 16 k3)                                    frequency index
+//   pass 1  thread a      : u[m] = x[m] * e^{i pi m/32}  (the m-part of the twist, constants)
+//                           y[k1] = DFT16_m(u) * T1[a][k1],  T1 = e^{i pi a/2048} * W1024^{a k1}
+//   xchg 1  (smem)        : thread (k1,q) gathers y[q + 4 m'][k1], m' = 0..15
+//   pass 2  thread (k1,q) : z[k2] = DFT16_m'(y) * W64^{q k2}
+//   xchg 2  (smem)        : thread (k1,q) gathers z[k1][q'][k2] for q'=0..3, k2 = q + 4 j
+//   pass 3  thread (k1,q) : X[k1 + 16 k2 + 256 k3] = DFT4_q'(z)      -> slot s = 4 j + k3
+// The inverse runs the adjoint passes in reverse order (no bit-reversal anywhere): the forward
+// output ownership (thread u, slot s) is exactly the inverse input ownership, so FFT-domain
+// accumulators never leave registers.  Frequency-domain arrays in device memory keep the
+// reference's natural bin order: register slot s of thread u is bin spf::bin_of(u, s).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SPF_HD __host__ __device__ __forceinline__
+#else
+#define SPF_HD inline __attribute__((always_inline))
+#endif
+
+#include "fft_consts.h"
+
+namespace spf {
+
+struct alignas(16) C2 {
+  double x, y;
+};
+
+constexpr int kN = 2048;        // polynomial degree (DEFAULT_128 l1_params)
+constexpr int kM = 1024;        // complex FFT length
+constexpr int kTeam = 64;       // threads per polynomial transform
+constexpr int kR = 16;          // complex points per thread
+constexpr int kXPad = 65;       // exchange-buffer row stride in complex elements (odd: conflict-free)
+constexpr int kXBuf = 16 * kXPad;  // complex elements per team exchange buffer (16640 B)
+constexpr int kT2Pad = 17;
+constexpr int kT1Elems = 16 * 64;
+constexpr int kT2Elems = 4 * kT2Pad;
+
+// Register slot s = 4 j + k3 of thread u = k1 + 16 q holds frequency bin
+//   k = k1 + 16 (q + 4 j) + 256 k3 = u + 64 * slot_row(s),
+// so FFT-domain arrays stay in the reference's natural bin order in memory and every slot is a
+// fully coalesced row of 64 consecutive complex values.
+SPF_HD constexpr int slot_row(int s) { return (s >> 2) + 4 * (s & 3); }
+SPF_HD constexpr int bin_of(int u, int s) { return u + 64 * slot_row(s); }
+
+SPF_HD C2 cadd(C2 a, C2 b) { return C2{a.x + b.x, a.y + b.y}; }
+SPF_HD C2 csub(C2 a, C2 b) { return C2{a.x - b.x, a.y - b.y}; }
+// a * (c + i s)
+SPF_HD C2 cmul_cs(C2 a, double c, double s) { return C2{a.x * c - a.y * s, a.x * s + a.y * c}; }
+SPF_HD C2 cmul(C2 a, C2 b) { return C2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+SPF_HD C2 cmul_conj(C2 a, C2 b) { return C2{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }  // a * conj(b)
+// acc += a * b
+SPF_HD void cmad(C2& acc, C2 a, C2 b) {
+  acc.x += a.x * b.x - a.y * b.y;
+  acc.y += a.x * b.y + a.y * b.x;
+}
+
+// 4-point DFT in place: (a,b,c,d) -> (X0,X1,X2,X3); INV uses e^{+...}
+template <bool INV>
+SPF_HD void bfly4(C2& a, C2& b, C2& c, C2& d) {
+  C2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
+  a = cadd(apc, bpd);
+  c = csub(apc, bpd);
+  if (!INV) {
+    b = C2{amc.x + bmd.y, amc.y - bmd.x};
+    d = C2{amc.x - bmd.y, amc.y + bmd.x};
+  } else {
+    b = C2{amc.x - bmd.y, amc.y + bmd.x};
+    d = C2{amc.x + bmd.y, amc.y - bmd.x};
+  }
+}
+
+// 16-point DFT, natural order in -> natural order out, all twiddles compile-time constants.
+template <bool INV>
+SPF_HD void dft16(C2 (&v)[16]) {
+#pragma unroll
+  for (int m0 = 0; m0 < 4; m0++) bfly4<INV>(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]);
+    // v[m0 + 4 kl] = Y[m0][kl];  twiddle W16^{m0 kl}
+#pragma unroll
+  for (int m0 = 1; m0 < 4; m0++) {
+#pragma unroll
+    for (int kl = 1; kl < 4; kl++) {
+      const int e = 4 * m0 * kl;  // angle pi*e/32 = 2 pi m0 kl / 16
+      const double c = spf_cos32(e), s = INV ? spf_sin32(e) : -spf_sin32(e);
+      v[m0 + 4 * kl] = cmul_cs(v[m0 + 4 * kl], c, s);
+    }
+  }
+#pragma unroll
+  for (int kl = 0; kl < 4; kl++) bfly4<INV>(v[4 * kl], v[4 * kl + 1], v[4 * kl + 2], v[4 * kl + 3]);
+  // v[4 kl + kh] = X[kl + 4 kh] -> natural order
+  C2 t[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) t[i] = v[i];
+#pragma unroll
+  for (int kl = 0; kl < 4; kl++) {
+#pragma unroll
+    for (int kh = 0; kh < 4; kh++) v[kl + 4 * kh] = t[4 * kl + kh];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward passes.  v[m] on entry to fwd_pass1 = (p[a + 64 m], p[a + 64 m + 1024]) as doubles.
+// ------------------------------------------------------------------------------------------
+SPF_HD void fwd_pass1(C2 (&v)[16], int a, const C2* T1) {
+#pragma unroll
+  for (int m = 1; m < 16; m++) v[m] = cmul_cs(v[m], spf_cos32(m), spf_sin32(m));
+  dft16<false>(v);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; k1++) v[k1] = cmul(v[k1], T1[k1 * 64 + a]);
+}
+SPF_HD void fwd_x1_write(const C2 (&v)[16], C2* buf, int a) {
+#pragma unroll
+  for (int k1 = 0; k1 < 16; k1++) buf[k1 * kXPad + a] = v[k1];
+}
+SPF_HD void fwd_x1_read(C2 (&v)[16], const C2* buf, int u) {
+  const int k1 = u & 15, q = u >> 4;
+#pragma unroll
+  for (int mp = 0; mp < 16; mp++) v[mp] = buf[k1 * kXPad + q + 4 * mp];
+}
+SPF_HD void fwd_pass2(C2 (&v)[16], int u, const C2* T2) {
+  const int q = u >> 4;
+  dft16<false>(v);
+#pragma unroll
+  for (int k2 = 1; k2 < 16; k2++) v[k2] = cmul(v[k2], T2[q * kT2Pad + k2]);
+}
+SPF_HD void fwd_x2_write(const C2 (&v)[16], C2* buf, int u) {
+#pragma unroll
+  for (int k2 = 0; k2 < 16; k2++) buf[k2 * kXPad + u] = v[k2];
+}
+SPF_HD void fwd_x2_read(C2 (&v)[16], const C2* buf, int u) {
+  const int k1 = u & 15, q = u >> 4;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+#pragma unroll
+    for (int qp = 0; qp < 4; qp++) v[4 * j + qp] = buf[(q + 4 * j) * kXPad + k1 + 16 * qp];
+  }
+}
+SPF_HD void fwd_pass3(C2 (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) bfly4<false>(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// inverse passes (adjoint of the forward ones).  On exit from inv_pass1,
+// v[m] = (re, im) with re -> coefficient a + 64 m, im -> coefficient a + 64 m + 1024, both
+// multiplied by 1024 (the 1/(N/2) of complex_untwist is folded into the key material).
+// ------------------------------------------------------------------------------------------
+SPF_HD void inv_pass3(C2 (&v)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) bfly4<true>(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+SPF_HD void inv_x2_write(const C2 (&v)[16], C2* buf, int u) {
+  const int k1 = u & 15, q = u >> 4;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+#pragma unroll
+    for (int qp = 0; qp < 4; qp++) buf[(q + 4 * j) * kXPad + k1 + 16 * qp] = v[4 * j + qp];
+  }
+}
+SPF_HD void inv_x2_read(C2 (&v)[16], const C2* buf, int u) {
+#pragma unroll
+  for (int k2 = 0; k2 < 16; k2++) v[k2] = buf[k2 * kXPad + u];
+}
+SPF_HD void inv_pass2(C2 (&v)[16], int u, const C2* T2) {
+  const int q = u >> 4;
+#pragma unroll
+  for (int k2 = 1; k2 < 16; k2++) v[k2] = cmul_conj(v[k2], T2[q * kT2Pad + k2]);
+  dft16<true>(v);
+}
+SPF_HD void inv_x1_write(const C2 (&v)[16], C2* buf, int u) {
+  const int k1 = u & 15, q = u >> 4;
+#pragma unroll
+  for (int mp = 0; mp < 16; mp++) buf[k1 * kXPad + q + 4 * mp] = v[mp];
+}
+SPF_HD void inv_x1_read(C2 (&v)[16], const C2* buf, int a) {
+#pragma unroll
+  for (int k1 = 0; k1 < 16; k1++) v[k1] = buf[k1 * kXPad + a];
+}
+SPF_HD void inv_pass1(C2 (&v)[16], int a, const C2* T1) {
+#pragma unroll
+  for (int k1 = 0; k1 < 16; k1++) v[k1] = cmul_conj(v[k1], T1[k1 * 64 + a]);
+  dft16<true>(v);
+#pragma unroll
+  for (int m = 1; m < 16; m++) v[m] = cmul_cs(v[m], spf_cos32(m), -spf_sin32(m));
+}
+
+// ------------------------------------------------------------------------------------------
+// scalar conversions
+// ------------------------------------------------------------------------------------------
+
+// int32 -> f64 without the conversion pipe: 2^52 + 2^31 + x is exact, subtract the bias.
+SPF_HD double i32_to_f64(int32_t x) {
+  uint64_t bits = 0x4330000000000000ull | (uint64_t)((uint32_t)x ^ 0x80000000u);
+  double d;
+#if defined(__CUDA_ARCH__)
+  d = __longlong_as_double((long long)bits);
+#else
+  __builtin_memcpy(&d, &bits, 8);
+#endif
+  return d - 4503601774854144.0;  // 2^52 + 2^31
+}
+
+// int64 -> f64, round to nearest even (what `as f64` does; entities/polynomial.rs:264-268).
+SPF_HD double i64_to_f64(int64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ll2double_rn((long long)x);
+#else
+  return (double)x;
+#endif
+}
+
+// f64 -> torus: complex_untwist's round() (half away from zero, simd/scalar.rs:32-33) followed by
+// vector_mod_pow2_q_f64 for q = 2^64 (scalar.rs:75-119) and the saturating `as i64`
+// (math/torus.rs:181-185), as pure integer arithmetic on the IEEE bits.
+SPF_HD uint64_t f64_to_torus(double x) {
+  uint64_t bits;
+#if defined(__CUDA_ARCH__)
+  bits = (uint64_t)__double_as_longlong(x);
+#else
+  __builtin_memcpy(&bits, &x, 8);
+#endif
+  const int e = (int)((bits >> 52) & 0x7FF);
+  const uint64_t mant = (bits & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+  const int sh = e - 1075;  // |x| = mant * 2^sh
+  uint64_t r;
+  if (e == 0) r = 0;
+  else if (sh >= 0) r = sh >= 64 ? 0 : mant << sh;
+  else {
+    const int rs = -sh;
+    r = rs >= 54 ? 0 : (mant + (1ull << (rs - 1))) >> rs;
+  }
+  if (bits >> 63) {
+    r = 0 - r;
+    // the reference maps negative odd multiples of 2^63 to i64::MAX (wrap to +2^63, then the
+    // saturating cast); keep the quirk so results stay bit-identical.
+    if (r == 0x8000000000000000ull) r = 0x7FFFFFFFFFFFFFFFull;
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// radix decomposition (math/radix.rs:67-114,155-162; simd/scalar.rs:52-72)
+// ------------------------------------------------------------------------------------------
+SPF_HD uint64_t radix_round(uint64_t x, int radix_log, int count) {
+  const int shift = 64 - radix_log * count;
+  return (x >> shift) + ((x >> (shift - 1)) & 1);
+}
+// one vector_next_decomp step on a scalar; returns the signed digit
+SPF_HD int32_t next_digit(uint64_t& s, int radix_log) {
+  const uint64_t mask = (1ull << radix_log) - 1;
+  uint64_t digit = s & mask;
+  s >>= radix_log;
+  const uint64_t carry = digit >> (radix_log - 1);
+  s += carry;
+  return (int32_t)((int64_t)digit - (int64_t)(carry << radix_log));
+}
+
+// (p * X^rot)[j] for 0 <= rot < 2N: entities/polynomial.rs:211-236 as a gather.
+SPF_HD uint64_t rotated_coeff(const uint64_t* p, int j, int rot) {
+  int idx = j - rot;          // in (-2N, N)
+  bool neg = false;
+  if (idx < 0) { idx += kN; neg = true; }
+  if (idx < 0) { idx += kN; neg = false; }
+  const uint64_t v = p[idx];
+  return neg ? 0 - v : v;
+}
+
+}  // namespace spf

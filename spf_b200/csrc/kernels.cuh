@@ -1,0 +1,283 @@
+// kernels.cuh -- sm_100a __global__ kernels for the circuit-bootstrapping hot path.
+// The per-team bodies live in team_ops.cuh (shared with the host emulator); this file adds the
+// CTA organisation: shared-memory carve-up, named barriers, grid mapping.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "team_ops.cuh"
+
+namespace spf {
+
+// One team = 2 warps.  Team-private named barrier ids 1..15 (0 is __syncthreads).
+struct DevCx {
+  int u;
+  int bar;
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+  }
+};
+
+struct DevTables {
+  const C2* T1;  // global copies of the twiddle tables
+  const C2* T2;
+};
+
+__device__ __forceinline__ void load_tables(C2* sT1, C2* sT2, const DevTables& t) {
+  for (int i = threadIdx.x; i < kT1Elems; i += blockDim.x) sT1[i] = t.T1[i];
+  for (int i = threadIdx.x; i < kT2Elems; i += blockDim.x) sT2[i] = t.T2[i];
+  __syncthreads();
+}
+
+constexpr int kTableBytes = (kT1Elems + kT2Elems) * 16;  // 17472
+
+// ------------------------------------------------------------------------------------------
+// K3: batched programmable bootstrap.  4 ciphertexts per CTA (one per team), one CTA per SM;
+// every team walks the 637 BSK rows in order, so a row is fetched from HBM once and then served
+// from L2 to all resident CTAs.
+// ------------------------------------------------------------------------------------------
+constexpr int kPbsTeams = 4;
+constexpr int kPbsTeamBytes = 2 * kN * 8 + kXBuf * 16 + 32 * 64 * 2;  // acc + xbuf + stash = 53504
+constexpr int kPbsSmem = kTableBytes + kPbsTeams * kPbsTeamBytes;      // 231488
+
+struct PbsBatch {
+  const uint64_t* lwe_in;   // [B][n+1]
+  const uint64_t* lut;      // shared GLWE LUT, or nullptr for CBS mode
+  size_t lut_stride;        // 0: one LUT for the whole batch, else per-ciphertext stride (elements)
+  uint64_t* glwe_out;       // [B][2][2048]
+  const C2* bsk;
+  int batch, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count;
+};
+
+__global__ void __launch_bounds__(kPbsTeams * kTeam, 1) pbs_kernel(PbsBatch P, DevTables tabs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  C2* sT1 = reinterpret_cast<C2*>(smem);
+  C2* sT2 = sT1 + kT1Elems;
+  load_tables(sT1, sT2, tabs);
+  const int team = threadIdx.x / kTeam;
+  const int c = blockIdx.x * kPbsTeams + team;
+  if (c >= P.batch) return;
+  unsigned char* base = smem + kTableBytes + team * kPbsTeamBytes;
+  uint64_t* acc = reinterpret_cast<uint64_t*>(base);
+  C2* xbuf = reinterpret_cast<C2*>(base + 2 * kN * 8);
+  int16_t* stash = reinterpret_cast<int16_t*>(base + 2 * kN * 8 + kXBuf * 16);
+  DevCx cx{(int)(threadIdx.x % kTeam), team + 1};
+  PbsArgs A;
+  A.lwe_in = P.lwe_in + (size_t)c * (P.lwe_n + 1);
+  A.lut = P.lut ? P.lut + (size_t)c * P.lut_stride : nullptr;
+  A.glwe_out = P.glwe_out + (size_t)c * 2 * kN;
+  A.bsk = P.bsk;
+  A.lwe_n = P.lwe_n;
+  A.log_chi = P.log_chi;
+  A.log_v = P.log_v;
+  A.cbs_radix_log = P.cbs_radix_log;
+  A.cbs_count = P.cbs_count;
+  pbs_team(cx, A, acc, stash, xbuf, sT1, sT2);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5+K6: trace (+ CBS pre-processing) and scheme switch, one team per (ciphertext, level).
+// ------------------------------------------------------------------------------------------
+constexpr int kTrTeams = 3;
+constexpr int kTrTeamBytes = 2 * kN * 8 + 32 * 64 * 8 + kXBuf * 16;  // g + state + xbuf = 65792
+constexpr int kTrSmem = kTableBytes + kTrTeams * kTrTeamBytes;        // 214848
+
+struct TraceSsBatch {
+  const uint64_t* glwe_in;  // mode 0: [B][2][2048] PBS outputs; mode 1: [B][...] GLWEs; mode 2: [B][l][2][2048] GLEVs
+  uint64_t* glev_out;       // optional [B][levels][2][2048] (mode 0/1)
+  C2* ggsw_out;             // optional [B][2][l][2][1024]
+  const C2* ak;
+  const C2* ssk;
+  const uint32_t* kinv;
+  int batch, levels, mode;
+  int cbs_radix_log, cbs_count, tr_radix_log, tr_count, ss_radix_log, ss_count;
+  double out_scale;
+};
+
+__global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(TraceSsBatch P, DevTables tabs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  C2* sT1 = reinterpret_cast<C2*>(smem);
+  C2* sT2 = sT1 + kT1Elems;
+  load_tables(sT1, sT2, tabs);
+  const int team = threadIdx.x / kTeam;
+  const int item = blockIdx.x * kTrTeams + team;
+  if (item >= P.batch * P.levels) return;
+  const int c = item / P.levels, level = item % P.levels;
+  unsigned char* base = smem + kTableBytes + team * kTrTeamBytes;
+  uint64_t* g = reinterpret_cast<uint64_t*>(base);
+  uint64_t* st = reinterpret_cast<uint64_t*>(base + 2 * kN * 8);
+  C2* xbuf = reinterpret_cast<C2*>(base + 2 * kN * 8 + 32 * 64 * 8);
+  DevCx cx{(int)(threadIdx.x % kTeam), team + 1};
+  TraceSsArgs A;
+  const size_t glwe = 2 * kN;
+  if (P.mode == 0) A.glwe_in = P.glwe_in + (size_t)c * glwe;
+  else if (P.mode == 1) A.glwe_in = P.glwe_in + (size_t)item * glwe;
+  else A.glwe_in = P.glwe_in + (size_t)item * glwe;
+  A.glev_out = P.glev_out ? P.glev_out + (size_t)item * glwe : nullptr;
+  A.ggsw_out = P.ggsw_out ? P.ggsw_out + (size_t)c * 2 * P.cbs_count * 2 * kM : nullptr;
+  A.ak = P.ak;
+  A.ssk = P.ssk;
+  A.kinv = P.kinv;
+  A.level = level;
+  A.mode = P.mode;
+  A.cbs_radix_log = P.cbs_radix_log;
+  A.cbs_count = P.cbs_count;
+  A.tr_radix_log = P.tr_radix_log;
+  A.tr_count = P.tr_count;
+  A.ss_radix_log = P.ss_radix_log;
+  A.ss_count = P.ss_count;
+  A.out_scale = P.out_scale;
+  trace_ss_team(cx, A, g, st, xbuf, sT1, sT2);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: runtime CMUX / external product, one team per GLWE output.
+// ------------------------------------------------------------------------------------------
+constexpr int kCmuxTeams = 4;
+constexpr int kCmuxTeamBytes = 32 * 64 * 8 + kXBuf * 16;          // state + xbuf = 33024
+constexpr int kCmuxSmem = kTableBytes + kCmuxTeams * kCmuxTeamBytes;  // 149568
+
+struct CmuxBatch {
+  uint64_t* out;          // [B][glwe_per_item][2][2048]
+  const uint64_t* d0;     // nullptr: plain external product of d1
+  const uint64_t* d1;
+  const C2* ggsw;         // 2^-10 scaled
+  size_t ggsw_stride;     // elements between consecutive items' GGSWs (0 = shared)
+  int batch;              // number of GLWE outputs
+  int glwe_per_item;      // 1 for cmux, l_cbs for glev_cmux (GLWEs sharing one GGSW)
+  int radix_log, count;
+};
+
+__global__ void __launch_bounds__(kCmuxTeams * kTeam, 1) cmux_kernel(CmuxBatch P, DevTables tabs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  C2* sT1 = reinterpret_cast<C2*>(smem);
+  C2* sT2 = sT1 + kT1Elems;
+  load_tables(sT1, sT2, tabs);
+  const int team = threadIdx.x / kTeam;
+  const int c = blockIdx.x * kCmuxTeams + team;
+  if (c >= P.batch) return;
+  unsigned char* base = smem + kTableBytes + team * kCmuxTeamBytes;
+  uint64_t* st = reinterpret_cast<uint64_t*>(base);
+  C2* xbuf = reinterpret_cast<C2*>(base + 32 * 64 * 8);
+  DevCx cx{(int)(threadIdx.x % kTeam), team + 1};
+  const size_t glwe = 2 * kN;
+  cmux_team(cx, P.out + (size_t)c * glwe, P.d0 ? P.d0 + (size_t)c * glwe : nullptr, P.d1 + (size_t)c * glwe,
+            P.ggsw + (size_t)(c / P.glwe_per_item) * P.ggsw_stride, st, xbuf, sT1, sT2, P.radix_log, P.count);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: LWE keyswitch L1 -> L0 (ops/keyswitch/lwe_keyswitch.rs:23-62), integer only.
+// out = (0, b) - sum_i sum_t digit_t(a_i) * KSK[i][l-1-t].  A CTA owns kKsBatch inputs and all
+// n0+1 output columns, so each KSK row is read once per kKsBatch ciphertexts.
+// ------------------------------------------------------------------------------------------
+constexpr int kKsBatch = 16;
+constexpr int kKsThreads = 320;
+
+struct KsBatch {
+  uint64_t* out;        // [B][n0+1]
+  const uint64_t* in;   // [B][n1+1]
+  const uint64_t* ksk;  // [n1][l][n0+1]
+  int batch, n1, n0, radix_log, count;
+};
+
+__global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t* st = reinterpret_cast<uint32_t*>(smem);  // [kKsBatch][n1] rounded states (l*logB <= 32 bits)
+  const int b0 = blockIdx.x * kKsBatch;
+  const int nb = min(kKsBatch, P.batch - b0);
+  for (int idx = threadIdx.x; idx < kKsBatch * P.n1; idx += blockDim.x) {
+    const int b = idx / P.n1, i = idx % P.n1;
+    st[idx] = b < nb ? (uint32_t)radix_round(P.in[(size_t)(b0 + b) * (P.n1 + 1) + i], P.radix_log, P.count) : 0u;
+  }
+  __syncthreads();
+  const int cols = P.n0 + 1;
+  const int c0 = threadIdx.x, c1 = threadIdx.x + kKsThreads;
+  const bool has0 = c0 < cols, has1 = c1 < cols;
+  uint64_t acc0[kKsBatch], acc1[kKsBatch];
+#pragma unroll
+  for (int b = 0; b < kKsBatch; b++) { acc0[b] = 0; acc1[b] = 0; }
+  const uint32_t mask = (1u << P.radix_log) - 1;
+  for (int i = 0; i < P.n1; i++) {
+    uint32_t s[kKsBatch];
+#pragma unroll
+    for (int b = 0; b < kKsBatch; b++) s[b] = st[b * P.n1 + i];
+    for (int t = 0; t < P.count; t++) {
+      const uint64_t* row = P.ksk + ((size_t)i * P.count + (P.count - 1 - t)) * cols;
+      const uint64_t k0 = has0 ? __ldg(reinterpret_cast<const unsigned long long*>(row + c0)) : 0;
+      const uint64_t k1 = has1 ? __ldg(reinterpret_cast<const unsigned long long*>(row + c1)) : 0;
+#pragma unroll
+      for (int b = 0; b < kKsBatch; b++) {
+        const uint32_t digit = s[b] & mask;
+        const uint32_t carry = digit >> (P.radix_log - 1);
+        s[b] = (s[b] >> P.radix_log) + carry;
+        const int64_t d = (int64_t)digit - ((int64_t)carry << P.radix_log);
+        acc0[b] += k0 * (uint64_t)d;
+        acc1[b] += k1 * (uint64_t)d;
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < kKsBatch; b++) {
+    if (b >= nb) break;
+    uint64_t* o = P.out + (size_t)(b0 + b) * cols;
+    const uint64_t body = P.in[(size_t)(b0 + b) * (P.n1 + 1) + P.n1];
+    if (has0) o[c0] = (c0 == P.n0 ? body : 0) - acc0[b];
+    if (has1) o[c1] = (c1 == P.n0 ? body : 0) - acc1[b];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: small integer ops
+// ------------------------------------------------------------------------------------------
+// sample_extract (ops/ciphertext/glwe_ciphertext_ops.rs:31-76), k = 1
+__global__ void sample_extract_kernel(uint64_t* out, const uint64_t* glwe, const uint32_t* idx, uint32_t idx_const,
+                                      int batch) {
+  const int c = blockIdx.y;
+  if (c >= batch) return;
+  const int h = idx ? (int)idx[c] : (int)idx_const;
+  const uint64_t* a = glwe + (size_t)c * 2 * kN;
+  uint64_t* o = out + (size_t)c * (kN + 1);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= kN; j += gridDim.x * blockDim.x) {
+    if (j == kN) o[j] = a[kN + h];
+    else o[j] = j <= h ? a[h - j] : 0 - a[h + kN - j];
+  }
+}
+
+// op 0: out = a + b (xor, evaluation.rs:53-55); op 1: out = a + trivial_one (not, :48-50);
+// op 2: out = a * X^n (mul_xn, :58-65)
+__global__ void glwe_elementwise_kernel(uint64_t* out, const uint64_t* a, const uint64_t* b, int op, uint32_t n,
+                                        size_t batch) {
+  const size_t total = batch * 2 * kN;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t c = e / (2 * kN);
+    const int r = (int)(e % (2 * kN)) / kN, j = (int)(e % kN);
+    const uint64_t* pa = a + c * 2 * kN + r * kN;
+    uint64_t v;
+    if (op == 0) v = pa[j] + b[e];
+    else if (op == 1) v = pa[j] + ((r == 1 && j == 0) ? (1ull << 63) : 0ull);
+    else v = rotated_coeff(pa, j, (int)(n & (2 * kN - 1)));
+    out[e] = v;
+  }
+}
+
+// FFT-domain polynomials: dst = src * scale (2^-10 to import reference-scale data, 2^10 to export)
+__global__ void fft_scale_kernel(C2* dst, const C2* src, size_t n, double scale) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const C2 x = src[e];
+    dst[e] = C2{x.x * scale, x.y * scale};
+  }
+}
+
+// FP64 peak probe: dependent-free DFMA chains on every SM (MEASURED_PEAKS.json has
+// no FP64 figure, the builder measures one).
+__global__ void dfma_probe_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000000001, c = 1e-12;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace spf

@@ -1,0 +1,399 @@
+// team_ops.cuh -- bodies of the hot-path kernels, written once for a TEAM of 64 threads and
+// compiled for BOTH the device (kernels.cu, barrier = named bar.sync) and the host emulator
+// (emu.cpp, barrier = pthread barrier over 64 host threads).  One team owns one GLWE
+// accumulator / one ciphertext at a time.
+//
+// Device conventions:
+//  * time domain: thread u owns coefficients j = u + 64*i, i = 0..31 of every polynomial
+//    (i < 16 -> real part of FFT point m = i, i >= 16 -> imaginary part of point m = i - 16);
+//  * frequency domain: thread u owns the 16 bins bin_of(u, s) = u + 64*slot_row(s); arrays are
+//    stored in the reference's natural bin order, so each slot is a coalesced 1 KiB row;
+//  * every FFT-domain key / GGSW resident on the device carries a factor 2^-10 (= 1/(N/2), the
+//    normalisation of complex_untwist, simd/scalar.rs:27); scaling by a power of two is exact
+//    so results are bit-identical to normalising after the inverse transform.
+#pragma once
+#include "fft16.cuh"
+
+namespace spf {
+
+constexpr double kInvM = 1.0 / 1024.0;
+
+SPF_HD C2 ldg_c2(const C2* p) {
+#if defined(__CUDA_ARCH__)
+  const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+  return C2{t.x, t.y};
+#else
+  return *p;
+#endif
+}
+SPF_HD C2 cscale(C2 a, double f) { return C2{a.x * f, a.y * f}; }
+SPF_HD uint64_t ldg_u64(const uint64_t* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(reinterpret_cast<const unsigned long long*>(p));
+#else
+  return *p;
+#endif
+}
+
+// ---- whole-polynomial transforms for a team ------------------------------------------------
+// xbuf must not be in use by any thread of the team on entry (the leading sync guarantees the
+// previous transform's reads are complete).
+template <class Cx>
+SPF_HD void team_fft_fwd(Cx& cx, C2 (&v)[16], C2* xbuf, const C2* T1, const C2* T2) {
+  fwd_pass1(v, cx.u, T1);
+  cx.sync();
+  fwd_x1_write(v, xbuf, cx.u);
+  cx.sync();
+  fwd_x1_read(v, xbuf, cx.u);
+  fwd_pass2(v, cx.u, T2);
+  cx.sync();
+  fwd_x2_write(v, xbuf, cx.u);
+  cx.sync();
+  fwd_x2_read(v, xbuf, cx.u);
+  fwd_pass3(v);
+}
+template <class Cx>
+SPF_HD void team_fft_inv(Cx& cx, C2 (&v)[16], C2* xbuf, const C2* T1, const C2* T2) {
+  inv_pass3(v);
+  cx.sync();
+  inv_x2_write(v, xbuf, cx.u);
+  cx.sync();
+  inv_x2_read(v, xbuf, cx.u);
+  inv_pass2(v, cx.u, T2);
+  cx.sync();
+  inv_x1_write(v, xbuf, cx.u);
+  cx.sync();
+  inv_x1_read(v, xbuf, cx.u);
+  inv_pass1(v, cx.u, T1);
+}
+
+// acc[p][s] += v[s] * G[p][s][u]   (glwe_polynomial_mad, ops/fft_ops.rs:107-124)
+SPF_HD void mad_glwe(C2 (&acc)[2][16], const C2 (&v)[16], const C2* g, int u) {
+#pragma unroll
+  for (int h = 0; h < 4; h++) {  // 4 slots x 2 polys in flight per batch
+    C2 b0[4], b1[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      b0[i] = ldg_c2(g + bin_of(u, 4 * h + i));
+      b1[i] = ldg_c2(g + kM + bin_of(u, 4 * h + i));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      cmad(acc[0][4 * h + i], v[4 * h + i], b0[i]);
+      cmad(acc[1][4 * h + i], v[4 * h + i], b1[i]);
+    }
+  }
+}
+
+SPF_HD void zero_acc(C2 (&acc)[2][16]) {
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int s = 0; s < 16; s++) acc[p][s] = C2{0.0, 0.0};
+}
+
+// Plain FFT of a torus polynomial (PolynomialRef::fft, entities/polynomial.rs:257-274):
+// u64 -> i64 -> f64, transform; result scaled by 2^-10 (device convention).
+template <class Cx, class F>
+SPF_HD void team_poly_fft(Cx& cx, C2 (&v)[16], F coef, C2* xbuf, const C2* T1, const C2* T2) {
+#pragma unroll
+  for (int m = 0; m < 16; m++) {
+    v[m].x = i64_to_f64((int64_t)coef(cx.u + 64 * m));
+    v[m].y = i64_to_f64((int64_t)coef(cx.u + 64 * m + kM));
+  }
+  team_fft_fwd(cx, v, xbuf, T1, T2);
+#pragma unroll
+  for (int s = 0; s < 16; s++) { v[s].x *= kInvM; v[s].y *= kInvM; }
+}
+
+// ---- generic gadget product -----------------------------------------------------------------
+// PolynomialRadixIterator::new (math/radix.rs:81-99): per-coefficient rounded state, kept in a
+// team-private smem array st[i*64 + u].
+template <class Cx, class F>
+SPF_HD void state_init(Cx& cx, uint64_t* st, int radix_log, int count, F coef) {
+#pragma unroll 4
+  for (int i = 0; i < 32; i++) st[i * 64 + cx.u] = radix_round(coef(cx.u + 64 * i), radix_log, count);
+}
+
+// decomposed_polynomial_glev_mad (ops/fft_ops.rs:67-98): for each digit (LSB first) FFT it and
+// multiply-accumulate against the GLEV's GLWE in REVERSE level order.  glev: [level][p][bin].
+template <class Cx>
+SPF_HD void gadget_mad(Cx& cx, C2 (&acc)[2][16], uint64_t* st, C2* xbuf, const C2* T1, const C2* T2,
+                       const C2* glev, int radix_log, int count) {
+  for (int t = 0; t < count; t++) {
+    C2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      uint64_t s0 = st[m * 64 + cx.u], s1 = st[(m + 16) * 64 + cx.u];
+      v[m].x = i32_to_f64(next_digit(s0, radix_log));
+      v[m].y = i32_to_f64(next_digit(s1, radix_log));
+      st[m * 64 + cx.u] = s0;
+      st[(m + 16) * 64 + cx.u] = s1;
+    }
+    team_fft_fwd(cx, v, xbuf, T1, T2);
+    mad_glwe(acc, v, glev + (size_t)(count - 1 - t) * 2 * kM, cx.u);
+  }
+}
+
+// ---- CMUX / external product (ops/fft_ops.rs:23-56,149-181) ---------------------------------
+// out = d0 + IFFT(GGSW [*] (d1 - d0)).  d0 == nullptr: plain external product of d1
+// (KeylessEvaluation::multiply_glwe_ggsw, parasol_runtime/src/crypto/evaluation.rs:104-123).
+// ggsw: [row][level][p][bin], 2^-10 scaled.  All GLWE pointers are global.
+template <class Cx>
+SPF_HD void cmux_team(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t* d1, const C2* ggsw,
+                      uint64_t* st, C2* xbuf, const C2* T1, const C2* T2, int radix_log, int count) {
+  C2 acc[2][16];
+  zero_acc(acc);
+  for (int r = 0; r < 2; r++) {
+    const uint64_t* a1 = d1 + r * kN;
+    const uint64_t* a0 = d0 ? d0 + r * kN : nullptr;
+    state_init(cx, st, radix_log, count,
+               [&](int j) { return a0 ? ldg_u64(a1 + j) - ldg_u64(a0 + j) : ldg_u64(a1 + j); });
+    gadget_mad(cx, acc, st, xbuf, T1, T2, ggsw + (size_t)r * count * 2 * kM, radix_log, count);
+  }
+#pragma unroll
+  for (int p = 0; p < 2; p++) {
+    team_fft_inv(cx, acc[p], xbuf, T1, T2);
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      const int j = cx.u + 64 * m;
+      uint64_t re = f64_to_torus(acc[p][m].x), im = f64_to_torus(acc[p][m].y);
+      if (d0) { re += ldg_u64(d0 + p * kN + j); im += ldg_u64(d0 + p * kN + j + kM); }
+      out[p * kN + j] = re;
+      out[p * kN + j + kM] = im;
+    }
+  }
+}
+
+// ---- programmable bootstrap (blind rotation) -------------------------------------------------
+// generalized_programmable_bootstrap (ops/bootstrapping/programmable_bootstrapping.rs:342-410)
+// for pbs_radix = (logB 16, l 2).  acc: team smem u64[2][2048]; stash: team smem int16[32*64].
+// bsk: [i][row][level][p][bin] (the reference's BootstrapKeyFft order), 2^-10 scaled.
+// lut == nullptr selects circuit-bootstrap mode: hi_noise_lwe_to_lo_noise_glwe
+// (circuit_bootstrapping.rs:387-428): b += q/4, LUT = fill_multifunctional_cbs_decomposition_lut
+// (:430-482) generated on the fly, log_v = ceil(log2(cbs_count)).
+struct PbsArgs {
+  const uint64_t* lwe_in;  // n + 1
+  const uint64_t* lut;     // GLWE [2][2048] or nullptr (CBS mode)
+  uint64_t* glwe_out;      // [2][2048]
+  const C2* bsk;
+  int lwe_n;
+  int log_chi, log_v;
+  int cbs_radix_log, cbs_count;  // CBS mode only
+};
+
+SPF_HD uint32_t modulus_switch(uint64_t x, int log_chi, int log_v, int log_modulus) {
+  // ops/ciphertext/lwe_ciphertext_ops.rs:129-142
+  const uint64_t mask = (1ull << log_modulus) - 1;
+  x <<= log_chi;
+  const int shift = 64 - (log_modulus - log_v);
+  const uint64_t rnd = (x >> (shift - 1)) & 1;
+  x >>= shift;
+  return (uint32_t)(((x + rnd) & mask) << log_v);
+}
+
+SPF_HD uint64_t cbs_lut_coeff(int idx, int cbs_radix_log, int cbs_count, int v) {
+  const int f = idx & (v - 1);
+  if (f >= cbs_count) return 0;
+  const int pb = cbs_radix_log * (f + 1) + 1;
+  return pb < 64 ? 0 - (1ull << (64 - pb)) : 0;  // Torus::encode(2^pb - 1, pb)
+}
+
+template <class Cx>
+SPF_HD void pbs_team(Cx& cx, const PbsArgs& A, uint64_t* acc, int16_t* stash, C2* xbuf, const C2* T1,
+                     const C2* T2) {
+  const int u = cx.u;
+  const int n = A.lwe_n;
+  const bool cbs = A.lut == nullptr;
+  const int log2n = 12;  // log2(2N)
+  // 1. acc = LUT * X^{-b~}   (programmable_bootstrapping.rs:378-390)
+  {
+    uint64_t b = ldg_u64(A.lwe_in + n);
+    if (cbs) b += 1ull << 62;  // lwe_rotate by Torus::encode(1, 2 bits) (circuit_bootstrapping.rs:403-408)
+    const int bt = (int)modulus_switch(b, A.log_chi, A.log_v, log2n);
+    const int rot = (2 * kN - bt) & (2 * kN - 1);
+    const int v = 1 << A.log_v;
+    for (int i = 0; i < 32; i++) {
+      const int j = u + 64 * i;
+      int idx = j - rot;
+      bool neg = false;
+      if (idx < 0) { idx += kN; neg = true; }
+      if (idx < 0) { idx += kN; neg = false; }
+      uint64_t ca, cb;
+      if (cbs) { ca = 0; cb = cbs_lut_coeff(idx, A.cbs_radix_log, A.cbs_count, v); }
+      else { ca = ldg_u64(A.lut + idx); cb = ldg_u64(A.lut + kN + idx); }
+      acc[j] = neg ? 0 - ca : ca;
+      acc[kN + j] = neg ? 0 - cb : cb;
+    }
+  }
+  cx.sync();
+  // 2. 637 CMUXes (programmable_bootstrapping.rs:396-409)
+  uint64_t a_next = n > 0 ? ldg_u64(A.lwe_in) : 0;
+  for (int i = 0; i < n; i++) {
+    const int at = (int)modulus_switch(a_next, A.log_chi, A.log_v, log2n);
+    if (i + 1 < n) a_next = ldg_u64(A.lwe_in + i + 1);
+    if (at == 0) continue;  // rot == acc: the CMUX adds IFFT(0) = 0 exactly
+    C2 f[2][16];
+    zero_acc(f);
+    const C2* ggsw = A.bsk + (size_t)i * 8 * kM;
+    for (int r = 0; r < 2; r++) {
+      const uint64_t* pr = acc + r * kN;
+      C2 v[16];
+      // diff = acc*X^{a~} - acc; round to 32 bits; two signed 16-bit digits, LSB first
+#pragma unroll
+      for (int i2 = 0; i2 < 32; i2++) {
+        const int j = u + 64 * i2;
+        const uint64_t diff = rotated_coeff(pr, j, at) - pr[j];
+        const uint32_t w = (uint32_t)radix_round(diff, 16, 2);
+        const int32_t d0 = (int32_t)(int16_t)(w & 0xFFFFu);
+        const int16_t d1 = (int16_t)((w >> 16) + ((w >> 15) & 1u));
+        stash[i2 * 64 + u] = d1;
+        if (i2 < 16) v[i2].x = i32_to_f64(d0); else v[i2 - 16].y = i32_to_f64(d0);
+      }
+      team_fft_fwd(cx, v, xbuf, T1, T2);
+      mad_glwe(f, v, ggsw + (size_t)(r * 2 + 1) * 2 * kM, u);  // LSB digit <-> last level
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        v[m].x = i32_to_f64((int32_t)stash[m * 64 + u]);
+        v[m].y = i32_to_f64((int32_t)stash[(m + 16) * 64 + u]);
+      }
+      team_fft_fwd(cx, v, xbuf, T1, T2);
+      mad_glwe(f, v, ggsw + (size_t)(r * 2 + 0) * 2 * kM, u);
+    }
+    // acc += IFFT(f)
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      team_fft_inv(cx, f[p], xbuf, T1, T2);
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const int j = u + 64 * m;
+        acc[p * kN + j] += f64_to_torus(f[p][m].x);
+        acc[p * kN + j + kM] += f64_to_torus(f[p][m].y);
+      }
+    }
+    cx.sync();  // next step gathers rotated coefficients written by other threads
+  }
+  // 3. result
+  for (int i = 0; i < 32; i++) {
+    const int j = u + 64 * i;
+    A.glwe_out[j] = acc[j];
+    A.glwe_out[kN + j] = acc[kN + j];
+  }
+}
+
+// ---- trace + scheme switch ---------------------------------------------------------------------
+// One team = one (ciphertext, cbs level) pair: mod_switch_trace_and_rotate for that level
+// (circuit_bootstrapping.rs:260-298), trace (ops/automorphisms/mod.rs:53-85) and that level's
+// share of scheme_switch_fft (ops/fft_ops.rs:225-279,403-442), fused.
+struct TraceSsArgs {
+  const uint64_t* glwe_in;  // PBS output [2][2048] (CBS) or the GLWE to trace
+  uint64_t* glev_out;       // optional: this level's traced GLWE [2][2048] (nullptr to skip)
+  C2* ggsw_out;             // optional: GGSW base [row][level][p][bin]
+  const C2* ak;             // [round][level][p][bin], 2^-10 scaled
+  const C2* ssk;            // [level][p][bin], 2^-10 scaled
+  const uint32_t* kinv;     // [11] inverse of k_r = N/2^(r-1)+1 modulo 2N
+  int level;                // cbs level i
+  int mode;                 // 0: CBS pre-processing + trace (+SS); 1: plain trace; 2: SS only (glwe_in = x_i)
+  int cbs_radix_log, cbs_count;
+  int tr_radix_log, tr_count;
+  int ss_radix_log, ss_count;
+  double out_scale;         // 1.0: GGSW stays device-resident (2^-10 convention); 1024.0: reference scale
+};
+
+// y[j] of sigma_k(p): polynomial_pow_k (ops/polynomial/mod.rs:62-87) as a gather.
+SPF_HD uint64_t automorph_coeff(const uint64_t* p, int j, uint32_t kinv) {
+  const uint32_t i = ((uint32_t)j * kinv) & (2 * kN - 1);
+  return i < (uint32_t)kN ? p[i] : 0 - p[i - kN];
+}
+
+template <class Cx>
+SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2048]*/, uint64_t* st,
+                          C2* xbuf, const C2* T1, const C2* T2) {
+  const int u = cx.u;
+  // ---- load / pre-process ----
+  if (A.mode == 0) {
+    // rotated.b[i'] += encode(1, 4(i'+1)+1) for i' <= level (cumulative, :284-285), * X^{-level},
+    // then glwe_mod_switch_and_expand_pow_2 by log2 N (glwe_ciphertext_ops.rs:268-281)
+    const int rot = (2 * kN - A.level) & (2 * kN - 1);
+    for (int i = 0; i < 32; i++) {
+      const int j = u + 64 * i;
+      int idx = j - rot;
+      bool neg = false;
+      if (idx < 0) { idx += kN; neg = true; }
+      if (idx < 0) { idx += kN; neg = false; }
+      uint64_t ca = ldg_u64(A.glwe_in + idx), cb = ldg_u64(A.glwe_in + kN + idx);
+      if (idx <= A.level) cb += 1ull << (64 - (A.cbs_radix_log * (idx + 1) + 1));
+      if (neg) { ca = 0 - ca; cb = 0 - cb; }
+      g[j] = (ca >> 11) + ((ca >> 10) & 1);
+      g[kN + j] = (cb >> 11) + ((cb >> 10) & 1);
+    }
+  } else {
+    for (int i = 0; i < 32; i++) {
+      const int j = u + 64 * i;
+      g[j] = ldg_u64(A.glwe_in + j);
+      g[kN + j] = ldg_u64(A.glwe_in + kN + j);
+    }
+  }
+  cx.sync();
+  // ---- trace ----
+  if (A.mode != 2) {
+    for (int r = 0; r < 11; r++) {
+      const uint32_t kinv = A.kinv[r];
+      C2 f[2][16];
+      zero_acc(f);
+      state_init(cx, st, A.tr_radix_log, A.tr_count, [&](int j) { return automorph_coeff(g, j, kinv); });
+      gadget_mad(cx, f, st, xbuf, T1, T2, A.ak + (size_t)r * A.tr_count * 2 * kM, A.tr_radix_log, A.tr_count);
+      // keyswitch_glwe_to_glwe (fft_ops.rs:457-495): ks = (0, y_b) - IFFT(sum); out += ks
+      team_fft_inv(cx, f[1], xbuf, T1, T2);
+      uint64_t db[32];
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const int j = u + 64 * m;
+        db[m] = automorph_coeff(g + kN, j, kinv) - f64_to_torus(f[1][m].x);
+        db[m + 16] = automorph_coeff(g + kN, j + kM, kinv) - f64_to_torus(f[1][m].y);
+      }
+      team_fft_inv(cx, f[0], xbuf, T1, T2);
+      cx.sync();  // every gather of this round is done
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const int j = u + 64 * m;
+        g[j] -= f64_to_torus(f[0][m].x);
+        g[j + kM] -= f64_to_torus(f[0][m].y);
+        g[kN + j] += db[m];
+        g[kN + j + kM] += db[m + 16];
+      }
+      cx.sync();
+    }
+    if (A.glev_out) {
+      for (int i = 0; i < 32; i++) {
+        const int j = u + 64 * i;
+        A.glev_out[j] = g[j];
+        A.glev_out[kN + j] = g[kN + j];
+      }
+    }
+  }
+  // ---- scheme switch share of this level (k = 1) ----
+  if (A.ggsw_out) {
+    const size_t glwe_f = 2 * kM;
+    C2* row0 = A.ggsw_out + ((size_t)0 * A.cbs_count + A.level) * glwe_f;
+    C2* row1 = A.ggsw_out + ((size_t)1 * A.cbs_count + A.level) * glwe_f;
+    C2 f[2][16];
+    // FFT(x.b): row 1 b-slot, and the a-slot of row 0 (update_encrypted_secret_key_component_fft)
+    team_poly_fft(cx, f[0], [&](int j) { return g[kN + j]; }, xbuf, T1, T2);
+#pragma unroll
+    for (int s = 0; s < 16; s++) { row1[kM + bin_of(u, s)] = cscale(f[0][s], A.out_scale); f[1][s] = C2{0.0, 0.0}; }
+    state_init(cx, st, A.ss_radix_log, A.ss_count, [&](int j) { return g[j]; });
+    gadget_mad(cx, f, st, xbuf, T1, T2, A.ssk, A.ss_radix_log, A.ss_count);
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      row0[bin_of(u, s)] = cscale(f[0][s], A.out_scale);
+      row0[kM + bin_of(u, s)] = cscale(f[1][s], A.out_scale);
+    }
+    // row 1 a-slot: FFT(x.a)
+    team_poly_fft(cx, f[0], [&](int j) { return g[j]; }, xbuf, T1, T2);
+#pragma unroll
+    for (int s = 0; s < 16; s++) row1[bin_of(u, s)] = cscale(f[0][s], A.out_scale);
+  }
+}
+
+}  // namespace spf

@@ -1,0 +1,88 @@
+"""The C-ABI library loads and exports every symbol include/spf_b200.h declares (no compute
+calls: this runs without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "spf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(spf_b200_\w+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported():
+    import spf_b200
+
+    lib = C.CDLL(spf_b200.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/spf_b200.h but not exported"
+    assert sorted(spf_b200.ABI) == syms, "spf_b200.ABI and include/spf_b200.h disagree"
+
+
+def test_sizes_match_reference_layouts():
+    """Entity sizes of SURVEY.md section 8 at DEFAULT_128."""
+    import spf_b200
+
+    l = spf_b200.lib()
+    p = spf_b200.default_128()
+    r = C.byref(p)
+    assert (p.lwe_n, p.glwe_k, p.glwe_n) == (637, 1, 2048)
+    assert [(x.radix_log, x.count) for x in (p.cbs, p.pbs, p.ks, p.ss, p.tr)] == [(4, 4), (16, 2), (2, 6), (3, 15), (7, 6)]
+    assert l.spf_b200_len_lwe_l0(r) == 638
+    assert l.spf_b200_len_lwe_l1(r) == 2049
+    assert l.spf_b200_len_glwe_l1(r) == 4096
+    assert l.spf_b200_len_glev_l1(r) == 16384
+    assert l.spf_b200_len_ggsw_l1(r) == 16384
+    assert l.spf_b200_len_bsk(r) * 16 == 83492864
+    assert l.spf_b200_len_ksk(r) * 8 == 62717952
+    assert l.spf_b200_len_ak(r) * 16 == 2162688
+    assert l.spf_b200_len_ssk(r) * 16 == 491520
+
+
+def test_sizes_agree_with_oracle(oracle):
+    import spf_b200
+
+    l = spf_b200.lib()
+    p = spf_b200.default_128()
+    op = oracle.default_128()
+    ol = oracle.lib()
+    assert l.spf_b200_len_bsk(C.byref(p)) == ol.orc_size_bsk_fft(C.byref(op))
+    assert l.spf_b200_len_ksk(C.byref(p)) == ol.orc_size_ksk(C.byref(op))
+    assert l.spf_b200_len_ak(C.byref(p)) == ol.orc_size_ak_fft(C.byref(op))
+    assert l.spf_b200_len_ssk(C.byref(p)) == ol.orc_size_ssk_fft(C.byref(op))
+
+
+def test_create_fails_loudly_without_gpu_or_with_bad_args(oracle):
+    """No CPU fallback: without a CUDA device create() must fail; bad params fail everywhere."""
+    import numpy as np
+    import spf_b200
+
+    l = spf_b200.lib()
+    p = spf_b200.default_128()
+    p.glwe_n = 1024
+    h = C.c_void_p()
+    rc = l.spf_b200_create(C.byref(p), None, 0, None, 0, None, 0, None, 0, 0, C.byref(h))
+    assert rc == -2 and b"specialised" in l.spf_b200_last_error(None)
+    p = spf_b200.default_128()
+    dummy = np.zeros(8, dtype=np.uint64)
+    rc = l.spf_b200_create(C.byref(p), dummy.ctypes.data, 8, dummy.ctypes.data, 8, dummy.ctypes.data, 8,
+                           dummy.ctypes.data, 8, 0, C.byref(h))
+    assert rc == -1 and b"key length" in l.spf_b200_last_error(None)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        n = [l.spf_b200_len_bsk(C.byref(p)), l.spf_b200_len_ksk(C.byref(p)), l.spf_b200_len_ssk(C.byref(p)),
+             l.spf_b200_len_ak(C.byref(p))]
+        rc = l.spf_b200_create(C.byref(p), dummy.ctypes.data, n[0], dummy.ctypes.data, n[1], dummy.ctypes.data, n[2],
+                               dummy.ctypes.data, n[3], 0, C.byref(h))
+        assert rc == -3 and b"no CPU fallback" in l.spf_b200_last_error(None)
