@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- circuit bootstraps / second on B200 (BASELINE.json metric, config 3).
+
+A "step" is one pass of the hot path over one batch of synthetic input: `--batch` (default 4096)
+independent L0 LWE ciphertexts -> 4096 L1 GGSW ciphertexts (circuit_bootstrap_via_trace_and_
+scheme_switch at DEFAULT_128).  One process per GPU; with N > 1 (torchrun) every rank holds a
+replica of the compute key (broadcast once from rank 0 over NCCL/NVLink) and bootstraps its own
+batch (weak scaling, no data-path collective: SURVEY.md section 8(e)).
+
+  value     CBS/s, inputs and outputs resident in HBM, CUDA-event time, max over ranks
+  e2e       same metric through the reference-facing host-pointer call
+            (spf_b200_circuit_bootstrap): pinned host buffers, H2D + D2H inside the timed region
+  roofline  the dominant kernel (pbs_kernel, blind rotation) against the FP64 CUDA-core peak
+            measured in this run by a DFMA probe (MEASURED_PEAKS.json has no FP64 figure), plus
+            its algorithmic HBM bytes against the measured HBM peak
+  cpu_baseline  the oracle (C restatement of the reference CPU path; the Rust reference cannot
+            be built in this image) on the box's host cores, bounded sample
+
+`--impl reference` times that CPU restatement alone (the reference arm of the contract).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "circuit_bootstraps_per_sec"
+UNIT = "CBS/s"
+# algorithmic work per unit at DEFAULT_128
+FLOP_PER_PBS = 263.5e6
+FLOP_PER_CBS = 293.3e6
+BSK_BYTES = 83492864
+PBS_IO_BYTES = 5104 + 32768  # LWE in + GLWE out per ciphertext
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4096, help="CBS per step per GPU (BASELINE config 3: 4096)")
+    ap.add_argument("--impl", default="spf_b200", choices=["spf_b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="CBS in the CPU baseline sample (0 = 2 per host thread)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--check", type=int, default=8, help="outputs decrypted with the oracle after the run (checker only)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workload: the harness' own seeds (the reference RNG is unseedable thread_rng())
+# ---------------------------------------------------------------------------------------------
+def encrypt_lwe0_numpy(sk: np.ndarray, bits: np.ndarray, std: float, seed: int) -> np.ndarray:
+    """b = <a,s> + m + e (ops/encryption/lwe_encryption.rs:36-61), vectorised; client-side input
+    generation only."""
+    rng = np.random.default_rng(seed)
+    n = sk.shape[0]
+    a = rng.integers(0, 1 << 64, (len(bits), n), dtype=np.uint64)
+    e = np.round(rng.normal(0.0, std, len(bits)) * 2.0 ** 64).astype(np.int64).astype(np.uint64)
+    b = (a * sk[None, :]).sum(axis=1, dtype=np.uint64) + (bits.astype(np.uint64) << np.uint64(63)) + e
+    return np.ascontiguousarray(np.concatenate([a, b[:, None]], axis=1))
+
+
+def cbs_lut(n: int = 2048) -> np.ndarray:
+    """fill_multifunctional_cbs_decomposition_lut (circuit_bootstrapping.rs:430-482) as a trivial GLWE."""
+    lut = np.zeros(2 * n, dtype=np.uint64)
+    i = np.arange(n)
+    pb = 4 * ((i % 4) + 1) + 1
+    lut[n:] = (np.uint64(0) - (np.uint64(1) << (64 - pb).astype(np.uint64)))
+    return lut
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline (the oracle port, all host threads) -- also the `--impl reference` arm
+# ---------------------------------------------------------------------------------------------
+def cpu_cbs_rate(keys, cts: np.ndarray, nthreads: int) -> tuple[float, float]:
+    import oracle as O
+
+    t0 = time.perf_counter()
+    O.circuit_bootstrap_batch(keys, cts, nthreads)
+    dt = time.perf_counter() - t0
+    return len(cts) / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle as O
+
+    keys = O.Keys()
+    nt = O.hw_threads()
+    sample = args.cpu_sample or 2 * nt
+    bits = np.random.default_rng(O.INPUT_SEED).integers(0, 2, sample)
+    cts = encrypt_lwe0_numpy(keys.lwe0_sk, bits, keys.params.lwe_std, O.INPUT_SEED)
+    for _ in range(max(args.warmup, 0) and 1):  # one warm-up pass is enough for a CPU loop
+        cpu_cbs_rate(keys, cts[: nt], nt)
+    total_t = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_cbs_rate(keys, cts, nt)
+        total_t += dt
+    value = sample * args.steps / total_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"cbs_batch{args.batch}_default128 (bounded sample of {sample} CBS per step)",
+                   "params": "DEFAULT_128", "batch_per_gpu": args.batch},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port",
+                         "sample": f"{sample} CBS per step x {args.steps} steps, oracle/spf_oracle.c (C restatement of "
+                                   "the reference CPU path; rustfft replaced by an in-tree radix-4 FFT), one op per "
+                                   "thread over all host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import spf_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; spf_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    p = spf_b200.default_128()
+    l = spf_b200.lib()
+    lens = [l.spf_b200_len_bsk(C.byref(p)), l.spf_b200_len_ksk(C.byref(p)), l.spf_b200_len_ssk(C.byref(p)),
+            l.spf_b200_len_ak(C.byref(p))]
+
+    # ---- compute key: generated once on rank 0, replicated to every GPU over NCCL -------------
+    keys = None
+    if rank == 0:
+        import oracle as O  # client-side keygen + the cpu_baseline leg; never on the measured path
+
+        keys = O.Keys()
+    d_bsk = torch.empty(lens[0] * 2, dtype=torch.float64, device=dev)
+    d_ksk = torch.empty(lens[1], dtype=torch.int64, device=dev)
+    d_ssk = torch.empty(lens[2] * 2, dtype=torch.float64, device=dev)
+    d_ak = torch.empty(lens[3] * 2, dtype=torch.float64, device=dev)
+    sk0 = torch.empty(p.lwe_n, dtype=torch.int64, device=dev)
+    if rank == 0:
+        d_bsk.copy_(torch.from_numpy(keys.bsk_fft.view(np.float64)))
+        d_ksk.copy_(torch.from_numpy(keys.ksk.view(np.int64)))
+        d_ssk.copy_(torch.from_numpy(keys.ssk_fft.view(np.float64)))
+        d_ak.copy_(torch.from_numpy(keys.ak_fft.view(np.float64)))
+        sk0.copy_(torch.from_numpy(keys.lwe0_sk.view(np.int64)))
+    key_bcast_ms = None
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for t in (d_bsk, d_ksk, d_ssk, d_ak, sk0):
+            dist.broadcast(t, src=0)
+        torch.cuda.synchronize()
+        key_bcast_ms = 1e3 * (time.perf_counter() - t0)
+    ev = spf_b200.Evaluation(d_bsk.data_ptr(), d_ksk.data_ptr(), d_ssk.data_ptr(), d_ak.data_ptr(), params=p,
+                             device=local, on_device=True)
+    del d_bsk, d_ksk, d_ssk, d_ak
+    torch.cuda.empty_cache()
+
+    # ---- inputs ---------------------------------------------------------------------------------
+    B = args.batch
+    lwe_sk = sk0.cpu().numpy().view(np.uint64)
+    bits = np.random.default_rng(0xB2000002 + rank).integers(0, 2, B)
+    cts = encrypt_lwe0_numpy(lwe_sk, bits, p.lwe_std, 0xB2000002 + rank)
+    h_in = torch.from_numpy(cts.view(np.int64)).pin_memory()
+    d_in = h_in.to(dev)
+    d_out = torch.empty(B * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ev.dev_circuit_bootstrap(d_out.data_ptr(), d_in.data_ptr(), B, reference_scale=False, stream=stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- timed region: K steps, CUDA events per step on the launching stream, L2 flushed between --
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ev.kernel_launches
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        step()
+        ends[i].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = ev.kernel_launches - launches0
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    value = world * B * args.steps / (dev_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (pbs_kernel), timed alone with CUDA events ------------
+    roofline = None
+    if rank == 0:
+        lut = torch.from_numpy(cbs_lut().view(np.int64)).to(dev)
+        rot = cts.copy()
+        rot[:, -1] += np.uint64(1 << 62)
+        d_rot = torch.from_numpy(rot.view(np.int64)).to(dev)
+        d_glwe = torch.empty(B * ev.len_glwe, dtype=torch.int64, device=dev)
+        for _ in range(2):
+            ev.dev_programmable_bootstrap(d_glwe.data_ptr(), d_rot.data_ptr(), lut.data_ptr(), 0, 2, B, stream=stream)
+        reps = max(2, min(args.steps, 5))
+        ks = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        ke = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        for i in range(reps):
+            flush.zero_()
+            ks[i].record()
+            ev.dev_programmable_bootstrap(d_glwe.data_ptr(), d_rot.data_ptr(), lut.data_ptr(), 0, 2, B, stream=stream)
+            ke[i].record()
+        torch.cuda.synchronize()
+        pbs_ms = sum(a.elapsed_time(b) for a, b in zip(ks, ke)) / reps
+        fp64_peak = ev.fp64_peak_tflops()
+        achieved = FLOP_PER_PBS * B / (pbs_ms * 1e-3) / 1e12
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        alg_bytes = BSK_BYTES + B * PBS_IO_BYTES
+        roofline = {
+            "kernel": "pbs_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved / fp64_peak if fp64_peak else None,
+            "peak_source": "measured in this run: spf_b200_fp64_peak (dependent-free DFMA probe on all SMs); "
+                           "MEASURED_PEAKS.json carries no FP64 figure",
+            "flop_per_launch": FLOP_PER_PBS * B, "ms_per_launch": pbs_ms,
+            "share_of_step": pbs_ms / (dev_ms / args.steps) if dev_ms else None,
+            "hbm": {"achieved": alg_bytes / (pbs_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / (pbs_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
+                    "peak_source": hbm_src},
+            "traffic": None,
+        }
+        del d_rot, d_glwe, lut
+
+    # ---- end to end through the host-pointer C ABI call (pinned buffers, copies inside) ---------
+    e2e = None
+    if not args.no_e2e:
+        h_out = torch.empty(B * ev.len_ggsw * 2, dtype=torch.float64).pin_memory()
+        lib = spf_b200.lib()
+
+        def host_step():
+            rc = lib.spf_b200_circuit_bootstrap(ev.handle, h_out.data_ptr(), h_in.data_ptr(), B)
+            if rc != 0:
+                raise RuntimeError(lib.spf_b200_last_error(ev.handle))
+
+        host_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            host_step()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * 8),
+               "d2h_bytes_per_step": int(h_out.numel() * 8), "steps": e2e_steps,
+               "api": "spf_b200_circuit_bootstrap (host pointers, pinned)"}
+        result_host = h_out.numpy().view(np.complex128).reshape(B, ev.len_ggsw)
+    else:
+        result_host = None
+
+    # ---- checker + CPU baseline (rank 0, N = 1 only for the baseline) --------------------------
+    check = None
+    cpu_baseline = None
+    if rank == 0:
+        import oracle as O
+
+        client = O.Client(keys)
+        if args.check > 0:
+            if result_host is None:
+                tmp = torch.empty(args.check * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
+                ev.dev_fft_rescale(tmp.data_ptr(), d_out.data_ptr(), args.check * ev.len_ggsw, to_device=False, stream=stream)
+                torch.cuda.synchronize()
+                sample_out = tmp.cpu().numpy().view(np.complex128).reshape(args.check, ev.len_ggsw)
+                idx = list(range(args.check))
+            else:
+                idx = np.linspace(0, B - 1, args.check).astype(int).tolist()
+                sample_out = result_host[idx]
+            ok = all(client.decrypt_ggsw_l1(g) == int(bits[i]) for g, i in zip(sample_out, idx))
+            check = {"decrypted": len(idx), "ok": bool(ok)}
+            if not ok:
+                raise SystemExit("bench.py: GPU outputs do not decrypt to the expected plaintexts")
+        if world == 1 and not args.no_cpu_baseline:
+            nt = O.hw_threads()
+            sample = args.cpu_sample or 2 * nt
+            cpu_cbs_rate(keys, cts[: min(nt, B)], nt)  # warm-up
+            rate, dt = cpu_cbs_rate(keys, cts[: min(sample, B)], nt)
+            cpu_baseline = {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
+                            "sample": f"{min(sample, B)} CBS of the same workload in {dt:.1f} s, oracle/spf_oracle.c "
+                                      "(C restatement of the reference CPU path), one single-threaded op per task over "
+                                      "all host threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cbs_batch{B}_default128 (BASELINE config 3: batched circuit bootstrapping, "
+                                   f"{B} independent LWE inputs per B200)",
+                       "params": "DEFAULT_128 (n=637, k=1, N=2048, pbs l=2 logB=16)", "batch_per_gpu": B,
+                       "parallelism": f"replicas x{world}, batch sharded, no data-path collective",
+                       "l2": "256 MiB memset between timed steps; the 83 MB BSK is re-fetched from HBM every step",
+                       "key_broadcast_ms": key_bcast_ms},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "check": check, "wall_s_timed_region": wall,
+        }
+        print(json.dumps(line))
+    ev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
