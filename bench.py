@@ -233,7 +233,12 @@ def run_gpu(args):
     d_in = h_in.to(dev)
     d_out = torch.empty(B * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) stream: kernels are launched on it through the C ABI and the
+    # CUDA events below are recorded on it (torch.cuda.Event records on the current stream)
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         ev.dev_circuit_bootstrap(d_out.data_ptr(), d_in.data_ptr(), B, reference_scale=False, stream=stream)
