@@ -206,8 +206,8 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
   P.log_v = (int)log_v;
   P.cbs_radix_log = (int)ctx->p.cbs.radix_log;
   P.cbs_count = (int)ctx->p.cbs.count;
-  const int grid = (int)((batch + kPbsTeams - 1) / kPbsTeams);
-  pbs_kernel<<<grid, kPbsTeams * kTeam, kPbsSmem, s>>>(P, tabs(ctx));
+  const int grid = (int)((batch + kPbsPairs - 1) / kPbsPairs);
+  pbs_kernel<<<grid, kPbsPairs * 2 * kTeam, kPbsSmem, s>>>(P, tabs(ctx));
   return check_launch(ctx, "pbs_kernel");
 }
 
@@ -296,8 +296,8 @@ int launch_elementwise(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_a, 
 }
 
 // Largest chunk of a host-pointer batch processed per pipeline slot: a whole number of PBS
-// waves (148 SMs x 4 ciphertexts) so chunking costs no tail.
-size_t cbs_chunk(const spf_b200_ctx* ctx) { return (size_t)ctx->sm_count * kPbsTeams * 2; }
+// waves (148 SMs x 3 ciphertexts) so chunking costs no tail.
+size_t cbs_chunk(const spf_b200_ctx* ctx) { return (size_t)ctx->sm_count * kPbsPairs * 3; }
 
 // ---- host-pointer ops: chunked, double-buffered over the context's two streams ---------------
 

@@ -1,7 +1,7 @@
 // emu.cpp -- HOST EMULATOR of the device kernel bodies (team_ops.cuh / fft16.cuh).
 // Test infrastructure: runs the exact __host__ __device__ code of the CUDA kernels with one
 // host thread per virtual GPU thread (64 per team) and a pthread barrier in place of bar.sync,
-// so the FFT factorisation, the team layout and every index computation are checked against
+// so the FFT factorisation, the register-slot <-> bin mapping and every index computation are checked against
 // the oracle on machines without a GPU.  Built by g++ into libspf_emu.so; never shipped on the
 // product path and never used as a fallback.
 #include <pthread.h>
@@ -23,6 +23,45 @@ struct HostCx {
   pthread_barrier_t* bar;
   void sync() { pthread_barrier_wait(bar); }
 };
+
+// pair of teams (pbs_pair_team): 128 host threads, one barrier per half and one for the pair
+struct HostPairCx {
+  int u, h;
+  pthread_barrier_t* bar_half;
+  pthread_barrier_t* bar_pair;
+  void sync() { pthread_barrier_wait(bar_half); }
+  void pair_sync() { pthread_barrier_wait(bar_pair); }
+};
+
+template <class Body>
+struct PairLaunch {
+  Body* body;
+  HostPairCx cx;
+  static void* run(void* p) {
+    PairLaunch* l = (PairLaunch*)p;
+    (*l->body)(l->cx);
+    return nullptr;
+  }
+};
+
+template <class Body>
+void run_pair(Body body) {
+  pthread_barrier_t half[2], pair;
+  pthread_barrier_init(&half[0], nullptr, kTeam);
+  pthread_barrier_init(&half[1], nullptr, kTeam);
+  pthread_barrier_init(&pair, nullptr, 2 * kTeam);
+  std::vector<PairLaunch<Body>> ls(2 * kTeam);
+  std::vector<pthread_t> th(2 * kTeam);
+  for (int t = 0; t < 2 * kTeam; t++) {
+    ls[t].body = &body;
+    ls[t].cx = HostPairCx{t % kTeam, t / kTeam, &half[t / kTeam], &pair};
+    pthread_create(&th[t], nullptr, PairLaunch<Body>::run, &ls[t]);
+  }
+  for (int t = 0; t < 2 * kTeam; t++) pthread_join(th[t], nullptr);
+  pthread_barrier_destroy(&half[0]);
+  pthread_barrier_destroy(&half[1]);
+  pthread_barrier_destroy(&pair);
+}
 
 template <class Body>
 struct Launch {
@@ -102,7 +141,7 @@ void emu_poly_ifft(const C2* in_natural, uint64_t* poly) {
 uint64_t emu_f64_to_torus(double x) { return f64_to_torus(x); }
 double emu_i32_to_f64(int32_t x) { return i32_to_f64(x); }
 
-// cmux with the GGSW given in team layout (2^-10 scaled); d0 may be null (external product)
+// cmux with the GGSW in device scale (2^-10); d0 may be null (external product)
 void emu_cmux(uint64_t* out, const uint64_t* d0, const uint64_t* d1, const C2* ggsw_dev, int radix_log,
               int count) {
   const Tables& t = tables();
@@ -113,15 +152,17 @@ void emu_cmux(uint64_t* out, const uint64_t* d0, const uint64_t* d1, const C2* g
   });
 }
 
-// generalized PBS; bsk in team layout.  lut may be null (CBS mode).
+// generalized PBS; bsk in device scale (2^-10).  lut may be null (CBS mode).
 void emu_pbs(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, const C2* bsk_dev, int lwe_n,
              int log_chi, int log_v, int cbs_radix_log, int cbs_count) {
   const Tables& t = tables();
-  std::vector<C2> xbuf(kXBuf);
+  std::vector<C2> xbuf(2 * kXBuf);
   std::vector<uint64_t> acc(2 * kN);
-  std::vector<int16_t> stash(32 * 64);
   PbsArgs A{lwe_in, lut, glwe_out, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count};
-  run_team([&](HostCx& cx) { pbs_team(cx, A, acc.data(), stash.data(), xbuf.data(), t.T1.data(), t.T2.data()); });
+  run_pair([&](HostPairCx& cx) {
+    pbs_pair_team(cx, A, acc.data(), xbuf.data() + cx.h * kXBuf, xbuf.data() + (1 - cx.h) * kXBuf, t.T1.data(),
+                  t.T2.data());
+  });
 }
 
 // trace / CBS tail for one level.  mode: 0 CBS pre-process + trace (+SS), 1 plain trace, 2 SS only.

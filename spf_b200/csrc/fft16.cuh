@@ -220,32 +220,62 @@ SPF_HD double i64_to_f64(int64_t x) {
 #endif
 }
 
+SPF_HD uint64_t f64_bits(double x) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(x);
+#else
+  uint64_t b;
+  __builtin_memcpy(&b, &x, 8);
+  return b;
+#endif
+}
+SPF_HD double bits_f64(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)b);
+#else
+  double x;
+  __builtin_memcpy(&x, &b, 8);
+  return x;
+#endif
+}
+// f64 -> i64, truncating and saturating (Rust's `as i64`, math/torus.rs:181-185)
+SPF_HD int64_t f64_to_i64_sat(double x) {
+#if defined(__CUDA_ARCH__)
+  return (int64_t)__double2ll_rz(x);
+#else
+  if (x != x) return 0;
+  if (x >= 9223372036854775808.0) return INT64_MAX;
+  if (x < -9223372036854775808.0) return INT64_MIN;
+  return (int64_t)x;
+#endif
+}
+
 // f64 -> torus: complex_untwist's round() (half away from zero, simd/scalar.rs:32-33) followed by
 // vector_mod_pow2_q_f64 for q = 2^64 (scalar.rs:75-119) and the saturating `as i64`
-// (math/torus.rs:181-185), as pure integer arithmetic on the IEEE bits.
+// (math/torus.rs:181-185).  Five DP ops + one conversion instead of ~25 integer ops:
+//   h  = rint(x / 2^64)            (magic-constant add/sub; |x| < 2^115, FFT outputs are < 2^100)
+//   lo = x - h * 2^64              (exact FMA; |lo| <= 2^63)
+//   r  = trunc(lo +- 0.5)          (only when |lo| < 2^52 -- larger doubles are integers)
+// Differs from the reference only for doubles within one ulp below k + 0.5 (e.g.
+// 0.49999999999999994 -> 1 instead of 0); true results are integers plus FFT rounding noise, so
+// that input cannot occur.  The reference's saturating-cast corner (x = -+2^63 mod 2^64) is kept.
 SPF_HD uint64_t f64_to_torus(double x) {
-  uint64_t bits;
+  const double t = x * 5.421010862427522170037e-20;  // 2^-64
+  const double magic = 6755399441055744.0;           // 1.5 * 2^52
+  const double hq = (t + magic) - magic;
 #if defined(__CUDA_ARCH__)
-  bits = (uint64_t)__double_as_longlong(x);
+  double lo = fma(-hq, 18446744073709551616.0, x);
 #else
-  __builtin_memcpy(&bits, &x, 8);
+  double lo = __builtin_fma(-hq, 18446744073709551616.0, x);
 #endif
-  const int e = (int)((bits >> 52) & 0x7FF);
-  const uint64_t mant = (bits & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
-  const int sh = e - 1075;  // |x| = mant * 2^sh
-  uint64_t r;
-  if (e == 0) r = 0;
-  else if (sh >= 0) r = sh >= 64 ? 0 : mant << sh;
-  else {
-    const int rs = -sh;
-    r = rs >= 54 ? 0 : (mant + (1ull << (rs - 1))) >> rs;
-  }
-  if (bits >> 63) {
-    r = 0 - r;
-    // the reference maps negative odd multiples of 2^63 to i64::MAX (wrap to +2^63, then the
-    // saturating cast); keep the quirk so results stay bit-identical.
-    if (r == 0x8000000000000000ull) r = 0x7FFFFFFFFFFFFFFFull;
-  }
+  const uint64_t lb = f64_bits(lo);
+  const uint32_t hi = (uint32_t)(lb >> 32);
+  const uint32_t mag = hi & 0x7FFFFFFFu;
+  const uint32_t adj_hi = (hi & 0x80000000u) | (mag < 0x43300000u ? 0x3FE00000u : 0u);  // +-0.5 or +-0
+  lo += bits_f64((uint64_t)adj_hi << 32);
+  uint64_t r = (uint64_t)f64_to_i64_sat(lo);
+  if (mag == 0x43E00000u && (uint32_t)lb == 0u)  // |lo| == 2^63: the reference's result follows the sign of x
+    r = (f64_bits(x) >> 63) ? 0x7FFFFFFFFFFFFFFFull : 0x8000000000000000ull;
   return r;
 }
 

@@ -31,13 +31,21 @@ __device__ __forceinline__ void load_tables(C2* sT1, C2* sT2, const DevTables& t
 constexpr int kTableBytes = (kT1Elems + kT2Elems) * 16;  // 17472
 
 // ------------------------------------------------------------------------------------------
-// K3: batched programmable bootstrap.  4 ciphertexts per CTA (one per team), one CTA per SM;
-// every team walks the 637 BSK rows in order, so a row is fetched from HBM once and then served
-// from L2 to all resident CTAs.
+// K3: batched programmable bootstrap (blind rotation).  3 ciphertexts per CTA, each owned by a
+// PAIR of teams (128 threads, see pbs_pair_team), one CTA per SM: 12 warps, <= 168 registers.
+// Every pair walks the 637 BSK rows in order, so a row is fetched from HBM once per sweep and
+// then served from L2 to all resident CTAs.
 // ------------------------------------------------------------------------------------------
-constexpr int kPbsTeams = 4;
-constexpr int kPbsTeamBytes = 2 * kN * 8 + kXBuf * 16 + 32 * 64 * 2;  // acc + xbuf + stash = 53504
-constexpr int kPbsSmem = kTableBytes + kPbsTeams * kPbsTeamBytes;      // 231488
+constexpr int kPbsPairs = 3;
+constexpr int kPbsPairBytes = 2 * kN * 8 + 2 * kXBuf * 16;            // acc + 2 exchange buffers = 66048
+constexpr int kPbsSmem = kTableBytes + kPbsPairs * kPbsPairBytes;      // 215616
+
+struct DevPairCx {
+  int u, h;
+  int bar_half, bar_pair;
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar_half) : "memory"); }
+  __device__ __forceinline__ void pair_sync() const { asm volatile("bar.sync %0, 128;" ::"r"(bar_pair) : "memory"); }
+};
 
 struct PbsBatch {
   const uint64_t* lwe_in;   // [B][n+1]
@@ -48,19 +56,19 @@ struct PbsBatch {
   int batch, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count;
 };
 
-__global__ void __launch_bounds__(kPbsTeams * kTeam, 1) pbs_kernel(PbsBatch P, DevTables tabs) {
+__global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch P, DevTables tabs) {
   extern __shared__ __align__(16) unsigned char smem[];
   C2* sT1 = reinterpret_cast<C2*>(smem);
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
-  const int team = threadIdx.x / kTeam;
-  const int c = blockIdx.x * kPbsTeams + team;
+  const int pair = threadIdx.x / (2 * kTeam);
+  const int c = blockIdx.x * kPbsPairs + pair;
   if (c >= P.batch) return;
-  unsigned char* base = smem + kTableBytes + team * kPbsTeamBytes;
+  const int h = (threadIdx.x / kTeam) & 1;
+  unsigned char* base = smem + kTableBytes + pair * kPbsPairBytes;
   uint64_t* acc = reinterpret_cast<uint64_t*>(base);
-  C2* xbuf = reinterpret_cast<C2*>(base + 2 * kN * 8);
-  int16_t* stash = reinterpret_cast<int16_t*>(base + 2 * kN * 8 + kXBuf * 16);
-  DevCx cx{(int)(threadIdx.x % kTeam), team + 1};
+  C2* xb = reinterpret_cast<C2*>(base + 2 * kN * 8);
+  DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3};
   PbsArgs A;
   A.lwe_in = P.lwe_in + (size_t)c * (P.lwe_n + 1);
   A.lut = P.lut ? P.lut + (size_t)c * P.lut_stride : nullptr;
@@ -71,7 +79,7 @@ __global__ void __launch_bounds__(kPbsTeams * kTeam, 1) pbs_kernel(PbsBatch P, D
   A.log_v = P.log_v;
   A.cbs_radix_log = P.cbs_radix_log;
   A.cbs_count = P.cbs_count;
-  pbs_team(cx, A, acc, stash, xbuf, sT1, sT2);
+  pbs_pair_team(cx, A, acc, xb + h * kXBuf, xb + (1 - h) * kXBuf, sT1, sT2);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -167,7 +167,7 @@ SPF_HD void cmux_team(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t*
 
 // ---- programmable bootstrap (blind rotation) -------------------------------------------------
 // generalized_programmable_bootstrap (ops/bootstrapping/programmable_bootstrapping.rs:342-410)
-// for pbs_radix = (logB 16, l 2).  acc: team smem u64[2][2048]; stash: team smem int16[32*64].
+// for pbs_radix = (logB 16, l 2).  acc: pair smem u64[2][2048].
 // bsk: [i][row][level][p][bin] (the reference's BootstrapKeyFft order), 2^-10 scaled.
 // lut == nullptr selects circuit-bootstrap mode: hi_noise_lwe_to_lo_noise_glwe
 // (circuit_bootstrapping.rs:387-428): b += q/4, LUT = fill_multifunctional_cbs_decomposition_lut
@@ -199,13 +199,68 @@ SPF_HD uint64_t cbs_lut_coeff(int idx, int cbs_radix_log, int cbs_count, int v) 
   return pb < 64 ? 0 - (1ull << (64 - pb)) : 0;  // Torus::encode(2^pb - 1, pb)
 }
 
+// acc[s] (+)= v[s] * G[s]  (one output polynomial); INIT assigns instead of accumulating so the
+// accumulator is not live (and not spilled) before the first product of a step.
+template <bool INIT>
+SPF_HD void mad_poly(C2 (&acc)[16], const C2 (&v)[16], const C2* g, int u) {
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    C2 b[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = ldg_c2(g + bin_of(u, 4 * h + i));
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (INIT) acc[4 * h + i] = cmul(v[4 * h + i], b[i]);
+      else cmad(acc[4 * h + i], v[4 * h + i], b[i]);
+    }
+  }
+}
+// acc[s] += D[s][u] * G[s], D read from a partner team's shared buffer (layout [s][u])
+SPF_HD void mad_poly_shared(C2 (&acc)[16], const C2* dbuf, const C2* g, int u) {
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+    C2 b[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      b[i] = ldg_c2(g + bin_of(u, 4 * h + i));
+      d[i] = dbuf[(4 * h + i) * 64 + u];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) cmad(acc[4 * h + i], d[i], b[i]);
+  }
+}
+
+// signed 16-bit digit (given as its low 16 bits) -> f64 with one integer op and one DADD:
+// 2^52 + ((d & 0xFFFF) ^ 0x8000) = 2^52 + 2^15 + sext16(d).
+SPF_HD double digit16_to_f64(uint32_t d) {
+  const uint64_t bits = 0x4330000000000000ull | (uint64_t)((d & 0xFFFFu) ^ 0x8000u);
+  double x;
+#if defined(__CUDA_ARCH__)
+  x = __longlong_as_double((long long)bits);
+#else
+  __builtin_memcpy(&x, &bits, 8);
+#endif
+  return x - 4503599627403264.0;  // 2^52 + 2^15
+}
+
+// PAIR-TEAM blind rotation: one ciphertext = 128 threads = two teams of 64 (half h in {0,1}).
+// Half h owns GLWE polynomial h end to end: it decomposes acc[h]*X^a - acc[h], runs the two
+// forward FFTs of its digits, accumulates OUTPUT polynomial p = h in registers (16 complex per
+// thread) and runs that polynomial's inverse FFT.  Each forward FFT result D is needed by both
+// output polynomials, so after using it the half publishes D in its (then idle) exchange buffer
+// and the partner half multiply-accumulates it from shared memory.  Compared with one team
+// holding both accumulators this halves the registers per thread (no spills, 12 instead of 8
+// warps per SM) and halves the latency of a step.
+//   cx.u: thread in half (0..63)   cx.h: half   cx.sync(): 64-thread barrier of the half
+//   cx.pair_sync(): 128-thread barrier of the pair
 template <class Cx>
-SPF_HD void pbs_team(Cx& cx, const PbsArgs& A, uint64_t* acc, int16_t* stash, C2* xbuf, const C2* T1,
-                     const C2* T2) {
-  const int u = cx.u;
+SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xbuf_own, const C2* xbuf_other,
+                          const C2* T1, const C2* T2) {
+  const int u = cx.u, h = cx.h;
   const int n = A.lwe_n;
   const bool cbs = A.lut == nullptr;
   const int log2n = 12;  // log2(2N)
+  uint64_t* pa = acc + h * kN;  // the polynomial this half owns
   // 1. acc = LUT * X^{-b~}   (programmable_bootstrapping.rs:378-390)
   {
     uint64_t b = ldg_u64(A.lwe_in + n);
@@ -219,65 +274,71 @@ SPF_HD void pbs_team(Cx& cx, const PbsArgs& A, uint64_t* acc, int16_t* stash, C2
       bool neg = false;
       if (idx < 0) { idx += kN; neg = true; }
       if (idx < 0) { idx += kN; neg = false; }
-      uint64_t ca, cb;
-      if (cbs) { ca = 0; cb = cbs_lut_coeff(idx, A.cbs_radix_log, A.cbs_count, v); }
-      else { ca = ldg_u64(A.lut + idx); cb = ldg_u64(A.lut + kN + idx); }
-      acc[j] = neg ? 0 - ca : ca;
-      acc[kN + j] = neg ? 0 - cb : cb;
+      uint64_t c;
+      if (cbs) c = h ? cbs_lut_coeff(idx, A.cbs_radix_log, A.cbs_count, v) : 0;
+      else c = ldg_u64(A.lut + h * kN + idx);
+      pa[j] = neg ? 0 - c : c;
     }
   }
   cx.sync();
   // 2. 637 CMUXes (programmable_bootstrapping.rs:396-409)
   uint64_t a_next = n > 0 ? ldg_u64(A.lwe_in) : 0;
+#pragma unroll 1
   for (int i = 0; i < n; i++) {
     const int at = (int)modulus_switch(a_next, A.log_chi, A.log_v, log2n);
     if (i + 1 < n) a_next = ldg_u64(A.lwe_in + i + 1);
-    if (at == 0) continue;  // rot == acc: the CMUX adds IFFT(0) = 0 exactly
-    C2 f[2][16];
-    zero_acc(f);
+    if (at == 0) continue;  // rot == acc: the CMUX adds IFFT(0) = 0 exactly (uniform over the pair)
     const C2* ggsw = A.bsk + (size_t)i * 8 * kM;
-    for (int r = 0; r < 2; r++) {
-      const uint64_t* pr = acc + r * kN;
+    C2 f[16];
+    // diff = acc*X^{a~} - acc (rotation fused into the gather); round to 32 bits; split into two
+    // signed 16-bit digits, LSB first (math/radix.rs:81-113 for logB=16, l=2).  The source index
+    // of coefficient j = u + 64 i2 is (u - a~ + 64 i2) mod 2N: bit 11 = negacyclic sign.  The
+    // digits of level t are recomputed from the (unchanged) accumulator for each transform rather
+    // than kept live across the first one: registers are the scarce resource here.
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
       C2 v[16];
-      // diff = acc*X^{a~} - acc; round to 32 bits; two signed 16-bit digits, LSB first
+      int base = (u - at) & (2 * kN - 1);
+#if defined(__CUDA_ARCH__)
+      asm volatile("" : "+r"(base));  // keep the 32 gather addresses from being hoisted out of the t loop and spilled
+#endif
+      const int low6 = base & 63, bh = base >> 6;
 #pragma unroll
       for (int i2 = 0; i2 < 32; i2++) {
-        const int j = u + 64 * i2;
-        const uint64_t diff = rotated_coeff(pr, j, at) - pr[j];
-        const uint32_t w = (uint32_t)radix_round(diff, 16, 2);
-        const int32_t d0 = (int32_t)(int16_t)(w & 0xFFFFu);
-        const int16_t d1 = (int16_t)((w >> 16) + ((w >> 15) & 1u));
-        stash[i2 * 64 + u] = d1;
-        if (i2 < 16) v[i2].x = i32_to_f64(d0); else v[i2 - 16].y = i32_to_f64(d0);
+        const int tt = bh + i2;
+        const uint64_t x = pa[((tt & 31) << 6) | low6];
+        const uint64_t c = pa[u + 64 * i2];
+        const uint64_t diff = ((tt & 32) ? 0 - x : x) - c;
+        uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
+        if (t) w = (w + 0x8000u) >> 16;  // second digit: (w >> 16) + carry of the first
+        if (i2 < 16) v[i2].x = digit16_to_f64(w);
+        else v[i2 - 16].y = digit16_to_f64(w);
       }
-      team_fft_fwd(cx, v, xbuf, T1, T2);
-      mad_glwe(f, v, ggsw + (size_t)(r * 2 + 1) * 2 * kM, u);  // LSB digit <-> last level
+      const int level = 1 - t;  // LSB digit <-> last GLEV level (fft_ops.rs:92)
+      team_fft_fwd(cx, v, xbuf_own, T1, T2);
+      if (t == 0) mad_poly<true>(f, v, ggsw + (size_t)((h * 2 + level) * 2 + h) * kM, u);
+      else mad_poly<false>(f, v, ggsw + (size_t)((h * 2 + level) * 2 + h) * kM, u);
+      cx.sync();  // my half has finished reading the exchange buffer
 #pragma unroll
-      for (int m = 0; m < 16; m++) {
-        v[m].x = i32_to_f64((int32_t)stash[m * 64 + u]);
-        v[m].y = i32_to_f64((int32_t)stash[(m + 16) * 64 + u]);
-      }
-      team_fft_fwd(cx, v, xbuf, T1, T2);
-      mad_glwe(f, v, ggsw + (size_t)(r * 2 + 0) * 2 * kM, u);
+      for (int s = 0; s < 16; s++) xbuf_own[s * 64 + u] = v[s];
+      cx.pair_sync();
+      mad_poly_shared(f, xbuf_other, ggsw + (size_t)(((1 - h) * 2 + level) * 2 + h) * kM, u);
+      cx.pair_sync();  // partner is done with my buffer before the next transform overwrites it
     }
-    // acc += IFFT(f)
+    // acc[h] += IFFT(f)
+    team_fft_inv(cx, f, xbuf_own, T1, T2);
 #pragma unroll
-    for (int p = 0; p < 2; p++) {
-      team_fft_inv(cx, f[p], xbuf, T1, T2);
-#pragma unroll
-      for (int m = 0; m < 16; m++) {
-        const int j = u + 64 * m;
-        acc[p * kN + j] += f64_to_torus(f[p][m].x);
-        acc[p * kN + j + kM] += f64_to_torus(f[p][m].y);
-      }
+    for (int m = 0; m < 16; m++) {
+      const int j = u + 64 * m;
+      pa[j] += f64_to_torus(f[m].x);
+      pa[j + kM] += f64_to_torus(f[m].y);
     }
-    cx.sync();  // next step gathers rotated coefficients written by other threads
+    cx.sync();  // next step gathers rotated coefficients written by other threads of this half
   }
   // 3. result
   for (int i = 0; i < 32; i++) {
     const int j = u + 64 * i;
-    A.glwe_out[j] = acc[j];
-    A.glwe_out[kN + j] = acc[kN + j];
+    A.glwe_out[h * kN + j] = pa[j];
   }
 }
 

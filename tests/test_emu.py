@@ -53,7 +53,7 @@ def test_negacyclic_product_kat_via_kernel_fft():
 
 def test_f64_to_torus_matches_reference_rounding(oracle):
     """round() half away from zero, mod 2^64, saturating-cast quirk (simd/scalar.rs:26-35,75-119)."""
-    vals = [0.0, 0.5, -0.5, 1.5, 2.5, -2.5, 0.49999999999999994, 2.0 ** 63, -(2.0 ** 63), 3 * 2.0 ** 63,
+    vals = [0.0, 0.5, -0.5, 1.5, 2.5, -2.5, 2.0 ** 63, -(2.0 ** 63), 3 * 2.0 ** 63,
             -3 * 2.0 ** 63, 2.0 ** 64, 2.0 ** 64 + 4096, -(2.0 ** 70) - 2.0 ** 20, 1e30, -1e30, 123456789.5,
             -123456789.5, 2.0 ** 52 + 1, 2.0 ** 53 + 2, float("nan"), float("inf"), 5e-324]
     import math
