@@ -215,8 +215,9 @@ def run_gpu(args):
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
-        for t in (d_bsk, d_ksk, d_ssk, d_ak, sk0):
-            dist.broadcast(t, src=0)
+        from spf_b200.multi import broadcast_compute_key
+
+        broadcast_compute_key([d_bsk, d_ksk, d_ssk, d_ak, sk0], src=0)
         torch.cuda.synchronize()
         key_bcast_ms = 1e3 * (time.perf_counter() - t0)
     ev = spf_b200.Evaluation(d_bsk.data_ptr(), d_ksk.data_ptr(), d_ssk.data_ptr(), d_ak.data_ptr(), params=p,

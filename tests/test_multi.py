@@ -1,0 +1,68 @@
+"""The N > 1 host path (key replication + batch sharding) on CPU with the gloo backend,
+world_size 2 (the GPU path uses the same code with NCCL; bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_shard_tiles_the_batch():
+    from spf_b200.multi import shard
+
+    for batch in (0, 1, 7, 8, 4096, 65536, 4097):
+        for world in (1, 2, 4, 8):
+            ranges = [shard(batch, world, r) for r in range(world)]
+            assert ranges[0][0] == 0
+            for (s0, c0), (s1, _) in zip(ranges, ranges[1:]):
+                assert s0 + c0 == s1
+            assert ranges[-1][0] + ranges[-1][1] == batch
+            counts = [c for _, c in ranges]
+            assert max(counts) - min(counts) <= 1
+    with pytest.raises(ValueError):
+        shard(8, 2, 2)
+
+
+def _worker(rank, world, port, out_q):
+    import torch
+    import torch.distributed as dist
+
+    from spf_b200.multi import broadcast_compute_key, max_over_ranks, shard
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        ref = [rng.standard_normal(4096), rng.integers(0, 1 << 62, 1000), rng.standard_normal(64), rng.standard_normal(128)]
+        if rank == 0:
+            key = [torch.from_numpy(np.array(a)) for a in ref]
+        else:
+            key = [torch.zeros(len(a), dtype=torch.float64 if a.dtype == np.float64 else torch.int64) for a in ref]
+        broadcast_compute_key(key, src=0)
+        same = all(np.array_equal(k.numpy(), a) for k, a in zip(key, ref))
+        start, count = shard(11, world, rank)
+        slow = max_over_ranks(1.0 + rank)
+        out_q.put((rank, same, start, count, slow))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_key_broadcast_and_sharding_world2():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == (0, True, 0, 6, 2.0)
+    assert res[1] == (1, True, 6, 5, 2.0)
