@@ -154,6 +154,47 @@ int spf_b200_dev_sample_extract_l1(spf_b200_ctx *ctx, uint64_t *d_lwe1_out, cons
 int spf_b200_dev_fft_rescale(spf_b200_ctx *ctx, double *d_dst, const double *d_src, size_t n, int to_device,
                              void *stream);
 
+/* ---- graph execution: CircuitProcessor::{spawn_graph, run_graph_blocking} --------------------
+ * (parasol_runtime/src/circuit_processor/mod.rs:573-655), level-synchronous and batched: all
+ * nodes of one (dependency level, op) group run as ONE kernel launch; intermediates stay in HBM. */
+
+/* FheOp (parasol_runtime/src/fhe_circuit.rs:34-127), same order. */
+typedef enum {
+  SPF_OP_INPUT_LWE0 = 0, SPF_OP_INPUT_LWE1, SPF_OP_INPUT_GLWE1, SPF_OP_INPUT_GGSW1, SPF_OP_INPUT_GLEV1,
+  SPF_OP_OUTPUT_LWE0, SPF_OP_OUTPUT_LWE1, SPF_OP_OUTPUT_GLWE1, SPF_OP_OUTPUT_GGSW1, SPF_OP_OUTPUT_GLEV1,
+  SPF_OP_SAMPLE_EXTRACT, SPF_OP_KEYSWITCH_L1_TO_L0, SPF_OP_NOT, SPF_OP_GLWE_ADD, SPF_OP_CMUX, SPF_OP_GLEV_CMUX,
+  SPF_OP_MULTIPLY_GGSW_GLWE, SPF_OP_CIRCUIT_BOOTSTRAP, SPF_OP_SCHEME_SWITCH,
+  SPF_OP_ZERO_LWE0, SPF_OP_ONE_LWE0, SPF_OP_ZERO_GLWE1, SPF_OP_ONE_GLWE1, SPF_OP_ZERO_GGSW1, SPF_OP_ONE_GGSW1,
+  SPF_OP_ZERO_GLEV1, SPF_OP_ONE_GLEV1, SPF_OP_RETIRE, SPF_OP_NOP, SPF_OP_MUL_XN
+} spf_op;
+
+/* One graph node.  `in` holds producer node indices by FheEdge (fhe_circuit.rs:174-198), -1 = none:
+ *   unary ops: in[0] = Unary;  GlweAdd: in[0] = Left, in[1] = Right;
+ *   CMux / GlevCMux: in[0] = Sel, in[1] = Low (selected when sel = 0), in[2] = High;
+ *   MultiplyGgswGlwe: in[0] = Glwe, in[1] = Ggsw.
+ * `arg` is SampleExtract's index / MulXN's exponent.  `io` is the host ciphertext buffer of an
+ * Input* node (read at every run) or Output* node (written at every run), reference layouts. */
+typedef struct {
+  uint32_t op;
+  uint32_t arg;
+  int32_t in[3];
+  void *io;
+} spf_node;
+
+typedef struct spf_b200_graph spf_b200_graph;
+
+/* Validates (Task::validate, circuit_processor/task.rs:24-179: wrong ciphertext kind, missing
+ * input, illegal sample-extract index, plus cycles -> SPF_E_GRAPH), levelises, allocates the
+ * device arena and uploads the per-group pointer tables.  Nodes may come in any order. */
+int spf_b200_graph_build(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes, spf_b200_graph **out);
+/* One blocking execution (run_graph_blocking): inputs H2D, all levels, outputs D2H. */
+int spf_b200_graph_run(spf_b200_graph *graph);
+void spf_b200_graph_destroy(spf_b200_graph *graph);
+int spf_b200_graph_levels(const spf_b200_graph *graph);
+uint64_t spf_b200_graph_launches(const spf_b200_graph *graph); /* kernel launches of the last run */
+/* build + run + destroy */
+int spf_b200_run_graph(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes);
+
 /* FP64 peak probe used by bench.py for the roofline denominator: runs a dependent-free DFMA
  * loop on every SM and returns achieved TFLOP/s (2 flops per DFMA). */
 int spf_b200_fp64_peak(spf_b200_ctx *ctx, double *tflops_out);

@@ -350,3 +350,105 @@ class Evaluation:
 
     def dev_fft_rescale(self, d_dst: int, d_src: int, n: int, to_device: bool, stream: int = 0):
         self._check(lib().spf_b200_dev_fft_rescale(self._h, d_dst, d_src, n, 1 if to_device else 0, stream or None))
+
+
+# ---------------------------------------------------------------------------------------------
+# Graph execution: FheCircuit + CircuitProcessor::run_graph_blocking
+# ---------------------------------------------------------------------------------------------
+class _Node(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("arg", C.c_uint32), ("inp", C.c_int32 * 3), ("io", C.c_void_p)]
+
+
+# FheOp (parasol_runtime/src/fhe_circuit.rs:34-127), same order as spf_op in include/spf_b200.h
+OPS = ["InputLwe0", "InputLwe1", "InputGlwe1", "InputGgsw1", "InputGlev1", "OutputLwe0", "OutputLwe1", "OutputGlwe1",
+       "OutputGgsw1", "OutputGlev1", "SampleExtract", "KeyswitchL1toL0", "Not", "GlweAdd", "CMux", "GlevCMux",
+       "MultiplyGgswGlwe", "CircuitBootstrap", "SchemeSwitch", "ZeroLwe0", "OneLwe0", "ZeroGlwe1", "OneGlwe1",
+       "ZeroGgsw1", "OneGgsw1", "ZeroGlev1", "OneGlev1", "Retire", "Nop", "MulXN"]
+OP = {name: i for i, name in enumerate(OPS)}
+
+ABI.update({
+    "spf_b200_graph_build": [_vp, C.POINTER(_Node), _sz, C.POINTER(_vp)],
+    "spf_b200_graph_run": [_vp],
+    "spf_b200_graph_destroy": [_vp],
+    "spf_b200_graph_levels": [_vp],
+    "spf_b200_graph_launches": [_vp],
+    "spf_b200_run_graph": [_vp, C.POINTER(_Node), _sz],
+})
+_RESTYPES.update({"spf_b200_graph_destroy": None, "spf_b200_graph_launches": C.c_uint64})
+
+
+class FheCircuit:
+    """A DAG of FheOp nodes (parasol_runtime/src/fhe_circuit.rs:205-208).  Edges are given when the
+    consumer is added, by the reference's FheEdge names: unary ops take `x`; GlweAdd takes
+    (left, right); CMux / GlevCMux take (sel, low, high); MultiplyGgswGlwe takes (glwe, ggsw).
+    Input / Output nodes carry the numpy buffer they read from / write into."""
+
+    def __init__(self):
+        self.nodes: list[tuple[int, int, tuple[int, int, int], np.ndarray | None]] = []
+
+    def add(self, op: str, *inputs: int, arg: int = 0, io: np.ndarray | None = None) -> int:
+        ins = tuple(inputs) + (-1,) * (3 - len(inputs))
+        if io is not None and not io.flags["C_CONTIGUOUS"]:
+            raise SpfError(-1, "io buffers must be C-contiguous")
+        self.nodes.append((OP[op], int(arg), ins, io))
+        return len(self.nodes) - 1
+
+    def _pack(self):
+        arr = (_Node * max(len(self.nodes), 1))()
+        for i, (op, arg, ins, io) in enumerate(self.nodes):
+            arr[i].op, arr[i].arg = op, arg
+            for e in range(3):
+                arr[i].inp[e] = ins[e]
+            arr[i].io = io.ctypes.data if io is not None else None
+        return arr
+
+
+class CircuitProcessor:
+    """CircuitProcessor (parasol_runtime/src/circuit_processor/mod.rs:62-655) on the GPU: a graph is
+    compiled once into per-level batched launches and can be run repeatedly."""
+
+    def __init__(self, evaluation: Evaluation):
+        self.ev = evaluation
+
+    def compile(self, circuit: FheCircuit) -> "CompiledGraph":
+        return CompiledGraph(self.ev, circuit)
+
+    def run_graph_blocking(self, circuit: FheCircuit) -> None:
+        """run_graph_blocking (mod.rs:641-655); raises SpfError(-4, ...) for malformed graphs as the
+        reference returns Err(RuntimeError)."""
+        g = self.compile(circuit)
+        try:
+            g.run()
+        finally:
+            g.close()
+
+
+class CompiledGraph:
+    def __init__(self, ev: Evaluation, circuit: FheCircuit):
+        self.ev = ev
+        self._keep = circuit  # keeps the io buffers alive
+        self._h = _vp()
+        arr = circuit._pack()
+        ev._check(lib().spf_b200_graph_build(ev.handle, arr, len(circuit.nodes), C.byref(self._h)))
+
+    def run(self):
+        self.ev._check(lib().spf_b200_graph_run(self._h))
+
+    @property
+    def levels(self) -> int:
+        return int(lib().spf_b200_graph_levels(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().spf_b200_graph_launches(self._h))
+
+    def close(self):
+        if self._h.value:
+            lib().spf_b200_graph_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

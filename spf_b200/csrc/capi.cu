@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -40,6 +42,10 @@ struct spf_b200_ctx {
   std::string err;
   std::atomic<uint64_t> launches{0};
   int sm_count = 148;
+  // device constants for the graph executor's Zero*/One* nodes (graph.cuh::ensure_constants)
+  void* consts = nullptr;
+  char *c_lwe0[2] = {nullptr, nullptr}, *c_glwe[2] = {nullptr, nullptr}, *c_glev[2] = {nullptr, nullptr},
+       *c_ggsw[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -192,7 +198,7 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
 // ---- kernel launch helpers (device pointers) ---------------------------------------------
 
 int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in, const uint64_t* d_lut, bool cbs,
-               uint32_t log_chi, uint32_t log_v, size_t batch, cudaStream_t s) {
+               uint32_t log_chi, uint32_t log_v, size_t batch, cudaStream_t s, const void* const* ptrs = nullptr) {
   if (batch == 0) return 0;
   PbsBatch P;
   P.lwe_in = d_lwe_in;
@@ -200,6 +206,7 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
   P.lut_stride = 0;
   P.glwe_out = d_glwe_out;
   P.bsk = ctx->bsk;
+  P.ptrs = ptrs;
   P.batch = (int)batch;
   P.lwe_n = (int)ctx->p.lwe_n;
   P.log_chi = (int)log_chi;
@@ -212,7 +219,7 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
 }
 
 int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_glev_out, C2* d_ggsw_out, int mode,
-                    int levels, double out_scale, size_t batch, cudaStream_t s) {
+                    int levels, double out_scale, size_t batch, cudaStream_t s, const void* const* ptrs = nullptr) {
   if (batch == 0) return 0;
   TraceSsBatch P;
   P.glwe_in = d_glwe_in;
@@ -221,6 +228,7 @@ int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_gl
   P.ak = ctx->ak;
   P.ssk = ctx->ssk;
   P.kinv = ctx->kinv;
+  P.ptrs = ptrs;
   P.batch = (int)batch;
   P.levels = levels;
   P.mode = mode;
@@ -238,7 +246,7 @@ int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_gl
 }
 
 int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const uint64_t* d_d1, const C2* d_ggsw,
-                size_t ggsw_stride, int glwe_per_item, size_t n_glwe, cudaStream_t s) {
+                size_t ggsw_stride, int glwe_per_item, size_t n_glwe, cudaStream_t s, const void* const* ptrs = nullptr) {
   if (n_glwe == 0) return 0;
   CmuxBatch P;
   P.out = d_out;
@@ -246,6 +254,7 @@ int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const 
   P.d1 = d_d1;
   P.ggsw = d_ggsw;
   P.ggsw_stride = ggsw_stride;
+  P.ptrs = ptrs;
   P.batch = (int)n_glwe;
   P.glwe_per_item = glwe_per_item;
   P.radix_log = (int)ctx->p.cbs.radix_log;
@@ -255,12 +264,14 @@ int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const 
   return check_launch(ctx, "cmux_kernel");
 }
 
-int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, size_t batch, cudaStream_t s) {
+int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, size_t batch, cudaStream_t s,
+                     const void* const* ptrs = nullptr) {
   if (batch == 0) return 0;
   KsBatch P;
   P.out = d_out;
   P.in = d_in;
   P.ksk = ctx->ksk;
+  P.ptrs = ptrs;
   P.batch = (int)batch;
   P.n1 = (int)(ctx->p.glwe_k * ctx->p.glwe_n);
   P.n0 = (int)ctx->p.lwe_n;
@@ -273,25 +284,26 @@ int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, s
 }
 
 int launch_sample_extract(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_glwe, const uint32_t* d_idx,
-                          uint32_t idx_all, size_t batch, cudaStream_t s) {
+                          uint32_t idx_all, size_t batch, cudaStream_t s, const void* const* ptrs = nullptr) {
   if (batch == 0) return 0;
   if (!d_idx && idx_all >= (uint32_t)kN) return fail(ctx, SPF_E_INVALID, "sample_extract index >= N");
   for (size_t off = 0; off < batch; off += 65535) {
     const int nb = (int)std::min<size_t>(65535, batch - off);
     dim3 grid(3, nb);
-    sample_extract_kernel<<<grid, 256, 0, s>>>(d_out + off * (kN + 1), d_glwe + off * 2 * kN,
-                                               d_idx ? d_idx + off : nullptr, idx_all, nb);
+    sample_extract_kernel<<<grid, 256, 0, s>>>(d_out + off * (kN + 1), d_glwe ? d_glwe + off * 2 * kN : nullptr,
+                                               ptrs ? ptrs + off : nullptr, d_idx ? d_idx + off : nullptr, idx_all, nb);
     if (int rc = check_launch(ctx, "sample_extract_kernel")) return rc;
   }
   return 0;
 }
 
 int launch_elementwise(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_a, const uint64_t* d_b, int op,
-                       uint32_t n, size_t batch, cudaStream_t s) {
+                       uint32_t n, size_t batch, cudaStream_t s, const void* const* ptrs = nullptr,
+                       const uint32_t* nvec = nullptr) {
   if (batch == 0) return 0;
   const size_t total = batch * 2 * kN;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 16);
-  glwe_elementwise_kernel<<<blocks, 256, 0, s>>>(d_out, d_a, d_b, op, n, batch);
+  glwe_elementwise_kernel<<<blocks, 256, 0, s>>>(d_out, d_a, d_b, ptrs, nvec, op, n, batch);
   return check_launch(ctx, "glwe_elementwise_kernel");
 }
 
@@ -422,7 +434,7 @@ void spf_b200_destroy(spf_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   cudaFree(ctx->bsk); cudaFree(ctx->ak); cudaFree(ctx->ssk); cudaFree(ctx->ksk);
-  cudaFree(ctx->T1); cudaFree(ctx->T2); cudaFree(ctx->kinv);
+  cudaFree(ctx->T1); cudaFree(ctx->T2); cudaFree(ctx->kinv); cudaFree(ctx->consts);
   for (int i = 0; i < 2; i++) {
     for (DevBuf& b : ctx->scratch[i]) cudaFree(b.p);
     if (ctx->stream[i]) cudaStreamDestroy(ctx->stream[i]);
@@ -678,3 +690,5 @@ int spf_b200_fp64_peak(spf_b200_ctx* ctx, double* tflops_out) {
 }
 
 }  // extern "C"
+
+#include "graph.cuh"

@@ -1,0 +1,413 @@
+// graph.cuh -- level-synchronous, batching executor for FheCircuit graphs (included by capi.cu).
+//
+// Replaces the one-rayon-task-per-op scheduling of CircuitProcessor::{dispatch,execute_task,
+// exec_op} (parasol_runtime/src/circuit_processor/mod.rs:130-546) for a whole graph at a time:
+// nodes are levelised by dependency depth, all nodes of one (level, op) group run as ONE batched
+// kernel launch, every intermediate ciphertext stays in HBM (GGSWs in the 2^-10 device scale),
+// and only Input*/Output* nodes touch host memory.  Validation mirrors Task::validate
+// (circuit_processor/task.rs:24-179): wrong input kinds / missing inputs / illegal sample-extract
+// index are reported as SPF_E_GRAPH with a message instead of a RuntimeError.
+#pragma once
+
+namespace {
+
+enum CtType { T_NONE = 0, T_LWE0, T_LWE1, T_GLWE1, T_GGSW1, T_GLEV1 };
+
+const char* kOpNames[] = {"InputLwe0", "InputLwe1", "InputGlwe1", "InputGgsw1", "InputGlev1", "OutputLwe0", "OutputLwe1",
+                          "OutputGlwe1", "OutputGgsw1", "OutputGlev1", "SampleExtract", "KeyswitchL1toL0", "Not", "GlweAdd",
+                          "CMux", "GlevCMux", "MultiplyGgswGlwe", "CircuitBootstrap", "SchemeSwitch", "ZeroLwe0", "OneLwe0",
+                          "ZeroGlwe1", "OneGlwe1", "ZeroGgsw1", "OneGgsw1", "ZeroGlev1", "OneGlev1", "Retire", "Nop", "MulXN"};
+
+struct OpInfo {
+  CtType out;
+  int n_in;
+  CtType in[3];
+};
+
+OpInfo op_info(uint32_t op) {
+  switch (op) {
+    case SPF_OP_INPUT_LWE0: return {T_LWE0, 0, {}};
+    case SPF_OP_INPUT_LWE1: return {T_LWE1, 0, {}};
+    case SPF_OP_INPUT_GLWE1: return {T_GLWE1, 0, {}};
+    case SPF_OP_INPUT_GGSW1: return {T_GGSW1, 0, {}};
+    case SPF_OP_INPUT_GLEV1: return {T_GLEV1, 0, {}};
+    case SPF_OP_OUTPUT_LWE0: return {T_NONE, 1, {T_LWE0}};
+    case SPF_OP_OUTPUT_LWE1: return {T_NONE, 1, {T_LWE1}};
+    case SPF_OP_OUTPUT_GLWE1: return {T_NONE, 1, {T_GLWE1}};
+    case SPF_OP_OUTPUT_GGSW1: return {T_NONE, 1, {T_GGSW1}};
+    case SPF_OP_OUTPUT_GLEV1: return {T_NONE, 1, {T_GLEV1}};
+    case SPF_OP_SAMPLE_EXTRACT: return {T_LWE1, 1, {T_GLWE1}};
+    case SPF_OP_KEYSWITCH_L1_TO_L0: return {T_LWE0, 1, {T_LWE1}};
+    case SPF_OP_NOT: return {T_GLWE1, 1, {T_GLWE1}};
+    case SPF_OP_GLWE_ADD: return {T_GLWE1, 2, {T_GLWE1, T_GLWE1}};
+    case SPF_OP_CMUX: return {T_GLWE1, 3, {T_GGSW1, T_GLWE1, T_GLWE1}};
+    case SPF_OP_GLEV_CMUX: return {T_GLEV1, 3, {T_GGSW1, T_GLEV1, T_GLEV1}};
+    case SPF_OP_MULTIPLY_GGSW_GLWE: return {T_GLWE1, 2, {T_GLWE1, T_GGSW1}};
+    case SPF_OP_CIRCUIT_BOOTSTRAP: return {T_GGSW1, 1, {T_LWE0}};
+    case SPF_OP_SCHEME_SWITCH: return {T_GGSW1, 1, {T_GLEV1}};
+    case SPF_OP_ZERO_LWE0: case SPF_OP_ONE_LWE0: return {T_LWE0, 0, {}};
+    case SPF_OP_ZERO_GLWE1: case SPF_OP_ONE_GLWE1: return {T_GLWE1, 0, {}};
+    case SPF_OP_ZERO_GGSW1: case SPF_OP_ONE_GGSW1: return {T_GGSW1, 0, {}};
+    case SPF_OP_ZERO_GLEV1: case SPF_OP_ONE_GLEV1: return {T_GLEV1, 0, {}};
+    case SPF_OP_MUL_XN: return {T_GLWE1, 1, {T_GLWE1}};
+    default: return {T_NONE, 0, {}};  // Retire, Nop
+  }
+}
+
+size_t ct_bytes(const spf_params* p, CtType t) {
+  switch (t) {
+    case T_LWE0: return spf_b200_len_lwe_l0(p) * 8;
+    case T_LWE1: return spf_b200_len_lwe_l1(p) * 8;
+    case T_GLWE1: return spf_b200_len_glwe_l1(p) * 8;
+    case T_GGSW1: return spf_b200_len_ggsw_l1(p) * 16;
+    case T_GLEV1: return spf_b200_len_glev_l1(p) * 8;
+    default: return 0;
+  }
+}
+size_t ct_host_bytes(const spf_params* p, CtType t) { return ct_bytes(p, t); }
+
+struct Group {
+  uint32_t op;
+  int level;
+  std::vector<int> ids;
+  size_t ptr_off = 0;   // offset (entries) into the device pointer table
+  size_t u32_off = 0;   // offset into the device u32 table
+  char* out_base = nullptr;
+  char* scratch = nullptr;  // CBS: PBS outputs
+};
+
+}  // namespace
+
+struct spf_b200_graph {
+  spf_b200_ctx* ctx = nullptr;
+  std::vector<spf_node> nodes;
+  std::vector<CtType> type;
+  std::vector<int> level;
+  std::vector<char*> dptr;  // device address of each node's output ciphertext
+  std::vector<Group> groups;
+  std::vector<int> inputs, outputs;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  void** d_ptrs = nullptr;
+  uint32_t* d_u32 = nullptr;
+  char* d_out_stage = nullptr;  // rescaled GGSW outputs
+  int n_levels = 0;
+  uint64_t launches_per_run = 0;
+};
+
+namespace {
+
+// Device constants for Zero*/One* nodes (mod.rs:95-105,475-506).  ZeroGgsw1/OneGgsw1 are real CBS
+// outputs of the trivial LWE 0/1, exactly as Evaluation::new computes them (evaluation.rs:161-197).
+int ensure_constants(spf_b200_ctx* ctx) {
+  if (ctx->consts) return 0;
+  const spf_params* p = &ctx->p;
+  const size_t lwe0 = ct_bytes(p, T_LWE0), glwe = ct_bytes(p, T_GLWE1), glev = ct_bytes(p, T_GLEV1), ggsw = ct_bytes(p, T_GGSW1);
+  const size_t total = 2 * (lwe0 + glwe + glev + ggsw);
+  std::vector<char> h(total, 0);
+  char* q = h.data();
+  // [lwe0 zero, lwe0 one, glwe zero, glwe one, glev zero, glev one, ggsw zero, ggsw one]
+  reinterpret_cast<uint64_t*>(q + lwe0)[p->lwe_n] = 1ull << 63;                      // trivial_lwe_l0_one
+  reinterpret_cast<uint64_t*>(q + 2 * lwe0 + glwe)[(size_t)p->glwe_k * p->glwe_n] = 1ull << 63;  // trivial one: b[0]
+  {
+    uint64_t* g1 = reinterpret_cast<uint64_t*>(q + 2 * lwe0 + 2 * glwe + glev);       // trivial_binary_glev(1)
+    for (uint32_t j = 0; j < p->cbs.count; j++)
+      g1[(size_t)j * spf_b200_len_glwe_l1(p) + (size_t)p->glwe_k * p->glwe_n] = 1ull << (64 - p->cbs.radix_log * (j + 1));
+  }
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMalloc(&ctx->consts, total));
+  CU(cudaMemcpy(ctx->consts, h.data(), total, cudaMemcpyHostToDevice));
+  char* d = static_cast<char*>(ctx->consts);
+  ctx->c_lwe0[0] = d; ctx->c_lwe0[1] = d + lwe0;
+  ctx->c_glwe[0] = d + 2 * lwe0; ctx->c_glwe[1] = d + 2 * lwe0 + glwe;
+  ctx->c_glev[0] = d + 2 * lwe0 + 2 * glwe; ctx->c_glev[1] = ctx->c_glev[0] + glev;
+  ctx->c_ggsw[0] = d + 2 * lwe0 + 2 * glwe + 2 * glev; ctx->c_ggsw[1] = ctx->c_ggsw[0] + ggsw;
+  // the two trivial LWEs are adjacent only if lwe0 is unpadded; bootstrap them one by one
+  for (int b = 0; b < 2; b++) {
+    if (int rc = spf_b200_dev_circuit_bootstrap(ctx, reinterpret_cast<double*>(ctx->c_ggsw[b]),
+                                                reinterpret_cast<const uint64_t*>(ctx->c_lwe0[b]), 1, 0, nullptr))
+      return rc;
+  }
+  CU(cudaStreamSynchronize(ctx->stream[0]));
+  return 0;
+}
+
+int graph_fail(spf_b200_ctx* ctx, const std::string& msg) { return fail(ctx, SPF_E_GRAPH, msg); }
+
+int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s) {
+  spf_b200_ctx* ctx = g->ctx;
+  const size_t n = G.ids.size();
+  const void* const* ptrs = reinterpret_cast<const void* const*>(g->d_ptrs + G.ptr_off);
+  switch (G.op) {
+    case SPF_OP_SAMPLE_EXTRACT:
+      return launch_sample_extract(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, g->d_u32 + G.u32_off, 0, n, s, ptrs);
+    case SPF_OP_KEYSWITCH_L1_TO_L0:
+      return launch_keyswitch(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, n, s, ptrs);
+    case SPF_OP_NOT:
+      return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, 1, 0, n, s, ptrs);
+    case SPF_OP_GLWE_ADD:
+      return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, 0, 0, n, s, ptrs);
+    case SPF_OP_MUL_XN:
+      return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, 2, 0, n, s, ptrs,
+                                g->d_u32 + G.u32_off);
+    case SPF_OP_CMUX:
+    case SPF_OP_MULTIPLY_GGSW_GLWE:
+      return launch_cmux(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, nullptr, 0, 1, n, s, ptrs);
+    case SPF_OP_GLEV_CMUX:
+      return launch_cmux(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, nullptr, 0, (int)ctx->p.cbs.count,
+                         n * ctx->p.cbs.count, s, ptrs);
+    case SPF_OP_CIRCUIT_BOOTSTRAP: {
+      if (int rc = launch_pbs(ctx, reinterpret_cast<uint64_t*>(G.scratch), nullptr, nullptr, true, 0, cbs_log_v(&ctx->p), n, s, ptrs))
+        return rc;
+      return launch_trace_ss(ctx, reinterpret_cast<const uint64_t*>(G.scratch), nullptr, reinterpret_cast<C2*>(G.out_base), 0,
+                             (int)ctx->p.cbs.count, 1.0, n, s);
+    }
+    case SPF_OP_SCHEME_SWITCH:
+      return launch_trace_ss(ctx, nullptr, nullptr, reinterpret_cast<C2*>(G.out_base), 2, (int)ctx->p.cbs.count, 1.0, n, s, ptrs);
+    default:
+      return 0;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void spf_b200_graph_destroy(spf_b200_graph* g);
+
+int spf_b200_graph_build(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, spf_b200_graph** out) {
+  if (!ctx) return SPF_E_INVALID;
+  if (!out || (!nodes && n)) return fail(ctx, SPF_E_INVALID, "NULL argument");
+  *out = nullptr;
+  const spf_params* p = &ctx->p;
+  std::unique_ptr<spf_b200_graph, void (*)(spf_b200_graph*)> g(new spf_b200_graph(), spf_b200_graph_destroy);
+  g->ctx = ctx;
+  g->nodes.assign(nodes, nodes + n);
+  g->type.resize(n);
+  g->level.assign(n, -1);
+  g->dptr.assign(n, nullptr);
+  // ---- validation (Task::validate_inputs / validate_op, task.rs:24-179) ----
+  for (size_t i = 0; i < n; i++) {
+    const spf_node& nd = g->nodes[i];
+    if (nd.op > SPF_OP_MUL_XN) return graph_fail(ctx, "node " + std::to_string(i) + ": unknown op " + std::to_string(nd.op));
+    const OpInfo oi = op_info(nd.op);
+    g->type[i] = oi.out;
+    for (int e = 0; e < 3; e++) {
+      const int src = nd.in[e];
+      if (e < oi.n_in) {
+        if (src < 0 || (size_t)src >= n)
+          return graph_fail(ctx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): missing ciphertext input on edge " + std::to_string(e));
+      } else if (src >= 0 && nd.op != SPF_OP_RETIRE && nd.op != SPF_OP_NOP) {
+        return graph_fail(ctx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): unexpected extra input edge");
+      }
+    }
+    if (nd.op == SPF_OP_SAMPLE_EXTRACT && nd.arg >= p->glwe_n)
+      return graph_fail(ctx, "illegal sample extract index " + std::to_string(nd.arg));
+    const bool is_io = nd.op <= SPF_OP_OUTPUT_GLEV1;
+    if (is_io && !nd.io) return graph_fail(ctx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): io pointer is NULL");
+  }
+  for (size_t i = 0; i < n; i++) {
+    const spf_node& nd = g->nodes[i];
+    const OpInfo oi = op_info(nd.op);
+    for (int e = 0; e < oi.n_in; e++) {
+      if (g->type[nd.in[e]] != oi.in[e])
+        return graph_fail(ctx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): input " + std::to_string(e) +
+                                   " from node " + std::to_string(nd.in[e]) + " (" + kOpNames[g->nodes[nd.in[e]].op] + ") has the wrong ciphertext kind");
+    }
+  }
+  // ---- levelise (iterative DFS with cycle detection) ----
+  {
+    std::vector<int> state(n, 0);  // 0 new, 1 on stack, 2 done
+    std::vector<std::pair<int, int>> stack;
+    for (size_t r = 0; r < n; r++) {
+      if (state[r]) continue;
+      stack.push_back({(int)r, 0});
+      state[r] = 1;
+      while (!stack.empty()) {
+        auto& [v, e] = stack.back();
+        const OpInfo oi = op_info(g->nodes[v].op);
+        if (e < oi.n_in) {
+          const int w = g->nodes[v].in[e++];
+          if (state[w] == 1) return graph_fail(ctx, "graph has a cycle through node " + std::to_string(w));
+          if (state[w] == 0) { state[w] = 1; stack.push_back({w, 0}); }
+        } else {
+          int lv = 0;
+          for (int k = 0; k < oi.n_in; k++) lv = std::max(lv, g->level[g->nodes[v].in[k]] + 1);
+          g->level[v] = lv;
+          state[v] = 2;
+          stack.pop_back();
+        }
+      }
+    }
+  }
+  for (size_t i = 0; i < n; i++) g->n_levels = std::max(g->n_levels, g->level[i] + 1);
+  if (int rc = ensure_constants(ctx)) return rc;
+  // ---- groups, arena layout, pointer tables ----
+  std::vector<std::vector<int>> by_level(g->n_levels);
+  for (size_t i = 0; i < n; i++) by_level[g->level[i]].push_back((int)i);
+  size_t arena = 0, n_ptrs = 0, n_u32 = 0, out_stage = 0;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  std::vector<size_t> out_off, scratch_off;
+  for (int lv = 0; lv < g->n_levels; lv++) {
+    std::map<uint32_t, std::vector<int>> ops;
+    for (int id : by_level[lv]) ops[g->nodes[id].op].push_back(id);
+    for (auto& kv : ops) {
+      const uint32_t op = kv.first;
+      if (op == SPF_OP_RETIRE || op == SPF_OP_NOP) continue;
+      Group G;
+      G.op = op;
+      G.level = lv;
+      G.ids = kv.second;
+      const OpInfo oi = op_info(op);
+      const bool is_const = op >= SPF_OP_ZERO_LWE0 && op <= SPF_OP_ONE_GLEV1;
+      const bool is_output = op >= SPF_OP_OUTPUT_LWE0 && op <= SPF_OP_OUTPUT_GLEV1;
+      size_t o = (size_t)-1, sc = (size_t)-1;
+      if (!is_const && !is_output) {
+        o = arena;
+        arena = align(arena + ct_bytes(p, oi.out) * G.ids.size());
+        if (op == SPF_OP_CIRCUIT_BOOTSTRAP) { sc = arena; arena = align(arena + ct_bytes(p, T_GLWE1) * G.ids.size()); }
+      }
+      if (op == SPF_OP_OUTPUT_GGSW1) out_stage += ct_bytes(p, T_GGSW1) * G.ids.size();
+      G.ptr_off = n_ptrs;
+      G.u32_off = n_u32;
+      if (op == SPF_OP_CMUX || op == SPF_OP_GLEV_CMUX || op == SPF_OP_MULTIPLY_GGSW_GLWE) n_ptrs += 3 * G.ids.size();
+      else if (op == SPF_OP_NOT || op == SPF_OP_GLWE_ADD || op == SPF_OP_MUL_XN) n_ptrs += 2 * G.ids.size();
+      else if (oi.n_in == 1 && !is_output) n_ptrs += G.ids.size();
+      if (op == SPF_OP_SAMPLE_EXTRACT || op == SPF_OP_MUL_XN) n_u32 += G.ids.size();
+      out_off.push_back(o);
+      scratch_off.push_back(sc);
+      g->groups.push_back(std::move(G));
+    }
+  }
+  CU(cudaSetDevice(ctx->device));
+  g->arena_bytes = std::max<size_t>(arena, 256);
+  CU(cudaMalloc(&g->arena, g->arena_bytes));
+  CU(cudaMalloc(&g->d_ptrs, std::max<size_t>(n_ptrs, 1) * sizeof(void*)));
+  CU(cudaMalloc(&g->d_u32, std::max<size_t>(n_u32, 1) * 4));
+  if (out_stage) CU(cudaMalloc(&g->d_out_stage, out_stage));
+  // device addresses of every node output (groups are in level order, so producers come first)
+  for (size_t gi = 0; gi < g->groups.size(); gi++) {
+    Group& G = g->groups[gi];
+    const OpInfo oi = op_info(G.op);
+    if (out_off[gi] != (size_t)-1) G.out_base = g->arena + out_off[gi];
+    if (scratch_off[gi] != (size_t)-1) G.scratch = g->arena + scratch_off[gi];
+    for (size_t k = 0; k < G.ids.size(); k++) {
+      const int id = G.ids[k];
+      switch (G.op) {
+        case SPF_OP_ZERO_LWE0: g->dptr[id] = ctx->c_lwe0[0]; break;
+        case SPF_OP_ONE_LWE0: g->dptr[id] = ctx->c_lwe0[1]; break;
+        case SPF_OP_ZERO_GLWE1: g->dptr[id] = ctx->c_glwe[0]; break;
+        case SPF_OP_ONE_GLWE1: g->dptr[id] = ctx->c_glwe[1]; break;
+        case SPF_OP_ZERO_GGSW1: g->dptr[id] = ctx->c_ggsw[0]; break;
+        case SPF_OP_ONE_GGSW1: g->dptr[id] = ctx->c_ggsw[1]; break;
+        case SPF_OP_ZERO_GLEV1: g->dptr[id] = ctx->c_glev[0]; break;
+        case SPF_OP_ONE_GLEV1: g->dptr[id] = ctx->c_glev[1]; break;
+        default:
+          if (G.out_base) g->dptr[id] = G.out_base + k * ct_bytes(p, oi.out);
+      }
+      if (G.op <= SPF_OP_INPUT_GLEV1) g->inputs.push_back(id);
+      if (G.op >= SPF_OP_OUTPUT_LWE0 && G.op <= SPF_OP_OUTPUT_GLEV1) g->outputs.push_back(id);
+    }
+  }
+  std::vector<void*> h_ptrs(std::max<size_t>(n_ptrs, 1), nullptr);
+  std::vector<uint32_t> h_u32(std::max<size_t>(n_u32, 1), 0);
+  for (Group& G : g->groups) {
+    const OpInfo oi = op_info(G.op);
+    for (size_t k = 0; k < G.ids.size(); k++) {
+      const spf_node& nd = g->nodes[G.ids[k]];
+      switch (G.op) {
+        case SPF_OP_CMUX:
+        case SPF_OP_GLEV_CMUX:  // in[0] = Sel, in[1] = Low (a), in[2] = High (b): out = sel ? b : a
+          h_ptrs[G.ptr_off + 3 * k + 0] = g->dptr[nd.in[0]];
+          h_ptrs[G.ptr_off + 3 * k + 1] = g->dptr[nd.in[1]];
+          h_ptrs[G.ptr_off + 3 * k + 2] = g->dptr[nd.in[2]];
+          break;
+        case SPF_OP_MULTIPLY_GGSW_GLWE:  // in[0] = Glwe, in[1] = Ggsw
+          h_ptrs[G.ptr_off + 3 * k + 0] = g->dptr[nd.in[1]];
+          h_ptrs[G.ptr_off + 3 * k + 1] = nullptr;
+          h_ptrs[G.ptr_off + 3 * k + 2] = g->dptr[nd.in[0]];
+          break;
+        case SPF_OP_NOT:
+        case SPF_OP_MUL_XN:
+          h_ptrs[G.ptr_off + 2 * k] = g->dptr[nd.in[0]];
+          if (G.op == SPF_OP_MUL_XN) h_u32[G.u32_off + k] = nd.arg;
+          break;
+        case SPF_OP_GLWE_ADD:
+          h_ptrs[G.ptr_off + 2 * k] = g->dptr[nd.in[0]];
+          h_ptrs[G.ptr_off + 2 * k + 1] = g->dptr[nd.in[1]];
+          break;
+        default:
+          if (oi.n_in == 1 && !(G.op >= SPF_OP_OUTPUT_LWE0 && G.op <= SPF_OP_OUTPUT_GLEV1)) {
+            h_ptrs[G.ptr_off + k] = g->dptr[nd.in[0]];
+            if (G.op == SPF_OP_SAMPLE_EXTRACT) h_u32[G.u32_off + k] = nd.arg;
+          }
+      }
+    }
+  }
+  CU(cudaMemcpy(g->d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(g->d_u32, h_u32.data(), h_u32.size() * 4, cudaMemcpyHostToDevice));
+  *out = g.release();
+  return 0;
+}
+
+// Executes the graph once: copies every Input* ciphertext from its io pointer, runs the levels,
+// copies every Output* ciphertext to its io pointer, and returns when the outputs are valid
+// (CircuitProcessor::run_graph_blocking, circuit_processor/mod.rs:641-655).
+int spf_b200_graph_run(spf_b200_graph* g) {
+  if (!g) return SPF_E_INVALID;
+  spf_b200_ctx* ctx = g->ctx;
+  const spf_params* p = &ctx->p;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream[0];
+  const uint64_t l0 = ctx->launches.load();
+  for (int id : g->inputs) {
+    const CtType t = g->type[id];
+    CU(cudaMemcpyAsync(g->dptr[id], g->nodes[id].io, ct_host_bytes(p, t), cudaMemcpyHostToDevice, s));
+    if (t == T_GGSW1)
+      if (int rc = launch_scale(ctx, reinterpret_cast<C2*>(g->dptr[id]), reinterpret_cast<const C2*>(g->dptr[id]),
+                                spf_b200_len_ggsw_l1(p), 1.0 / 1024.0, s))
+        return rc;
+  }
+  for (const Group& G : g->groups)
+    if (int rc = run_group(g, G, s)) return rc;
+  size_t stage = 0;
+  for (int id : g->outputs) {
+    const int src = g->nodes[id].in[0];
+    const CtType t = g->type[src];
+    const char* from = g->dptr[src];
+    if (t == T_GGSW1) {
+      char* tmp = g->d_out_stage + stage;
+      stage += ct_bytes(p, T_GGSW1);
+      if (int rc = launch_scale(ctx, reinterpret_cast<C2*>(tmp), reinterpret_cast<const C2*>(from), spf_b200_len_ggsw_l1(p), 1024.0, s))
+        return rc;
+      from = tmp;
+    }
+    CU(cudaMemcpyAsync(g->nodes[id].io, from, ct_host_bytes(p, t), cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  g->launches_per_run = ctx->launches.load() - l0;
+  return 0;
+}
+
+void spf_b200_graph_destroy(spf_b200_graph* g) {
+  if (!g) return;
+  cudaSetDevice(g->ctx->device);
+  cudaFree(g->arena);
+  cudaFree(g->d_ptrs);
+  cudaFree(g->d_u32);
+  cudaFree(g->d_out_stage);
+  delete g;
+}
+
+int spf_b200_graph_levels(const spf_b200_graph* g) { return g ? g->n_levels : -1; }
+uint64_t spf_b200_graph_launches(const spf_b200_graph* g) { return g ? g->launches_per_run : 0; }
+
+int spf_b200_run_graph(spf_b200_ctx* ctx, const spf_node* nodes, size_t n) {
+  spf_b200_graph* g = nullptr;
+  if (int rc = spf_b200_graph_build(ctx, nodes, n, &g)) return rc;
+  const int rc = spf_b200_graph_run(g);
+  spf_b200_graph_destroy(g);
+  return rc;
+}
+
+}  // extern "C"

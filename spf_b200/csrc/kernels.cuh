@@ -53,6 +53,7 @@ struct PbsBatch {
   size_t lut_stride;        // 0: one LUT for the whole batch, else per-ciphertext stride (elements)
   uint64_t* glwe_out;       // [B][2][2048]
   const C2* bsk;
+  const void* const* ptrs;  // optional device table: ptrs[c] = LWE input of item c (graph executor)
   int batch, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count;
 };
 
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   C2* xb = reinterpret_cast<C2*>(base + 2 * kN * 8);
   DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3};
   PbsArgs A;
-  A.lwe_in = P.lwe_in + (size_t)c * (P.lwe_n + 1);
+  A.lwe_in = P.ptrs ? static_cast<const uint64_t*>(P.ptrs[c]) : P.lwe_in + (size_t)c * (P.lwe_n + 1);
   A.lut = P.lut ? P.lut + (size_t)c * P.lut_stride : nullptr;
   A.glwe_out = P.glwe_out + (size_t)c * 2 * kN;
   A.bsk = P.bsk;
@@ -96,6 +97,7 @@ struct TraceSsBatch {
   const C2* ak;
   const C2* ssk;
   const uint32_t* kinv;
+  const void* const* ptrs;  // optional device table: ptrs[c] = input (GLWE or GLEV base) of item c
   int batch, levels, mode;
   int cbs_radix_log, cbs_count, tr_radix_log, tr_count, ss_radix_log, ss_count;
   double out_scale;
@@ -117,8 +119,8 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(TraceSsBa
   DevCx cx{(int)(threadIdx.x % kTeam), team + 1};
   TraceSsArgs A;
   const size_t glwe = 2 * kN;
-  if (P.mode == 0) A.glwe_in = P.glwe_in + (size_t)c * glwe;
-  else if (P.mode == 1) A.glwe_in = P.glwe_in + (size_t)item * glwe;
+  if (P.ptrs) A.glwe_in = static_cast<const uint64_t*>(P.ptrs[c]) + (P.mode == 2 ? (size_t)level * glwe : 0);
+  else if (P.mode == 0) A.glwe_in = P.glwe_in + (size_t)c * glwe;
   else A.glwe_in = P.glwe_in + (size_t)item * glwe;
   A.glev_out = P.glev_out ? P.glev_out + (size_t)item * glwe : nullptr;
   A.ggsw_out = P.ggsw_out ? P.ggsw_out + (size_t)c * 2 * P.cbs_count * 2 * kM : nullptr;
@@ -150,6 +152,7 @@ struct CmuxBatch {
   const uint64_t* d1;
   const C2* ggsw;         // 2^-10 scaled
   size_t ggsw_stride;     // elements between consecutive items' GGSWs (0 = shared)
+  const void* const* ptrs;  // optional device table, 3 per item: {ggsw, d0 (may be null), d1} (graph executor)
   int batch;              // number of GLWE outputs
   int glwe_per_item;      // 1 for cmux, l_cbs for glev_cmux (GLWEs sharing one GGSW)
   int radix_log, count;
@@ -168,6 +171,15 @@ __global__ void __launch_bounds__(kCmuxTeams * kTeam, 1) cmux_kernel(CmuxBatch P
   C2* xbuf = reinterpret_cast<C2*>(base + 32 * 64 * 8);
   DevCx cx{(int)(threadIdx.x % kTeam), team + 1};
   const size_t glwe = 2 * kN;
+  if (P.ptrs) {
+    const int item = c / P.glwe_per_item;
+    const size_t off = (size_t)(c % P.glwe_per_item) * glwe;
+    const uint64_t* d0 = static_cast<const uint64_t*>(P.ptrs[3 * item + 1]);
+    cmux_team(cx, P.out + (size_t)c * glwe, d0 ? d0 + off : nullptr,
+              static_cast<const uint64_t*>(P.ptrs[3 * item + 2]) + off, static_cast<const C2*>(P.ptrs[3 * item]), st,
+              xbuf, sT1, sT2, P.radix_log, P.count);
+    return;
+  }
   cmux_team(cx, P.out + (size_t)c * glwe, P.d0 ? P.d0 + (size_t)c * glwe : nullptr, P.d1 + (size_t)c * glwe,
             P.ggsw + (size_t)(c / P.glwe_per_item) * P.ggsw_stride, st, xbuf, sT1, sT2, P.radix_log, P.count);
 }
@@ -184,6 +196,7 @@ struct KsBatch {
   uint64_t* out;        // [B][n0+1]
   const uint64_t* in;   // [B][n1+1]
   const uint64_t* ksk;  // [n1][l][n0+1]
+  const void* const* ptrs;  // optional device table: ptrs[b] = L1 LWE input of item b
   int batch, n1, n0, radix_log, count;
 };
 
@@ -194,7 +207,8 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
   const int nb = min(kKsBatch, P.batch - b0);
   for (int idx = threadIdx.x; idx < kKsBatch * P.n1; idx += blockDim.x) {
     const int b = idx / P.n1, i = idx % P.n1;
-    st[idx] = b < nb ? (uint32_t)radix_round(P.in[(size_t)(b0 + b) * (P.n1 + 1) + i], P.radix_log, P.count) : 0u;
+    const uint64_t* src = b < nb ? (P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + b]) : P.in + (size_t)(b0 + b) * (P.n1 + 1)) : nullptr;
+    st[idx] = src ? (uint32_t)radix_round(src[i], P.radix_log, P.count) : 0u;
   }
   __syncthreads();
   const int cols = P.n0 + 1;
@@ -227,7 +241,7 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
   for (int b = 0; b < kKsBatch; b++) {
     if (b >= nb) break;
     uint64_t* o = P.out + (size_t)(b0 + b) * cols;
-    const uint64_t body = P.in[(size_t)(b0 + b) * (P.n1 + 1) + P.n1];
+    const uint64_t body = (P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + b]) : P.in + (size_t)(b0 + b) * (P.n1 + 1))[P.n1];
     if (has0) o[c0] = (c0 == P.n0 ? body : 0) - acc0[b];
     if (has1) o[c1] = (c1 == P.n0 ? body : 0) - acc1[b];
   }
@@ -237,12 +251,12 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
 // K7: small integer ops
 // ------------------------------------------------------------------------------------------
 // sample_extract (ops/ciphertext/glwe_ciphertext_ops.rs:31-76), k = 1
-__global__ void sample_extract_kernel(uint64_t* out, const uint64_t* glwe, const uint32_t* idx, uint32_t idx_const,
-                                      int batch) {
+__global__ void sample_extract_kernel(uint64_t* out, const uint64_t* glwe, const void* const* ptrs, const uint32_t* idx,
+                                      uint32_t idx_const, int batch) {
   const int c = blockIdx.y;
   if (c >= batch) return;
   const int h = idx ? (int)idx[c] : (int)idx_const;
-  const uint64_t* a = glwe + (size_t)c * 2 * kN;
+  const uint64_t* a = ptrs ? static_cast<const uint64_t*>(ptrs[c]) : glwe + (size_t)c * 2 * kN;
   uint64_t* o = out + (size_t)c * (kN + 1);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j <= kN; j += gridDim.x * blockDim.x) {
     if (j == kN) o[j] = a[kN + h];
@@ -252,17 +266,17 @@ __global__ void sample_extract_kernel(uint64_t* out, const uint64_t* glwe, const
 
 // op 0: out = a + b (xor, evaluation.rs:53-55); op 1: out = a + trivial_one (not, :48-50);
 // op 2: out = a * X^n (mul_xn, :58-65)
-__global__ void glwe_elementwise_kernel(uint64_t* out, const uint64_t* a, const uint64_t* b, int op, uint32_t n,
-                                        size_t batch) {
+__global__ void glwe_elementwise_kernel(uint64_t* out, const uint64_t* a, const uint64_t* b, const void* const* ptrs,
+                                        const uint32_t* nvec, int op, uint32_t n, size_t batch) {
   const size_t total = batch * 2 * kN;
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t c = e / (2 * kN);
     const int r = (int)(e % (2 * kN)) / kN, j = (int)(e % kN);
-    const uint64_t* pa = a + c * 2 * kN + r * kN;
+    const uint64_t* pa = (ptrs ? static_cast<const uint64_t*>(ptrs[2 * c]) : a + c * 2 * kN) + r * kN;
     uint64_t v;
-    if (op == 0) v = pa[j] + b[e];
+    if (op == 0) v = pa[j] + (ptrs ? static_cast<const uint64_t*>(ptrs[2 * c + 1])[r * kN + j] : b[e]);
     else if (op == 1) v = pa[j] + ((r == 1 && j == 0) ? (1ull << 63) : 0ull);
-    else v = rotated_coeff(pa, j, (int)(n & (2 * kN - 1)));
+    else v = rotated_coeff(pa, j, (int)((nvec ? nvec[c] : n) & (2 * kN - 1)));
     out[e] = v;
   }
 }

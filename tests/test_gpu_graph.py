@@ -1,0 +1,155 @@
+"""The level-synchronous graph executor (spf_b200_graph_*; CircuitProcessor equivalent) on the GPU,
+modelled on parasol_runtime/src/circuit_processor/tests/{mod.rs,faults.rs}."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def proc(evaluation):
+    import spf_b200
+
+    return spf_b200.CircuitProcessor(evaluation)
+
+
+def test_copy_and_constants(keys, client, proc):
+    """circuit_processor/tests/mod.rs:53-120: Input -> Output copies; Zero/One constants."""
+    import spf_b200
+
+    g_in = client.encrypt_glwe_l1([1, 0, 1])
+    l0_in = client.encrypt_lwe_l0(1)
+    g_out = np.zeros_like(g_in)
+    l0_out = np.zeros_like(l0_in)
+    z, o = np.zeros(keys.glwe_len, dtype=np.uint64), np.zeros(keys.glwe_len, dtype=np.uint64)
+    gz, go = np.zeros(keys.ggsw_fft_len, dtype=np.complex128), np.zeros(keys.ggsw_fft_len, dtype=np.complex128)
+    c = spf_b200.FheCircuit()
+    c.add("OutputGlwe1", c.add("InputGlwe1", io=g_in), io=g_out)
+    c.add("OutputLwe0", c.add("InputLwe0", io=l0_in), io=l0_out)
+    c.add("OutputGlwe1", c.add("ZeroGlwe1"), io=z)
+    c.add("OutputGlwe1", c.add("OneGlwe1"), io=o)
+    c.add("OutputGgsw1", c.add("ZeroGgsw1"), io=gz)
+    c.add("OutputGgsw1", c.add("OneGgsw1"), io=go)
+    c.add("Retire")
+    proc.run_graph_blocking(c)
+    assert np.array_equal(g_out, g_in) and np.array_equal(l0_out, l0_in)
+    assert client.decrypt_glwe_l1(z)[:2].tolist() == [0, 0] and client.decrypt_glwe_l1(o)[:2].tolist() == [1, 0]
+    assert client.decrypt_ggsw_l1(gz) == 0 and client.decrypt_ggsw_l1(go) == 1
+
+
+def test_sample_extract_keyswitch_cbs_cmux(oracle, keys, client, proc):
+    """mod.rs:122-193: sample extract, keyswitch, CBS + CMux through the graph; every intermediate
+    stays on the device.  Integer nodes are bit-exact against the oracle."""
+    import spf_b200
+
+    bits = [1, 0, 1, 1]
+    src = client.encrypt_glwe_l1(bits)
+    a, b = client.encrypt_glwe_l1([0]), client.encrypt_glwe_l1([1])
+    outs = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in bits]
+    l0s = [np.zeros(keys.lwe0_len, dtype=np.uint64) for _ in bits]
+    c = spf_b200.FheCircuit()
+    x = c.add("InputGlwe1", io=src)
+    na, nb = c.add("InputGlwe1", io=a), c.add("InputGlwe1", io=b)
+    for i in range(len(bits)):
+        l0 = c.add("KeyswitchL1toL0", c.add("SampleExtract", x, arg=i))
+        c.add("OutputLwe0", l0, io=l0s[i])
+        sel = c.add("CircuitBootstrap", l0)
+        c.add("OutputGlwe1", c.add("CMux", sel, na, nb), io=outs[i])
+    g = proc.compile(c)
+    g.run()
+    assert g.levels == 6
+    for i, bit in enumerate(bits):
+        assert np.array_equal(l0s[i], oracle.keyswitch_lwe(keys, oracle.sample_extract(keys, src, i)))
+        assert client.decrypt_glwe_l1(outs[i])[0] == bit
+    launches = g.launches
+    g.run()  # re-running a compiled graph re-reads the inputs
+    assert g.launches == launches
+    g.close()
+    # 4 chains, but one launch per (level, op) group: SE, KS, PBS + trace/SS, CMUX
+    assert launches <= 6
+
+
+def test_not_add_mulxn_multiply(oracle, keys, client, proc):
+    import spf_b200
+
+    a, b = client.encrypt_glwe_l1([1, 0, 1, 0]), client.encrypt_glwe_l1([1, 1, 0, 0])
+    ggsw = client.encrypt_ggsw_l1(1)
+    o = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(4)]
+    c = spf_b200.FheCircuit()
+    na, nb, ng = c.add("InputGlwe1", io=a), c.add("InputGlwe1", io=b), c.add("InputGgsw1", io=ggsw)
+    c.add("OutputGlwe1", c.add("Not", na), io=o[0])
+    c.add("OutputGlwe1", c.add("GlweAdd", na, nb), io=o[1])
+    c.add("OutputGlwe1", c.add("MulXN", na, arg=2), io=o[2])
+    c.add("OutputGlwe1", c.add("MultiplyGgswGlwe", na, ng), io=o[3])
+    proc.run_graph_blocking(c)
+    assert np.array_equal(o[0], oracle.glwe_not(keys, a))
+    assert np.array_equal(o[1], a + b)
+    assert np.array_equal(o[2], oracle.glwe_mul_xn(keys, a, 2))
+    assert oracle.torus_distance(o[3], oracle.multiply_glwe_ggsw(keys, a, ggsw)).max() <= 2.0 ** -30
+
+
+def test_glev_cmux_and_scheme_switch_nodes(oracle, keys, client, proc):
+    import spf_b200
+
+    d0, d1 = client.encrypt_glev_l1([0, 1]), client.encrypt_glev_l1([1, 1])
+    sel = client.encrypt_ggsw_l1(1)
+    out_glev = np.zeros(keys.glev_len, dtype=np.uint64)
+    out_ggsw = np.zeros(keys.ggsw_fft_len, dtype=np.complex128)
+    c = spf_b200.FheCircuit()
+    n0, n1, ns = c.add("InputGlev1", io=d0), c.add("InputGlev1", io=d1), c.add("InputGgsw1", io=sel)
+    m = c.add("GlevCMux", ns, n0, n1)
+    c.add("OutputGlev1", m, io=out_glev)
+    c.add("OutputGgsw1", c.add("SchemeSwitch", m), io=out_ggsw)
+    proc.run_graph_blocking(c)
+    assert oracle.torus_distance(out_glev, oracle.glev_cmux(keys, d0, d1, sel)).max() <= 2.0 ** -30
+    # the selected GLEV encrypts [1, 1]: as a GGSW its last-row level-0 GLWE decodes to 1 at coeffs 0, 1
+    msgs = client.ggsw_level_messages(out_ggsw)
+    assert msgs[1, 0, :3].tolist() == [1, 1, 0]
+
+
+@pytest.mark.parametrize("a,b", [(2, 7), (255, 1), (170, 85), (0, 0)])
+def test_basic_add_8bit(keys, client, proc, a, b):
+    """BASELINE config 1 (examples/basic_add: encrypted uint8 a + b; parasol_cpu/src/proc/ops/add.rs:13-80):
+    16 x (SampleExtract -> KeyswitchL1toL0 -> CircuitBootstrap) + a ripple-carry MUX tree."""
+    from spf_b200.circuits import ripple_carry_adder
+
+    w = 8
+    ab = [client.encrypt_glwe_l1([(a >> i) & 1]) for i in range(w)]
+    bb = [client.encrypt_glwe_l1([(b >> i) & 1]) for i in range(w)]
+    outs = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w + 1)]
+    g = proc.compile(ripple_carry_adder(ab, bb, outs))
+    g.run()
+    got = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(outs))
+    assert got == a + b
+    assert g.levels == 4 + 2 * w + 1
+    g.close()
+
+
+def test_malformed_graphs(keys, client, proc):
+    """circuit_processor/tests/faults.rs:10-118 -> SPF_E_GRAPH (-4) with a message."""
+    import spf_b200
+
+    glwe = client.encrypt_glwe_l1([1])
+    lwe0 = client.encrypt_lwe_l0(1)
+
+    def expect(c, text):
+        with pytest.raises(spf_b200.SpfError) as e:
+            proc.run_graph_blocking(c)
+        assert e.value.code == -4 and text in str(e.value), str(e.value)
+
+    c = spf_b200.FheCircuit()
+    c.add("CircuitBootstrap", c.add("InputGlwe1", io=glwe))  # GLWE into an LWE0 port
+    expect(c, "wrong ciphertext kind")
+    c = spf_b200.FheCircuit()
+    c.add("CMux", c.add("InputGlwe1", io=glwe), -1, -1)  # missing inputs
+    expect(c, "missing ciphertext input")
+    c = spf_b200.FheCircuit()
+    c.add("SampleExtract", c.add("InputGlwe1", io=glwe), arg=2048)
+    expect(c, "illegal sample extract")
+    c = spf_b200.FheCircuit()
+    c.nodes.append((spf_b200.OP["Not"], 0, (1, -1, -1), None))  # 0 <- 1 <- 0
+    c.nodes.append((spf_b200.OP["Not"], 0, (0, -1, -1), None))
+    expect(c, "cycle")
+    c = spf_b200.FheCircuit()
+    c.add("KeyswitchL1toL0", c.add("InputLwe0", io=lwe0))
+    expect(c, "wrong ciphertext kind")
