@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="CBS in the CPU baseline sample (0 = 2 per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-add", action="store_true", help="skip the Parasol 8/32-bit add latency measurement")
     ap.add_argument("--check", type=int, default=8, help="outputs decrypted with the oracle after the run (checker only)")
     return ap.parse_args()
 
@@ -167,6 +168,79 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def cpu_add_latency(keys, a_bits, b_bits, nthreads):
+    """The same add on the CPU port with the reference's execution model: every ready op is one
+    single-threaded task, independent tasks of a dependency level spread over the host threads."""
+    import ctypes as C
+
+    import oracle as O
+
+    l = O.lib()
+    p = keys.params
+    w = len(a_bits)
+    t0 = time.perf_counter()
+    glwes = np.stack(a_bits + b_bits)
+    l1 = np.stack([O.sample_extract(keys, g, 0) for g in glwes])
+    l0 = np.zeros((2 * w, keys.lwe0_len), dtype=np.uint64)
+    l.orc_keyswitch_lwe_batch(l0, l1, 2 * w, keys.ksk, C.byref(p), nthreads)
+    ggsw = O.circuit_bootstrap_batch(keys, l0, nthreads)
+    sa, sb = ggsw[:w], ggsw[w:]
+    zero = np.zeros(keys.glwe_len, dtype=np.uint64)
+    one = zero.copy()
+    one[p.glwe_k * p.glwe_n] = np.uint64(1 << 63)
+    carry, ncarry = zero, one
+    outs = []
+
+    def cmux_level(sels, lows, highs):
+        out = np.zeros((len(sels), keys.glwe_len), dtype=np.uint64)
+        l.orc_cmux_batch(out, np.ascontiguousarray(np.stack(lows)), np.ascontiguousarray(np.stack(highs)),
+                         np.ascontiguousarray(np.stack(sels)), len(sels), C.byref(p), min(nthreads, len(sels)))
+        return out
+
+    for i in range(w):
+        r = cmux_level([sb[i]] * 4, [carry, ncarry, zero, carry], [ncarry, carry, carry, one])
+        r2 = cmux_level([sa[i]] * 2, [r[0], r[2]], [r[1], r[3]])
+        outs.append(r2[0])
+        carry = r2[1]
+        ncarry = O.glwe_not(keys, carry)
+    outs.append(carry)
+    return time.perf_counter() - t0, outs
+
+
+def measure_add_latency(ev, keys, args):
+    import oracle as O  # client-side encrypt/decrypt + the CPU baseline; never on the measured path
+
+    import spf_b200
+    from spf_b200.circuits import ripple_carry_adder
+
+    client = O.Client(keys)
+    proc = spf_b200.CircuitProcessor(ev)
+    res = {"graph": "hand-built ripple-carry MUX tree (functionally equivalent to mux_circuits' BDD adder, not "
+                    "node-for-node; SURVEY.md section 7)", "includes": "H2D of 2w GLWE inputs + D2H of w+1 GLWE outputs"}
+    for w, a, b in ((8, 2, 7), (32, 0xDEADBEEF, 0x12345679)):
+        ab = [client.encrypt_glwe_l1([(a >> i) & 1]) for i in range(w)]
+        bb = [client.encrypt_glwe_l1([(b >> i) & 1]) for i in range(w)]
+        outs = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w + 1)]
+        g = proc.compile(ripple_carry_adder(ab, bb, outs))
+        g.run()
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            g.run()
+            ts.append(time.perf_counter() - t0)
+        got = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(outs))
+        entry = {"gpu_ms": 1e3 * float(np.median(ts)), "gpu_ms_min": 1e3 * min(ts), "levels": g.levels,
+                 "launches": g.launches, "correct": got == a + b}
+        g.close()
+        if not args.no_cpu_baseline:
+            nt = O.hw_threads()
+            dt, couts = cpu_add_latency(keys, ab, bb, nt)
+            cgot = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(couts))
+            entry.update({"cpu_port_ms": 1e3 * dt, "cpu_threads": nt, "cpu_correct": cgot == a + b})
+        res[f"add{w}"] = entry
+    return res
 
 
 # ---------------------------------------------------------------------------------------------
@@ -379,6 +453,12 @@ def run_gpu(args):
                                       "(C restatement of the reference CPU path), one single-threaded op per task over "
                                       "all host threads"}
 
+    # ---- Parasol add latency (the metric's second half): encrypted w-bit add through the graph
+    #      executor (16/64 x SampleExtract -> Keyswitch -> CBS, then the ripple-carry MUX tree) ------
+    add_latency = None
+    if rank == 0 and world == 1 and not args.no_add:
+        add_latency = measure_add_latency(ev, keys, args)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -392,6 +472,7 @@ def run_gpu(args):
                        "key_broadcast_ms": key_bcast_ms},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "check": check, "wall_s_timed_region": wall,
+            "parasol_add_latency": add_latency,
         }
         print(json.dumps(line))
     ev.close()

@@ -121,7 +121,8 @@ def test_basic_add_8bit(keys, client, proc, a, b):
     g.run()
     got = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(outs))
     assert got == a + b
-    assert g.levels == 4 + 2 * w + 1
+    assert g.levels <= 4 + 3 * w + 1  # front end (4) + <= 3 levels per bit (2 CMUX + Not) + outputs
+    assert g.launches <= 2 * g.levels  # one launch per (level, op) group, not per node
     g.close()
 
 
