@@ -278,8 +278,16 @@ int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, s
   P.radix_log = (int)ctx->p.ks.radix_log;
   P.count = (int)ctx->p.ks.count;
   if (P.n0 + 1 > 2 * kKsThreads) return fail(ctx, SPF_E_UNSUPPORTED, "l0 dimension too large for the keyswitch kernel");
-  const int grid = (int)((batch + kKsBatch - 1) / kKsBatch);
-  keyswitch_kernel<<<grid, kKsThreads, kKsBatch * P.n1 * 4, s>>>(P);
+  if (P.count > kKsMaxLevels) return fail(ctx, SPF_E_UNSUPPORTED, "ks_radix.count too large for the keyswitch kernel");
+  const int tiles = (int)((batch + kKsBatch - 1) / kKsBatch);
+  // split the sweep over the n1 mask elements so that at least ~2 CTAs per SM are in flight even
+  // for small batches (a single CTA streaming the whole 62.7 MB KSK is latency-bound)
+  int splits = 1;
+  while (tiles * splits < 2 * ctx->sm_count && splits < 64 && (P.n1 / (splits * 2)) >= 16) splits *= 2;
+  P.slice = (P.n1 + splits - 1) / splits;
+  if (splits > 1) CU(cudaMemsetAsync(d_out, 0, batch * (size_t)(P.n0 + 1) * 8, s));
+  dim3 grid(tiles, splits);
+  keyswitch_kernel<<<grid, kKsThreads, (size_t)kKsBatch * P.slice * 4, s>>>(P);
   return check_launch(ctx, "keyswitch_kernel");
 }
 

@@ -186,11 +186,16 @@ __global__ void __launch_bounds__(kCmuxTeams * kTeam, 1) cmux_kernel(CmuxBatch P
 
 // ------------------------------------------------------------------------------------------
 // K4: LWE keyswitch L1 -> L0 (ops/keyswitch/lwe_keyswitch.rs:23-62), integer only.
-// out = (0, b) - sum_i sum_t digit_t(a_i) * KSK[i][l-1-t].  A CTA owns kKsBatch inputs and all
-// n0+1 output columns, so each KSK row is read once per kKsBatch ciphertexts.
+// out = (0, b) - sum_i sum_t digit_t(a_i) * KSK[i][l-1-t].  A CTA owns kKsBatch inputs, all n0+1
+// output columns and a contiguous slice of the mask index i (grid.y = split-K over i, so small
+// batches still spread the 62.7 MB KSK sweep over the whole GPU); each KSK row is read once per
+// kKsBatch ciphertexts.  The rows of mask element i+1 are prefetched into registers while
+// element i is accumulated.  With more than one slice the partial sums are combined with u64
+// atomics into a zero-initialised output (wrapping adds commute, so the result is bit-exact).
 // ------------------------------------------------------------------------------------------
 constexpr int kKsBatch = 16;
 constexpr int kKsThreads = 320;
+constexpr int kKsMaxLevels = 8;
 
 struct KsBatch {
   uint64_t* out;        // [B][n0+1]
@@ -198,17 +203,21 @@ struct KsBatch {
   const uint64_t* ksk;  // [n1][l][n0+1]
   const void* const* ptrs;  // optional device table: ptrs[b] = L1 LWE input of item b
   int batch, n1, n0, radix_log, count;
+  int slice;            // mask elements per grid.y slice (n1 when not split)
 };
 
 __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t* st = reinterpret_cast<uint32_t*>(smem);  // [kKsBatch][n1] rounded states (l*logB <= 32 bits)
+  uint32_t* st = reinterpret_cast<uint32_t*>(smem);  // [kKsBatch][slice] rounded states (l*logB <= 32 bits)
   const int b0 = blockIdx.x * kKsBatch;
   const int nb = min(kKsBatch, P.batch - b0);
-  for (int idx = threadIdx.x; idx < kKsBatch * P.n1; idx += blockDim.x) {
-    const int b = idx / P.n1, i = idx % P.n1;
+  const int i_begin = blockIdx.y * P.slice;
+  const int ni = min(P.slice, P.n1 - i_begin);
+  const bool split = gridDim.y > 1;
+  for (int idx = threadIdx.x; idx < kKsBatch * ni; idx += blockDim.x) {
+    const int b = idx / ni, i = idx % ni;
     const uint64_t* src = b < nb ? (P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + b]) : P.in + (size_t)(b0 + b) * (P.n1 + 1)) : nullptr;
-    st[idx] = src ? (uint32_t)radix_round(src[i], P.radix_log, P.count) : 0u;
+    st[b * P.slice + i] = src ? (uint32_t)radix_round(src[i_begin + i], P.radix_log, P.count) : 0u;
   }
   __syncthreads();
   const int cols = P.n0 + 1;
@@ -218,32 +227,56 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
 #pragma unroll
   for (int b = 0; b < kKsBatch; b++) { acc0[b] = 0; acc1[b] = 0; }
   const uint32_t mask = (1u << P.radix_log) - 1;
-  for (int i = 0; i < P.n1; i++) {
-    uint32_t s[kKsBatch];
+  const int L = P.count;
+  uint64_t k0[kKsMaxLevels], k1[kKsMaxLevels], n0v[kKsMaxLevels], n1v[kKsMaxLevels];
+  auto load_rows = [&](int i, uint64_t (&r0)[kKsMaxLevels], uint64_t (&r1)[kKsMaxLevels]) {
+    const uint64_t* row = P.ksk + (size_t)(i_begin + i) * L * cols;
 #pragma unroll
-    for (int b = 0; b < kKsBatch; b++) s[b] = st[b * P.n1 + i];
-    for (int t = 0; t < P.count; t++) {
-      const uint64_t* row = P.ksk + ((size_t)i * P.count + (P.count - 1 - t)) * cols;
-      const uint64_t k0 = has0 ? __ldg(reinterpret_cast<const unsigned long long*>(row + c0)) : 0;
-      const uint64_t k1 = has1 ? __ldg(reinterpret_cast<const unsigned long long*>(row + c1)) : 0;
-#pragma unroll
-      for (int b = 0; b < kKsBatch; b++) {
-        const uint32_t digit = s[b] & mask;
-        const uint32_t carry = digit >> (P.radix_log - 1);
-        s[b] = (s[b] >> P.radix_log) + carry;
-        const int64_t d = (int64_t)digit - ((int64_t)carry << P.radix_log);
-        acc0[b] += k0 * (uint64_t)d;
-        acc1[b] += k1 * (uint64_t)d;
+    for (int t = 0; t < kKsMaxLevels; t++) {
+      if (t < L) {  // digit t (LSB first) pairs with level l-1-t (lev_ciphertext_ops.rs:36)
+        const uint64_t* r = row + (size_t)(L - 1 - t) * cols;
+        r0[t] = has0 ? __ldg(reinterpret_cast<const unsigned long long*>(r + c0)) : 0;
+        r1[t] = has1 ? __ldg(reinterpret_cast<const unsigned long long*>(r + c1)) : 0;
       }
     }
+  };
+  if (ni > 0) load_rows(0, k0, k1);
+  for (int i = 0; i < ni; i++) {
+    if (i + 1 < ni) load_rows(i + 1, n0v, n1v);
+#pragma unroll
+    for (int b = 0; b < kKsBatch; b++) {
+      uint32_t s = st[b * P.slice + i];
+#pragma unroll
+      for (int t = 0; t < kKsMaxLevels; t++) {
+        if (t < L) {
+          const uint32_t digit = s & mask;
+          const uint32_t carry = digit >> (P.radix_log - 1);
+          s = (s >> P.radix_log) + carry;
+          const int64_t d = (int64_t)digit - ((int64_t)carry << P.radix_log);
+          acc0[b] += k0[t] * (uint64_t)d;
+          acc1[b] += k1[t] * (uint64_t)d;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < kKsMaxLevels; t++) { k0[t] = n0v[t]; k1[t] = n1v[t]; }
   }
 #pragma unroll
   for (int b = 0; b < kKsBatch; b++) {
     if (b >= nb) break;
     uint64_t* o = P.out + (size_t)(b0 + b) * cols;
-    const uint64_t body = (P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + b]) : P.in + (size_t)(b0 + b) * (P.n1 + 1))[P.n1];
-    if (has0) o[c0] = (c0 == P.n0 ? body : 0) - acc0[b];
-    if (has1) o[c1] = (c1 == P.n0 ? body : 0) - acc1[b];
+    uint64_t body = 0;
+    if (blockIdx.y == 0)
+      body = (P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + b]) : P.in + (size_t)(b0 + b) * (P.n1 + 1))[P.n1];
+    const uint64_t v0 = (c0 == P.n0 ? body : 0) - acc0[b];
+    const uint64_t v1 = (c1 == P.n0 ? body : 0) - acc1[b];
+    if (split) {
+      if (has0) atomicAdd(reinterpret_cast<unsigned long long*>(o + c0), (unsigned long long)v0);
+      if (has1) atomicAdd(reinterpret_cast<unsigned long long*>(o + c1), (unsigned long long)v1);
+    } else {
+      if (has0) o[c0] = v0;
+      if (has1) o[c1] = v1;
+    }
   }
 }
 
