@@ -113,6 +113,14 @@ int validate_params(const spf_params* p) {
   return 0;
 }
 
+// Work items per CTA: the full complement when the batch fills the GPU, fewer for small batches
+// so that every item gets an SM (and its shared-memory / FP64 pipes) to itself.
+int per_cta(const spf_b200_ctx* ctx, size_t items, int max_per_cta) {
+  int per = max_per_cta;
+  while (per > 1 && items <= (size_t)ctx->sm_count * (per - 1)) per--;
+  return per;
+}
+
 int launch_scale(spf_b200_ctx* ctx, C2* dst, const C2* src, size_t n, double scale, cudaStream_t s) {
   if (n == 0) return 0;
   const int threads = 256;
@@ -213,9 +221,29 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
   P.log_v = (int)log_v;
   P.cbs_radix_log = (int)ctx->p.cbs.radix_log;
   P.cbs_count = (int)ctx->p.cbs.count;
-  const int grid = (int)((batch + kPbsPairs - 1) / kPbsPairs);
-  pbs_kernel<<<grid, kPbsPairs * 2 * kTeam, kPbsSmem, s>>>(P, tabs(ctx));
-  return check_launch(ctx, "pbs_kernel");
+  // Whole waves (148 SMs x 3 ciphertexts) run 3 pairs per CTA; a trailing partial wave is launched
+  // separately with fewer pairs per CTA so its ciphertexts get an SM each instead of leaving most
+  // of the GPU idle while a few SMs grind through 3 (4096 = 9 waves + 100 ciphertexts).
+  const size_t wave = (size_t)ctx->sm_count * kPbsPairs;
+  size_t head = batch, tail = 0;
+  if (batch > wave && batch % wave != 0 && batch % wave <= (size_t)ctx->sm_count * (kPbsPairs - 1)) {
+    tail = batch % wave;
+    head = batch - tail;
+  }
+  for (int part = 0; part < 2; part++) {
+    const size_t off = part == 0 ? 0 : head, cnt = part == 0 ? head : tail;
+    if (cnt == 0) continue;
+    PbsBatch Q = P;
+    Q.batch = (int)cnt;
+    Q.lwe_in = P.lwe_in ? P.lwe_in + off * (size_t)(P.lwe_n + 1) : nullptr;
+    Q.glwe_out = P.glwe_out + off * 2 * kN;
+    Q.ptrs = P.ptrs ? P.ptrs + off : nullptr;
+    const int per = per_cta(ctx, cnt, kPbsPairs);  // small batches: one ciphertext per SM (latency)
+    const int grid = (int)((cnt + per - 1) / per);
+    pbs_kernel<<<grid, per * 2 * kTeam, kTableBytes + per * kPbsPairBytes, s>>>(Q, tabs(ctx));
+    if (int rc = check_launch(ctx, "pbs_kernel")) return rc;
+  }
+  return 0;
 }
 
 int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_glev_out, C2* d_ggsw_out, int mode,
@@ -240,8 +268,9 @@ int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_gl
   P.ss_count = (int)ctx->p.ss.count;
   P.out_scale = out_scale;
   const size_t items = batch * (size_t)levels;
-  const int grid = (int)((items + kTrTeams - 1) / kTrTeams);
-  trace_ss_kernel<<<grid, kTrTeams * kTeam, kTrSmem, s>>>(P, tabs(ctx));
+  const int per = per_cta(ctx, items, kTrTeams);
+  const int grid = (int)((items + per - 1) / per);
+  trace_ss_kernel<<<grid, per * kTeam, kTableBytes + per * kTrTeamBytes, s>>>(P, tabs(ctx));
   return check_launch(ctx, "trace_ss_kernel");
 }
 
@@ -259,8 +288,9 @@ int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const 
   P.glwe_per_item = glwe_per_item;
   P.radix_log = (int)ctx->p.cbs.radix_log;
   P.count = (int)ctx->p.cbs.count;
-  const int grid = (int)((n_glwe + kCmuxTeams - 1) / kCmuxTeams);
-  cmux_kernel<<<grid, kCmuxTeams * kTeam, kCmuxSmem, s>>>(P, tabs(ctx));
+  const int per = per_cta(ctx, n_glwe, kCmuxTeams);
+  const int grid = (int)((n_glwe + per - 1) / per);
+  cmux_kernel<<<grid, per * kTeam, kTableBytes + per * kCmuxTeamBytes, s>>>(P, tabs(ctx));
   return check_launch(ctx, "cmux_kernel");
 }
 

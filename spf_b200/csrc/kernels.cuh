@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
   const int pair = threadIdx.x / (2 * kTeam);
-  const int c = blockIdx.x * kPbsPairs + pair;
+  const int c = blockIdx.x * (blockDim.x / (2 * kTeam)) + pair;  // 1..kPbsPairs pairs per CTA (fewer for small batches)
   if (c >= P.batch) return;
   const int h = (threadIdx.x / kTeam) & 1;
   unsigned char* base = smem + kTableBytes + pair * kPbsPairBytes;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(TraceSsBa
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
   const int team = threadIdx.x / kTeam;
-  const int item = blockIdx.x * kTrTeams + team;
+  const int item = blockIdx.x * (blockDim.x / kTeam) + team;
   if (item >= P.batch * P.levels) return;
   const int c = item / P.levels, level = item % P.levels;
   unsigned char* base = smem + kTableBytes + team * kTrTeamBytes;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kCmuxTeams * kTeam, 1) cmux_kernel(CmuxBatch P
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
   const int team = threadIdx.x / kTeam;
-  const int c = blockIdx.x * kCmuxTeams + team;
+  const int c = blockIdx.x * (blockDim.x / kTeam) + team;
   if (c >= P.batch) return;
   unsigned char* base = smem + kTableBytes + team * kCmuxTeamBytes;
   uint64_t* st = reinterpret_cast<uint64_t*>(base);
