@@ -29,8 +29,11 @@ struct HostPairCx {
   int u, h;
   pthread_barrier_t* bar_half;
   pthread_barrier_t* bar_pair;
+  uint32_t stash[16];  // stands in for the thread's tensor-memory columns
   void sync() { pthread_barrier_wait(bar_half); }
   void pair_sync() { pthread_barrier_wait(bar_pair); }
+  void stash_put(const uint32_t (&d)[16]) { memcpy(stash, d, sizeof(stash)); }
+  void stash_get(uint32_t (&d)[16]) { memcpy(d, stash, sizeof(stash)); }
 };
 
 template <class Body>
@@ -54,7 +57,7 @@ void run_pair(Body body) {
   std::vector<pthread_t> th(2 * kTeam);
   for (int t = 0; t < 2 * kTeam; t++) {
     ls[t].body = &body;
-    ls[t].cx = HostPairCx{t % kTeam, t / kTeam, &half[t / kTeam], &pair};
+    ls[t].cx = HostPairCx{t % kTeam, t / kTeam, &half[t / kTeam], &pair, {}};
     pthread_create(&th[t], nullptr, PairLaunch<Body>::run, &ls[t]);
   }
   for (int t = 0; t < 2 * kTeam; t++) pthread_join(th[t], nullptr);

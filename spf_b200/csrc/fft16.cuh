@@ -274,7 +274,9 @@ SPF_HD uint64_t f64_to_torus(double x) {
   const uint32_t adj_hi = (hi & 0x80000000u) | (mag < 0x43300000u ? 0x3FE00000u : 0u);  // +-0.5 or +-0
   lo += bits_f64((uint64_t)adj_hi << 32);
   uint64_t r = (uint64_t)f64_to_i64_sat(lo);
-  if (mag == 0x43E00000u && (uint32_t)lb == 0u)  // |lo| == 2^63: the reference's result follows the sign of x
+  // |lo| <= 2^63 by construction, so mag == 0x43E00000 means |lo| == 2^63 exactly: the reference's
+  // result then follows the sign of x.  Probability ~2^-53 per coefficient: a real branch.
+  if (__builtin_expect(mag == 0x43E00000u, 0))
     r = (f64_bits(x) >> 63) ? 0x7FFFFFFFFFFFFFFFull : 0x8000000000000000ull;
   return r;
 }
