@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspf_b200.so")
+# SPF_B200_LIB selects an alternative build of the same library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("SPF_B200_LIB") or os.path.join(_HERE, "libspf_b200.so")
 
 
 class SpfError(RuntimeError):

@@ -221,29 +221,13 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
   P.log_v = (int)log_v;
   P.cbs_radix_log = (int)ctx->p.cbs.radix_log;
   P.cbs_count = (int)ctx->p.cbs.count;
-  // Whole waves (148 SMs x 3 ciphertexts) run 3 pairs per CTA; a trailing partial wave is launched
-  // separately with fewer pairs per CTA so its ciphertexts get an SM each instead of leaving most
-  // of the GPU idle while a few SMs grind through 3 (4096 = 9 waves + 100 ciphertexts).
-  const size_t wave = (size_t)ctx->sm_count * kPbsPairs;
-  size_t head = batch, tail = 0;
-  if (batch > wave && batch % wave != 0 && batch % wave <= (size_t)ctx->sm_count * (kPbsPairs - 1)) {
-    tail = batch % wave;
-    head = batch - tail;
-  }
-  for (int part = 0; part < 2; part++) {
-    const size_t off = part == 0 ? 0 : head, cnt = part == 0 ? head : tail;
-    if (cnt == 0) continue;
-    PbsBatch Q = P;
-    Q.batch = (int)cnt;
-    Q.lwe_in = P.lwe_in ? P.lwe_in + off * (size_t)(P.lwe_n + 1) : nullptr;
-    Q.glwe_out = P.glwe_out + off * 2 * kN;
-    Q.ptrs = P.ptrs ? P.ptrs + off : nullptr;
-    const int per = per_cta(ctx, cnt, kPbsPairs);  // small batches: one ciphertext per SM (latency)
-    const int grid = (int)((cnt + per - 1) / per);
-    pbs_kernel<<<grid, per * 2 * kTeam, kTableBytes + per * kPbsPairBytes, s>>>(Q, tabs(ctx));
-    if (int rc = check_launch(ctx, "pbs_kernel")) return rc;
-  }
-  return 0;
+  // A pair (one ciphertext) is latency-bound: measured alone on an SM it takes the same ~10 ms per
+  // PBS as when three share the SM, so a trailing partial wave cannot be sped up by spreading it
+  // out; small batches still get one ciphertext per SM so they do not queue behind each other.
+  const int per = per_cta(ctx, batch, kPbsPairs);
+  const int grid = (int)((batch + per - 1) / per);
+  pbs_kernel<<<grid, per * 2 * kTeam, kTableBytes + per * kPbsPairBytes, s>>>(P, tabs(ctx));
+  return check_launch(ctx, "pbs_kernel");
 }
 
 int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_glev_out, C2* d_ggsw_out, int mode,

@@ -43,30 +43,9 @@ constexpr int kPbsSmem = kTableBytes + kPbsPairs * kPbsPairBytes;      // 215616
 struct DevPairCx {
   int u, h;
   int bar_half, bar_pair;
-  uint32_t taddr;  // this warp's tensor-memory window: lane quarter 32*(warp%4), 16 private columns
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar_half) : "memory"); }
   __device__ __forceinline__ void pair_sync() const { asm volatile("bar.sync %0, 128;" ::"r"(bar_pair) : "memory"); }
-  // 16 x 32-bit words per thread parked in TMEM (thread i of the warp <-> TMEM lane base+i, 16 columns)
-  __device__ __forceinline__ void stash_put(const uint32_t (&d)[16]) const {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]), "r"(d[8]),
-        "r"(d[9]), "r"(d[10]), "r"(d[11]), "r"(d[12]), "r"(d[13]), "r"(d[14]), "r"(d[15])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  }
-  __device__ __forceinline__ void stash_get(uint32_t (&d)[16]) const {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(d[8]),
-          "=r"(d[9]), "=r"(d[10]), "=r"(d[11]), "=r"(d[12]), "=r"(d[13]), "=r"(d[14]), "=r"(d[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  }
 };
-
-constexpr int kPbsTmemCols = 64;  // 3 warps per TMEM lane quarter x 16 columns, rounded up to a power of two
 
 struct PbsBatch {
   const uint64_t* lwe_in;   // [B][n+1]
@@ -82,24 +61,15 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   extern __shared__ __align__(16) unsigned char smem[];
   C2* sT1 = reinterpret_cast<C2*>(smem);
   C2* sT2 = sT1 + kT1Elems;
-  __shared__ uint32_t tmem_base;
-  const int warp = threadIdx.x / 32;
-  if (warp == 0) {  // one warp allocates the CTA's tensor-memory columns and frees them at the end
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(&tmem_base)), "n"(kPbsTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  load_tables(sT1, sT2, tabs);  // ends with __syncthreads()
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  load_tables(sT1, sT2, tabs);
   const int pair = threadIdx.x / (2 * kTeam);
   const int c = blockIdx.x * (blockDim.x / (2 * kTeam)) + pair;  // 1..kPbsPairs pairs per CTA (fewer for small batches)
+  if (c >= P.batch) return;
   const int h = (threadIdx.x / kTeam) & 1;
   unsigned char* base = smem + kTableBytes + pair * kPbsPairBytes;
   uint64_t* acc = reinterpret_cast<uint64_t*>(base);
   C2* xb = reinterpret_cast<C2*>(base + 2 * kN * 8);
-  DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3,
-               tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 16)};
+  DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3};
   PbsArgs A;
   A.lwe_in = P.ptrs ? static_cast<const uint64_t*>(P.ptrs[c]) : P.lwe_in + (size_t)c * (P.lwe_n + 1);
   A.lut = P.lut ? P.lut + (size_t)c * P.lut_stride : nullptr;
@@ -110,11 +80,7 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   A.log_v = P.log_v;
   A.cbs_radix_log = P.cbs_radix_log;
   A.cbs_count = P.cbs_count;
-  if (c < P.batch) pbs_pair_team(cx, A, acc, xb + h * kXBuf, xb + (1 - h) * kXBuf, sT1, sT2);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kPbsTmemCols) : "memory");
+  pbs_pair_team(cx, A, acc, xb + h * kXBuf, xb + (1 - h) * kXBuf, sT1, sT2);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -253,7 +253,6 @@ SPF_HD double digit16_to_f64(uint32_t d) {
 // warps per SM) and halves the latency of a step.
 //   cx.u: thread in half (0..63)   cx.h: half   cx.sync(): 64-thread barrier of the half
 //   cx.pair_sync(): 128-thread barrier of the pair
-//   cx.stash_put/get(uint32_t[16]): 64 B of thread-private scratch that survives a transform
 template <class Cx>
 SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xbuf_own, const C2* xbuf_other,
                           const C2* T1, const C2* T2) {
@@ -294,13 +293,15 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xbuf_own,
     // diff = acc*X^{a~} - acc (rotation fused into the gather); round to 32 bits; split into two
     // signed 16-bit digits, LSB first (math/radix.rs:81-113 for logB=16, l=2).  The source index
     // of coefficient j = u + 64 i2 is (u - a~ + 64 i2) mod 2N: bit 11 = negacyclic sign.  The
-    // second digits (2 x 16 bit per word) wait in the thread's private tensor-memory columns
-    // (cx.stash_put/get: tcgen05.st/ld) while the first transform runs: registers and shared
-    // memory are both full, TMEM is otherwise idle in this kernel.
-    C2 v[16];
-    {
-      uint32_t d1[16];
-      const int base = (u - at) & (2 * kN - 1);
+    // digits of level t are recomputed from the (unchanged) accumulator for each transform rather
+    // than kept live across the first one: registers are the scarce resource here.
+#pragma unroll 1
+    for (int t = 0; t < 2; t++) {
+      C2 v[16];
+      int base = (u - at) & (2 * kN - 1);
+#if defined(__CUDA_ARCH__)
+      asm volatile("" : "+r"(base));  // keep the 32 gather addresses from being hoisted out of the t loop and spilled
+#endif
       const int low6 = base & 63, bh = base >> 6;
 #pragma unroll
       for (int i2 = 0; i2 < 32; i2++) {
@@ -308,20 +309,10 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xbuf_own,
         const uint64_t x = pa[((tt & 31) << 6) | low6];
         const uint64_t c = pa[u + 64 * i2];
         const uint64_t diff = ((tt & 32) ? 0 - x : x) - c;
-        const uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
-        const uint32_t w1 = (w + 0x8000u) >> 16;  // (w >> 16) + carry of the first digit
-        if (i2 < 16) { v[i2].x = digit16_to_f64(w); d1[i2] = w1 & 0xFFFFu; }
-        else { v[i2 - 16].y = digit16_to_f64(w); d1[i2 - 16] |= w1 << 16; }
-      }
-      cx.stash_put(d1);
-    }
-#pragma unroll 1
-    for (int t = 0; t < 2; t++) {
-      if (t == 1) {
-        uint32_t d1[16];
-        cx.stash_get(d1);
-#pragma unroll
-        for (int m = 0; m < 16; m++) { v[m].x = digit16_to_f64(d1[m]); v[m].y = digit16_to_f64(d1[m] >> 16); }
+        uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
+        if (t) w = (w + 0x8000u) >> 16;  // second digit: (w >> 16) + carry of the first
+        if (i2 < 16) v[i2].x = digit16_to_f64(w);
+        else v[i2 - 16].y = digit16_to_f64(w);
       }
       const int level = 1 - t;  // LSB digit <-> last GLEV level (fft_ops.rs:92)
       team_fft_fwd(cx, v, xbuf_own, T1, T2);
