@@ -163,8 +163,7 @@ void emu_pbs(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, co
   std::vector<uint64_t> acc(2 * kN);
   PbsArgs A{lwe_in, lut, glwe_out, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count};
   run_pair([&](HostPairCx& cx) {
-    pbs_pair_team(cx, A, acc.data(), xbuf.data() + cx.h * kXBuf, xbuf.data() + (1 - cx.h) * kXBuf, t.T1.data(),
-                  t.T2.data());
+    pbs_pair_team(cx, A, acc.data(), xbuf.data(), t.T1.data(), t.T2.data());
   });
 }
 

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   A.log_v = P.log_v;
   A.cbs_radix_log = P.cbs_radix_log;
   A.cbs_count = P.cbs_count;
-  pbs_pair_team(cx, A, acc, xb + h * kXBuf, xb + (1 - h) * kXBuf, sT1, sT2);
+  pbs_pair_team(cx, A, acc, xb, sT1, sT2);
 }
 
 // ------------------------------------------------------------------------------------------

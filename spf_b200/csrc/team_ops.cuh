@@ -243,24 +243,59 @@ SPF_HD double digit16_to_f64(uint32_t d) {
   return x - 4503599627403264.0;  // 2^52 + 2^15
 }
 
-// PAIR-TEAM blind rotation: one ciphertext = 128 threads = two teams of 64 (half h in {0,1}).
-// Half h owns GLWE polynomial h end to end: it decomposes acc[h]*X^a - acc[h], runs the two
-// forward FFTs of its digits, accumulates OUTPUT polynomial p = h in registers (16 complex per
-// thread) and runs that polynomial's inverse FFT.  Each forward FFT result D is needed by both
-// output polynomials, so after using it the half publishes D in its (then idle) exchange buffer
-// and the partner half multiply-accumulates it from shared memory.  Compared with one team
-// holding both accumulators this halves the registers per thread (no spills, 12 instead of 8
-// warps per SM) and halves the latency of a step.
+// PAIR-TEAM blind rotation, BIN-SPLIT: one ciphertext = 128 threads = two teams of 64 (half h).
+// Time domain: half h owns GLWE polynomial h (decomposition of acc[h]*X^a - acc[h], passes 1-2 of
+// its two forward FFTs, passes 2-1 of its inverse FFT, accumulator update).  Frequency domain:
+// half h owns the bins with bit 7 == h of ALL polynomials: after pass 2 each half leaves its
+// spectrum-in-progress in its exchange buffer, and BOTH halves run the final radix-4 pass on
+// their 8 bins per thread of BOTH digit polynomials, multiply-accumulate them against the BSK
+// into both output polynomials (f[2][8], the same 64 registers as one full polynomial) and run
+// the first inverse pass before handing the halves of each output polynomial back through the
+// exchange buffers.  No spectrum is ever published a second time: compared with sharing whole
+// FFT outputs this removes 128 KiB of shared-memory traffic per CMUX step.
+// Both digit levels come out of ONE gather pass over the accumulator; the second level waits
+// packed 2x16 bit in 16 registers while the first is transformed.
 //   cx.u: thread in half (0..63)   cx.h: half   cx.sync(): 64-thread barrier of the half
 //   cx.pair_sync(): 128-thread barrier of the pair
+//   xb: the pair's two exchange buffers, xb + h*kXBuf belongs to half h.
+
+// Register slot s' = 4 jj + k3 of thread u in half h holds bin u + 64 * (2h + jj + 4 k3).
+SPF_HD constexpr int split_bin(int u, int h, int s) { return u + 64 * (2 * h + (s >> 2) + 4 * (s & 3)); }
+
+// final forward pass on this half's bins of digit polynomial b (spectrum-in-progress in xb[b]),
+// then f[p] (+)= D * G[b][level][p]
+template <bool INIT>
+SPF_HD void mad_split(C2 (&f)[2][8], const C2* xbb, const C2* g /* GGSW row b, level: [p][bin] */, int u, int h) {
+  const int k1 = u & 15, q = u >> 4;
+#pragma unroll
+  for (int jj = 0; jj < 2; jj++) {
+    C2 d[4], g0[4], g1[4];
+#pragma unroll
+    for (int qp = 0; qp < 4; qp++) d[qp] = xbb[(q + 4 * (2 * h + jj)) * kXPad + k1 + 16 * qp];
+#pragma unroll
+    for (int k3 = 0; k3 < 4; k3++) {
+      g0[k3] = ldg_c2(g + split_bin(u, h, 4 * jj + k3));
+      g1[k3] = ldg_c2(g + kM + split_bin(u, h, 4 * jj + k3));
+    }
+    bfly4<false>(d[0], d[1], d[2], d[3]);
+#pragma unroll
+    for (int k3 = 0; k3 < 4; k3++) {
+      const int s = 4 * jj + k3;
+      if (INIT) { f[0][s] = cmul(d[k3], g0[k3]); f[1][s] = cmul(d[k3], g1[k3]); }
+      else { cmad(f[0][s], d[k3], g0[k3]); cmad(f[1][s], d[k3], g1[k3]); }
+    }
+  }
+}
+
 template <class Cx>
-SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xbuf_own, const C2* xbuf_other,
-                          const C2* T1, const C2* T2) {
+SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const C2* T1, const C2* T2) {
   const int u = cx.u, h = cx.h;
+  const int k1 = u & 15, q = u >> 4;
   const int n = A.lwe_n;
   const bool cbs = A.lut == nullptr;
   const int log2n = 12;  // log2(2N)
   uint64_t* pa = acc + h * kN;  // the polynomial this half owns
+  C2* xown = xb + h * kXBuf;
   // 1. acc = LUT * X^{-b~}   (programmable_bootstrapping.rs:378-390)
   {
     uint64_t b = ldg_u64(A.lwe_in + n);
@@ -289,49 +324,82 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xbuf_own,
     if (i + 1 < n) a_next = ldg_u64(A.lwe_in + i + 1);
     if (at == 0) continue;  // rot == acc: the CMUX adds IFFT(0) = 0 exactly (uniform over the pair)
     const C2* ggsw = A.bsk + (size_t)i * 8 * kM;
-    C2 f[16];
-    // diff = acc*X^{a~} - acc (rotation fused into the gather); round to 32 bits; split into two
-    // signed 16-bit digits, LSB first (math/radix.rs:81-113 for logB=16, l=2).  The source index
-    // of coefficient j = u + 64 i2 is (u - a~ + 64 i2) mod 2N: bit 11 = negacyclic sign.  The
-    // digits of level t are recomputed from the (unchanged) accumulator for each transform rather
-    // than kept live across the first one: registers are the scarce resource here.
-#pragma unroll 1
-    for (int t = 0; t < 2; t++) {
+    C2 f[2][8];
+    {
       C2 v[16];
-      int base = (u - at) & (2 * kN - 1);
-#if defined(__CUDA_ARCH__)
-      asm volatile("" : "+r"(base));  // keep the 32 gather addresses from being hoisted out of the t loop and spilled
-#endif
-      const int low6 = base & 63, bh = base >> 6;
+      uint32_t pk[16];
+      // diff = acc*X^{a~} - acc (rotation fused into the gather); round to 32 bits; split into two
+      // signed 16-bit digits, LSB first (math/radix.rs:81-113 for logB=16, l=2).  The source index
+      // of coefficient j = u + 64 i2 is (u - a~ + 64 i2) mod 2N: bit 11 = negacyclic sign.
+      {
+        const int base = (u - at) & (2 * kN - 1);
+        const int low6 = base & 63, bh = base >> 6;
 #pragma unroll
-      for (int i2 = 0; i2 < 32; i2++) {
-        const int tt = bh + i2;
-        const uint64_t x = pa[((tt & 31) << 6) | low6];
-        const uint64_t c = pa[u + 64 * i2];
-        const uint64_t diff = ((tt & 32) ? 0 - x : x) - c;
-        uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
-        if (t) w = (w + 0x8000u) >> 16;  // second digit: (w >> 16) + carry of the first
-        if (i2 < 16) v[i2].x = digit16_to_f64(w);
-        else v[i2 - 16].y = digit16_to_f64(w);
+        for (int i2 = 0; i2 < 32; i2++) {
+          const int tt = bh + i2;
+          const uint64_t x = pa[((tt & 31) << 6) | low6];
+          const uint64_t c = pa[u + 64 * i2];
+          const uint64_t diff = ((tt & 32) ? 0 - x : x) - c;
+          const uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
+          const uint32_t d1 = (w + 0x8000u) >> 16;  // second digit: (w >> 16) + carry of the first
+          if (i2 < 16) { v[i2].x = digit16_to_f64(w); pk[i2] = d1; }
+          else { v[i2 - 16].y = digit16_to_f64(w); pk[i2 - 16] |= d1 << 16; }
+        }
       }
-      const int level = 1 - t;  // LSB digit <-> last GLEV level (fft_ops.rs:92)
-      team_fft_fwd(cx, v, xbuf_own, T1, T2);
-      if (t == 0) mad_poly<true>(f, v, ggsw + (size_t)((h * 2 + level) * 2 + h) * kM, u);
-      else mad_poly<false>(f, v, ggsw + (size_t)((h * 2 + level) * 2 + h) * kM, u);
-      cx.sync();  // my half has finished reading the exchange buffer
 #pragma unroll
-      for (int s = 0; s < 16; s++) xbuf_own[s * 64 + u] = v[s];
-      cx.pair_sync();
-      mad_poly_shared(f, xbuf_other, ggsw + (size_t)(((1 - h) * 2 + level) * 2 + h) * kM, u);
-      cx.pair_sync();  // partner is done with my buffer before the next transform overwrites it
+      for (int t = 0; t < 2; t++) {
+        const int level = 1 - t;  // LSB digit <-> last GLEV level (fft_ops.rs:92)
+        if (t == 1) {
+#pragma unroll
+          for (int m = 0; m < 16; m++) { v[m].x = digit16_to_f64(pk[m]); v[m].y = digit16_to_f64(pk[m] >> 16); }
+        }
+        fwd_pass1(v, u, T1);
+        if (t == 1) cx.pair_sync();  // both halves have consumed the level-0 spectra
+        fwd_x1_write(v, xown, u);
+        cx.sync();
+        fwd_x1_read(v, xown, u);
+        fwd_pass2(v, u, T2);
+        cx.sync();
+        fwd_x2_write(v, xown, u);
+        cx.pair_sync();
+        if (t == 0) mad_split<true>(f, xb, ggsw + (size_t)((0 * 2 + level) * 2) * kM, u, h);
+        else mad_split<false>(f, xb, ggsw + (size_t)((0 * 2 + level) * 2) * kM, u, h);
+        mad_split<false>(f, xb + kXBuf, ggsw + (size_t)((1 * 2 + level) * 2) * kM, u, h);
+      }
     }
-    // acc[h] += IFFT(f)
-    team_fft_inv(cx, f, xbuf_own, T1, T2);
+    // first inverse pass on this half's bins of both output polynomials, hand them to their owners
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-      const int j = u + 64 * m;
-      pa[j] += f64_to_torus(f[m].x);
-      pa[j + kM] += f64_to_torus(f[m].y);
+    for (int p = 0; p < 2; p++) {
+      bfly4<true>(f[p][0], f[p][1], f[p][2], f[p][3]);
+      bfly4<true>(f[p][4], f[p][5], f[p][6], f[p][7]);
+    }
+    cx.pair_sync();  // both halves have consumed the level-1 spectra
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) {
+#pragma unroll
+        for (int qp = 0; qp < 4; qp++)
+          xb[p * kXBuf + (q + 4 * (2 * h + jj)) * kXPad + k1 + 16 * qp] = f[p][4 * jj + qp];
+      }
+    }
+    cx.pair_sync();
+    // acc[h] += IFFT(output polynomial h)
+    {
+      C2 w[16];
+      inv_x2_read(w, xown, u);
+      inv_pass2(w, u, T2);
+      cx.sync();
+      inv_x1_write(w, xown, u);
+      cx.sync();
+      inv_x1_read(w, xown, u);
+      inv_pass1(w, u, T1);
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const int j = u + 64 * m;
+        pa[j] += f64_to_torus(w[m].x);
+        pa[j + kM] += f64_to_torus(w[m].y);
+      }
     }
     cx.sync();  // next step gathers rotated coefficients written by other threads of this half
   }
