@@ -221,11 +221,15 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
   P.log_v = (int)log_v;
   P.cbs_radix_log = (int)ctx->p.cbs.radix_log;
   P.cbs_count = (int)ctx->p.cbs.count;
-  // A pair (one ciphertext) is latency-bound: measured alone on an SM it takes the same ~10 ms per
-  // PBS as when three share the SM, so a trailing partial wave cannot be sped up by spreading it
-  // out; small batches still get one ciphertext per SM so they do not queue behind each other.
+  // A pair (one ciphertext) is largely latency-bound: alone on an SM it takes ~7 ms per PBS, ~9 ms
+  // when three share the SM; small batches get one ciphertext per SM so they do not queue behind
+  // each other, large ones run as persistent pairs (see pbs_kernel).
   const int per = per_cta(ctx, batch, kPbsPairs);
+#ifdef SPF_PBS_NOPERSIST
   const int grid = (int)((batch + per - 1) / per);
+#else
+  const int grid = (int)std::min<size_t>((batch + per - 1) / per, (size_t)ctx->sm_count);  // persistent pairs
+#endif
   pbs_kernel<<<grid, per * 2 * kTeam, kTableBytes + per * kPbsPairBytes, s>>>(P, tabs(ctx));
   return check_launch(ctx, "pbs_kernel");
 }

@@ -252,13 +252,14 @@ SPF_HD int64_t f64_to_i64_sat(double x) {
 
 // f64 -> torus: complex_untwist's round() (half away from zero, simd/scalar.rs:32-33) followed by
 // vector_mod_pow2_q_f64 for q = 2^64 (scalar.rs:75-119) and the saturating `as i64`
-// (math/torus.rs:181-185).  Five DP ops + one conversion instead of ~25 integer ops:
-//   h  = rint(x / 2^64)            (magic-constant add/sub; |x| < 2^115, FFT outputs are < 2^100)
-//   lo = x - h * 2^64              (exact FMA; |lo| <= 2^63)
-//   r  = trunc(lo +- 0.5)          (only when |lo| < 2^52 -- larger doubles are integers)
-// Differs from the reference only for doubles within one ulp below k + 0.5 (e.g.
-// 0.49999999999999994 -> 1 instead of 0); true results are integers plus FFT rounding noise, so
-// that input cannot occur.  The reference's saturating-cast corner (x = -+2^63 mod 2^64) is kept.
+// (math/torus.rs:181-185).  Four DP ops + one conversion instead of ~25 integer ops:
+//   h  = rint(x / 2^64) * 2^64     (add/sub of 1.5*2^116, whose ulp is 2^64; |x| < 2^115, FFT
+//                                   outputs are < 2^100)
+//   lo = x - h                     (exact; |lo| <= 2^63)
+//   r  = trunc(lo +- 0.5)          with the add rounded TOWARD ZERO: doubles >= 2^52 are integers
+//                                   and keep their value, smaller ones get round-half-away exactly.
+// The reference's saturating-cast corner (x = -+2^63 mod 2^64) is kept.
+#ifdef SPF_TORUS_OLD
 SPF_HD uint64_t f64_to_torus(double x) {
   const double t = x * 5.421010862427522170037e-20;  // 2^-64
   const double magic = 6755399441055744.0;           // 1.5 * 2^52
@@ -280,6 +281,30 @@ SPF_HD uint64_t f64_to_torus(double x) {
     r = (f64_bits(x) >> 63) ? 0x7FFFFFFFFFFFFFFFull : 0x8000000000000000ull;
   return r;
 }
+#else
+SPF_HD uint64_t f64_to_torus(double x) {
+  const double magic = 124615124604835863084731911901282304.0;  // 1.5 * 2^116
+  const double hq = (x + magic) - magic;
+  const double lo = x - hq;
+  const uint32_t hi = (uint32_t)(f64_bits(lo) >> 32);
+  const double half = bits_f64((uint64_t)((hi & 0x80000000u) | 0x3FE00000u) << 32);  // copysign(0.5, lo)
+#if defined(__CUDA_ARCH__)
+  uint64_t r = (uint64_t)__double2ll_rz(__dadd_rz(lo, half));
+#else
+  const long double y = (long double)lo + (long double)half;  // exact in the 64-bit x87 significand
+  uint64_t r;
+  if (y != y) r = 0;
+  else if (y >= 9223372036854775808.0L) r = (uint64_t)INT64_MAX;
+  else if (y < -9223372036854775808.0L) r = (uint64_t)INT64_MIN;
+  else r = (uint64_t)(int64_t)y;
+#endif
+  // |lo| <= 2^63 by construction, so exponent 0x43E means |lo| == 2^63 exactly: the reference's
+  // result then follows the sign of x.  Probability ~2^-53 per coefficient: a real branch.
+  if (__builtin_expect((hi & 0x7FFFFFFFu) == 0x43E00000u, 0))
+    r = (f64_bits(x) >> 63) ? 0x7FFFFFFFFFFFFFFFull : 0x8000000000000000ull;
+  return r;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------
 // radix decomposition (math/radix.rs:67-114,155-162; simd/scalar.rs:52-72)
