@@ -195,6 +195,39 @@ uint64_t spf_b200_graph_launches(const spf_b200_graph *graph); /* kernel launche
 /* build + run + destroy */
 int spf_b200_run_graph(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes);
 
+/* ---- serialized keys and ciphertexts ------------------------------------------
+ * The reference serialises with bincode 1.3.3 (Cargo.lock:244-245), fixed-width little-endian
+ * integers: every sunscreen_tfhe entity is one sequence `u64 length || elements`
+ * (sunscreen_tfhe/src/dst.rs:31-33; Torus<u64> is a transparent u64, math/torus.rs:217-220;
+ * Complex<f64> is re, im).  ComputeKey = bs_key || ks_key || ss_key || auto_key
+ * (parasol_runtime/src/crypto/keys.rs:306-318).  Parsing follows safe_bincode::deserialize
+ * (parasol_runtime/src/safe_bincode.rs:16-27): reads are limited to GetSize::get_size(params)
+ * bytes, trailing bytes are allowed, every length must equal the entity's OverlaySize::size
+ * (check_is_valid, dst.rs:510-516); violations return SPF_E_INVALID (the reference returns Err).
+ * These functions need no GPU and no context; errors are reported through
+ * spf_b200_last_error(NULL). */
+typedef enum { SPF_CT_LWE0 = 0, SPF_CT_LWE1 = 1, SPF_CT_GLWE1 = 2, SPF_CT_GLEV1 = 3 } spf_ct_kind;
+
+/* exact byte count of bincode::serialize(&ComputeKey) */
+size_t spf_b200_serialized_size_compute_key(const spf_params *p);
+/* ComputeKey::get_size (keys.rs:326-349), the deserialisation byte limit (>= the exact size) */
+size_t spf_b200_serialized_limit_compute_key(const spf_params *p);
+/* offsets[i] = byte offset inside buf of the first element of {bs_key, ks_key, ss_key, auto_key};
+ * element counts are spf_b200_len_{bsk,ksk,ssk,ak}.  Zero-copy: nothing is allocated. */
+int spf_b200_parse_compute_key(const spf_params *params, const uint8_t *buf, size_t len, size_t offsets[4]);
+int spf_b200_write_compute_key(const spf_params *params, uint8_t *out, size_t cap, const double *bsk_fft,
+                               const uint64_t *ksk, const double *ssk_fft, const double *ak_fft, size_t *written);
+/* safe_bincode::deserialize::<ComputeKey> + Evaluation::new in one call: a key file written by the
+ * reference loads unmodified. */
+int spf_b200_create_from_serialized(const spf_params *params, const uint8_t *buf, size_t len, int device,
+                                    spf_b200_ctx **out);
+/* L0LweCiphertext / L1LweCiphertext / L1GlweCiphertext / L1GlevCiphertext (encryption.rs:22-116,
+ * GetSize at :454-519).  L1GgswCiphertext is deliberately not serialisable (encryption.rs:94-98). */
+size_t spf_b200_serialized_size_ciphertext(const spf_params *p, int kind);
+int spf_b200_parse_ciphertext(const spf_params *params, int kind, const uint8_t *buf, size_t len, size_t *offset);
+int spf_b200_write_ciphertext(const spf_params *params, int kind, const uint64_t *data, uint8_t *out, size_t cap,
+                              size_t *written);
+
 /* FP64 peak probe used by bench.py for the roofline denominator: runs a dependent-free DFMA
  * loop on every SM and returns achieved TFLOP/s (2 flops per DFMA). */
 int spf_b200_fp64_peak(spf_b200_ctx *ctx, double *tflops_out);

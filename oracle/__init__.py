@@ -460,3 +460,32 @@ def glwe_not(keys: Keys, glwe) -> np.ndarray:
     out = np.zeros(keys.glwe_len, dtype=np.uint64)
     lib().orc_glwe_not(out, np.ascontiguousarray(glwe), C.byref(keys.params))
     return out
+
+
+# ---- serialized layouts (numpy restatement; checker for spf_b200.serialize) -------------------------
+# bincode 1.3.3, fixint little-endian (Cargo.lock:244-245): a sequence is `u64 len || elements`;
+# every sunscreen_tfhe entity is a single `data` sequence (sunscreen_tfhe/src/dst.rs:31-33).
+
+def bincode_seq(a: np.ndarray) -> bytes:
+    """bincode::serialize of one entity: Torus<u64> -> u64 LE, Complex<f64> -> (re, im) f64 LE."""
+    a = np.ascontiguousarray(a).reshape(-1)
+    body = a.astype("<c16") if a.dtype.kind == "c" else a.astype("<u8")
+    return np.uint64(a.size).astype("<u8").tobytes() + body.tobytes()
+
+
+def bincode_compute_key(keys: Keys) -> bytes:
+    """ComputeKey field order bs_key, ks_key, ss_key, auto_key (parasol_runtime/src/crypto/keys.rs:306-318)."""
+    return b"".join(bincode_seq(a) for a in (keys.bsk_fft, keys.ksk, keys.ssk_fft, keys.ak_fft))
+
+
+def bincode_secret_key(keys: Keys) -> bytes:
+    """SecretKey = lwe_0 || glwe_1 (keys.rs:100-105)."""
+    return bincode_seq(keys.lwe0_sk) + bincode_seq(keys.glwe1_sk)
+
+
+def compute_key_get_size(p: Params) -> int:
+    """ComputeKey::get_size (keys.rs:326-349): all four keys counted as Complex<f64> + 4 length fields."""
+    l = lib()
+    n = l.orc_size_bsk_fft(C.byref(p)) + l.orc_size_ksk(C.byref(p)) + l.orc_size_ssk_fft(C.byref(p)) + \
+        l.orc_size_ak_fft(C.byref(p))
+    return int(n) * 16 + 4 * 8

@@ -92,6 +92,14 @@ ABI = {
     "spf_b200_dev_sample_extract_l1": [_vp, _vp, _vp, _vp, C.c_uint32, _sz, _vp],
     "spf_b200_dev_fft_rescale": [_vp, _vp, _vp, _sz, C.c_int, _vp],
     "spf_b200_fp64_peak": [_vp, C.POINTER(C.c_double)],
+    "spf_b200_serialized_size_compute_key": [C.POINTER(Params)],
+    "spf_b200_serialized_limit_compute_key": [C.POINTER(Params)],
+    "spf_b200_parse_compute_key": [C.POINTER(Params), _vp, _sz, C.POINTER(_sz * 4)],
+    "spf_b200_write_compute_key": [C.POINTER(Params), _vp, _sz, _vp, _vp, _vp, _vp, C.POINTER(_sz)],
+    "spf_b200_create_from_serialized": [C.POINTER(Params), _vp, _sz, C.c_int, C.POINTER(_vp)],
+    "spf_b200_serialized_size_ciphertext": [C.POINTER(Params), C.c_int],
+    "spf_b200_parse_ciphertext": [C.POINTER(Params), C.c_int, _vp, _sz, C.POINTER(_sz)],
+    "spf_b200_write_ciphertext": [C.POINTER(Params), C.c_int, _vp, _vp, _sz, C.POINTER(_sz)],
 }
 _RESTYPES = {
     "spf_b200_default_128": None,
@@ -100,7 +108,8 @@ _RESTYPES = {
     "spf_b200_kernel_launches": C.c_uint64,
     **{n: _sz for n in ("spf_b200_len_lwe_l0", "spf_b200_len_lwe_l1", "spf_b200_len_glwe_l1", "spf_b200_len_glev_l1",
                         "spf_b200_len_ggsw_l1", "spf_b200_len_bsk", "spf_b200_len_ksk", "spf_b200_len_ssk",
-                        "spf_b200_len_ak")},
+                        "spf_b200_len_ak", "spf_b200_serialized_size_compute_key",
+                        "spf_b200_serialized_limit_compute_key", "spf_b200_serialized_size_ciphertext")},
 }
 
 
@@ -177,6 +186,15 @@ class Evaluation:
         self.len_glwe = l.spf_b200_len_glwe_l1(C.byref(p))
         self.len_glev = l.spf_b200_len_glev_l1(C.byref(p))
         self.len_ggsw = l.spf_b200_len_ggsw_l1(C.byref(p))
+
+    @classmethod
+    def from_serialized(cls, data: bytes, params: Params | None = None, device: int = 0) -> "Evaluation":
+        """safe_bincode::deserialize::<ComputeKey>(data, params) (safe_bincode.rs:16-27) followed by
+        Evaluation::new: loads a compute-key file written by the reference, unmodified."""
+        from . import serialize
+
+        bsk, ksk, ssk, ak = serialize.load_compute_key(data, params)
+        return cls(bsk, ksk, ssk, ak, params=params, device=device)
 
     # -- plumbing --------------------------------------------------------------------------
     def close(self):

@@ -718,3 +718,4 @@ int spf_b200_fp64_peak(spf_b200_ctx* ctx, double* tflops_out) {
 }  // extern "C"
 
 #include "graph.cuh"
+#include "serial.inl"
