@@ -29,11 +29,23 @@ struct HostPairCx {
   int u, h;
   pthread_barrier_t* bar_half;
   pthread_barrier_t* bar_pair;
-  uint32_t stash[16];  // stands in for the thread's tensor-memory columns
   void sync() { pthread_barrier_wait(bar_half); }
   void pair_sync() { pthread_barrier_wait(bar_pair); }
-  void stash_put(const uint32_t (&d)[16]) { memcpy(stash, d, sizeof(stash)); }
-  void stash_get(uint32_t (&d)[16]) { memcpy(d, stash, sizeof(stash)); }
+  // the device keeps the thread's 16 pass-1 twiddles in tensor memory; here they come from the table
+  template <bool CONJ>
+  void t1_mul(C2 (&v)[16], const C2* T1) {
+    for (int k1 = 0; k1 < 16; k1++) v[k1] = CONJ ? cmul_conj(v[k1], T1[k1 * 64 + u]) : cmul(v[k1], T1[k1 * 64 + u]);
+  }
+  template <bool CONJ>
+  void t2_mul(C2 (&v)[16], const C2* T2) {
+    const int q = u >> 4;
+    for (int k2 = 1; k2 < 16; k2++) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
+  }
+  // the device keeps a private copy of the thread's own accumulator coefficients in tensor memory
+  void own_load(uint64_t (&own)[32], const uint64_t* pa) {
+    for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
+  }
+  void own_store(const uint64_t (&)[32]) {}
 };
 
 template <class Body>
@@ -57,7 +69,7 @@ void run_pair(Body body) {
   std::vector<pthread_t> th(2 * kTeam);
   for (int t = 0; t < 2 * kTeam; t++) {
     ls[t].body = &body;
-    ls[t].cx = HostPairCx{t % kTeam, t / kTeam, &half[t / kTeam], &pair, {}};
+    ls[t].cx = HostPairCx{t % kTeam, t / kTeam, &half[t / kTeam], &pair};
     pthread_create(&th[t], nullptr, PairLaunch<Body>::run, &ls[t]);
   }
   for (int t = 0; t < 2 * kTeam; t++) pthread_join(th[t], nullptr);

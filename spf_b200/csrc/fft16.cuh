@@ -112,10 +112,15 @@ SPF_HD void dft16(C2 (&v)[16]) {
 // ------------------------------------------------------------------------------------------
 // forward passes.  v[m] on entry to fwd_pass1 = (p[a + 64 m], p[a + 64 m + 1024]) as doubles.
 // ------------------------------------------------------------------------------------------
-SPF_HD void fwd_pass1(C2 (&v)[16], int a, const C2* T1) {
+// pass 1 without its thread-dependent twiddle (applied by the caller: table in shared memory
+// below, or the thread's tensor-memory columns in the blind-rotation kernel)
+SPF_HD void fwd_pass1_core(C2 (&v)[16]) {
 #pragma unroll
   for (int m = 1; m < 16; m++) v[m] = cmul_cs(v[m], spf_cos32(m), spf_sin32(m));
   dft16<false>(v);
+}
+SPF_HD void fwd_pass1(C2 (&v)[16], int a, const C2* T1) {
+  fwd_pass1_core(v);
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1++) v[k1] = cmul(v[k1], T1[k1 * 64 + a]);
 }
@@ -187,12 +192,15 @@ SPF_HD void inv_x1_read(C2 (&v)[16], const C2* buf, int a) {
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1++) v[k1] = buf[k1 * kXPad + a];
 }
-SPF_HD void inv_pass1(C2 (&v)[16], int a, const C2* T1) {
-#pragma unroll
-  for (int k1 = 0; k1 < 16; k1++) v[k1] = cmul_conj(v[k1], T1[k1 * 64 + a]);
+SPF_HD void inv_pass1_core(C2 (&v)[16]) {
   dft16<true>(v);
 #pragma unroll
   for (int m = 1; m < 16; m++) v[m] = cmul_cs(v[m], spf_cos32(m), -spf_sin32(m));
+}
+SPF_HD void inv_pass1(C2 (&v)[16], int a, const C2* T1) {
+#pragma unroll
+  for (int k1 = 0; k1 < 16; k1++) v[k1] = cmul_conj(v[k1], T1[k1 * 64 + a]);
+  inv_pass1_core(v);
 }
 
 // ------------------------------------------------------------------------------------------

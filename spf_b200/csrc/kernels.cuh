@@ -40,11 +40,129 @@ constexpr int kPbsPairs = 3;
 constexpr int kPbsPairBytes = 2 * kN * 8 + 2 * kXBuf * 16;            // acc + 2 exchange buffers = 66048
 constexpr int kPbsSmem = kTableBytes + kPbsPairs * kPbsPairBytes;      // 215616
 
+#ifndef SPF_PBS_TMEM_T1
+#define SPF_PBS_TMEM_T1 1   // pass-1 twiddles (per thread) in tensor memory
+#endif
+#ifndef SPF_PBS_TMEM_T2
+#define SPF_PBS_TMEM_T2 0   // pass-2 twiddles in tensor memory (measured slower: 9.2 vs 8.6 ms per wave)
+#endif
+#ifndef SPF_PBS_TMEM_OWN
+#define SPF_PBS_TMEM_OWN 1  // private copy of the thread's own accumulator coefficients in tensor memory
+#endif
+
+// tensor-memory helpers (32x32b shape: thread i of a warp <-> TMEM lane 32*(warp%4)+i, one
+// 32-bit word per column)
+__device__ __forceinline__ void tmem_ld16(uint32_t (&r)[16], uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// TMEM columns: [0,64) T1, [64,128) T2 (shared by the three warps of a lane quarter, which have
+// the same thread-in-team index), [128 + 64 p, +64) own coefficients of pair p's warps.
+constexpr int kPbsTmemCols = 512;
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 struct DevPairCx {
   int u, h;
   int bar_half, bar_pair;
+  uint32_t t1_taddr;   // this warp's lane quarter, column 0 of the T1 block (T2 block at +64)
+  uint32_t own_taddr;  // this warp's private 64 columns
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar_half) : "memory"); }
   __device__ __forceinline__ void pair_sync() const { asm volatile("bar.sync %0, 128;" ::"r"(bar_pair) : "memory"); }
+  // v[k1] *= T1[k1][u] (or its conjugate).  The 16 twiddles of a thread never change, so they sit
+  // in the thread's tensor-memory columns instead of a shared-memory table: 16 LDS.128 per
+  // transform (12 % of the kernel's shared-memory wavefronts) become 4 tcgen05.ld on a path the
+  // LSU pipe does not see.
+  template <bool CONJ>
+  __device__ __forceinline__ void t1_mul(C2 (&v)[16], const C2* T1) const {
+#if SPF_PBS_TMEM_T1
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16(r0, t1_taddr + 32 * half);
+      tmem_ld16(r1, t1_taddr + 32 * half + 16);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const C2 w0{__hiloint2double((int)r0[4 * i + 1], (int)r0[4 * i]), __hiloint2double((int)r0[4 * i + 3], (int)r0[4 * i + 2])};
+        const C2 w1{__hiloint2double((int)r1[4 * i + 1], (int)r1[4 * i]), __hiloint2double((int)r1[4 * i + 3], (int)r1[4 * i + 2])};
+        const int ka = 8 * half + i, kb = 8 * half + 4 + i;
+        v[ka] = CONJ ? cmul_conj(v[ka], w0) : cmul(v[ka], w0);
+        v[kb] = CONJ ? cmul_conj(v[kb], w1) : cmul(v[kb], w1);
+      }
+    }
+#else
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) v[k1] = CONJ ? cmul_conj(v[k1], T1[k1 * 64 + u]) : cmul(v[k1], T1[k1 * 64 + u]);
+#endif
+  }
+  // v[k2] *= T2[q][k2], k2 = 1..15
+  template <bool CONJ>
+  __device__ __forceinline__ void t2_mul(C2 (&v)[16], const C2* T2) const {
+#if SPF_PBS_TMEM_T2
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16(r0, t1_taddr + 64 + 32 * half);
+      tmem_ld16(r1, t1_taddr + 64 + 32 * half + 16);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const C2 w0{__hiloint2double((int)r0[4 * i + 1], (int)r0[4 * i]), __hiloint2double((int)r0[4 * i + 3], (int)r0[4 * i + 2])};
+        const C2 w1{__hiloint2double((int)r1[4 * i + 1], (int)r1[4 * i]), __hiloint2double((int)r1[4 * i + 3], (int)r1[4 * i + 2])};
+        const int ka = 8 * half + i, kb = 8 * half + 4 + i;
+        if (ka != 0) v[ka] = CONJ ? cmul_conj(v[ka], w0) : cmul(v[ka], w0);
+        v[kb] = CONJ ? cmul_conj(v[kb], w1) : cmul(v[kb], w1);
+      }
+    }
+#else
+    const int q = u >> 4;
+#pragma unroll
+    for (int k2 = 1; k2 < 16; k2++) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
+#endif
+  }
+  __device__ __forceinline__ void own_load(uint64_t (&own)[32], const uint64_t* pa) const {
+#if SPF_PBS_TMEM_OWN
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      uint32_t r[16];
+      tmem_ld16(r, own_taddr + 16 * c);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 8; i++) own[8 * c + i] = ((uint64_t)r[2 * i + 1] << 32) | r[2 * i];
+    }
+#else
+#pragma unroll
+    for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
+#endif
+  }
+  __device__ __forceinline__ void own_store(const uint64_t (&own)[32]) const {
+#if SPF_PBS_TMEM_OWN
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      uint32_t r[16];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { r[2 * i] = (uint32_t)own[8 * c + i]; r[2 * i + 1] = (uint32_t)(own[8 * c + i] >> 32); }
+      tmem_st16(own_taddr + 16 * c, r);
+    }
+    tmem_wait_st();
+#endif
+  }
 };
 
 struct PbsBatch {
@@ -62,13 +180,46 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   C2* sT1 = reinterpret_cast<C2*>(smem);
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
+  uint32_t t1_taddr = 0;
+#if SPF_PBS_TMEM_T1 || SPF_PBS_TMEM_T2 || SPF_PBS_TMEM_OWN
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(&tmem_base)), "n"(kPbsTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  t1_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  if (warp < 4) {  // every lane quarter is shared by warps w, w+4, w+8, which have the same u
+    const int uu = (warp & 1) * 32 + (threadIdx.x & 31);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; k1++) {
+      const C2 w = sT1[k1 * 64 + uu];
+      tmem_st4(t1_taddr + 4 * k1, (uint32_t)__double2loint(w.x), (uint32_t)__double2hiint(w.x),
+               (uint32_t)__double2loint(w.y), (uint32_t)__double2hiint(w.y));
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) {
+      const C2 w = k2 ? sT2[(uu >> 4) * kT2Pad + k2] : C2{1.0, 0.0};
+      tmem_st4(t1_taddr + 64 + 4 * k2, (uint32_t)__double2loint(w.x), (uint32_t)__double2hiint(w.x),
+               (uint32_t)__double2loint(w.y), (uint32_t)__double2hiint(w.y));
+    }
+    tmem_wait_st();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
   const int pair = threadIdx.x / (2 * kTeam);
   const int npairs = blockDim.x / (2 * kTeam);  // 1..kPbsPairs pairs per CTA (fewer for small batches)
   const int h = (threadIdx.x / kTeam) & 1;
   unsigned char* base = smem + kTableBytes + pair * kPbsPairBytes;
   uint64_t* acc = reinterpret_cast<uint64_t*>(base);
   C2* xb = reinterpret_cast<C2*>(base + 2 * kN * 8);
-  DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3};
+  DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3, t1_taddr, t1_taddr + 128 + 64 * pair};
   // Persistent pairs: slot (pair, CTA) takes ciphertexts slot, slot + slots, ...  Slots are numbered
   // pair-major so that a trailing partial round leaves at most one busy pair on as many SMs as
   // possible (a pair alone on an SM runs ~1.3x faster than one sharing it with two others).
@@ -85,6 +236,12 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
     A.cbs_count = P.cbs_count;
     pbs_pair_team(cx, A, acc, xb, sT1, sT2);
   }
+#if SPF_PBS_TMEM_T1 || SPF_PBS_TMEM_T2 || SPF_PBS_TMEM_OWN
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kPbsTmemCols) : "memory");
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

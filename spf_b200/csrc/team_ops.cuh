@@ -338,6 +338,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
   uint64_t own[32];
 #pragma unroll
   for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
+  cx.own_store(own);
 #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const int at = (int)modulus_switch(a_next, A.log_chi, A.log_v, log2n);
@@ -372,12 +373,14 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
 #pragma unroll
           for (int m = 0; m < 16; m++) { v[m].x = digit16_to_f64(pk[m]); v[m].y = digit16_to_f64(pk[m] >> 16); }
         }
-        fwd_pass1(v, u, T1);
+        fwd_pass1_core(v);
+        cx.template t1_mul<false>(v, T1);  // v[k1] *= T1[k1][u]
         if (t == 1) cx.pair_sync();  // both halves have consumed the level-0 spectra
         fwd_x1_write(v, xown, u);
         cx.sync();
         fwd_x1_read(v, xown, u);
-        fwd_pass2(v, u, T2);
+        dft16<false>(v);
+        cx.template t2_mul<false>(v, T2);  // v[k2] *= W64^(q k2)
         cx.sync();
         fwd_x2_write(v, xown, u);
         cx.pair_sync();
@@ -407,20 +410,24 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     {
       C2 w[16];
       inv_x2_read(w, xown, u);
-      inv_pass2(w, u, T2);
+      cx.template t2_mul<true>(w, T2);
+      dft16<true>(w);
       cx.sync();
       inv_x1_write(w, xown, u);
       cx.sync();
       inv_x1_read(w, xown, u);
-      inv_pass1(w, u, T1);
+      cx.template t1_mul<true>(w, T1);  // w[k1] *= conj(T1[k1][u])
+      inv_pass1_core(w);
+      cx.own_load(own, pa);  // own[i2] = pa[u + 64 i2] (device: from the thread's tensor-memory copy)
 #pragma unroll
       for (int m = 0; m < 16; m++) {
         const int j = u + 64 * m;
-        own[m] = pa[j] + f64_to_torus(w[m].x);
-        own[m + 16] = pa[j + kM] + f64_to_torus(w[m].y);
+        own[m] += f64_to_torus(w[m].x);
+        own[m + 16] += f64_to_torus(w[m].y);
         pa[j] = own[m];
         pa[j + kM] = own[m + 16];
       }
+      cx.own_store(own);
     }
     cx.sync();  // next step gathers rotated coefficients written by other threads of this half
   }
