@@ -46,6 +46,8 @@ struct HostPairCx {
     for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
   }
   void own_store(const uint64_t (&)[32]) {}
+  void f_store(const C2 (&)[2][8]) {}  // device: accumulators parked in tensor memory between digit levels
+  void f_load(C2 (&)[2][8]) {}
 };
 
 template <class Body>

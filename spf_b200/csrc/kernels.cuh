@@ -46,6 +46,9 @@ constexpr int kPbsSmem = kTableBytes + kPbsPairs * kPbsPairBytes;      // 215616
 #ifndef SPF_PBS_TMEM_T2
 #define SPF_PBS_TMEM_T2 0   // pass-2 twiddles in tensor memory (measured slower: 9.2 vs 8.6 ms per wave)
 #endif
+#ifndef SPF_PBS_TMEM_F
+#define SPF_PBS_TMEM_F 1    // accumulators parked in tensor memory while the second digit level is transformed
+#endif
 #ifndef SPF_PBS_TMEM_OWN
 #define SPF_PBS_TMEM_OWN 1  // private copy of the thread's own accumulator coefficients in tensor memory
 #endif
@@ -81,7 +84,7 @@ struct DevPairCx {
   int u, h;
   int bar_half, bar_pair;
   uint32_t t1_taddr;   // this warp's lane quarter, column 0 of the T1 block (T2 block at +64)
-  uint32_t own_taddr;  // this warp's private 64 columns
+  uint32_t own_taddr;  // this warp's private 64 columns (accumulator stash: +192)
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar_half) : "memory"); }
   __device__ __forceinline__ void pair_sync() const { asm volatile("bar.sync %0, 128;" ::"r"(bar_pair) : "memory"); }
   // v[k1] *= T1[k1][u] (or its conjugate).  The 16 twiddles of a thread never change, so they sit
@@ -136,6 +139,37 @@ struct DevPairCx {
     for (int k2 = 1; k2 < 16; k2++) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
 #endif
   }
+  __device__ __forceinline__ void f_store(const C2 (&f)[2][8]) const {
+#if SPF_PBS_TMEM_F
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      uint32_t r[16];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const C2 x = f[c >> 1][4 * (c & 1) + i];
+        r[4 * i] = (uint32_t)__double2loint(x.x); r[4 * i + 1] = (uint32_t)__double2hiint(x.x);
+        r[4 * i + 2] = (uint32_t)__double2loint(x.y); r[4 * i + 3] = (uint32_t)__double2hiint(x.y);
+      }
+      tmem_st16(own_taddr + 192 + 16 * c, r);
+    }
+    tmem_wait_st();
+#endif
+  }
+  __device__ __forceinline__ void f_load(C2 (&f)[2][8]) const {
+#if SPF_PBS_TMEM_F
+    uint32_t r[4][16];
+#pragma unroll
+    for (int c = 0; c < 4; c++) tmem_ld16(r[c], own_taddr + 192 + 16 * c);
+    tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        f[c >> 1][4 * (c & 1) + i] = C2{__hiloint2double((int)r[c][4 * i + 1], (int)r[c][4 * i]),
+                                        __hiloint2double((int)r[c][4 * i + 3], (int)r[c][4 * i + 2])};
+    }
+#endif
+  }
   __device__ __forceinline__ void own_load(uint64_t (&own)[32], const uint64_t* pa) const {
 #if SPF_PBS_TMEM_OWN
 #pragma unroll
@@ -181,7 +215,7 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
   uint32_t t1_taddr = 0;
-#if SPF_PBS_TMEM_T1 || SPF_PBS_TMEM_T2 || SPF_PBS_TMEM_OWN
+#if SPF_PBS_TMEM_T1 || SPF_PBS_TMEM_T2 || SPF_PBS_TMEM_OWN || SPF_PBS_TMEM_F
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -236,7 +270,7 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
     A.cbs_count = P.cbs_count;
     pbs_pair_team(cx, A, acc, xb, sT1, sT2);
   }
-#if SPF_PBS_TMEM_T1 || SPF_PBS_TMEM_T2 || SPF_PBS_TMEM_OWN
+#if SPF_PBS_TMEM_T1 || SPF_PBS_TMEM_T2 || SPF_PBS_TMEM_OWN || SPF_PBS_TMEM_F
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0)

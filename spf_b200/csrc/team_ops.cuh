@@ -383,10 +383,12 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         cx.template t2_mul<false>(v, T2);  // v[k2] *= W64^(q k2)
         cx.sync();
         fwd_x2_write(v, xown, u);
+        if (t == 1) cx.f_load(f);
         cx.pair_sync();
         if (t == 0) mad_split<true>(f, xb, ggsw + (size_t)((0 * 2 + level) * 2) * kM, u, h);
         else mad_split<false>(f, xb, ggsw + (size_t)((0 * 2 + level) * 2) * kM, u, h);
         mad_split<false>(f, xb + kXBuf, ggsw + (size_t)((1 * 2 + level) * 2) * kM, u, h);
+        if (t == 0) cx.f_store(f);  // device: parked in tensor memory while the second transform runs
       }
     }
     // first inverse pass on this half's bins of both output polynomials, hand them to their owners
