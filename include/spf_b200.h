@@ -195,6 +195,19 @@ uint64_t spf_b200_graph_launches(const spf_b200_graph *graph); /* kernel launche
 /* build + run + destroy */
 int spf_b200_run_graph(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes);
 
+/* ---- the same graph sharded over the GPUs of one box ---------------------------
+ * One process per GPU; every rank builds the same graph over the same inputs and a replica of the
+ * compute key.  Each CircuitBootstrap group (a dependency level's ready batch -- the only expensive
+ * ops) is laid out as `world` equal chunks; rank r bootstraps chunk r and then calls `exchange`,
+ * which must complete the buffer on every rank (an in-place all-gather: on entry chunk r of
+ * d_buf[world][chunk_bytes] is valid on rank r, on return -- in stream order -- all chunks are valid
+ * everywhere).  spf_b200/multi.py provides the NCCL implementation.  All other ops run replicated.
+ * Returns nonzero from `exchange` abort the run with SPF_E_GRAPH. */
+typedef int (*spf_exchange_fn)(void *user, void *d_buf, size_t chunk_bytes, int world, void *stream);
+int spf_b200_graph_build_sharded(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes, int world,
+                                 spf_b200_graph **out);
+int spf_b200_graph_run_sharded(spf_b200_graph *graph, int rank, int world, spf_exchange_fn exchange, void *user);
+
 /* ---- serialized keys and ciphertexts ------------------------------------------
  * The reference serialises with bincode 1.3.3 (Cargo.lock:244-245), fixed-width little-endian
  * integers: every sunscreen_tfhe entity is one sequence `u64 length || elements`

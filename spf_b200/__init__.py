@@ -392,7 +392,11 @@ ABI.update({
     "spf_b200_graph_levels": [_vp],
     "spf_b200_graph_launches": [_vp],
     "spf_b200_run_graph": [_vp, C.POINTER(_Node), _sz],
+    "spf_b200_graph_build_sharded": [_vp, C.POINTER(_Node), _sz, C.c_int, C.POINTER(_vp)],
+    "spf_b200_graph_run_sharded": [_vp, C.c_int, C.c_int, _vp, _vp],
 })
+# spf_exchange_fn(user, d_buf, chunk_bytes, world, stream) -> int
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
 _RESTYPES.update({"spf_b200_graph_destroy": None, "spf_b200_graph_launches": C.c_uint64})
 
 
@@ -429,8 +433,8 @@ class CircuitProcessor:
     def __init__(self, evaluation: Evaluation):
         self.ev = evaluation
 
-    def compile(self, circuit: FheCircuit) -> "CompiledGraph":
-        return CompiledGraph(self.ev, circuit)
+    def compile(self, circuit: FheCircuit, world: int = 1, rank: int = 0, exchange=None) -> "CompiledGraph":
+        return CompiledGraph(self.ev, circuit, world=world, rank=rank, exchange=exchange)
 
     def run_graph_blocking(self, circuit: FheCircuit) -> None:
         """run_graph_blocking (mod.rs:641-655); raises SpfError(-4, ...) for malformed graphs as the
@@ -443,15 +447,42 @@ class CircuitProcessor:
 
 
 class CompiledGraph:
-    def __init__(self, ev: Evaluation, circuit: FheCircuit):
+    """A levelised graph resident on one GPU.  With world > 1 the graph is laid out for a sharded
+    run (spf_b200_graph_build_sharded): every CircuitBootstrap level is split into `world` chunks,
+    this rank computes chunk `rank` and `exchange(d_buf, chunk_bytes, world, stream)` (see
+    spf_b200.multi.NcclExchange) all-gathers the rest."""
+
+    def __init__(self, ev: Evaluation, circuit: FheCircuit, world: int = 1, rank: int = 0, exchange=None):
         self.ev = ev
         self._keep = circuit  # keeps the io buffers alive
         self._h = _vp()
+        self.world, self.rank = int(world), int(rank)
         arr = circuit._pack()
-        ev._check(lib().spf_b200_graph_build(ev.handle, arr, len(circuit.nodes), C.byref(self._h)))
+        ev._check(lib().spf_b200_graph_build_sharded(ev.handle, arr, len(circuit.nodes), self.world, C.byref(self._h)))
+        self._exchange = exchange
+        self._cb_error = None
+
+        def _cb(user, d_buf, chunk_bytes, world_, stream):
+            try:
+                self._exchange(int(d_buf), int(chunk_bytes), int(world_), int(stream or 0))
+                return 0
+            except Exception as e:  # never let an exception cross the C ABI
+                self._cb_error = e
+                return 1
+
+        self._cb = EXCHANGE_FN(_cb) if exchange is not None else None
 
     def run(self):
-        self.ev._check(lib().spf_b200_graph_run(self._h))
+        if self.world == 1:
+            self.ev._check(lib().spf_b200_graph_run(self._h))
+            return
+        if self._cb is None:
+            raise SpfError(-1, "a sharded graph needs an exchange callable")
+        self._cb_error = None
+        rc = lib().spf_b200_graph_run_sharded(self._h, self.rank, self.world, C.cast(self._cb, _vp), None)
+        if self._cb_error is not None:
+            raise self._cb_error
+        self.ev._check(rc)
 
     @property
     def levels(self) -> int:
@@ -462,7 +493,7 @@ class CompiledGraph:
         return int(lib().spf_b200_graph_launches(self._h))
 
     def close(self):
-        if self._h.value:
+        if getattr(self, "_h", None) is not None and self._h.value:
             lib().spf_b200_graph_destroy(self._h)
             self._h = _vp()
 

@@ -44,3 +44,70 @@ def ripple_carry_adder(a_bits: list[np.ndarray], b_bits: list[np.ndarray], out_b
             ncarry = c.add("Not", carry)
     c.add("OutputGlwe1", carry, io=out_bits[w])
     return c
+
+
+def _front(c: FheCircuit, ct):
+    """InputGlwe1 -> SampleExtract(0) -> KeyswitchL1toL0 -> CircuitBootstrap (fhe_circuit.rs:473-494)."""
+    x = c.add("InputGlwe1", io=ct)
+    x = c.add("SampleExtract", x, arg=0)
+    x = c.add("KeyswitchL1toL0", x)
+    return c.add("CircuitBootstrap", x)
+
+
+def _refresh(c: FheCircuit, glwe_node: int) -> int:
+    """Turn a computed GLWE bit back into a selector: SampleExtract(0) -> KeyswitchL1toL0 ->
+    CircuitBootstrap, the hop between two dependency levels of a Parasol program."""
+    x = c.add("SampleExtract", glwe_node, arg=0)
+    x = c.add("KeyswitchL1toL0", x)
+    return c.add("CircuitBootstrap", x)
+
+
+def _adder_nodes(c: FheCircuit, sa: list[int], sb: list[int]) -> list[int]:
+    """Ripple-carry MUX tree over selector nodes; returns the GLWE nodes of the w sum bits + carry."""
+    zero, one = c.add("ZeroGlwe1"), c.add("OneGlwe1")
+    carry, ncarry = zero, one
+    outs = []
+    for i in range(len(sa)):
+        s0 = c.add("CMux", sb[i], carry, ncarry)
+        s1 = c.add("CMux", sb[i], ncarry, carry)
+        outs.append(c.add("CMux", sa[i], s0, s1))
+        c0 = c.add("CMux", sb[i], zero, carry)
+        c1 = c.add("CMux", sb[i], carry, one)
+        carry = c.add("CMux", sa[i], c0, c1)
+        if i + 1 < len(sa):
+            ncarry = c.add("Not", carry)
+    outs.append(carry)
+    return outs
+
+
+def _greater_than_node(c: FheCircuit, sx: list[int], sy: list[int]) -> int:
+    """x > y over selector nodes, LSB first: gt' = (x_i == y_i) ? gt : x_i, one ripple MUX chain
+    (the comparison the reference derives from a BDD, parasol_cpu/src/proc/ops/comparisons.rs:62-98)."""
+    zero, one = c.add("ZeroGlwe1"), c.add("OneGlwe1")
+    gt = zero
+    for i in range(len(sx)):
+        lo = c.add("CMux", sy[i], gt, zero)   # x_i = 0: y_i ? 0 : gt
+        hi = c.add("CMux", sy[i], one, gt)    # x_i = 1: y_i ? gt : 1
+        gt = c.add("CMux", sx[i], lo, hi)
+    return gt
+
+
+def add_then_greater_than(a_bits, b_bits, c_bits, out_sum, out_gt, programs: int = 1) -> FheCircuit:
+    """`programs` independent two-level Parasol-style programs in ONE graph: s = a + b (w-bit,
+    wrapping), then s > c.  Level structure per program: 3w circuit bootstraps of the encrypted
+    inputs, w more of the sum bits between the two instructions (the shape of BASELINE config 4's
+    multi-instruction programs; the multiplier's BDD generator itself is above the boundary and out
+    of scope).  a_bits/b_bits/c_bits: [programs][w] L1 GLWE inputs; out_sum [programs][w],
+    out_gt [programs] output buffers."""
+    c = FheCircuit()
+    for p in range(programs):
+        w = len(a_bits[p])
+        sa = [_front(c, x) for x in a_bits[p]]
+        sb = [_front(c, x) for x in b_bits[p]]
+        sc = [_front(c, x) for x in c_bits[p]]
+        s = _adder_nodes(c, sa, sb)[:w]
+        for i in range(w):
+            c.add("OutputGlwe1", s[i], io=out_sum[p][i])
+        ss = [_refresh(c, n) for n in s]
+        c.add("OutputGlwe1", _greater_than_node(c, ss, sc), io=out_gt[p])
+    return c

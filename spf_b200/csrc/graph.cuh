@@ -93,6 +93,7 @@ struct spf_b200_graph {
   char* d_out_stage = nullptr;  // rescaled GGSW outputs
   int n_levels = 0;
   uint64_t launches_per_run = 0;
+  int world = 1;  // CircuitBootstrap groups are laid out as `world` equal chunks (spf_b200_graph_build_sharded)
 };
 
 namespace {
@@ -134,7 +135,11 @@ int ensure_constants(spf_b200_ctx* ctx) {
 
 int graph_fail(spf_b200_ctx* ctx, const std::string& msg) { return fail(ctx, SPF_E_GRAPH, msg); }
 
-int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s) {
+// Items per rank of a sharded CircuitBootstrap group: equal chunks (the last ones may be short or
+// empty) so that one all-gather of world * chunk items puts every GGSW on every rank.
+size_t cbs_chunk_items(size_t n, int world) { return (n + (size_t)world - 1) / (size_t)world; }
+
+int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s, int rank = 0, int world = 1) {
   spf_b200_ctx* ctx = g->ctx;
   const size_t n = G.ids.size();
   const void* const* ptrs = reinterpret_cast<const void* const*>(g->d_ptrs + G.ptr_off);
@@ -157,10 +162,16 @@ int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s) {
       return launch_cmux(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, nullptr, 0, (int)ctx->p.cbs.count,
                          n * ctx->p.cbs.count, s, ptrs);
     case SPF_OP_CIRCUIT_BOOTSTRAP: {
-      if (int rc = launch_pbs(ctx, reinterpret_cast<uint64_t*>(G.scratch), nullptr, nullptr, true, 0, cbs_log_v(&ctx->p), n, s, ptrs))
+      // sharded run: this rank bootstraps only its chunk; the caller's exchange fills in the rest
+      const size_t chunk = cbs_chunk_items(n, world);
+      const size_t start = std::min(n, chunk * (size_t)rank), cnt = std::min(n - start, chunk);
+      if (cnt == 0) return 0;
+      const size_t glwe = ct_bytes(&ctx->p, T_GLWE1), ggsw = ct_bytes(&ctx->p, T_GGSW1);
+      if (int rc = launch_pbs(ctx, reinterpret_cast<uint64_t*>(G.scratch + start * glwe), nullptr, nullptr, true, 0,
+                              cbs_log_v(&ctx->p), cnt, s, ptrs + start))
         return rc;
-      return launch_trace_ss(ctx, reinterpret_cast<const uint64_t*>(G.scratch), nullptr, reinterpret_cast<C2*>(G.out_base), 0,
-                             (int)ctx->p.cbs.count, 1.0, n, s);
+      return launch_trace_ss(ctx, reinterpret_cast<const uint64_t*>(G.scratch + start * glwe), nullptr,
+                             reinterpret_cast<C2*>(G.out_base + start * ggsw), 0, (int)ctx->p.cbs.count, 1.0, cnt, s);
     }
     case SPF_OP_SCHEME_SWITCH:
       return launch_trace_ss(ctx, nullptr, nullptr, reinterpret_cast<C2*>(G.out_base), 2, (int)ctx->p.cbs.count, 1.0, n, s, ptrs);
@@ -174,14 +185,17 @@ int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s) {
 extern "C" {
 
 void spf_b200_graph_destroy(spf_b200_graph* g);
+int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user);
 
-int spf_b200_graph_build(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, spf_b200_graph** out) {
+int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, int world, spf_b200_graph** out) {
   if (!ctx) return SPF_E_INVALID;
   if (!out || (!nodes && n)) return fail(ctx, SPF_E_INVALID, "NULL argument");
+  if (world < 1 || world > 1024) return fail(ctx, SPF_E_INVALID, "world must be in 1..1024");
   *out = nullptr;
   const spf_params* p = &ctx->p;
   std::unique_ptr<spf_b200_graph, void (*)(spf_b200_graph*)> g(new spf_b200_graph(), spf_b200_graph_destroy);
   g->ctx = ctx;
+  g->world = world;
   g->nodes.assign(nodes, nodes + n);
   g->type.resize(n);
   g->level.assign(n, -1);
@@ -240,6 +254,53 @@ int spf_b200_graph_build(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, spf
       }
     }
   }
+  // ---- align the expensive ops ----
+  // ASAP levels scatter the refresh chains (SampleExtract -> KeyswitchL1toL0 -> CircuitBootstrap)
+  // between two instructions of a program over as many levels as the producing MUX tree is deep
+  // (a ripple-carry adder yields one sum bit per two levels), which would run w one-ciphertext
+  // bootstraps back to back.  Nodes of those three ops that have the same number of circuit
+  // bootstraps upstream (their "stage") are therefore delayed to the level of the latest one, so
+  // that a stage bootstraps as ONE batch; delaying a node is always legal, consumers are re-levelled.
+  {
+    std::vector<int> order(n);
+    for (size_t i = 0; i < n; i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return g->level[a] < g->level[b]; });  // topological
+    std::vector<int> stage(n, 0);
+    for (int v : order) {
+      const OpInfo oi = op_info(g->nodes[v].op);
+      for (int k = 0; k < oi.n_in; k++) {
+        const int w = g->nodes[v].in[k];
+        stage[v] = std::max(stage[v], stage[w] + (g->nodes[w].op == SPF_OP_CIRCUIT_BOOTSTRAP ? 1 : 0));
+      }
+    }
+    auto slot = [&](int v) -> int {  // alignment class of node v, or -1
+      switch (g->nodes[v].op) {
+        case SPF_OP_SAMPLE_EXTRACT: return 3 * stage[v];
+        case SPF_OP_KEYSWITCH_L1_TO_L0: return 3 * stage[v] + 1;
+        case SPF_OP_CIRCUIT_BOOTSTRAP: return 3 * stage[v] + 2;
+        default: return -1;
+      }
+    };
+    int n_slots = 0;
+    for (size_t i = 0; i < n; i++) n_slots = std::max(n_slots, slot((int)i) + 1);
+    std::vector<int> floor_lv(n_slots, 0);
+    for (int iter = 0; iter < 3 * n_slots + 2; iter++) {
+      bool changed = false;
+      for (int v : order) {  // re-level with the current floors (order stays topological: levels only grow
+        const OpInfo oi = op_info(g->nodes[v].op);  //  along edges, and inputs precede consumers in `order`)
+        int lv = 0;
+        for (int k = 0; k < oi.n_in; k++) lv = std::max(lv, g->level[g->nodes[v].in[k]] + 1);
+        const int sl = slot(v);
+        if (sl >= 0) lv = std::max(lv, floor_lv[sl]);
+        g->level[v] = lv;
+      }
+      for (int v : order) {
+        const int sl = slot(v);
+        if (sl >= 0 && g->level[v] > floor_lv[sl]) { floor_lv[sl] = g->level[v]; changed = true; }
+      }
+      if (!changed) break;
+    }
+  }
   for (size_t i = 0; i < n; i++) g->n_levels = std::max(g->n_levels, g->level[i] + 1);
   if (int rc = ensure_constants(ctx)) return rc;
   // ---- groups, arena layout, pointer tables ----
@@ -264,7 +325,9 @@ int spf_b200_graph_build(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, spf
       size_t o = (size_t)-1, sc = (size_t)-1;
       if (!is_const && !is_output) {
         o = arena;
-        arena = align(arena + ct_bytes(p, oi.out) * G.ids.size());
+        // CircuitBootstrap outputs are padded to `world` equal chunks (in-place all-gather layout)
+        const size_t slots = op == SPF_OP_CIRCUIT_BOOTSTRAP ? cbs_chunk_items(G.ids.size(), world) * (size_t)world : G.ids.size();
+        arena = align(arena + ct_bytes(p, oi.out) * slots);
         if (op == SPF_OP_CIRCUIT_BOOTSTRAP) { sc = arena; arena = align(arena + ct_bytes(p, T_GLWE1) * G.ids.size()); }
       }
       if (op == SPF_OP_OUTPUT_GGSW1) out_stage += ct_bytes(p, T_GGSW1) * G.ids.size();
@@ -350,12 +413,24 @@ int spf_b200_graph_build(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, spf
   return 0;
 }
 
+int spf_b200_graph_build(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, spf_b200_graph** out) {
+  return spf_b200_graph_build_sharded(ctx, nodes, n, 1, out);
+}
+
 // Executes the graph once: copies every Input* ciphertext from its io pointer, runs the levels,
 // copies every Output* ciphertext to its io pointer, and returns when the outputs are valid
 // (CircuitProcessor::run_graph_blocking, circuit_processor/mod.rs:641-655).
-int spf_b200_graph_run(spf_b200_graph* g) {
+// Sharded over `world` ranks (one process per GPU, every rank runs the same graph on the same
+// inputs): each CircuitBootstrap group -- the only expensive ops -- is split into `world` equal
+// chunks, rank r bootstraps chunk r, then `exchange` (an all-gather over NVLink, see
+// spf_b200/multi.py) completes the group's GGSWs on every rank; the cheap ops in between
+// (sample extract, keyswitch, the MUX tree) run replicated, so no other data moves.
+int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user) {
   if (!g) return SPF_E_INVALID;
   spf_b200_ctx* ctx = g->ctx;
+  if (world != g->world || rank < 0 || rank >= world)
+    return fail(ctx, SPF_E_INVALID, "rank/world do not match the graph's sharded layout");
+  if (world > 1 && !exchange) return fail(ctx, SPF_E_INVALID, "a sharded run needs an exchange callback");
   const spf_params* p = &ctx->p;
   CU(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream[0];
@@ -368,8 +443,14 @@ int spf_b200_graph_run(spf_b200_graph* g) {
                                 spf_b200_len_ggsw_l1(p), 1.0 / 1024.0, s))
         return rc;
   }
-  for (const Group& G : g->groups)
-    if (int rc = run_group(g, G, s)) return rc;
+  for (const Group& G : g->groups) {
+    if (int rc = run_group(g, G, s, rank, world)) return rc;
+    if (world > 1 && G.op == SPF_OP_CIRCUIT_BOOTSTRAP) {
+      const size_t chunk_bytes = cbs_chunk_items(G.ids.size(), world) * ct_bytes(p, T_GGSW1);
+      if (int rc = exchange(user, G.out_base, chunk_bytes, world, s))
+        return fail(ctx, SPF_E_GRAPH, "exchange callback failed with status " + std::to_string(rc));
+    }
+  }
   size_t stage = 0;
   for (int id : g->outputs) {
     const int src = g->nodes[id].in[0];
@@ -397,6 +478,12 @@ void spf_b200_graph_destroy(spf_b200_graph* g) {
   cudaFree(g->d_u32);
   cudaFree(g->d_out_stage);
   delete g;
+}
+
+int spf_b200_graph_run(spf_b200_graph* g) {
+  if (!g) return SPF_E_INVALID;
+  if (g->world != 1) return fail(g->ctx, SPF_E_INVALID, "graph was built sharded: use spf_b200_graph_run_sharded");
+  return spf_b200_graph_run_sharded(g, 0, 1, nullptr, nullptr);
 }
 
 int spf_b200_graph_levels(const spf_b200_graph* g) { return g ? g->n_levels : -1; }

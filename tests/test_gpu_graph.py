@@ -154,3 +154,77 @@ def test_malformed_graphs(keys, client, proc):
     c = spf_b200.FheCircuit()
     c.add("KeyswitchL1toL0", c.add("InputLwe0", io=lwe0))
     expect(c, "wrong ciphertext kind")
+
+
+def _two_level_program(client, keys, w, programs, rng):
+    import spf_b200
+    from spf_b200.circuits import add_then_greater_than
+
+    vals = [(int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w))) for _ in range(programs)]
+    enc = lambda v: [client.encrypt_glwe_l1([(v >> i) & 1]) for i in range(w)]
+    a, b, c = ([enc(v[k]) for v in vals] for k in range(3))
+    out_sum = [[np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w)] for _ in range(programs)]
+    out_gt = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(programs)]
+    return vals, add_then_greater_than(a, b, c, out_sum, out_gt, programs), out_sum, out_gt
+
+
+def _check_program(client, vals, w, out_sum, out_gt):
+    for (a, b, c), s_bits, gt in zip(vals, out_sum, out_gt):
+        s = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(s_bits))
+        assert s == (a + b) % (1 << w)
+        assert int(client.decrypt_glwe_l1(gt)[0]) == int(s > c)
+
+
+def test_add_then_compare_two_level_program(keys, client, proc):
+    """A two-instruction program (add, then greater-than on the refreshed sum bits): two circuit-
+    bootstrap levels in one graph, as in BASELINE config 4's multi-level programs."""
+    rng = np.random.default_rng(11)
+    w = 6
+    vals, circ, out_sum, out_gt = _two_level_program(client, keys, w, 2, rng)
+    g = proc.compile(circ)
+    g.run()
+    _check_program(client, vals, w, out_sum, out_gt)
+    g.close()
+
+
+def test_sharded_run_emulated_on_one_gpu(keys, client, evaluation):
+    """spf_b200_graph_run_sharded with world = 2, both ranks emulated on this GPU: rank r computes
+    only chunk r of every CircuitBootstrap level; the exchange callback parks the rank's own chunk
+    and fills in the peer's chunk from the peer's previous pass.  After (levels + 1) alternating
+    passes every level has seen correct peer data, and rank 0's outputs must decrypt correctly."""
+    import ctypes as C
+
+    import spf_b200
+
+    rng = np.random.default_rng(12)
+    w, world = 4, 2
+    vals, circ, out_sum, out_gt = _two_level_program(client, keys, w, 1, rng)
+    cudart = C.CDLL("libcudart.so.12")
+    parked = {0: {}, 1: {}}  # rank -> exchange index -> host copy of that rank's chunk
+    counter = {"i": 0}
+
+    def make_exchange(rank):
+        def exchange(d_buf, chunk_bytes, world_, stream):
+            assert world_ == world
+            i = counter["i"]
+            counter["i"] += 1
+            assert cudart.cudaStreamSynchronize(C.c_void_p(stream)) == 0
+            mine = np.empty(chunk_bytes, dtype=np.uint8)
+            assert cudart.cudaMemcpy(C.c_void_p(mine.ctypes.data), C.c_void_p(d_buf + rank * chunk_bytes), C.c_size_t(chunk_bytes), 2) == 0
+            parked[rank][i] = mine
+            peer = parked[1 - rank].get(i)
+            if peer is not None:
+                assert cudart.cudaMemcpy(C.c_void_p(d_buf + (1 - rank) * chunk_bytes), C.c_void_p(peer.ctypes.data), C.c_size_t(chunk_bytes), 1) == 0
+        return exchange
+
+    graphs = [spf_b200.CompiledGraph(evaluation, circ, world=world, rank=r, exchange=make_exchange(r)) for r in range(world)]
+    for _ in range(3):  # two bootstrap levels -> correct after three alternating passes
+        for r in (1, 0):
+            counter["i"] = 0
+            graphs[r].run()
+    assert counter["i"] == 2  # one exchange per circuit-bootstrap level
+    _check_program(client, vals, w, out_sum, out_gt)
+    # a graph laid out for a sharded run refuses the unsharded entry point
+    assert spf_b200.lib().spf_b200_graph_run(graphs[0]._h) == -1
+    for g in graphs:
+        g.close()

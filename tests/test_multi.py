@@ -66,3 +66,54 @@ def test_key_broadcast_and_sharding_world2():
         assert p.exitcode == 0
     assert res[0] == (0, True, 0, 6, 2.0)
     assert res[1] == (1, True, 6, 5, 2.0)
+
+
+def test_cbs_chunks_cover_the_level():
+    from spf_b200.multi import cbs_chunk
+
+    for n in (0, 1, 7, 64, 96, 148, 149, 4096):
+        for world in (1, 2, 3, 4, 8):
+            ch = cbs_chunk(n, world)
+            assert ch * world >= n and (ch - 1) * world < n or n == 0
+            covered = sum(min(max(n - r * ch, 0), ch) for r in range(world))
+            assert covered == n
+
+
+def _exchange_worker(rank, world, port, out_q):
+    import torch
+    import torch.distributed as dist
+
+    from spf_b200.multi import all_gather_chunks
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        chunk = 4096 + 64
+        full = (torch.arange(world * chunk, dtype=torch.int64) * 2654435761 % 251).to(torch.uint8)
+        buf = torch.full((world * chunk,), 0xEE, dtype=torch.uint8)   # garbage everywhere ...
+        buf[rank * chunk:(rank + 1) * chunk] = full[rank * chunk:(rank + 1) * chunk]  # ... but my own chunk
+        all_gather_chunks(buf, chunk, world, rank)
+        out_q.put((rank, bool(torch.equal(buf, full))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_level_exchange_world2_gloo():
+    """The per-level GGSW all-gather of a sharded graph run on CPU tensors."""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

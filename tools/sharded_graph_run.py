@@ -1,0 +1,73 @@
+"""Run `programs` two-level encrypted programs (32-bit add, then greater-than) as ONE graph sharded
+over the GPUs of a box (BASELINE config 4's execution model) and report latency.
+launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P tools/sharded_graph_run.py [width] [programs] [runs]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle as O  # key / input generation and decryption only
+import spf_b200
+from spf_b200.circuits import add_then_greater_than
+from spf_b200.multi import NcclExchange, broadcast_compute_key
+
+w = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+programs = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+runs = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+# every rank derives the same keys and inputs from the harness seeds (in production: one broadcast)
+keys = O.Keys()
+client = O.Client(keys)
+kt = [torch.from_numpy(np.ascontiguousarray(a).view(np.float64 if a.dtype == np.complex128 else np.int64)).cuda()
+      for a in (keys.bsk_fft, keys.ksk, keys.ssk_fft, keys.ak_fft)]
+t0 = time.perf_counter()
+broadcast_compute_key(kt, src=0)
+torch.cuda.synchronize()
+bcast_ms = 1e3 * (time.perf_counter() - t0)
+ev = spf_b200.Evaluation(*[t.data_ptr() for t in kt], device=local, on_device=True)
+
+rng = np.random.default_rng(2024)
+vals = [(int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w))) for _ in range(programs)]
+enc = lambda v: [client.encrypt_glwe_l1([(v >> i) & 1]) for i in range(w)]
+a, b, c = ([enc(v[k]) for v in vals] for k in range(3))
+out_sum = [[np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w)] for _ in range(programs)]
+out_gt = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(programs)]
+circ = add_then_greater_than(a, b, c, out_sum, out_gt, programs)
+ex = NcclExchange(rank) if world > 1 else None
+g = spf_b200.CompiledGraph(ev, circ, world=world, rank=rank, exchange=ex)
+times = []
+for _ in range(runs + 1):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    g.run()
+    times.append(1e3 * (time.perf_counter() - t0))
+ok = True
+for (x, y, z), s_bits, gt in zip(vals, out_sum, out_gt):
+    s = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(s_bits))
+    ok &= s == (x + y) % (1 << w) and int(client.decrypt_glwe_l1(gt)[0]) == int(s > z)
+t = torch.tensor([min(times[1:])], dtype=torch.float64, device="cuda")
+oks = torch.tensor([int(ok)], device="cuda")
+if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(json.dumps({"workload": f"{programs} x (add{w} then greater-than) in one graph", "n_gpus": world,
+                      "cbs_per_level": [3 * w * programs, w * programs], "levels": g.levels, "launches": g.launches,
+                      "graph_ms_max_over_ranks": float(t.item()), "correct_on_all_ranks": bool(oks.item()),
+                      "key_broadcast_ms": bcast_ms, "exchanges_per_run": (ex.calls // (runs + 1)) if ex else 0,
+                      "exchange_bytes_per_run": (ex.bytes // (runs + 1)) if ex else 0}))
+if world > 1:
+    dist.destroy_process_group()
