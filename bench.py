@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="CBS per step per GPU (BASELINE config 3: 4096)")
     ap.add_argument("--impl", default="spf_b200", choices=["spf_b200", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=0, help="CBS in the CPU baseline sample (0 = 2 per host thread)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="CBS in the CPU baseline sample (0 = about 10 s of work on all host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-add", action="store_true", help="skip the Parasol 8/32-bit add latency measurement")
@@ -81,6 +81,17 @@ def cbs_lut(n: int = 2048) -> np.ndarray:
     pb = 4 * ((i % 4) + 1) + 1
     lut[n:] = (np.uint64(0) - (np.uint64(1) << (64 - pb).astype(np.uint64)))
     return lut
+
+
+def ncu_traffic(batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one pbs_kernel launch at this batch size, from
+    the committed `ncu --set full` capture (profiles/pbs_kernel_dram_traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "pbs_kernel_dram_traffic.json")))
+        e = t["by_batch"].get(str(batch))
+        return None if e is None else {"bytes_per_launch": e["dram_read_bytes"] + e["dram_write_bytes"], **e, "source": t["source"]}
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -136,6 +147,13 @@ def cpu_cbs_rate(keys, cts: np.ndarray, nthreads: int) -> tuple[float, float]:
     return len(cts) / dt, dt
 
 
+def cpu_sample_size(rate: float, nt: int, batch: int, seconds: float = 10.0) -> int:
+    """CBS in one bounded CPU sample: about `seconds` of work on all host threads, a multiple of the
+    thread count, never more than the GPU batch."""
+    n = int(rate * seconds) // nt * nt
+    return int(max(2 * nt, min(n, batch)))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -144,11 +162,12 @@ def run_reference(args):
 
     keys = O.Keys()
     nt = O.hw_threads()
-    sample = args.cpu_sample or 2 * nt
+    probe_bits = np.random.default_rng(O.INPUT_SEED).integers(0, 2, 2 * nt)
+    probe = encrypt_lwe0_numpy(keys.lwe0_sk, probe_bits, keys.params.lwe_std, O.INPUT_SEED)
+    rate0, _ = cpu_cbs_rate(keys, probe, nt)  # warm-up pass, also sizes the sample
+    sample = args.cpu_sample or cpu_sample_size(rate0, nt, args.batch)
     bits = np.random.default_rng(O.INPUT_SEED).integers(0, 2, sample)
     cts = encrypt_lwe0_numpy(keys.lwe0_sk, bits, keys.params.lwe_std, O.INPUT_SEED)
-    for _ in range(max(args.warmup, 0) and 1):  # one warm-up pass is enough for a CPU loop
-        cpu_cbs_rate(keys, cts[: nt], nt)
     total_t = 0.0
     for _ in range(args.steps):
         _, dt = cpu_cbs_rate(keys, cts, nt)
@@ -387,7 +406,7 @@ def run_gpu(args):
             "hbm": {"achieved": alg_bytes / (pbs_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes / (pbs_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
                     "peak_source": hbm_src},
-            "traffic": None,
+            "traffic": ncu_traffic(B),
         }
         del d_rot, d_glwe, lut
 
@@ -445,8 +464,8 @@ def run_gpu(args):
                 raise SystemExit("bench.py: GPU outputs do not decrypt to the expected plaintexts")
         if world == 1 and not args.no_cpu_baseline:
             nt = O.hw_threads()
-            sample = args.cpu_sample or 2 * nt
-            cpu_cbs_rate(keys, cts[: min(nt, B)], nt)  # warm-up
+            rate0, _ = cpu_cbs_rate(keys, cts[: min(2 * nt, B)], nt)  # warm-up, also sizes the sample
+            sample = args.cpu_sample or cpu_sample_size(rate0, nt, B)
             rate, dt = cpu_cbs_rate(keys, cts[: min(sample, B)], nt)
             cpu_baseline = {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
                             "sample": f"{min(sample, B)} CBS of the same workload in {dt:.1f} s, oracle/spf_oracle.c "
