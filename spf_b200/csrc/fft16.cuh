@@ -60,10 +60,18 @@ SPF_HD C2 csub(C2 a, C2 b) { return C2{a.x - b.x, a.y - b.y}; }
 SPF_HD C2 cmul_cs(C2 a, double c, double s) { return C2{a.x * c - a.y * s, a.x * s + a.y * c}; }
 SPF_HD C2 cmul(C2 a, C2 b) { return C2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 SPF_HD C2 cmul_conj(C2 a, C2 b) { return C2{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }  // a * conj(b)
-// acc += a * b
+// acc += a * b as four chained FMAs (written out: `acc += a.x*b.x - a.y*b.y` compiles to
+// DMUL + DFMA + DADD per component because floating-point adds are not reassociated)
+SPF_HD double spf_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return fma(a, b, c);
+#else
+  return __builtin_fma(a, b, c);
+#endif
+}
 SPF_HD void cmad(C2& acc, C2 a, C2 b) {
-  acc.x += a.x * b.x - a.y * b.y;
-  acc.y += a.x * b.y + a.y * b.x;
+  acc.x = spf_fma(-a.y, b.y, spf_fma(a.x, b.x, acc.x));
+  acc.y = spf_fma(a.y, b.x, spf_fma(a.x, b.y, acc.y));
 }
 
 // 4-point DFT in place: (a,b,c,d) -> (X0,X1,X2,X3); INV uses e^{+...}
@@ -81,32 +89,91 @@ SPF_HD void bfly4(C2& a, C2& b, C2& c, C2& d) {
   }
 }
 
-// 16-point DFT, natural order in -> natural order out, all twiddles compile-time constants.
+// ---- deferred-scale arithmetic --------------------------------------------------------------
+// Inside the in-register transforms a value is a pair (v, s): the true value is s * v, where s is a
+// real constant that is known at compile time once the loops are unrolled (on the device every s
+// below folds into FMA immediates; the host emulator simply computes them).  A rotation by a
+// constant angle then costs 2 FMAs instead of the 4 operations of a complex multiply:
+//   e^{i t} = cos t (1 + i tan t)  or  sin t (cot t + i)     (whichever factor is larger in magnitude)
+// and the factored-out cos / sin goes into s; adding two values of different scale costs one FMA
+// per component (a + (s_b / s_a) b, scale s_a), the same as the plain add.  A 16-point DFT with its
+// inter-stage twiddles therefore needs 128 + 18 instead of 128 + 36 FP64 instructions, the twist of
+// pass 1 30 instead of 60 (Linzer-Feig style FMA butterflies).
+SPF_HD constexpr double spf_abs(double x) { return x < 0 ? -x : x; }
+// (v, s) *= e^{i pi e / 32}
+SPF_HD void rot_s(C2& v, double& s, int e) {
+  e &= 63;
+  if (e == 0) return;
+  const double c = spf_cos32(e), sn = spf_sin32(e);
+  if (spf_abs(c) >= spf_abs(sn)) {
+    const double t = sn / c;
+    v = C2{spf_fma(-t, v.y, v.x), spf_fma(t, v.x, v.y)};
+    s *= c;
+  } else {
+    const double t = c / sn;
+    v = C2{spf_fma(t, v.x, -v.y), spf_fma(t, v.y, v.x)};
+    s *= sn;
+  }
+}
+// 4-point DFT of (a, sa) .. (d, sd); all four results carry scale sa.
 template <bool INV>
-SPF_HD void dft16(C2 (&v)[16]) {
+SPF_HD void bfly4_s(C2& a, C2& b, C2& c, C2& d, double sa, double sb, double sc, double sd) {
+  const double rc = sc / sa, rd = sd / sb, rb = sb / sa;
+  const C2 apc{spf_fma(rc, c.x, a.x), spf_fma(rc, c.y, a.y)}, amc{spf_fma(-rc, c.x, a.x), spf_fma(-rc, c.y, a.y)};
+  const C2 bpd{spf_fma(rd, d.x, b.x), spf_fma(rd, d.y, b.y)}, bmd{spf_fma(-rd, d.x, b.x), spf_fma(-rd, d.y, b.y)};
+  a = C2{spf_fma(rb, bpd.x, apc.x), spf_fma(rb, bpd.y, apc.y)};
+  c = C2{spf_fma(-rb, bpd.x, apc.x), spf_fma(-rb, bpd.y, apc.y)};
+  if (!INV) {
+    b = C2{spf_fma(rb, bmd.y, amc.x), spf_fma(-rb, bmd.x, amc.y)};
+    d = C2{spf_fma(-rb, bmd.y, amc.x), spf_fma(rb, bmd.x, amc.y)};
+  } else {
+    b = C2{spf_fma(-rb, bmd.y, amc.x), spf_fma(rb, bmd.x, amc.y)};
+    d = C2{spf_fma(rb, bmd.y, amc.x), spf_fma(-rb, bmd.x, amc.y)};
+  }
+}
+
+// 16-point DFT, natural order in -> natural order out, all twiddles compile-time constants.
+// Inputs (v[i], s[i]); every output carries the INPUT scale s[0] (each butterfly group takes the
+// scale of its first element, and the first element of every second-layer group descends from
+// v[0] without a twiddle), so the results are plain values whenever s[0] == 1.
+template <bool INV>
+SPF_HD void dft16_s(C2 (&v)[16], double (&s)[16]) {
 #pragma unroll
-  for (int m0 = 0; m0 < 4; m0++) bfly4<INV>(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12]);
-    // v[m0 + 4 kl] = Y[m0][kl];  twiddle W16^{m0 kl}
+  for (int m0 = 0; m0 < 4; m0++) {
+    bfly4_s<INV>(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12], s[m0], s[m0 + 4], s[m0 + 8], s[m0 + 12]);
+    s[m0 + 4] = s[m0 + 8] = s[m0 + 12] = s[m0];
+  }
+  // v[m0 + 4 kl] = Y[m0][kl];  twiddle W16^{m0 kl}
 #pragma unroll
   for (int m0 = 1; m0 < 4; m0++) {
 #pragma unroll
     for (int kl = 1; kl < 4; kl++) {
       const int e = 4 * m0 * kl;  // angle pi*e/32 = 2 pi m0 kl / 16
-      const double c = spf_cos32(e), s = INV ? spf_sin32(e) : -spf_sin32(e);
-      v[m0 + 4 * kl] = cmul_cs(v[m0 + 4 * kl], c, s);
+      rot_s(v[m0 + 4 * kl], s[m0 + 4 * kl], INV ? e : 64 - e);
     }
   }
 #pragma unroll
-  for (int kl = 0; kl < 4; kl++) bfly4<INV>(v[4 * kl], v[4 * kl + 1], v[4 * kl + 2], v[4 * kl + 3]);
+  for (int kl = 0; kl < 4; kl++) {
+    bfly4_s<INV>(v[4 * kl], v[4 * kl + 1], v[4 * kl + 2], v[4 * kl + 3], s[4 * kl], s[4 * kl + 1], s[4 * kl + 2], s[4 * kl + 3]);
+    s[4 * kl + 1] = s[4 * kl + 2] = s[4 * kl + 3] = s[4 * kl];
+  }
   // v[4 kl + kh] = X[kl + 4 kh] -> natural order
   C2 t[16];
+  double ts[16];
 #pragma unroll
-  for (int i = 0; i < 16; i++) t[i] = v[i];
+  for (int i = 0; i < 16; i++) { t[i] = v[i]; ts[i] = s[i]; }
 #pragma unroll
   for (int kl = 0; kl < 4; kl++) {
 #pragma unroll
-    for (int kh = 0; kh < 4; kh++) v[kl + 4 * kh] = t[4 * kl + kh];
+    for (int kh = 0; kh < 4; kh++) { v[kl + 4 * kh] = t[4 * kl + kh]; s[kl + 4 * kh] = ts[4 * kl + kh]; }
   }
+}
+template <bool INV>
+SPF_HD void dft16(C2 (&v)[16]) {
+  double s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = 1.0;
+  dft16_s<INV>(v, s);  // unit input scales -> unit output scales
 }
 
 // ------------------------------------------------------------------------------------------
@@ -115,9 +182,11 @@ SPF_HD void dft16(C2 (&v)[16]) {
 // pass 1 without its thread-dependent twiddle (applied by the caller: table in shared memory
 // below, or the thread's tensor-memory columns in the blind-rotation kernel)
 SPF_HD void fwd_pass1_core(C2 (&v)[16]) {
+  double s[16];
+  s[0] = 1.0;
 #pragma unroll
-  for (int m = 1; m < 16; m++) v[m] = cmul_cs(v[m], spf_cos32(m), spf_sin32(m));
-  dft16<false>(v);
+  for (int m = 1; m < 16; m++) { s[m] = 1.0; rot_s(v[m], s[m], m); }
+  dft16_s<false>(v, s);  // the twist factors fold into the butterflies; outputs carry s[0] = 1
 }
 SPF_HD void fwd_pass1(C2 (&v)[16], int a, const C2* T1) {
   fwd_pass1_core(v);
@@ -192,10 +261,20 @@ SPF_HD void inv_x1_read(C2 (&v)[16], const C2* buf, int a) {
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1++) v[k1] = buf[k1 * kXPad + a];
 }
-SPF_HD void inv_pass1_core(C2 (&v)[16]) {
-  dft16<true>(v);
+// Inverse pass 1 with the untwist left as a deferred scale: true outputs are s[m] * v[m]
+// (consumed by f64_to_torus_s, whose first two operations absorb the factor as FMAs).
+SPF_HD void inv_pass1_core_s(C2 (&v)[16], double (&s)[16]) {
 #pragma unroll
-  for (int m = 1; m < 16; m++) v[m] = cmul_cs(v[m], spf_cos32(m), -spf_sin32(m));
+  for (int i = 0; i < 16; i++) s[i] = 1.0;
+  dft16_s<true>(v, s);
+#pragma unroll
+  for (int m = 1; m < 16; m++) rot_s(v[m], s[m], 64 - m);
+}
+SPF_HD void inv_pass1_core(C2 (&v)[16]) {
+  double s[16];
+  inv_pass1_core_s(v, s);
+#pragma unroll
+  for (int m = 1; m < 16; m++) v[m] = C2{v[m].x * s[m], v[m].y * s[m]};
 }
 SPF_HD void inv_pass1(C2 (&v)[16], int a, const C2* T1) {
 #pragma unroll
@@ -267,33 +346,12 @@ SPF_HD int64_t f64_to_i64_sat(double x) {
 //   r  = trunc(lo +- 0.5)          with the add rounded TOWARD ZERO: doubles >= 2^52 are integers
 //                                   and keep their value, smaller ones get round-half-away exactly.
 // The reference's saturating-cast corner (x = -+2^63 mod 2^64) is kept.
-#ifdef SPF_TORUS_OLD
-SPF_HD uint64_t f64_to_torus(double x) {
-  const double t = x * 5.421010862427522170037e-20;  // 2^-64
-  const double magic = 6755399441055744.0;           // 1.5 * 2^52
-  const double hq = (t + magic) - magic;
-#if defined(__CUDA_ARCH__)
-  double lo = fma(-hq, 18446744073709551616.0, x);
-#else
-  double lo = __builtin_fma(-hq, 18446744073709551616.0, x);
-#endif
-  const uint64_t lb = f64_bits(lo);
-  const uint32_t hi = (uint32_t)(lb >> 32);
-  const uint32_t mag = hi & 0x7FFFFFFFu;
-  const uint32_t adj_hi = (hi & 0x80000000u) | (mag < 0x43300000u ? 0x3FE00000u : 0u);  // +-0.5 or +-0
-  lo += bits_f64((uint64_t)adj_hi << 32);
-  uint64_t r = (uint64_t)f64_to_i64_sat(lo);
-  // |lo| <= 2^63 by construction, so mag == 0x43E00000 means |lo| == 2^63 exactly: the reference's
-  // result then follows the sign of x.  Probability ~2^-53 per coefficient: a real branch.
-  if (__builtin_expect(mag == 0x43E00000u, 0))
-    r = (f64_bits(x) >> 63) ? 0x7FFFFFFFFFFFFFFFull : 0x8000000000000000ull;
-  return r;
-}
-#else
-SPF_HD uint64_t f64_to_torus(double x) {
+// f64_to_torus(sc * xs) with the scale absorbed into the first two operations as FMAs
+template <bool SCALED>
+SPF_HD uint64_t f64_to_torus_impl(double xs, double sc) {
   const double magic = 124615124604835863084731911901282304.0;  // 1.5 * 2^116
-  const double hq = (x + magic) - magic;
-  const double lo = x - hq;
+  const double hq = (SCALED ? spf_fma(sc, xs, magic) : xs + magic) - magic;
+  const double lo = SCALED ? spf_fma(sc, xs, -hq) : xs - hq;
   const uint32_t hi = (uint32_t)(f64_bits(lo) >> 32);
   const double half = bits_f64((uint64_t)((hi & 0x80000000u) | 0x3FE00000u) << 32);  // copysign(0.5, lo)
 #if defined(__CUDA_ARCH__)
@@ -309,10 +367,11 @@ SPF_HD uint64_t f64_to_torus(double x) {
   // |lo| <= 2^63 by construction, so exponent 0x43E means |lo| == 2^63 exactly: the reference's
   // result then follows the sign of x.  Probability ~2^-53 per coefficient: a real branch.
   if (__builtin_expect((hi & 0x7FFFFFFFu) == 0x43E00000u, 0))
-    r = (f64_bits(x) >> 63) ? 0x7FFFFFFFFFFFFFFFull : 0x8000000000000000ull;
+    r = ((f64_bits(xs) ^ (SCALED ? f64_bits(sc) : 0ull)) >> 63) ? 0x7FFFFFFFFFFFFFFFull : 0x8000000000000000ull;  // sign of sc * xs
   return r;
 }
-#endif
+SPF_HD uint64_t f64_to_torus(double x) { return f64_to_torus_impl<false>(x, 1.0); }
+SPF_HD uint64_t f64_to_torus_s(double xs, double sc) { return f64_to_torus_impl<true>(xs, sc); }
 
 // ------------------------------------------------------------------------------------------
 // radix decomposition (math/radix.rs:67-114,155-162; simd/scalar.rs:52-72)

@@ -419,13 +419,14 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       cx.sync();
       inv_x1_read(w, xown, u);
       cx.template t1_mul<true>(w, T1);  // w[k1] *= conj(T1[k1][u])
-      inv_pass1_core(w);
+      double ws[16];
+      inv_pass1_core_s(w, ws);  // true value ws[m] * w[m]: the untwist's real factor rides into the conversion
       cx.own_load(own, pa);  // own[i2] = pa[u + 64 i2] (device: from the thread's tensor-memory copy)
 #pragma unroll
       for (int m = 0; m < 16; m++) {
         const int j = u + 64 * m;
-        own[m] += f64_to_torus(w[m].x);
-        own[m + 16] += f64_to_torus(w[m].y);
+        own[m] += f64_to_torus_s(w[m].x, ws[m]);
+        own[m + 16] += f64_to_torus_s(w[m].y, ws[m]);
         pa[j] = own[m];
         pa[j + kM] = own[m + 16];
       }
