@@ -347,8 +347,12 @@ SPF_HD int64_t f64_to_i64_sat(double x) {
 //                                   and keep their value, smaller ones get round-half-away exactly.
 // The reference's saturating-cast corner (x = -+2^63 mod 2^64) is kept.
 // f64_to_torus(sc * xs) with the scale absorbed into the first two operations as FMAs
-template <bool SCALED>
-SPF_HD uint64_t f64_to_torus_impl(double xs, double sc) {
+// CORNER = false leaves the saturating-cast corner to the caller: *mag_max accumulates the largest
+// |lo| exponent word seen, and a caller that finds kTorusCornerMag in it afterwards redoes its
+// values with f64_to_torus_s (one test per 32 conversions instead of ~8 predicated instructions each).
+constexpr uint32_t kTorusCornerMag = 0x43E00000u;  // high word of 2^63
+template <bool SCALED, bool CORNER>
+SPF_HD uint64_t f64_to_torus_impl(double xs, double sc, uint32_t* mag_max) {
   const double magic = 124615124604835863084731911901282304.0;  // 1.5 * 2^116
   const double hq = (SCALED ? spf_fma(sc, xs, magic) : xs + magic) - magic;
   const double lo = SCALED ? spf_fma(sc, xs, -hq) : xs - hq;
@@ -365,13 +369,21 @@ SPF_HD uint64_t f64_to_torus_impl(double xs, double sc) {
   else r = (uint64_t)(int64_t)y;
 #endif
   // |lo| <= 2^63 by construction, so exponent 0x43E means |lo| == 2^63 exactly: the reference's
-  // result then follows the sign of x.  Probability ~2^-53 per coefficient: a real branch.
-  if (__builtin_expect((hi & 0x7FFFFFFFu) == 0x43E00000u, 0))
-    r = ((f64_bits(xs) ^ (SCALED ? f64_bits(sc) : 0ull)) >> 63) ? 0x7FFFFFFFFFFFFFFFull : 0x8000000000000000ull;  // sign of sc * xs
+  // result then follows the sign of x.  Probability ~2^-53 per coefficient.
+  const uint32_t mag = hi & 0x7FFFFFFFu;
+  if (CORNER) {
+    if (__builtin_expect(mag == kTorusCornerMag, 0))
+      r = ((f64_bits(xs) ^ (SCALED ? f64_bits(sc) : 0ull)) >> 63) ? 0x7FFFFFFFFFFFFFFFull : 0x8000000000000000ull;  // sign of sc * xs
+  } else {
+    *mag_max = mag > *mag_max ? mag : *mag_max;
+  }
   return r;
 }
-SPF_HD uint64_t f64_to_torus(double x) { return f64_to_torus_impl<false>(x, 1.0); }
-SPF_HD uint64_t f64_to_torus_s(double xs, double sc) { return f64_to_torus_impl<true>(xs, sc); }
+SPF_HD uint64_t f64_to_torus(double x) { return f64_to_torus_impl<false, true>(x, 1.0, nullptr); }
+SPF_HD uint64_t f64_to_torus_s(double xs, double sc) { return f64_to_torus_impl<true, true>(xs, sc, nullptr); }
+SPF_HD uint64_t f64_to_torus_s_fast(double xs, double sc, uint32_t& mag_max) {
+  return f64_to_torus_impl<true, false>(xs, sc, &mag_max);
+}
 
 // ------------------------------------------------------------------------------------------
 // radix decomposition (math/radix.rs:67-114,155-162; simd/scalar.rs:52-72)

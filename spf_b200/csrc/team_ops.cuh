@@ -256,6 +256,17 @@ SPF_HD double digit16_to_f64(uint32_t d) {
   return x - 4503599627403264.0;  // 2^52 + 2^15
 }
 
+// Signed 16-bit digit sitting in the LOW half of d (upper half ignored) -> f64 with one IMAD and one
+// DADD: the low word (d << 16) + 2^31 of a double with exponent 2^36 (ulp 2^-16) reads as
+// 2^36 + 2^15 + sext16(d).
+SPF_HD double digit_lo16_to_f64(uint32_t d) {
+  return bits_f64(0x4230000000000000ull | (uint64_t)(uint32_t)(d * 65536u + 0x80000000u)) - 68719509504.0;  // 2^36 + 2^15
+}
+// the same for a digit sitting in the HIGH half of d (lower half ignored): one LOP3 and one DADD
+SPF_HD double digit_hi16_to_f64(uint32_t d) {
+  return bits_f64(0x4230000000000000ull | (uint64_t)(uint32_t)((d & 0xFFFF0000u) ^ 0x80000000u)) - 68719509504.0;
+}
+
 // PAIR-TEAM blind rotation, BIN-SPLIT: one ciphertext = 128 threads = two teams of 64 (half h).
 // Time domain: half h owns GLWE polynomial h (decomposition of acc[h]*X^a - acc[h], passes 1-2 of
 // its two forward FFTs, passes 2-1 of its inverse FFT, accumulator update).  Frequency domain:
@@ -354,16 +365,19 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       // of coefficient j = u + 64 i2 is (u - a~ + 64 i2) mod 2N: bit 11 = negacyclic sign.
       {
         const int base = (u - at) & (2 * kN - 1);
-        const int low6 = base & 63, bh = base >> 6;
+        // byte address of source row tt = (base >> 6) + i2 (mod 32) of this thread's column:
+        // rows are 512 B apart, so the row index lives in bits 9..13 of the offset
+        const char* col = reinterpret_cast<const char*>(pa) + 8 * (base & 63);
+        const uint32_t bh9 = (uint32_t)(base >> 6) << 9;
 #pragma unroll
         for (int i2 = 0; i2 < 32; i2++) {
-          const int tt = bh + i2;
-          const uint64_t x = pa[((tt & 31) << 6) | low6];
-          const uint64_t diff = ((tt & 32) ? 0 - x : x) - own[i2];
+          const uint32_t t9 = bh9 + 512u * i2;  // bit 14 = negacyclic sign
+          const uint64_t x = *reinterpret_cast<const uint64_t*>(col + (t9 & 0x3E00u));
+          const uint64_t diff = ((t9 & 0x4000u) ? 0 - x : x) - own[i2];
           const uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
-          const uint32_t d1 = (w + 0x8000u) >> 16;  // second digit: (w >> 16) + carry of the first
-          if (i2 < 16) { v[i2].x = digit16_to_f64(w); pk[i2] = d1; }
-          else { v[i2 - 16].y = digit16_to_f64(w); pk[i2 - 16] |= d1 << 16; }
+          const uint32_t w1 = w + 0x8000u;  // high half = second digit: (w >> 16) + carry of the first
+          if (i2 < 16) { v[i2].x = digit_lo16_to_f64(w); pk[i2] = w1 >> 16; }
+          else { v[i2 - 16].y = digit_lo16_to_f64(w); pk[i2 - 16] |= w1 & 0xFFFF0000u; }
         }
       }
 #pragma unroll
@@ -371,7 +385,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         const int level = 1 - t;  // LSB digit <-> last GLEV level (fft_ops.rs:92)
         if (t == 1) {
 #pragma unroll
-          for (int m = 0; m < 16; m++) { v[m].x = digit16_to_f64(pk[m]); v[m].y = digit16_to_f64(pk[m] >> 16); }
+          for (int m = 0; m < 16; m++) { v[m].x = digit_lo16_to_f64(pk[m]); v[m].y = digit_hi16_to_f64(pk[m]); }
         }
         fwd_pass1_core(v);
         cx.template t1_mul<false>(v, T1);  // v[k1] *= T1[k1][u]
@@ -422,13 +436,32 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       double ws[16];
       inv_pass1_core_s(w, ws);  // true value ws[m] * w[m]: the untwist's real factor rides into the conversion
       cx.own_load(own, pa);  // own[i2] = pa[u + 64 i2] (device: from the thread's tensor-memory copy)
+      // The saturating-cast corner of the conversion (probability ~2^-53 per value) is tested once
+      // per 8 values: the fast conversion only tracks the largest exponent word it saw.
 #pragma unroll
-      for (int m = 0; m < 16; m++) {
-        const int j = u + 64 * m;
-        own[m] += f64_to_torus_s(w[m].x, ws[m]);
-        own[m + 16] += f64_to_torus_s(w[m].y, ws[m]);
-        pa[j] = own[m];
-        pa[j + kM] = own[m + 16];
+      for (int m4 = 0; m4 < 16; m4 += 4) {
+        uint32_t mag_max = 0;
+        uint64_t r[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          r[2 * i] = f64_to_torus_s_fast(w[m4 + i].x, ws[m4 + i], mag_max);
+          r[2 * i + 1] = f64_to_torus_s_fast(w[m4 + i].y, ws[m4 + i], mag_max);
+        }
+        if (__builtin_expect(mag_max == kTorusCornerMag, 0)) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            r[2 * i] = f64_to_torus_s(w[m4 + i].x, ws[m4 + i]);
+            r[2 * i + 1] = f64_to_torus_s(w[m4 + i].y, ws[m4 + i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int m = m4 + i, j = u + 64 * m;
+          own[m] += r[2 * i];
+          own[m + 16] += r[2 * i + 1];
+          pa[j] = own[m];
+          pa[j + kM] = own[m + 16];
+        }
       }
       cx.own_store(own);
     }
