@@ -208,16 +208,21 @@ SPF_HD void fwd_pass2(C2 (&v)[16], int u, const C2* T2) {
 #pragma unroll
   for (int k2 = 1; k2 < 16; k2++) v[k2] = cmul(v[k2], T2[q * kT2Pad + k2]);
 }
+// Second exchange, IN PLACE: thread (k1, q) stores z[k2] at (row k1, column q + 4 k2), exactly the
+// 16 locations it has just read in fwd_x1_read, so no barrier is needed between that read and this
+// write (each thread only overwrites what it alone consumed).  The reader of pass 3, thread
+// (k1, q), finds z of thread (k1, q') for k2 = q + 4 j at column q' + 4 q + 16 j of row k1.
 SPF_HD void fwd_x2_write(const C2 (&v)[16], C2* buf, int u) {
+  const int k1 = u & 15, q = u >> 4;
 #pragma unroll
-  for (int k2 = 0; k2 < 16; k2++) buf[k2 * kXPad + u] = v[k2];
+  for (int k2 = 0; k2 < 16; k2++) buf[k1 * kXPad + q + 4 * k2] = v[k2];
 }
 SPF_HD void fwd_x2_read(C2 (&v)[16], const C2* buf, int u) {
   const int k1 = u & 15, q = u >> 4;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
 #pragma unroll
-    for (int qp = 0; qp < 4; qp++) v[4 * j + qp] = buf[(q + 4 * j) * kXPad + k1 + 16 * qp];
+    for (int qp = 0; qp < 4; qp++) v[4 * j + qp] = buf[k1 * kXPad + qp + 4 * q + 16 * j];
   }
 }
 SPF_HD void fwd_pass3(C2 (&v)[16]) {
@@ -234,17 +239,20 @@ SPF_HD void inv_pass3(C2 (&v)[16]) {
 #pragma unroll
   for (int j = 0; j < 4; j++) bfly4<true>(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
+// Inverse direction, same in-place layout: inv_x2_read takes the 16 locations (row k1, column
+// q + 4 k2) that inv_x1_write of the same thread overwrites next, so no barrier separates them.
 SPF_HD void inv_x2_write(const C2 (&v)[16], C2* buf, int u) {
   const int k1 = u & 15, q = u >> 4;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
 #pragma unroll
-    for (int qp = 0; qp < 4; qp++) buf[(q + 4 * j) * kXPad + k1 + 16 * qp] = v[4 * j + qp];
+    for (int qp = 0; qp < 4; qp++) buf[k1 * kXPad + qp + 4 * q + 16 * j] = v[4 * j + qp];
   }
 }
 SPF_HD void inv_x2_read(C2 (&v)[16], const C2* buf, int u) {
+  const int k1 = u & 15, q = u >> 4;
 #pragma unroll
-  for (int k2 = 0; k2 < 16; k2++) v[k2] = buf[k2 * kXPad + u];
+  for (int k2 = 0; k2 < 16; k2++) v[k2] = buf[k1 * kXPad + q + 4 * k2];
 }
 SPF_HD void inv_pass2(C2 (&v)[16], int u, const C2* T2) {
   const int q = u >> 4;

@@ -59,8 +59,7 @@ SPF_HD void team_fft_fwd(Cx& cx, C2 (&v)[16], C2* xbuf, const C2* T1, const C2* 
   cx.sync();
   fwd_x1_read(v, xbuf, cx.u);
   fwd_pass2(v, cx.u, T2);
-  cx.sync();
-  fwd_x2_write(v, xbuf, cx.u);
+  fwd_x2_write(v, xbuf, cx.u);  // in place: overwrites only what this thread has just read
   cx.sync();
   fwd_x2_read(v, xbuf, cx.u);
   fwd_pass3(v);
@@ -73,8 +72,7 @@ SPF_HD void team_fft_inv(Cx& cx, C2 (&v)[16], C2* xbuf, const C2* T1, const C2* 
   cx.sync();
   inv_x2_read(v, xbuf, cx.u);
   inv_pass2(v, cx.u, T2);
-  cx.sync();
-  inv_x1_write(v, xbuf, cx.u);
+  inv_x1_write(v, xbuf, cx.u);  // in place
   cx.sync();
   inv_x1_read(v, xbuf, cx.u);
   inv_pass1(v, cx.u, T1);
@@ -297,7 +295,7 @@ SPF_HD void mad_split(C2 (&f)[2][8], const C2* xbb, const C2* g /* GGSW row b, l
   for (int jj = 0; jj < 2; jj++) {
     C2 d[4], g0[4], g1[4];
 #pragma unroll
-    for (int qp = 0; qp < 4; qp++) d[qp] = xbb[(q + 4 * (2 * h + jj)) * kXPad + k1 + 16 * qp];
+    for (int qp = 0; qp < 4; qp++) d[qp] = xbb[k1 * kXPad + qp + 4 * q + 16 * (2 * h + jj)];
 #pragma unroll
     for (int k3 = 0; k3 < 4; k3++) {
       g0[k3] = ldg_c2_pinned(g + split_bin(u, h, 4 * jj + k3));
@@ -395,8 +393,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         fwd_x1_read(v, xown, u);
         dft16<false>(v);
         cx.template t2_mul<false>(v, T2);  // v[k2] *= W64^(q k2)
-        cx.sync();
-        fwd_x2_write(v, xown, u);
+        fwd_x2_write(v, xown, u);  // in place: no barrier after fwd_x1_read
         if (t == 1) cx.f_load(f);
         cx.pair_sync();
         if (t == 0) mad_split<true>(f, xb, ggsw + (size_t)((0 * 2 + level) * 2) * kM, u, h);
@@ -411,14 +408,14 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       bfly4<true>(f[p][0], f[p][1], f[p][2], f[p][3]);
       bfly4<true>(f[p][4], f[p][5], f[p][6], f[p][7]);
     }
-    cx.pair_sync();  // both halves have consumed the level-1 spectra
+    // in place: every thread overwrites exactly the 8 locations per buffer it read in mad_split
 #pragma unroll
     for (int p = 0; p < 2; p++) {
 #pragma unroll
       for (int jj = 0; jj < 2; jj++) {
 #pragma unroll
         for (int qp = 0; qp < 4; qp++)
-          xb[p * kXBuf + (q + 4 * (2 * h + jj)) * kXPad + k1 + 16 * qp] = f[p][4 * jj + qp];
+          xb[p * kXBuf + k1 * kXPad + qp + 4 * q + 16 * (2 * h + jj)] = f[p][4 * jj + qp];
       }
     }
     cx.pair_sync();
@@ -428,8 +425,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       inv_x2_read(w, xown, u);
       cx.template t2_mul<true>(w, T2);
       dft16<true>(w);
-      cx.sync();
-      inv_x1_write(w, xown, u);
+      inv_x1_write(w, xown, u);  // in place: no barrier after inv_x2_read
       cx.sync();
       inv_x1_read(w, xown, u);
       cx.template t1_mul<true>(w, T1);  // w[k1] *= conj(T1[k1][u])
