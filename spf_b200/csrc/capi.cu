@@ -34,6 +34,7 @@ struct spf_b200_ctx {
   spf_params p{};
   C2 *bsk = nullptr, *ak = nullptr, *ssk = nullptr;
   uint64_t* ksk = nullptr;
+  uint64_t* ksk_colsum = nullptr;  // keyswitch_kernel's per-block column sums of the KSK
   C2 *T1 = nullptr, *T2 = nullptr;
   uint32_t* kinv = nullptr;
   cudaStream_t stream[2] = {nullptr, nullptr};
@@ -168,8 +169,15 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
   CUB(cudaFuncSetAttribute(pbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPbsSmem));
   CUB(cudaFuncSetAttribute(trace_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
   CUB(cudaFuncSetAttribute(cmux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCmuxSmem));
-  CUB(cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           kKsBatch * (int)(params->glwe_k * params->glwe_n) * 4));
+  {
+    const int ks_smem = kKsBatch * (int)(params->glwe_k * params->glwe_n + kKsBlock) * 4;
+    switch (params->ks.count) {
+#define SPF_KS_CASE(L) case L: CUB(cudaFuncSetAttribute(keyswitch_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, ks_smem)); break;
+      SPF_KS_CASE(1) SPF_KS_CASE(2) SPF_KS_CASE(3) SPF_KS_CASE(4) SPF_KS_CASE(5) SPF_KS_CASE(6) SPF_KS_CASE(7) SPF_KS_CASE(8)
+#undef SPF_KS_CASE
+      default: break;
+    }
+  }
   // constant tables
   {
     std::vector<C2> T1(kT1Elems), T2(kT2Elems);
@@ -197,6 +205,14 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
       launch_scale(ctx, ctx->ssk, ctx->ssk, ssk_len, 1.0 / 1024.0, ctx->stream[0]) ||
       launch_scale(ctx, ctx->ak, ctx->ak, ak_len, 1.0 / 1024.0, ctx->stream[0]))
     return bail(SPF_E_CUDA);
+  {  // per-block column sums of the KSK for the unsigned-digit keyswitch (kernels.cuh K4)
+    const int n1 = (int)(params->glwe_k * params->glwe_n), cols = (int)params->lwe_n + 1;
+    const int nblk = (n1 + kKsBlock - 1) / kKsBlock;
+    CUB(cudaMalloc(&ctx->ksk_colsum, sizeof(uint64_t) * (size_t)nblk * cols));
+    ksk_colsum_kernel<<<dim3((cols + 127) / 128, nblk), 128, 0, ctx->stream[0]>>>(ctx->ksk_colsum, ctx->ksk, n1,
+                                                                                   (int)params->ks.count, cols);
+    CUB(cudaGetLastError());
+  }
   CUB(cudaStreamSynchronize(ctx->stream[0]));
 #undef CUB
   *out = ctx;
@@ -289,6 +305,7 @@ int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, s
   P.out = d_out;
   P.in = d_in;
   P.ksk = ctx->ksk;
+  P.colsum = ctx->ksk_colsum;
   P.ptrs = ptrs;
   P.batch = (int)batch;
   P.n1 = (int)(ctx->p.glwe_k * ctx->p.glwe_n);
@@ -301,11 +318,17 @@ int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, s
   // split the sweep over the n1 mask elements so that at least ~2 CTAs per SM are in flight even
   // for small batches (a single CTA streaming the whole 62.7 MB KSK is latency-bound)
   int splits = 1;
-  while (tiles * splits < 2 * ctx->sm_count && splits < 64 && (P.n1 / (splits * 2)) >= 16) splits *= 2;
-  P.slice = (P.n1 + splits - 1) / splits;
+  while (tiles * splits < 2 * ctx->sm_count && splits < 64 && (P.n1 / (splits * 2)) >= kKsBlock) splits *= 2;
+  P.slice = ((P.n1 + splits - 1) / splits + kKsBlock - 1) / kKsBlock * kKsBlock;  // whole column-sum blocks
+  splits = (P.n1 + P.slice - 1) / P.slice;
   if (splits > 1) CU(cudaMemsetAsync(d_out, 0, batch * (size_t)(P.n0 + 1) * 8, s));
   dim3 grid(tiles, splits);
-  keyswitch_kernel<<<grid, kKsThreads, (size_t)kKsBatch * P.slice * 4, s>>>(P);
+  const size_t smem = (size_t)kKsBatch * P.slice * 4;
+  switch (P.count) {  // the level count is a template parameter (fully unrolled digit loop)
+#define SPF_KS_CASE(L) case L: keyswitch_kernel<L><<<grid, kKsThreads, smem, s>>>(P); break;
+    SPF_KS_CASE(1) SPF_KS_CASE(2) SPF_KS_CASE(3) SPF_KS_CASE(4) SPF_KS_CASE(5) SPF_KS_CASE(6) SPF_KS_CASE(7) SPF_KS_CASE(8)
+#undef SPF_KS_CASE
+  }
   return check_launch(ctx, "keyswitch_kernel");
 }
 
@@ -459,7 +482,7 @@ void spf_b200_destroy(spf_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  cudaFree(ctx->bsk); cudaFree(ctx->ak); cudaFree(ctx->ssk); cudaFree(ctx->ksk);
+  cudaFree(ctx->bsk); cudaFree(ctx->ak); cudaFree(ctx->ssk); cudaFree(ctx->ksk); cudaFree(ctx->ksk_colsum);
   cudaFree(ctx->T1); cudaFree(ctx->T2); cudaFree(ctx->kinv); cudaFree(ctx->consts);
   for (int i = 0; i < 2; i++) {
     for (DevBuf& b : ctx->scratch[i]) cudaFree(b.p);

@@ -400,6 +400,15 @@ SPF_HD uint64_t radix_round(uint64_t x, int radix_log, int count) {
   const int shift = 64 - radix_log * count;
   return (x >> shift) + ((x >> (shift - 1)) & 1);
 }
+// Balanced digits without a carry chain: with r = radix_round(x) and r' = r + sum_t (B/2) B^t, the
+// bit field t of r' is the UNSIGNED digit u_t = d_t + B/2 of the balanced representation
+// (sum d_t B^t = r mod B^count, d_t in [-B/2, B/2)), which is unique -- so d_t = u_t - B/2 equals what
+// PolynomialRadixIterator (math/radix.rs:81-113) emits LSB first with its carry.
+SPF_HD uint64_t radix_offset(int radix_log, int count) {
+  uint64_t o = 0;
+  for (int t = 0; t < count; t++) o += (1ull << (radix_log - 1)) << (t * radix_log);
+  return o;
+}
 // one vector_next_decomp step on a scalar; returns the signed digit
 SPF_HD int32_t next_digit(uint64_t& s, int radix_log) {
   const uint64_t mask = (1ull << radix_log) - 1;

@@ -387,32 +387,69 @@ __global__ void __launch_bounds__(kCmuxTeams * kTeam, 1) cmux_kernel(CmuxBatch P
 // kKsBatch ciphertexts.  The rows of mask element i+1 are prefetched into registers while
 // element i is accumulated.  With more than one slice the partial sums are combined with u64
 // atomics into a zero-initialised output (wrapping adds commute, so the result is bit-exact).
+//
+// Balanced digits d in [-B/2, B/2) are handled as UNSIGNED digits u = d + B/2 read straight out of
+// the bit fields of round(a_i) + sum_t (B/2) B^t (no carry chain, see radix_offset), so that one
+// u64 multiply-add is two 32-bit IMADs (IMAD.WIDE.U32 for the low word, IMAD for the high word);
+// the surplus (B/2) * sum_{i,t} KSK[i][t] is a constant of the key, precomputed per block of
+// kKsBlock mask elements (ksk_colsum_kernel) and subtracted once per CTA.
 // ------------------------------------------------------------------------------------------
 constexpr int kKsBatch = 16;
 constexpr int kKsThreads = 320;
 constexpr int kKsMaxLevels = 8;
+constexpr int kKsBlock = 32;  // mask elements per precomputed column-sum block; slices are multiples of it
 
 struct KsBatch {
   uint64_t* out;        // [B][n0+1]
   const uint64_t* in;   // [B][n1+1]
   const uint64_t* ksk;  // [n1][l][n0+1]
+  const uint64_t* colsum;  // [ceil(n1 / kKsBlock)][n0+1]: sum over the block's i and all levels of ksk
   const void* const* ptrs;  // optional device table: ptrs[b] = L1 LWE input of item b
   int batch, n1, n0, radix_log, count;
-  int slice;            // mask elements per grid.y slice (n1 when not split)
+  int slice;            // mask elements per grid.y slice (n1 when not split), a multiple of kKsBlock
 };
 
+// colsum[blk][c] = sum_{i in block blk} sum_t ksk[i][t][c]   (one thread per (blk, c); run once per key)
+__global__ void ksk_colsum_kernel(uint64_t* colsum, const uint64_t* ksk, int n1, int levels, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, blk = blockIdx.y;
+  if (c >= cols) return;
+  uint64_t acc = 0;
+  const int i1 = min(n1, (blk + 1) * kKsBlock);
+  for (int i = blk * kKsBlock; i < i1; i++)
+    for (int t = 0; t < levels; t++) acc += ksk[((size_t)i * levels + t) * cols + c];
+  colsum[(size_t)blk * cols + c] = acc;
+}
+
+// acc += k * u (mod 2^64) for a 32-bit u as two IMADs: the compiler does not form the accumulating
+// IMAD.WIDE from C (it multiplies, then adds with carry: 5 instructions).
+__device__ __forceinline__ void mad_u64_u32(uint64_t& acc, uint64_t k, uint32_t u) {
+  asm("{\n\t"
+      ".reg .u32 klo, khi, alo, ahi;\n\t"
+      "mov.b64 {klo, khi}, %1;\n\t"
+      "mad.wide.u32 %0, klo, %2, %0;\n\t"
+      "mov.b64 {alo, ahi}, %0;\n\t"
+      "mad.lo.u32 ahi, khi, %2, ahi;\n\t"
+      "mov.b64 %0, {alo, ahi};\n\t"
+      "}"
+      : "+l"(acc)
+      : "l"(k), "r"(u));
+}
+
+template <int L>
 __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t* st = reinterpret_cast<uint32_t*>(smem);  // [kKsBatch][slice] rounded states (l*logB <= 32 bits)
+  uint32_t* st = reinterpret_cast<uint32_t*>(smem);  // [kKsBatch][slice] rounded + offset states (l*logB <= 31 bits)
   const int b0 = blockIdx.x * kKsBatch;
   const int nb = min(kKsBatch, P.batch - b0);
   const int i_begin = blockIdx.y * P.slice;
   const int ni = min(P.slice, P.n1 - i_begin);
   const bool split = gridDim.y > 1;
+  const uint32_t off = (uint32_t)radix_offset(P.radix_log, P.count);
   for (int idx = threadIdx.x; idx < kKsBatch * ni; idx += blockDim.x) {
     const int b = idx / ni, i = idx % ni;
     const uint64_t* src = b < nb ? (P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + b]) : P.in + (size_t)(b0 + b) * (P.n1 + 1)) : nullptr;
-    st[b * P.slice + i] = src ? (uint32_t)radix_round(src[i_begin + i], P.radix_log, P.count) : 0u;
+    // padding rows of a ragged tile get the all-(B/2) state: unsigned digits B/2 = signed digits 0
+    st[b * P.slice + i] = (src ? (uint32_t)radix_round(src[i_begin + i], P.radix_log, P.count) : 0u) + off;
   }
   __syncthreads();
   const int cols = P.n0 + 1;
@@ -422,17 +459,14 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
 #pragma unroll
   for (int b = 0; b < kKsBatch; b++) { acc0[b] = 0; acc1[b] = 0; }
   const uint32_t mask = (1u << P.radix_log) - 1;
-  const int L = P.count;
-  uint64_t k0[kKsMaxLevels], k1[kKsMaxLevels], n0v[kKsMaxLevels], n1v[kKsMaxLevels];
-  auto load_rows = [&](int i, uint64_t (&r0)[kKsMaxLevels], uint64_t (&r1)[kKsMaxLevels]) {
+  uint64_t k0[L], k1[L], n0v[L], n1v[L];
+  auto load_rows = [&](int i, uint64_t (&r0)[L], uint64_t (&r1)[L]) {
     const uint64_t* row = P.ksk + (size_t)(i_begin + i) * L * cols;
 #pragma unroll
-    for (int t = 0; t < kKsMaxLevels; t++) {
-      if (t < L) {  // digit t (LSB first) pairs with level l-1-t (lev_ciphertext_ops.rs:36)
-        const uint64_t* r = row + (size_t)(L - 1 - t) * cols;
-        r0[t] = has0 ? __ldg(reinterpret_cast<const unsigned long long*>(r + c0)) : 0;
-        r1[t] = has1 ? __ldg(reinterpret_cast<const unsigned long long*>(r + c1)) : 0;
-      }
+    for (int t = 0; t < L; t++) {  // digit t (LSB first) pairs with level l-1-t (lev_ciphertext_ops.rs:36)
+      const uint64_t* r = row + (size_t)(L - 1 - t) * cols;
+      r0[t] = has0 ? __ldg(reinterpret_cast<const unsigned long long*>(r + c0)) : 0;
+      r1[t] = has1 ? __ldg(reinterpret_cast<const unsigned long long*>(r + c1)) : 0;
     }
   };
   if (ni > 0) load_rows(0, k0, k1);
@@ -442,20 +476,24 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
     for (int b = 0; b < kKsBatch; b++) {
       uint32_t s = st[b * P.slice + i];
 #pragma unroll
-      for (int t = 0; t < kKsMaxLevels; t++) {
-        if (t < L) {
-          const uint32_t digit = s & mask;
-          const uint32_t carry = digit >> (P.radix_log - 1);
-          s = (s >> P.radix_log) + carry;
-          const int64_t d = (int64_t)digit - ((int64_t)carry << P.radix_log);
-          acc0[b] += k0[t] * (uint64_t)d;
-          acc1[b] += k1[t] * (uint64_t)d;
-        }
+      for (int t = 0; t < L; t++) {
+        const uint32_t u = s & mask;  // unsigned digit = signed digit + B/2
+        s >>= P.radix_log;
+        mad_u64_u32(acc0[b], k0[t], u);
+        mad_u64_u32(acc1[b], k1[t], u);
       }
     }
 #pragma unroll
-    for (int t = 0; t < kKsMaxLevels; t++) { k0[t] = n0v[t]; k1[t] = n1v[t]; }
+    for (int t = 0; t < L; t++) { k0[t] = n0v[t]; k1[t] = n1v[t]; }
   }
+  // (B/2) * sum of this slice's KSK rows
+  uint64_t s0 = 0, s1 = 0;
+  for (int blk = i_begin / kKsBlock; blk * kKsBlock < i_begin + ni; blk++) {
+    if (has0) s0 += P.colsum[(size_t)blk * cols + c0];
+    if (has1) s1 += P.colsum[(size_t)blk * cols + c1];
+  }
+  s0 <<= P.radix_log - 1;
+  s1 <<= P.radix_log - 1;
 #pragma unroll
   for (int b = 0; b < kKsBatch; b++) {
     if (b >= nb) break;
@@ -463,8 +501,8 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
     uint64_t body = 0;
     if (blockIdx.y == 0)
       body = (P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + b]) : P.in + (size_t)(b0 + b) * (P.n1 + 1))[P.n1];
-    const uint64_t v0 = (c0 == P.n0 ? body : 0) - acc0[b];
-    const uint64_t v1 = (c1 == P.n0 ? body : 0) - acc1[b];
+    const uint64_t v0 = (c0 == P.n0 ? body : 0) - (acc0[b] - s0);
+    const uint64_t v1 = (c1 == P.n0 ? body : 0) - (acc1[b] - s1);
     if (split) {
       if (has0) atomicAdd(reinterpret_cast<unsigned long long*>(o + c0), (unsigned long long)v0);
       if (has1) atomicAdd(reinterpret_cast<unsigned long long*>(o + c1), (unsigned long long)v1);

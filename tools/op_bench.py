@@ -1,0 +1,97 @@
+"""Per-op device throughput for the ops of parasol_runtime/benches/fhe_ops.rs:40-85 (cmux, keyswitch,
+sample extract, circuit bootstrap, PBS) with inputs resident in HBM, next to the CPU port's
+single-thread time per op.  HBM-bound ops are reported against MEASURED_PEAKS.json's copy bandwidth
+with the algorithmic bytes of SURVEY.md 8(d).  usage: python tools/op_bench.py [batch]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle as O  # keygen / CPU timing only
+import spf_b200
+from bench import encrypt_lwe0_numpy
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+dev = torch.device("cuda", 0)
+keys = O.Keys()
+client = O.Client(keys)
+ev = spf_b200.Evaluation(keys.bsk_fft, keys.ksk, keys.ssk_fft, keys.ak_fft)
+stream = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(stream)
+s = stream.cuda_stream
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+try:
+    hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    hbm = 6650.0
+rng = np.random.default_rng(3)
+
+
+def timed(fn, reps=3):
+    fn()
+    ms = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return min(ms)
+
+
+def rand_u64(*shape):
+    return torch.from_numpy(rng.integers(0, 1 << 63, shape, dtype=np.int64)).to(dev)
+
+
+rows = []
+# ---- CMUX: one selector per op (the runtime's CMux nodes), 360 448 algorithmic bytes per op ----
+one = client.encrypt_ggsw_l1(1)
+sel = torch.from_numpy(np.ascontiguousarray(one).view(np.float64)).to(dev)
+d_sel = torch.empty(B * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
+ev.dev_fft_rescale(d_sel.data_ptr(), sel.data_ptr(), ev.len_ggsw, to_device=True, stream=s)  # reference -> device scale
+d_sel.view(B, -1)[1:] = d_sel.view(B, -1)[0]
+a, b, out = rand_u64(B, ev.len_glwe), rand_u64(B, ev.len_glwe), rand_u64(B, ev.len_glwe)
+ms = timed(lambda: ev.dev_cmux(out.data_ptr(), d_sel.data_ptr(), ev.len_ggsw, a.data_ptr(), b.data_ptr(), B, stream=s))
+bytes_op = ev.len_ggsw * 16 + 3 * ev.len_glwe * 8
+rows.append({"op": "cmux", "batch": B, "ms": ms, "ops_per_s": B / ms * 1e3, "algorithmic_gb_s": B * bytes_op / ms / 1e6,
+             "hbm_frac": B * bytes_op / ms / 1e6 / hbm})
+del d_sel, a, b, out
+# ---- keyswitch L1 -> L0: KSK read once per 16 ciphertexts ----
+l1 = rand_u64(B, ev.len_lwe_l1)
+l0 = torch.empty(B * ev.len_lwe_l0, dtype=torch.int64, device=dev)
+ms = timed(lambda: ev.dev_keyswitch_lwe_l1_lwe_l0(l0.data_ptr(), l1.data_ptr(), B, stream=s))
+ksk_bytes = keys.ksk.nbytes
+alg = ksk_bytes + B * (ev.len_lwe_l1 + ev.len_lwe_l0) * 8
+rows.append({"op": "keyswitch_l1_l0", "batch": B, "ms": ms, "ops_per_s": B / ms * 1e3, "algorithmic_gb_s": alg / ms / 1e6,
+             "hbm_frac": alg / ms / 1e6 / hbm, "u64_mad_per_s": B * 2048 * 6 * 638 / ms * 1e3,
+             "note": "integer MAD bound for large batches: the KSK is swept once per 16 ciphertexts from L2"})
+# ---- sample extract ----
+g = rand_u64(B, ev.len_glwe)
+l1o = torch.empty(B * ev.len_lwe_l1, dtype=torch.int64, device=dev)
+ms = timed(lambda: ev.dev_sample_extract_l1(l1o.data_ptr(), g.data_ptr(), 0, 0, B, stream=s))
+alg = B * (ev.len_glwe // 2 + ev.len_lwe_l1) * 8  # reads the a polynomial + one b coefficient
+rows.append({"op": "sample_extract", "batch": B, "ms": ms, "ops_per_s": B / ms * 1e3, "algorithmic_gb_s": alg / ms / 1e6,
+             "hbm_frac": alg / ms / 1e6 / hbm})
+del g, l1o, l1, l0
+# ---- CBS and PBS ----
+bits = rng.integers(0, 2, B)
+cts = torch.from_numpy(encrypt_lwe0_numpy(keys.lwe0_sk, bits, keys.params.lwe_std, 5).view(np.int64)).to(dev)
+ggsw = torch.empty(B * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
+ms = timed(lambda: ev.dev_circuit_bootstrap(ggsw.data_ptr(), cts.data_ptr(), B, reference_scale=False, stream=s), reps=2)
+rows.append({"op": "circuit_bootstrap", "batch": B, "ms": ms, "ops_per_s": B / ms * 1e3, "fp64_tflops": 293.3e6 * B / ms / 1e9})
+for r in rows:
+    print(json.dumps(r), flush=True)
+# ---- CPU port, single thread, one op each (the reference's bench measures exactly these) ----
+cpu = {}
+g0, g1 = client.encrypt_glwe_l1([0]), client.encrypt_glwe_l1([1])
+t0 = time.perf_counter(); O.cmux(keys, g0, g1, one); cpu["cmux_ms"] = 1e3 * (time.perf_counter() - t0)
+l1c = O.sample_extract(keys, g1, 0)
+t0 = time.perf_counter(); O.sample_extract(keys, g1, 0); cpu["sample_extract_ms"] = 1e3 * (time.perf_counter() - t0)
+t0 = time.perf_counter(); l0c = O.keyswitch_lwe(keys, l1c); cpu["keyswitch_ms"] = 1e3 * (time.perf_counter() - t0)
+t0 = time.perf_counter(); O.circuit_bootstrap(keys, l0c); cpu["circuit_bootstrap_ms"] = 1e3 * (time.perf_counter() - t0)
+print(json.dumps({"cpu_port_single_thread": cpu}), flush=True)
