@@ -106,6 +106,42 @@ void run_team(Body body) {
   pthread_barrier_destroy(&bar);
 }
 
+// 8 teams of one CTA (cmux_wide): one barrier per team and one for all 512 threads
+struct HostWideCx {
+  int u, team;
+  pthread_barrier_t* bar_team;
+  pthread_barrier_t* bar_cta;
+  void sync() { pthread_barrier_wait(bar_team); }
+  void cta_sync() { pthread_barrier_wait(bar_cta); }
+};
+template <class Body>
+struct WideLaunch {
+  Body* body;
+  HostWideCx cx;
+  static void* run(void* p) {
+    WideLaunch* l = (WideLaunch*)p;
+    (*l->body)(l->cx);
+    return nullptr;
+  }
+};
+template <class Body>
+void run_wide(Body body) {
+  const int nt = kWideTeams * kTeam;
+  pthread_barrier_t team[kWideTeams], cta;
+  for (int i = 0; i < kWideTeams; i++) pthread_barrier_init(&team[i], nullptr, kTeam);
+  pthread_barrier_init(&cta, nullptr, nt);
+  std::vector<WideLaunch<Body>> ls(nt);
+  std::vector<pthread_t> th(nt);
+  for (int t = 0; t < nt; t++) {
+    ls[t].body = &body;
+    ls[t].cx = HostWideCx{t % kTeam, t / kTeam, &team[t / kTeam], &cta};
+    pthread_create(&th[t], nullptr, WideLaunch<Body>::run, &ls[t]);
+  }
+  for (int t = 0; t < nt; t++) pthread_join(th[t], nullptr);
+  for (int i = 0; i < kWideTeams; i++) pthread_barrier_destroy(&team[i]);
+  pthread_barrier_destroy(&cta);
+}
+
 struct Tables {
   std::vector<C2> T1, T2;
   Tables() : T1(kT1Elems), T2(kT2Elems) { fill_twiddle_tables(T1.data(), T2.data()); }
@@ -169,6 +205,16 @@ void emu_cmux(uint64_t* out, const uint64_t* d0, const uint64_t* d1, const C2* g
   });
 }
 
+// the latency-oriented 8-team version of the same op (count must be 4)
+void emu_cmux_wide(uint64_t* out, const uint64_t* d0, const uint64_t* d1, const C2* ggsw_dev, int radix_log,
+                   int count) {
+  const Tables& t = tables();
+  std::vector<C2> xbuf(kWideTeams * kXBuf);
+  run_wide([&](HostWideCx& cx) {
+    cmux_wide(cx, out, d0, d1, ggsw_dev, xbuf.data(), t.T1.data(), t.T2.data(), radix_log, count);
+  });
+}
+
 // generalized PBS; bsk in device scale (2^-10).  lut may be null (CBS mode).
 void emu_pbs(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, const C2* bsk_dev, int lwe_n,
              int log_chi, int log_v, int cbs_radix_log, int cbs_count) {
@@ -187,12 +233,12 @@ void emu_trace_ss(const uint64_t* glwe_in, uint64_t* glev_out, C2* ggsw_out_dev,
                   int tr_count, int ss_radix_log, int ss_count) {
   const Tables& t = tables();
   std::vector<C2> xbuf(kXBuf);
-  std::vector<uint64_t> g(2 * kN), st(32 * 64);
+  std::vector<uint64_t> g(2 * kN);
   uint32_t kinv[11];
   fill_kinv(kinv);
   TraceSsArgs A{glwe_in, glev_out, ggsw_out_dev, ak_dev, ssk_dev, kinv, level, mode, cbs_radix_log,
                 cbs_count, tr_radix_log, tr_count, ss_radix_log, ss_count, 1.0};
-  run_team([&](HostCx& cx) { trace_ss_team(cx, A, g.data(), st.data(), xbuf.data(), t.T1.data(), t.T2.data()); });
+  run_team([&](HostCx& cx) { trace_ss_team(cx, A, g.data(), xbuf.data(), t.T1.data(), t.T2.data()); });
 }
 
 }  // extern "C"

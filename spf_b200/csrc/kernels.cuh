@@ -281,9 +281,9 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
 // ------------------------------------------------------------------------------------------
 // K5+K6: trace (+ CBS pre-processing) and scheme switch, one team per (ciphertext, level).
 // ------------------------------------------------------------------------------------------
-constexpr int kTrTeams = 3;
-constexpr int kTrTeamBytes = 2 * kN * 8 + 32 * 64 * 8 + kXBuf * 16;  // g + state + xbuf = 65792
-constexpr int kTrSmem = kTableBytes + kTrTeams * kTrTeamBytes;        // 214848
+constexpr int kTrTeams = 4;
+constexpr int kTrTeamBytes = 2 * kN * 8 + kXBuf * 16;                 // g + xbuf = 49408 (digits are stateless)
+constexpr int kTrSmem = kTableBytes + kTrTeams * kTrTeamBytes;        // 215104
 
 struct TraceSsBatch {
   const uint64_t* glwe_in;  // mode 0: [B][2][2048] PBS outputs; mode 1: [B][...] GLWEs; mode 2: [B][l][2][2048] GLEVs
@@ -309,8 +309,7 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(TraceSsBa
   const int c = item / P.levels, level = item % P.levels;
   unsigned char* base = smem + kTableBytes + team * kTrTeamBytes;
   uint64_t* g = reinterpret_cast<uint64_t*>(base);
-  uint64_t* st = reinterpret_cast<uint64_t*>(base + 2 * kN * 8);
-  C2* xbuf = reinterpret_cast<C2*>(base + 2 * kN * 8 + 32 * 64 * 8);
+  C2* xbuf = reinterpret_cast<C2*>(base + 2 * kN * 8);
   DevCx cx{(int)(threadIdx.x % kTeam), team + 1};
   TraceSsArgs A;
   const size_t glwe = 2 * kN;
@@ -331,7 +330,7 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(TraceSsBa
   A.ss_radix_log = P.ss_radix_log;
   A.ss_count = P.ss_count;
   A.out_scale = P.out_scale;
-  trace_ss_team(cx, A, g, st, xbuf, sT1, sT2);
+  trace_ss_team(cx, A, g, xbuf, sT1, sT2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -377,6 +376,39 @@ __global__ void __launch_bounds__(kCmuxTeams * kTeam, 1) cmux_kernel(CmuxBatch P
   }
   cmux_team(cx, P.out + (size_t)c * glwe, P.d0 ? P.d0 + (size_t)c * glwe : nullptr, P.d1 + (size_t)c * glwe,
             P.ggsw + (size_t)(c / P.glwe_per_item) * P.ggsw_stride, st, xbuf, sT1, sT2, P.radix_log, P.count);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2w: latency-oriented CMUX, one CTA of 8 teams per GLWE output (cmux_wide); chosen by
+// launch_cmux when there are fewer outputs than SMs (the ripple MUX chain of a Parasol program).
+// ------------------------------------------------------------------------------------------
+constexpr int kWideSmem = kTableBytes + kWideTeams * kXBuf * 16;  // 150592
+
+struct DevWideCx {
+  int u, team;
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(team + 1) : "memory"); }
+  __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+};
+
+__global__ void __launch_bounds__(kWideTeams * kTeam, 1) cmux_wide_kernel(CmuxBatch P, DevTables tabs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  C2* sT1 = reinterpret_cast<C2*>(smem);
+  C2* sT2 = sT1 + kT1Elems;
+  load_tables(sT1, sT2, tabs);
+  C2* xb = reinterpret_cast<C2*>(smem + kTableBytes);
+  DevWideCx cx{(int)(threadIdx.x % kTeam), (int)(threadIdx.x / kTeam)};
+  const int c = blockIdx.x;
+  const size_t glwe = 2 * kN;
+  if (P.ptrs) {
+    const int item = c / P.glwe_per_item;
+    const size_t off = (size_t)(c % P.glwe_per_item) * glwe;
+    const uint64_t* d0 = static_cast<const uint64_t*>(P.ptrs[3 * item + 1]);
+    cmux_wide(cx, P.out + (size_t)c * glwe, d0 ? d0 + off : nullptr, static_cast<const uint64_t*>(P.ptrs[3 * item + 2]) + off,
+              static_cast<const C2*>(P.ptrs[3 * item]), xb, sT1, sT2, P.radix_log, P.count);
+  } else {
+    cmux_wide(cx, P.out + (size_t)c * glwe, P.d0 ? P.d0 + (size_t)c * glwe : nullptr, P.d1 + (size_t)c * glwe,
+              P.ggsw + (size_t)(c / P.glwe_per_item) * P.ggsw_stride, xb, sT1, sT2, P.radix_log, P.count);
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -146,6 +146,29 @@ SPF_HD void gadget_mad(Cx& cx, C2 (&acc)[2][16], uint64_t* st, C2* xbuf, const C
   }
 }
 
+// Stateless variant: the digits of level t are read straight out of the bit fields of
+// round(coef(j)) + radix_offset (no carry chain, so no per-coefficient state to keep between levels);
+// coef is re-evaluated per level.  Frees the 16 KiB state array: one more team fits on an SM.
+template <class Cx, class F>
+SPF_HD void gadget_mad_stateless(Cx& cx, C2 (&acc)[2][16], F coef, C2* xbuf, const C2* T1, const C2* T2, const C2* glev,
+                                 int radix_log, int count) {
+  const uint64_t off = radix_offset(radix_log, count);
+  const uint64_t dmask = (1ull << radix_log) - 1;
+  const int32_t half = 1 << (radix_log - 1);
+  for (int t = 0; t < count; t++) {
+    C2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      const uint64_t r0 = radix_round(coef(cx.u + 64 * m), radix_log, count) + off;
+      const uint64_t r1 = radix_round(coef(cx.u + 64 * m + kM), radix_log, count) + off;
+      v[m].x = i32_to_f64((int32_t)((r0 >> (t * radix_log)) & dmask) - half);
+      v[m].y = i32_to_f64((int32_t)((r1 >> (t * radix_log)) & dmask) - half);
+    }
+    team_fft_fwd(cx, v, xbuf, T1, T2);
+    mad_glwe(acc, v, glev + (size_t)(count - 1 - t) * 2 * kM, cx.u);
+  }
+}
+
 // ---- CMUX / external product (ops/fft_ops.rs:23-56,149-181) ---------------------------------
 // out = d0 + IFFT(GGSW [*] (d1 - d0)).  d0 == nullptr: plain external product of d1
 // (KeylessEvaluation::multiply_glwe_ggsw, parasol_runtime/src/crypto/evaluation.rs:104-123).
@@ -496,8 +519,8 @@ SPF_HD uint64_t automorph_coeff(const uint64_t* p, int j, uint32_t kinv) {
 }
 
 template <class Cx>
-SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2048]*/, uint64_t* st,
-                          C2* xbuf, const C2* T1, const C2* T2) {
+SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2048]*/, C2* xbuf, const C2* T1,
+                          const C2* T2) {
   const int u = cx.u;
   // ---- load / pre-process ----
   if (A.mode == 0) {
@@ -530,8 +553,8 @@ SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2
       const uint32_t kinv = A.kinv[r];
       C2 f[2][16];
       zero_acc(f);
-      state_init(cx, st, A.tr_radix_log, A.tr_count, [&](int j) { return automorph_coeff(g, j, kinv); });
-      gadget_mad(cx, f, st, xbuf, T1, T2, A.ak + (size_t)r * A.tr_count * 2 * kM, A.tr_radix_log, A.tr_count);
+      gadget_mad_stateless(cx, f, [&](int j) { return automorph_coeff(g, j, kinv); }, xbuf, T1, T2,
+                           A.ak + (size_t)r * A.tr_count * 2 * kM, A.tr_radix_log, A.tr_count);
       // keyswitch_glwe_to_glwe (fft_ops.rs:457-495): ks = (0, y_b) - IFFT(sum); out += ks
       team_fft_inv(cx, f[1], xbuf, T1, T2);
       uint64_t db[32];
@@ -571,8 +594,7 @@ SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2
     team_poly_fft(cx, f[0], [&](int j) { return g[kN + j]; }, xbuf, T1, T2);
 #pragma unroll
     for (int s = 0; s < 16; s++) { row1[kM + bin_of(u, s)] = cscale(f[0][s], A.out_scale); f[1][s] = C2{0.0, 0.0}; }
-    state_init(cx, st, A.ss_radix_log, A.ss_count, [&](int j) { return g[j]; });
-    gadget_mad(cx, f, st, xbuf, T1, T2, A.ssk, A.ss_radix_log, A.ss_count);
+    gadget_mad_stateless(cx, f, [&](int j) { return g[j]; }, xbuf, T1, T2, A.ssk, A.ss_radix_log, A.ss_count);
 #pragma unroll
     for (int s = 0; s < 16; s++) {
       row0[bin_of(u, s)] = cscale(f[0][s], A.out_scale);
@@ -582,6 +604,98 @@ SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2
     team_poly_fft(cx, f[0], [&](int j) { return g[j]; }, xbuf, T1, T2);
 #pragma unroll
     for (int s = 0; s < 16; s++) row1[bin_of(u, s)] = cscale(f[0][s], A.out_scale);
+  }
+}
+
+// ---- WIDE CMUX: one CMUX / external product on 8 teams ------------------------------------------
+// A CMUX inside a ripple MUX chain (one per dependency level) is pure latency: cmux_team runs its
+// 8 forward transforms, 16 multiply-accumulates and 2 inverse transforms one after the other on 64
+// threads.  Here team j = 4 r + t transforms digit t of polynomial r of d1 - d0 (digits straight
+// from the bit fields of the rounded value, see radix_offset), all 8 concurrently; then every
+// thread of the CTA finishes the radix-4 pass for ONE group of 4 bins of ONE output polynomial over
+// all 8 spectra and multiply-accumulates it against the GGSW; teams 0 and 1 run the two inverse
+// transforms.  Critical path: 1 forward + 1 MAD phase + 1 inverse instead of 8 + 16 + 2.
+//   cx.u / cx.team: thread in team, team 0..7;  cx.sync(): team barrier;  cx.cta_sync(): all 512
+//   xb: 8 exchange buffers.  count must be 4 (k = 1): 2 polynomials x 4 levels = 8 teams.
+constexpr int kWideTeams = 8;
+template <class Cx>
+SPF_HD void cmux_wide(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t* d1, const C2* ggsw, C2* xb,
+                      const C2* T1, const C2* T2, int radix_log, int count) {
+  const int u = cx.u, team = cx.team;
+  const int r = team / count, t = team % count;
+  C2* xown = xb + team * kXBuf;
+  {
+    const uint64_t off = radix_offset(radix_log, count);
+    const uint64_t dmask = (1ull << radix_log) - 1;
+    const int32_t half = 1 << (radix_log - 1);
+    C2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      const int j = r * kN + u + 64 * m;
+      const uint64_t x0 = d0 ? ldg_u64(d1 + j) - ldg_u64(d0 + j) : ldg_u64(d1 + j);
+      const uint64_t x1 = d0 ? ldg_u64(d1 + j + kM) - ldg_u64(d0 + j + kM) : ldg_u64(d1 + j + kM);
+      const uint64_t r0 = radix_round(x0, radix_log, count) + off, r1 = radix_round(x1, radix_log, count) + off;
+      v[m].x = i32_to_f64((int32_t)((r0 >> (t * radix_log)) & dmask) - half);
+      v[m].y = i32_to_f64((int32_t)((r1 >> (t * radix_log)) & dmask) - half);
+    }
+    fwd_pass1(v, u, T1);
+    fwd_x1_write(v, xown, u);
+    cx.sync();
+    fwd_x1_read(v, xown, u);
+    fwd_pass2(v, u, T2);
+    fwd_x2_write(v, xown, u);  // in place
+  }
+  cx.cta_sync();
+  // ---- MAD: thread (p, k1, k2) owns bins k1 + 16 k2 + 256 k3, k3 = 0..3, of output polynomial p ----
+  const int tid = team * kTeam + u;
+  const int p = tid >> 8, k1 = tid & 15, k2 = (tid >> 4) & 15;
+  C2 f[4];
+#pragma unroll
+  for (int jb = 0; jb < 2 * 4; jb += 4) {  // 4 spectra per batch: their GGSW values are requested together
+    C2 g[4][4], d[4][4];
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      const int j = jb + jj, rr = j / count, tt = j % count;  // digit tt <-> GGSW level count-1-tt (fft_ops.rs:92)
+      const C2* grow = ggsw + ((size_t)(rr * count + (count - 1 - tt)) * 2 + p) * kM;
+#pragma unroll
+      for (int k3 = 0; k3 < 4; k3++) g[jj][k3] = ldg_c2(grow + k1 + 16 * k2 + 256 * k3);
+#pragma unroll
+      for (int qp = 0; qp < 4; qp++) d[jj][qp] = xb[j * kXBuf + k1 * kXPad + qp + 4 * k2];
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      bfly4<false>(d[jj][0], d[jj][1], d[jj][2], d[jj][3]);
+#pragma unroll
+      for (int k3 = 0; k3 < 4; k3++) {
+        if (jb + jj == 0) f[k3] = cmul(d[jj][k3], g[jj][k3]);
+        else cmad(f[k3], d[jj][k3], g[jj][k3]);
+      }
+    }
+  }
+  bfly4<true>(f[0], f[1], f[2], f[3]);
+  cx.cta_sync();  // every spectrum has been consumed: buffers 0 and 1 take the two outputs
+#pragma unroll
+  for (int qp = 0; qp < 4; qp++) xb[p * kXBuf + k1 * kXPad + qp + 4 * k2] = f[qp];
+  cx.cta_sync();
+  if (team < 2) {  // team p finishes the inverse transform of output polynomial p
+    C2 w[16];
+    double ws[16];
+    inv_x2_read(w, xown, u);
+    inv_pass2(w, u, T2);
+    inv_x1_write(w, xown, u);  // in place
+    cx.sync();
+    inv_x1_read(w, xown, u);
+#pragma unroll
+    for (int k1i = 0; k1i < 16; k1i++) w[k1i] = cmul_conj(w[k1i], T1[k1i * 64 + u]);
+    inv_pass1_core_s(w, ws);
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      const int j = team * kN + u + 64 * m;
+      uint64_t re = f64_to_torus_s(w[m].x, ws[m]), im = f64_to_torus_s(w[m].y, ws[m]);
+      if (d0) { re += ldg_u64(d0 + j); im += ldg_u64(d0 + j + kM); }
+      out[j] = re;
+      out[j + kM] = im;
+    }
   }
 }
 

@@ -83,6 +83,25 @@ def test_cmux_matches_oracle(oracle, keys, client):
         assert client.decrypt_glwe_l1(out)[:3].tolist() == ([1, 0, 1] if sel else [0, 1, 1])
 
 
+def test_cmux_wide_matches_oracle(oracle, keys, client):
+    """The latency-oriented 8-team CMUX (cmux_wide: carry-free digits, all 8 transforms concurrent)
+    against the oracle, including the plain external product (d0 = NULL)."""
+    a = client.encrypt_glwe_l1([0, 1, 1])
+    b = client.encrypt_glwe_l1([1, 0, 1])
+    for sel in (0, 1):
+        ggsw = client.encrypt_ggsw_l1(sel)
+        ref = oracle.cmux(keys, a, b, ggsw)
+        out = np.zeros_like(ref)
+        E.lib().emu_cmux_wide(out, a.ctypes.data, b, E.to_device_scale(ggsw), 4, 4)
+        assert oracle.torus_distance(ref, out).max() < 1e-11
+        assert client.decrypt_glwe_l1(out)[:3].tolist() == ([1, 0, 1] if sel else [0, 1, 1])
+    ggsw = client.encrypt_ggsw_l1(1)
+    ref = oracle.multiply_glwe_ggsw(keys, b, ggsw)
+    out = np.zeros_like(ref)
+    E.lib().emu_cmux_wide(out, None, b, E.to_device_scale(ggsw), 4, 4)
+    assert oracle.torus_distance(ref, out).max() < 1e-11
+
+
 def test_pbs_first_steps_match_oracle(oracle, keys, client):
     """Blind-rotation steps on identical inputs.  After ONE step nothing has been decomposed that
     carries FFT rounding noise, so kernel body and oracle agree to ~2^-34 of the torus (the f64
