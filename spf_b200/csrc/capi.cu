@@ -167,6 +167,7 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
     CUB(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
   }
   CUB(cudaFuncSetAttribute(pbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPbsSmem));
+  CUB(cudaFuncSetAttribute(pbs_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadSmem));
   CUB(cudaFuncSetAttribute(trace_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
   CUB(cudaFuncSetAttribute(cmux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCmuxSmem));
   CUB(cudaFuncSetAttribute(cmux_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideSmem));
@@ -241,6 +242,10 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
   // A pair (one ciphertext) is largely latency-bound: alone on an SM it takes ~7 ms per PBS, ~9 ms
   // when three share the SM; small batches get one ciphertext per SM so they do not queue behind
   // each other, large ones run as persistent pairs (see pbs_kernel).
+  if (batch <= (size_t)ctx->sm_count) {  // latency mode: one ciphertext per SM on four teams
+    pbs_quad_kernel<<<(int)batch, 4 * kTeam, kQuadSmem, s>>>(P, tabs(ctx));
+    return check_launch(ctx, "pbs_quad_kernel");
+  }
   const int per = per_cta(ctx, batch, kPbsPairs);
 #ifdef SPF_PBS_NOPERSIST
   const int grid = (int)((batch + per - 1) / per);

@@ -142,6 +142,52 @@ void run_wide(Body body) {
   pthread_barrier_destroy(&cta);
 }
 
+// four teams of one ciphertext (pbs_quad_team)
+struct HostQuadCx {
+  int u, h, t;
+  pthread_barrier_t* bar_team;
+  pthread_barrier_t* bar_quad;
+  void sync() { pthread_barrier_wait(bar_team); }
+  void quad_sync() { pthread_barrier_wait(bar_quad); }
+  template <bool CONJ>
+  void t1_mul(C2 (&v)[16], const C2* T1) {
+    for (int k1 = 0; k1 < 16; k1++) v[k1] = CONJ ? cmul_conj(v[k1], T1[k1 * 64 + u]) : cmul(v[k1], T1[k1 * 64 + u]);
+  }
+  template <bool CONJ>
+  void t2_mul(C2 (&v)[16], const C2* T2) {
+    const int q = u >> 4;
+    for (int k2 = 1; k2 < 16; k2++) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
+  }
+};
+template <class Body>
+struct QuadLaunch {
+  Body* body;
+  HostQuadCx cx;
+  static void* run(void* p) {
+    QuadLaunch* l = (QuadLaunch*)p;
+    (*l->body)(l->cx);
+    return nullptr;
+  }
+};
+template <class Body>
+void run_quad(Body body) {
+  const int nt = 4 * kTeam;
+  pthread_barrier_t team[4], quad;
+  for (int i = 0; i < 4; i++) pthread_barrier_init(&team[i], nullptr, kTeam);
+  pthread_barrier_init(&quad, nullptr, nt);
+  std::vector<QuadLaunch<Body>> ls(nt);
+  std::vector<pthread_t> th(nt);
+  for (int t = 0; t < nt; t++) {
+    const int tm = t / kTeam;
+    ls[t].body = &body;
+    ls[t].cx = HostQuadCx{t % kTeam, tm >> 1, tm & 1, &team[tm], &quad};
+    pthread_create(&th[t], nullptr, QuadLaunch<Body>::run, &ls[t]);
+  }
+  for (int t = 0; t < nt; t++) pthread_join(th[t], nullptr);
+  for (int i = 0; i < 4; i++) pthread_barrier_destroy(&team[i]);
+  pthread_barrier_destroy(&quad);
+}
+
 struct Tables {
   std::vector<C2> T1, T2;
   Tables() : T1(kT1Elems), T2(kT2Elems) { fill_twiddle_tables(T1.data(), T2.data()); }
@@ -225,6 +271,16 @@ void emu_pbs(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, co
   run_pair([&](HostPairCx& cx) {
     pbs_pair_team(cx, A, acc.data(), xbuf.data(), t.T1.data(), t.T2.data());
   });
+}
+
+// the latency-mode (four-team) blind rotation
+void emu_pbs_quad(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, const C2* bsk_dev, int lwe_n,
+                  int log_chi, int log_v, int cbs_radix_log, int cbs_count) {
+  const Tables& t = tables();
+  std::vector<C2> xbuf(4 * kXBuf);
+  std::vector<uint64_t> acc(2 * kN);
+  PbsArgs A{lwe_in, lut, glwe_out, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count};
+  run_quad([&](HostQuadCx& cx) { pbs_quad_team(cx, A, acc.data(), xbuf.data(), t.T1.data(), t.T2.data()); });
 }
 
 // trace / CBS tail for one level.  mode: 0 CBS pre-process + trace (+SS), 1 plain trace, 2 SS only.

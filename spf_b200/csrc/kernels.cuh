@@ -199,23 +199,11 @@ struct DevPairCx {
   }
 };
 
-struct PbsBatch {
-  const uint64_t* lwe_in;   // [B][n+1]
-  const uint64_t* lut;      // shared GLWE LUT, or nullptr for CBS mode
-  size_t lut_stride;        // 0: one LUT for the whole batch, else per-ciphertext stride (elements)
-  uint64_t* glwe_out;       // [B][2][2048]
-  const C2* bsk;
-  const void* const* ptrs;  // optional device table: ptrs[c] = LWE input of item c (graph executor)
-  int batch, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count;
-};
-
-__global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch P, DevTables tabs) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  C2* sT1 = reinterpret_cast<C2*>(smem);
-  C2* sT2 = sT1 + kT1Elems;
-  load_tables(sT1, sT2, tabs);
-  uint32_t t1_taddr = 0;
-#if SPF_PBS_TMEM_T1 || SPF_PBS_TMEM_T2 || SPF_PBS_TMEM_OWN || SPF_PBS_TMEM_F
+// Tensor-memory scratchpad of the pair / quad team kernels: one 512-column allocation per CTA.
+// Columns [0,64) pass-1 twiddles and [64,128) pass-2 twiddles of the thread (shared by the warps of
+// a lane quarter, which have the same thread-in-team index), [128 + 64 p, +64) and [320 + 64 p, +64)
+// private to the warps of pair p.  Returns this warp's lane-quarter base address.
+__device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2, uint32_t& alloc_base) {
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -226,7 +214,8 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  t1_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  alloc_base = tmem_base;
+  const uint32_t t1_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   if (warp < 4) {  // every lane quarter is shared by warps w, w+4, w+8, which have the same u
     const int uu = (warp & 1) * 32 + (threadIdx.x & 31);
 #pragma unroll
@@ -246,7 +235,33 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#endif
+  return t1_taddr;
+}
+// every thread of the CTA must call this before exiting
+__device__ __forceinline__ void pair_tmem_free(uint32_t alloc_base) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(alloc_base), "n"(kPbsTmemCols) : "memory");
+}
+
+struct PbsBatch {
+  const uint64_t* lwe_in;   // [B][n+1]
+  const uint64_t* lut;      // shared GLWE LUT, or nullptr for CBS mode
+  size_t lut_stride;        // 0: one LUT for the whole batch, else per-ciphertext stride (elements)
+  uint64_t* glwe_out;       // [B][2][2048]
+  const C2* bsk;
+  const void* const* ptrs;  // optional device table: ptrs[c] = LWE input of item c (graph executor)
+  int batch, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count;
+};
+
+__global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch P, DevTables tabs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  C2* sT1 = reinterpret_cast<C2*>(smem);
+  C2* sT2 = sT1 + kT1Elems;
+  load_tables(sT1, sT2, tabs);
+  uint32_t tmem_alloc;
+  const uint32_t t1_taddr = pair_tmem_init(sT1, sT2, tmem_alloc);
   const int pair = threadIdx.x / (2 * kTeam);
   const int npairs = blockDim.x / (2 * kTeam);  // 1..kPbsPairs pairs per CTA (fewer for small batches)
   const int h = (threadIdx.x / kTeam) & 1;
@@ -270,12 +285,72 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
     A.cbs_count = P.cbs_count;
     pbs_pair_team(cx, A, acc, xb, sT1, sT2);
   }
-#if SPF_PBS_TMEM_T1 || SPF_PBS_TMEM_T2 || SPF_PBS_TMEM_OWN || SPF_PBS_TMEM_F
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kPbsTmemCols) : "memory");
-#endif
+  pair_tmem_free(tmem_alloc);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3q: latency mode of the blind rotation, one ciphertext per CTA on 4 teams (pbs_quad_team);
+// chosen by launch_pbs when the batch has at most one ciphertext per SM.
+// ------------------------------------------------------------------------------------------
+constexpr int kQuadSmem = kTableBytes + 2 * kN * 8 + 4 * kXBuf * 16;  // 116800
+
+struct DevQuadCx {
+  int u, h, t;
+  uint32_t t1_taddr;
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(1 + 2 * h + t) : "memory"); }
+  __device__ __forceinline__ void quad_sync() const { __syncthreads(); }
+  template <bool CONJ>
+  __device__ __forceinline__ void t1_mul(C2 (&v)[16], const C2* T1) const {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16(r0, t1_taddr + 32 * half);
+      tmem_ld16(r1, t1_taddr + 32 * half + 16);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const C2 w0{__hiloint2double((int)r0[4 * i + 1], (int)r0[4 * i]), __hiloint2double((int)r0[4 * i + 3], (int)r0[4 * i + 2])};
+        const C2 w1{__hiloint2double((int)r1[4 * i + 1], (int)r1[4 * i]), __hiloint2double((int)r1[4 * i + 3], (int)r1[4 * i + 2])};
+        const int ka = 8 * half + i, kb = 8 * half + 4 + i;
+        v[ka] = CONJ ? cmul_conj(v[ka], w0) : cmul(v[ka], w0);
+        v[kb] = CONJ ? cmul_conj(v[kb], w1) : cmul(v[kb], w1);
+      }
+    }
+  }
+  template <bool CONJ>
+  __device__ __forceinline__ void t2_mul(C2 (&v)[16], const C2* T2) const {
+    const int q = u >> 4;
+#pragma unroll
+    for (int k2 = 1; k2 < 16; k2++) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
+  }
+};
+
+__global__ void __launch_bounds__(4 * kTeam, 1) pbs_quad_kernel(PbsBatch P, DevTables tabs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  C2* sT1 = reinterpret_cast<C2*>(smem);
+  C2* sT2 = sT1 + kT1Elems;
+  load_tables(sT1, sT2, tabs);
+  uint32_t tmem_alloc;
+  const uint32_t t1_taddr = pair_tmem_init(sT1, sT2, tmem_alloc);
+  uint64_t* acc = reinterpret_cast<uint64_t*>(smem + kTableBytes);
+  C2* xb = reinterpret_cast<C2*>(smem + kTableBytes + 2 * kN * 8);
+  const int team = threadIdx.x / kTeam;
+  DevQuadCx cx{(int)(threadIdx.x % kTeam), team >> 1, team & 1, t1_taddr};
+  for (int c = blockIdx.x; c < P.batch; c += gridDim.x) {
+    PbsArgs A;
+    A.lwe_in = P.ptrs ? static_cast<const uint64_t*>(P.ptrs[c]) : P.lwe_in + (size_t)c * (P.lwe_n + 1);
+    A.lut = P.lut ? P.lut + (size_t)c * P.lut_stride : nullptr;
+    A.glwe_out = P.glwe_out + (size_t)c * 2 * kN;
+    A.bsk = P.bsk;
+    A.lwe_n = P.lwe_n;
+    A.log_chi = P.log_chi;
+    A.log_v = P.log_v;
+    A.cbs_radix_log = P.cbs_radix_log;
+    A.cbs_count = P.cbs_count;
+    pbs_quad_team(cx, A, acc, xb, sT1, sT2);
+    cx.quad_sync();
+  }
+  pair_tmem_free(tmem_alloc);
 }
 
 // ------------------------------------------------------------------------------------------

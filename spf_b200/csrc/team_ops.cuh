@@ -493,6 +493,139 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
   }
 }
 
+// QUAD-TEAM blind rotation (latency mode, batches of at most one ciphertext per SM): one ciphertext
+// = 256 threads = 4 teams (h, t): team (h, t) transforms digit level t of polynomial h, all four
+// forward transforms of a CMUX step run concurrently, the bins are split four ways for the
+// multiply-accumulate (f[2][4] per thread) and teams (p, 0) finish the inverse transform of output
+// polynomial p.  The critical path of a step is one forward transform + one MAD phase + one inverse
+// instead of two + two + one; the arithmetic per coefficient is identical to pbs_pair_team.
+//   cx.u, cx.h, cx.t;  cx.sync(): team barrier;  cx.quad_sync(): the ciphertext's 256 threads
+//   xb: 4 exchange buffers, team (h, t) owns xb + (2 h + t) * kXBuf.
+template <class Cx>
+SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const C2* T1, const C2* T2) {
+  const int u = cx.u, h = cx.h, t = cx.t, g = 2 * h + t;
+  const int k1 = u & 15, q = u >> 4;
+  const int n = A.lwe_n;
+  const bool cbs = A.lut == nullptr;
+  const int log2n = 12;  // log2(2N)
+  uint64_t* pa = acc + h * kN;
+  C2* xown = xb + g * kXBuf;
+  // 1. acc = LUT * X^{-b~}: team (h, t) fills half t of polynomial h
+  {
+    uint64_t b = ldg_u64(A.lwe_in + n);
+    if (cbs) b += 1ull << 62;
+    const int bt = (int)modulus_switch(b, A.log_chi, A.log_v, log2n);
+    const int rot = (2 * kN - bt) & (2 * kN - 1);
+    const int v = 1 << A.log_v;
+    for (int i = 16 * t; i < 16 * t + 16; i++) {
+      const int j = u + 64 * i;
+      int idx = j - rot;
+      bool neg = false;
+      if (idx < 0) { idx += kN; neg = true; }
+      if (idx < 0) { idx += kN; neg = false; }
+      uint64_t c;
+      if (cbs) c = h ? cbs_lut_coeff(idx, A.cbs_radix_log, A.cbs_count, v) : 0;
+      else c = ldg_u64(A.lut + h * kN + idx);
+      pa[j] = neg ? 0 - c : c;
+    }
+  }
+  cx.quad_sync();
+  uint64_t a_next = n > 0 ? ldg_u64(A.lwe_in) : 0;
+  uint64_t own[32];
+#pragma unroll
+  for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    const int at = (int)modulus_switch(a_next, A.log_chi, A.log_v, log2n);
+    if (i + 1 < n) a_next = ldg_u64(A.lwe_in + i + 1);
+    if (at == 0) continue;
+    const C2* ggsw = A.bsk + (size_t)i * 8 * kM;
+    {
+      C2 v[16];
+      const int base = (u - at) & (2 * kN - 1);
+      const char* col = reinterpret_cast<const char*>(pa) + 8 * (base & 63);
+      const uint32_t bh9 = (uint32_t)(base >> 6) << 9;
+#pragma unroll
+      for (int i2 = 0; i2 < 32; i2++) {
+        const uint32_t t9 = bh9 + 512u * i2;
+        const uint64_t x = *reinterpret_cast<const uint64_t*>(col + (t9 & 0x3E00u));
+        const uint64_t diff = ((t9 & 0x4000u) ? 0 - x : x) - own[i2];
+        const uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
+        // digit 0: low half of w; digit 1: high half of w + 0x8000 (math/radix.rs:81-113, logB = 16, l = 2)
+        const double d = t ? digit_hi16_to_f64(w + 0x8000u) : digit_lo16_to_f64(w);
+        if (i2 < 16) v[i2].x = d; else v[i2 - 16].y = d;
+      }
+      fwd_pass1_core(v);
+      cx.template t1_mul<false>(v, T1);
+      fwd_x1_write(v, xown, u);
+      cx.sync();
+      fwd_x1_read(v, xown, u);
+      dft16<false>(v);
+      cx.template t2_mul<false>(v, T2);
+      fwd_x2_write(v, xown, u);  // in place
+    }
+    cx.quad_sync();
+    // MAD: team g owns the bins u + 64 (g + 4 k3) of every polynomial
+    C2 f[2][4];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {  // spectrum of team b = (hb, tb): digit tb <-> GLEV level 1 - tb
+      const C2* grow = ggsw + (size_t)(((b >> 1) * 2 + (1 - (b & 1))) * 2) * kM;
+      C2 d[4], g0[4], g1[4];
+#pragma unroll
+      for (int qp = 0; qp < 4; qp++) d[qp] = xb[b * kXBuf + k1 * kXPad + qp + 4 * q + 16 * g];
+#pragma unroll
+      for (int k3 = 0; k3 < 4; k3++) {
+        g0[k3] = ldg_c2_pinned(grow + u + 64 * (g + 4 * k3));
+        g1[k3] = ldg_c2_pinned(grow + kM + u + 64 * (g + 4 * k3));
+      }
+      bfly4<false>(d[0], d[1], d[2], d[3]);
+#pragma unroll
+      for (int k3 = 0; k3 < 4; k3++) {
+        if (b == 0) { f[0][k3] = cmul(d[k3], g0[k3]); f[1][k3] = cmul(d[k3], g1[k3]); }
+        else { cmad(f[0][k3], d[k3], g0[k3]); cmad(f[1][k3], d[k3], g1[k3]); }
+      }
+    }
+    // first inverse pass; output polynomial p goes (in place) into the buffer of team (p, 0)
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      bfly4<true>(f[p][0], f[p][1], f[p][2], f[p][3]);
+#pragma unroll
+      for (int qp = 0; qp < 4; qp++) xb[2 * p * kXBuf + k1 * kXPad + qp + 4 * q + 16 * g] = f[p][qp];
+    }
+    cx.quad_sync();
+    if (t == 0) {
+      C2 w[16];
+      double ws[16];
+      inv_x2_read(w, xown, u);
+      cx.template t2_mul<true>(w, T2);
+      dft16<true>(w);
+      inv_x1_write(w, xown, u);  // in place
+      cx.sync();
+      inv_x1_read(w, xown, u);
+      cx.template t1_mul<true>(w, T1);
+      inv_pass1_core_s(w, ws);
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const int j = u + 64 * m;
+        own[m] += f64_to_torus_s(w[m].x, ws[m]);
+        own[m + 16] += f64_to_torus_s(w[m].y, ws[m]);
+        pa[j] = own[m];
+        pa[j + kM] = own[m + 16];
+      }
+    }
+    cx.quad_sync();
+    if (t == 1) {
+#pragma unroll
+      for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
+    }
+  }
+  // 3. result: team (h, t) stores half t of polynomial h
+  for (int i = 16 * t; i < 16 * t + 16; i++) {
+    const int j = u + 64 * i;
+    A.glwe_out[h * kN + j] = pa[j];
+  }
+}
+
 // ---- trace + scheme switch ---------------------------------------------------------------------
 // One team = one (ciphertext, cbs level) pair: mod_switch_trace_and_rotate for that level
 // (circuit_bootstrapping.rs:260-298), trace (ops/automorphisms/mod.rs:53-85) and that level's

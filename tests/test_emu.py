@@ -129,6 +129,37 @@ def test_pbs_first_steps_match_oracle(oracle, keys, client):
         assert ph.max() < 2.0 ** -25, nsteps
 
 
+def test_pbs_quad_matches_pair_and_oracle(oracle, keys, client):
+    """The latency-mode four-team blind rotation (pbs_quad_team): one step against the oracle
+    (same tolerance as the pair version), a few steps against the pair version in phase, and a full
+    PBS by its multi-function LUT phase pattern."""
+    import ctypes as C
+    bsk_dev = E.to_device_scale(keys.bsk_fft)
+    ct = client.encrypt_lwe_l0(1)
+    p = oracle.default_128()
+    p.lwe_n = 1
+    sub = np.concatenate([ct[:1], ct[-1:]])
+    rot = sub.copy(); rot[-1] = np.uint64((int(rot[-1]) + (1 << 62)) & ((1 << 64) - 1))
+    lut = np.zeros(4096, dtype=np.uint64)
+    oracle.lib().orc_cbs_lut(lut, C.byref(p))
+    ref = np.zeros(4096, dtype=np.uint64)
+    oracle.lib().orc_pbs_generalized(ref, rot, lut, keys.bsk_fft, 0, 2, C.byref(p))
+    out = np.zeros(4096, dtype=np.uint64)
+    E.lib().emu_pbs_quad(out, sub, None, bsk_dev, 1, 0, 2, 4, 4)
+    assert oracle.torus_distance(ref, out).max() < 1e-10
+    sub = np.concatenate([ct[:5], ct[-1:]])
+    a, b = np.zeros(4096, dtype=np.uint64), np.zeros(4096, dtype=np.uint64)
+    E.lib().emu_pbs(a, sub, None, bsk_dev, 5, 0, 2, 4, 4)
+    E.lib().emu_pbs_quad(b, sub, None, bsk_dev, 5, 0, 2, 4, 4)
+    assert oracle.torus_distance(client.decrypt_glwe_l1_raw(a), client.decrypt_glwe_l1_raw(b)).max() < 2.0 ** -22  # 5 steps of digit-flip noise (DESIGN.md section 5)
+    glwe = np.zeros(4096, dtype=np.uint64)
+    E.lib().emu_pbs_quad(glwe, ct, None, bsk_dev, 637, 0, 2, 4, 4)
+    ph = client.decrypt_glwe_l1_raw(glwe)
+    for i in range(4):
+        want = (1 << (64 - (4 * (i + 1) + 1)))
+        assert abs(int(np.int64(ph[i])) - want) < want // 8
+
+
 def test_full_cbs_decrypts_like_fresh_ggsw(oracle, keys, client):
     """Whole CBS through the kernel bodies (PBS -> 4 x (pre-process, trace) -> scheme switch),
     checked as can_circuit_bootstrap_via_trace_ss does (circuit_bootstrapping.rs:777-803)."""
