@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -39,6 +40,7 @@ struct spf_b200_ctx {
   uint32_t* kinv = nullptr;
   cudaStream_t stream[2] = {nullptr, nullptr};
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};  // host-pointer CBS pipeline: staging buffer of a slot is free again
   DevBuf scratch[2][6];  // per pipeline slot: grow-only device scratch
   std::string err;
   std::atomic<uint64_t> launches{0};
@@ -165,6 +167,7 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
   for (int i = 0; i < 2; i++) {
     CUB(cudaStreamCreateWithFlags(&ctx->stream[i], cudaStreamNonBlocking));
     CUB(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
   }
   CUB(cudaFuncSetAttribute(pbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPbsSmem));
   CUB(cudaFuncSetAttribute(pbs_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadSmem));
@@ -369,7 +372,14 @@ int launch_elementwise(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_a, 
 
 // Largest chunk of a host-pointer batch processed per pipeline slot: a whole number of PBS
 // waves (148 SMs x 3 ciphertexts) so chunking costs no tail.
-size_t cbs_chunk(const spf_b200_ctx* ctx) { return (size_t)ctx->sm_count * kPbsPairs * 3; }
+size_t cbs_chunk(const spf_b200_ctx* ctx) {
+  static const long waves = [] {
+    const char* e = getenv("SPF_B200_CHUNK_WAVES");  // tuning knob for the host-pointer pipeline
+    const long w = e ? atol(e) : 0;
+    return w > 0 ? w : 1;
+  }();
+  return (size_t)ctx->sm_count * kPbsPairs * (size_t)waves;
+}
 
 // ---- host-pointer ops: chunked, double-buffered over the context's two streams ---------------
 
@@ -499,6 +509,7 @@ void spf_b200_destroy(spf_b200_ctx* ctx) {
     for (DevBuf& b : ctx->scratch[i]) cudaFree(b.p);
     if (ctx->stream[i]) cudaStreamDestroy(ctx->stream[i]);
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
   }
   delete ctx;
 }
@@ -584,20 +595,38 @@ int spf_b200_circuit_bootstrap(spf_b200_ctx* ctx, double* ggsw_out, const uint64
   if (batch == 0) return 0;
   if (!ggsw_out || !lwe0_in) return fail(ctx, SPF_E_INVALID, "NULL buffer");
   const size_t lwe = spf_b200_len_lwe_l0(&ctx->p), glwe = len_glwe(&ctx->p), ggsw = spf_b200_len_ggsw_l1(&ctx->p);
-  return run_chunks(ctx, batch, cbs_chunk(ctx), [&](int slot, size_t off, size_t n) -> int {
-    cudaStream_t s = ctx->stream[slot];
+  // Pipeline: every kernel on ONE compute stream (a second stream's bootstraps would only fight the
+  // first one's for the SMs), the 256 KiB-per-ciphertext results leave on a copy stream from two
+  // alternating staging buffers; events order the hand-over, the host never waits inside the loop.
+  CU(cudaSetDevice(ctx->device));
+  const size_t chunk = std::min(cbs_chunk(ctx), batch);
+  cudaStream_t comp = ctx->stream[0], copy = ctx->stream[1];
+  for (int slot = 0; slot < 2; slot++) {
+    if (int rc = ensure(ctx, ctx->scratch[slot][0], chunk * lwe * 8)) return rc;
+    if (int rc = ensure(ctx, ctx->scratch[slot][1], chunk * glwe * 8)) return rc;
+    if (int rc = ensure(ctx, ctx->scratch[slot][2], chunk * ggsw * 16)) return rc;
+  }
+  int slot = 0, rc = 0;
+  size_t k = 0;
+  for (size_t off = 0; off < batch && rc == 0; off += chunk, slot ^= 1, k++) {
+    const size_t n = std::min(chunk, batch - off);
     DevBuf* sc = ctx->scratch[slot];
-    if (int rc = ensure(ctx, sc[0], n * lwe * 8)) return rc;
-    if (int rc = ensure(ctx, sc[1], n * glwe * 8)) return rc;
-    if (int rc = ensure(ctx, sc[2], n * ggsw * 16)) return rc;
-    CU(cudaMemcpyAsync(sc[0].p, lwe0_in + off * lwe, n * lwe * 8, cudaMemcpyHostToDevice, s));
-    if (int rc = launch_pbs(ctx, (uint64_t*)sc[1].p, (const uint64_t*)sc[0].p, nullptr, true, 0, cbs_log_v(&ctx->p), n, s))
-      return rc;
-    if (int rc = launch_trace_ss(ctx, (const uint64_t*)sc[1].p, nullptr, (C2*)sc[2].p, 0, (int)ctx->p.cbs.count, 1024.0, n, s))
-      return rc;
-    CU(cudaMemcpyAsync(ggsw_out + off * ggsw * 2, sc[2].p, n * ggsw * 16, cudaMemcpyDeviceToHost, s));
-    return 0;
-  });
+    if (k >= 2) CU(cudaStreamWaitEvent(comp, ctx->ev_copied[slot], 0));  // staging buffer drained
+    CU(cudaMemcpyAsync(sc[0].p, lwe0_in + off * lwe, n * lwe * 8, cudaMemcpyHostToDevice, comp));
+    rc = launch_pbs(ctx, (uint64_t*)sc[1].p, (const uint64_t*)sc[0].p, nullptr, true, 0, cbs_log_v(&ctx->p), n, comp);
+    if (rc == 0)
+      rc = launch_trace_ss(ctx, (const uint64_t*)sc[1].p, nullptr, (C2*)sc[2].p, 0, (int)ctx->p.cbs.count, 1024.0, n, comp);
+    if (rc) break;
+    CU(cudaEventRecord(ctx->ev[slot], comp));
+    CU(cudaStreamWaitEvent(copy, ctx->ev[slot], 0));
+    CU(cudaMemcpyAsync(ggsw_out + off * ggsw * 2, sc[2].p, n * ggsw * 16, cudaMemcpyDeviceToHost, copy));
+    CU(cudaEventRecord(ctx->ev_copied[slot], copy));
+  }
+  const cudaError_t e0 = cudaStreamSynchronize(comp), e1 = cudaStreamSynchronize(copy);
+  if (rc) return rc;
+  if (e0 != cudaSuccess || e1 != cudaSuccess)
+    return fail(ctx, SPF_E_CUDA, std::string("circuit_bootstrap pipeline: ") + cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+  return 0;
 }
 
 int spf_b200_programmable_bootstrap(spf_b200_ctx* ctx, uint64_t* glwe_out, const uint64_t* lwe0_in,
