@@ -226,3 +226,30 @@ def test_large_batch_cbs_sampled(oracle, keys, client, evaluation):
         assert client.decrypt_ggsw_l1(out[i]) == bits[i], i
     i = 599
     assert np.array_equal(client.ggsw_level_messages(out[i]), client.ggsw_expected_messages(int(bits[i])))
+
+
+def test_kernel_selection_thresholds(oracle, keys, client, evaluation):
+    """launch_pbs / launch_cmux switch kernels at one item per SM (148): the latency kernels
+    (pbs_quad_kernel, cmux_wide_kernel) below, the throughput kernels (pair teams, one team per CMUX)
+    above.  Both sides must decrypt correctly; within a kernel, results do not depend on the batch."""
+    rng = np.random.default_rng(21)
+    bits = rng.integers(0, 2, 300)
+    cts = client.encrypt_lwe_l0_batch(bits.tolist())
+    quad = evaluation.circuit_bootstrap(cts[:148])     # one ciphertext per SM on four teams
+    pair = evaluation.circuit_bootstrap(cts[:150])     # pair teams, two per SM
+    pair2 = evaluation.circuit_bootstrap(cts)          # pair teams, three per SM
+    assert np.array_equal(pair, pair2[:150])
+    for i in (0, 77, 147):
+        assert client.decrypt_ggsw_l1(quad[i]) == bits[i] == client.decrypt_ggsw_l1(pair[i])
+    assert client.decrypt_ggsw_l1(pair2[299]) == bits[299]
+    # CMUX: the same 149 ops through the bulk kernel, the first 148 through the wide kernel
+    a, b = client.encrypt_glwe_l1([0, 1]), client.encrypt_glwe_l1([1, 1])
+    sel = np.stack([quad[i] for i in range(148)] + [pair[148]])
+    A, B = np.stack([a] * 149), np.stack([b] * 149)
+    bulk = evaluation.cmux(sel, A, B)
+    wide = evaluation.cmux(sel[:148], A[:148], B[:148])
+    for i in (0, 5, 100, 147):
+        want = oracle.cmux(keys, a, b, sel[i])
+        assert oracle.torus_distance(want, bulk[i]).max() <= 2.0 ** -30
+        assert oracle.torus_distance(want, wide[i]).max() <= 2.0 ** -30
+        assert client.decrypt_glwe_l1(wide[i])[:2].tolist() == ([1, 1] if bits[i] else [0, 1])
