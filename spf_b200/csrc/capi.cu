@@ -36,6 +36,8 @@ struct spf_b200_ctx {
   C2 *bsk = nullptr, *ak = nullptr, *ssk = nullptr;
   uint64_t* ksk = nullptr;
   uint64_t* ksk_colsum = nullptr;  // keyswitch_kernel's per-block column sums of the KSK
+  uint4* ks_bfrag = nullptr;       // keyswitch_tc_kernel: KSK byte planes in mma B-fragment order (nullptr: shape unsupported)
+  uint64_t* ks_tc_colsum = nullptr;  // keyswitch_tc_kernel: per-(chunk, level) column sums
   C2 *T1 = nullptr, *T2 = nullptr;
   uint32_t* kinv = nullptr;
   cudaStream_t stream[2] = {nullptr, nullptr};
@@ -217,6 +219,19 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
     ksk_colsum_kernel<<<dim3((cols + 127) / 128, nblk), 128, 0, ctx->stream[0]>>>(ctx->ksk_colsum, ctx->ksk, n1,
                                                                                    (int)params->ks.count, cols);
     CUB(cudaGetLastError());
+    // tensor-core keyswitch (kernels.cuh K4t): KSK byte planes in fragment order + per-chunk column sums
+    const int L = (int)params->ks.count, lb = (int)params->ks.radix_log;
+    if (n1 % kKtIC == 0 && L * lb + 1 <= 16 && lb <= 8) {
+      const int n_tiles = (cols + kKtN - 1) / kKtN * (kKtN / 8), ks_total = n1 * L / 32, chunks = n1 / kKtIC * L;
+      const size_t slots = (size_t)n_tiles * ks_total * 32;
+      CUB(cudaMalloc(&ctx->ks_bfrag, slots * 4 * sizeof(uint4)));
+      CUB(cudaMalloc(&ctx->ks_tc_colsum, sizeof(uint64_t) * (size_t)chunks * cols));
+      ks_tc_prepare_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, ctx->stream[0]>>>(ctx->ks_bfrag, ctx->ksk, n1, L, cols, n_tiles);
+      CUB(cudaGetLastError());
+      ks_tc_colsum_kernel<<<dim3((cols + 127) / 128, chunks), 128, 0, ctx->stream[0]>>>(ctx->ks_tc_colsum, ctx->ksk, n1, L, cols);
+      CUB(cudaGetLastError());
+      CUB(cudaFuncSetAttribute(keyswitch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKtSmem));
+    }
   }
   CUB(cudaStreamSynchronize(ctx->stream[0]));
 #undef CUB
@@ -326,6 +341,19 @@ int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, s
   P.n0 = (int)ctx->p.lwe_n;
   P.radix_log = (int)ctx->p.ks.radix_log;
   P.count = (int)ctx->p.ks.count;
+  if (ctx->ks_bfrag && !getenv("SPF_B200_KS_NO_TC")) {  // dense contraction on the int8 tensor cores (K4t)
+    KsTcBatch T;
+    T.out = d_out; T.in = d_in; T.ptrs = ptrs; T.bfrag = ctx->ks_bfrag; T.colsum = ctx->ks_tc_colsum;
+    T.batch = P.batch; T.n1 = P.n1; T.n0 = P.n0; T.radix_log = P.radix_log; T.count = P.count;
+    const int gx = (int)((batch + kKtM - 1) / kKtM), gy = (P.n0 + 1 + kKtN - 1) / kKtN;
+    const int chunks = P.n1 / kKtIC * P.count;
+    int z = std::max(1, std::min(chunks, (2 * ctx->sm_count + gx * gy - 1) / (gx * gy)));  // split K until the GPU is full
+    T.chunks_per_cta = (chunks + z - 1) / z;
+    z = (chunks + T.chunks_per_cta - 1) / T.chunks_per_cta;
+    if (z > 1) CU(cudaMemsetAsync(d_out, 0, batch * (size_t)(P.n0 + 1) * 8, s));
+    keyswitch_tc_kernel<<<dim3(gx, gy, z), 256, kKtSmem, s>>>(T);
+    return check_launch(ctx, "keyswitch_tc_kernel");
+  }
   if (P.n0 + 1 > 2 * kKsThreads) return fail(ctx, SPF_E_UNSUPPORTED, "l0 dimension too large for the keyswitch kernel");
   if (P.count > kKsMaxLevels) return fail(ctx, SPF_E_UNSUPPORTED, "ks_radix.count too large for the keyswitch kernel");
   const int tiles = (int)((batch + kKsBatch - 1) / kKsBatch);
@@ -503,7 +531,7 @@ void spf_b200_destroy(spf_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  cudaFree(ctx->bsk); cudaFree(ctx->ak); cudaFree(ctx->ssk); cudaFree(ctx->ksk); cudaFree(ctx->ksk_colsum);
+  cudaFree(ctx->bsk); cudaFree(ctx->ak); cudaFree(ctx->ssk); cudaFree(ctx->ksk); cudaFree(ctx->ksk_colsum); cudaFree(ctx->ks_bfrag); cudaFree(ctx->ks_tc_colsum);
   cudaFree(ctx->T1); cudaFree(ctx->T2); cudaFree(ctx->kinv); cudaFree(ctx->consts);
   for (int i = 0; i < 2; i++) {
     for (DevBuf& b : ctx->scratch[i]) cudaFree(b.p);

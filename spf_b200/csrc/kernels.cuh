@@ -621,6 +621,172 @@ __global__ void __launch_bounds__(kKsThreads) keyswitch_kernel(KsBatch P) {
 }
 
 // ------------------------------------------------------------------------------------------
+// K4t: the keyswitch as a dense integer contraction on the tensor cores.
+//   out[b][c] = (0, body_b) - sum_{k=(i,t)} d[b][k] * KSK[k][c]   is   [B x 12288] x [12288 x 638] mod 2^64.
+// With unsigned digits u = d + B/2 in {0..B-1} (see K4) and the KSK split into its 8 BYTE PLANES,
+//   sum_k u[b][k] * KSK[k][c] = sum_j 2^(8j) * (U x P_j)[b][c],   P_j[k][c] = byte j of KSK[k][c],
+// every U x P_j is an exact u8 x u8 -> s32 GEMM (12288 * 3 * 255 < 2^24), i.e. 8 int8 tensor-core
+// GEMMs whose results are recombined with shifts in the epilogue; the surplus (B/2) * sum_k KSK[k][c]
+// is the same per-key constant as in K4.  mma.sync.m16n8k32.u8.u8.s32 (IMMA.16832: measured 572 T
+// MAC/s on this part); the KSK planes are stored fragment-major (ks_tc_prepare_kernel) so a warp
+// streams 2 KiB of B fragments per k-step with four 16-byte loads per lane.
+// CTA tile: 128 ciphertexts x 32 columns, 8 warps = 2 (rows) x 4 (n-tiles), warp tile 64 x 8 x 8 planes
+// (128 s32 accumulators per thread).  K is walked in chunks of (512 mask elements, one digit level);
+// the chunk's rounded states sit in shared memory as u16 and the u8 A fragments are cut out of them
+// with two shifts, two masks and one byte permute per register.  grid.z splits K; partial results
+// are combined with u64 atomics (wrapping adds commute: bit-exact).
+// ------------------------------------------------------------------------------------------
+constexpr int kKtM = 128, kKtN = 32, kKtIC = 512;
+constexpr int kKtRow = kKtIC + 8;                          // u16 per smem row (+16 B: conflict-free LDS.64)
+constexpr int kKtSmem = kKtM * kKtRow * 2;                 // 133120
+
+struct KsTcBatch {
+  uint64_t* out;            // [B][n0+1], zero-initialised when gridDim.z > 1
+  const uint64_t* in;       // [B][n1+1]
+  const void* const* ptrs;  // optional: ptrs[b] = L1 LWE input of item b
+  const uint4* bfrag;       // [n_tiles][k_steps][32 lanes][4] : per lane 8 planes x (b0, b1)
+  const uint64_t* colsum;   // [chunks][n0+1]: sum over the chunk's (i, t) of ksk, chunk = c * L + t
+  int batch, n1, n0, radix_log, count;
+  int chunks_per_cta;       // (i-chunk, level) pairs per grid.z slice
+};
+
+// bfrag[(nt * KS + ks) * 32 + lane] = {plane 0: b0, b1, plane 1: b0, b1}, ... 4 x uint4 per lane; k-step ks covers
+// k = ks * 32 .. +31 with k = t * n1 + i (digit t <-> KSK level L-1-t); b0 holds rows k = 4 (lane % 4) .. +3
+// of column nt * 8 + lane / 4, b1 the rows 16 further (PTX ISA, m16n8k32 B fragment).
+__global__ void ks_tc_prepare_kernel(uint4* bfrag, const uint64_t* ksk, int n1, int levels, int cols, int n_tiles) {
+  const int ks_total = n1 * levels / 32;
+  const size_t lane_slot = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // (nt, ks, lane)
+  if (lane_slot >= (size_t)n_tiles * ks_total * 32) return;
+  const int lane = (int)(lane_slot & 31), ks = (int)((lane_slot >> 5) % ks_total), nt = (int)((lane_slot >> 5) / ks_total);
+  const int col = nt * 8 + (lane >> 2);
+  uint32_t w[16];
+#pragma unroll
+  for (int x = 0; x < 16; x++) w[x] = 0;
+  if (col < cols) {
+    for (int r = 0; r < 2; r++)
+      for (int e = 0; e < 4; e++) {
+        const int k = ks * 32 + 4 * (lane & 3) + 16 * r + e, t = k / n1, i = k % n1;
+        const uint64_t v = ksk[((size_t)i * levels + (levels - 1 - t)) * cols + col];
+        for (int j = 0; j < 8; j++) w[2 * j + r] |= (uint32_t)((v >> (8 * j)) & 0xFF) << (8 * e);
+      }
+  }
+  for (int x = 0; x < 4; x++) bfrag[lane_slot * 4 + x] = make_uint4(w[4 * x], w[4 * x + 1], w[4 * x + 2], w[4 * x + 3]);
+}
+
+// colsum[c * levels + t][col] = sum_{i in chunk c} ksk[i][levels-1-t][col]
+__global__ void ks_tc_colsum_kernel(uint64_t* colsum, const uint64_t* ksk, int n1, int levels, int cols) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x, chunk = blockIdx.y;
+  if (col >= cols) return;
+  const int c = chunk / levels, t = chunk % levels;
+  uint64_t acc = 0;
+  for (int i = c * kKtIC; i < (c + 1) * kKtIC && i < n1; i++) acc += ksk[((size_t)i * levels + (levels - 1 - t)) * cols + col];
+  colsum[(size_t)chunk * cols + col] = acc;
+}
+
+__device__ __forceinline__ void imma_16832_u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 1) keyswitch_tc_kernel(KsTcBatch P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint16_t* st = reinterpret_cast<uint16_t*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int b0 = blockIdx.x * kKtM;
+  const int nt = blockIdx.y * (kKtN / 8) + wn;
+  const int L = P.count, chunks_per_t = P.n1 / kKtIC, total_chunks = chunks_per_t * L;
+  const int ks_per_t = P.n1 / 32, ks_total = ks_per_t * L;
+  const int kc_begin = blockIdx.z * P.chunks_per_cta, kc_end = min(kc_begin + P.chunks_per_cta, total_chunks);
+  const uint32_t off = (uint32_t)radix_offset(P.radix_log, L);
+  const uint32_t dmask = ((1u << P.radix_log) - 1) * 0x00010001u;
+  int acc[4][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+#pragma unroll
+      for (int x = 0; x < 4; x++) acc[mt][j][x] = 0;
+  int staged_c = -1;
+  for (int kc = kc_begin; kc < kc_end; kc++) {
+    const int c = kc / L, t = kc % L;  // chunk order: mask-element chunk outer, digit level inner
+    if (c != staged_c) {
+      __syncthreads();  // previous chunk's fragments have been read
+      for (int idx = threadIdx.x; idx < kKtM * kKtIC; idx += blockDim.x) {
+        const int b = idx / kKtIC, i = idx % kKtIC;
+        uint32_t v = off;  // padding rows: all digits B/2 (their outputs are never stored)
+        if (b0 + b < P.batch) {
+          const uint64_t* src = P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + b]) : P.in + (size_t)(b0 + b) * (P.n1 + 1);
+          v += (uint32_t)radix_round(src[c * kKtIC + i], P.radix_log, L);
+        }
+        st[b * kKtRow + i] = (uint16_t)v;
+      }
+      __syncthreads();
+      staged_c = c;
+    }
+    const int shift = P.radix_log * t;
+    const uint4* bp = P.bfrag + ((size_t)nt * ks_total + (size_t)t * ks_per_t + (size_t)c * (kKtIC / 32)) * 32 * 4 + lane * 4;
+    uint4 bq[4];
+#pragma unroll
+    for (int x = 0; x < 4; x++) bq[x] = __ldg(bp + x);
+#pragma unroll 1
+    for (int ks = 0; ks < kKtIC / 32; ks++) {
+      uint4 bn[4];
+      if (ks + 1 < kKtIC / 32) {
+#pragma unroll
+        for (int x = 0; x < 4; x++) bn[x] = __ldg(bp + (size_t)(ks + 1) * 32 * 4 + x);
+      }
+      const uint32_t bw[16] = {bq[0].x, bq[0].y, bq[0].z, bq[0].w, bq[1].x, bq[1].y, bq[1].z, bq[1].w,
+                               bq[2].x, bq[2].y, bq[2].z, bq[2].w, bq[3].x, bq[3].y, bq[3].z, bq[3].w};
+#pragma unroll
+      for (int mt = 0; mt < 4; mt++) {
+        // A fragment: a0 (row g, k 4 q4..+3), a1 (row g+8), a2 (row g, k + 16), a3 (row g+8, k + 16)
+        uint32_t a[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          const int row = wm * 64 + mt * 16 + g + 8 * (x & 1);
+          const uint2 w = *reinterpret_cast<const uint2*>(st + row * kKtRow + ks * 32 + 4 * q4 + 16 * (x >> 1));
+          a[x] = __byte_perm((w.x >> shift) & dmask, (w.y >> shift) & dmask, 0x6420);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) imma_16832_u8(acc[mt][j], a, bw[2 * j], bw[2 * j + 1]);
+      }
+      if (ks + 1 < kKtIC / 32) {
+#pragma unroll
+        for (int x = 0; x < 4; x++) bq[x] = bn[x];
+      }
+    }
+  }
+  // ---- epilogue: recombine the byte planes, remove the digit offset, subtract from (0, body) ----
+  const int cols = P.n0 + 1;
+  const bool split = gridDim.z > 1;
+#pragma unroll
+  for (int x = 0; x < 4; x++) {  // c0: (row g, col 2 q4), c1: (g, 2 q4 + 1), c2: (g + 8, 2 q4), c3: (g + 8, 2 q4 + 1)
+    const int col = nt * 8 + 2 * q4 + (x & 1);
+    if (col >= cols) continue;
+    uint64_t surplus = 0;
+    for (int kc = kc_begin; kc < kc_end; kc++) surplus += P.colsum[(size_t)kc * cols + col];
+    surplus <<= P.radix_log - 1;
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) {
+      const int b = b0 + wm * 64 + mt * 16 + g + 8 * (x >> 1);
+      if (b >= P.batch) continue;
+      uint64_t sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) sum += (uint64_t)(uint32_t)acc[mt][j][x] << (8 * j);
+      uint64_t body = 0;
+      if (col == P.n0 && blockIdx.z == 0)
+        body = (P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b]) : P.in + (size_t)b * (P.n1 + 1))[P.n1];
+      const uint64_t v = body - (sum - surplus);
+      uint64_t* o = P.out + (size_t)b * cols + col;
+      if (split) atomicAdd(reinterpret_cast<unsigned long long*>(o), (unsigned long long)v);
+      else *o = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K7: small integer ops
 // ------------------------------------------------------------------------------------------
 // sample_extract (ops/ciphertext/glwe_ciphertext_ops.rs:31-76), k = 1
