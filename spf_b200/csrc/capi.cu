@@ -43,7 +43,7 @@ struct spf_b200_ctx {
   cudaStream_t stream[2] = {nullptr, nullptr};
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};  // host-pointer CBS pipeline: staging buffer of a slot is free again
-  DevBuf scratch[2][6];  // per pipeline slot: grow-only device scratch
+  DevBuf scratch[2][7];  // per pipeline slot: grow-only device scratch ([6]: keyswitch digit states)
   std::string err;
   std::atomic<uint64_t> launches{0};
   int sm_count = 148;
@@ -343,7 +343,12 @@ int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, s
   P.count = (int)ctx->p.ks.count;
   if (ctx->ks_bfrag && !getenv("SPF_B200_KS_NO_TC")) {  // dense contraction on the int8 tensor cores (K4t)
     KsTcBatch T;
-    T.out = d_out; T.in = d_in; T.ptrs = ptrs; T.bfrag = ctx->ks_bfrag; T.colsum = ctx->ks_tc_colsum;
+    DevBuf& st16 = ctx->scratch[s == ctx->stream[1] ? 1 : 0][6];
+    if (int rc = ensure(ctx, st16, batch * (size_t)P.n1 * 2)) return rc;
+    ks_tc_states_kernel<<<std::min<int>((int)((batch * (size_t)P.n1 + 255) / 256), ctx->sm_count * 8), 256, 0, s>>>(
+        (uint16_t*)st16.p, d_in, ptrs, P.batch, P.n1, P.radix_log, P.count);
+    if (int rc = check_launch(ctx, "ks_tc_states_kernel")) return rc;
+    T.out = d_out; T.in = d_in; T.ptrs = ptrs; T.st16 = (const uint16_t*)st16.p; T.bfrag = ctx->ks_bfrag; T.colsum = ctx->ks_tc_colsum;
     T.batch = P.batch; T.n1 = P.n1; T.n0 = P.n0; T.radix_log = P.radix_log; T.count = P.count;
     const int gx = (int)((batch + kKtM - 1) / kKtM), gy = (P.n0 + 1 + kKtN - 1) / kKtN;
     const int chunks = P.n1 / kKtIC * P.count;

@@ -644,6 +644,7 @@ struct KsTcBatch {
   uint64_t* out;            // [B][n0+1], zero-initialised when gridDim.z > 1
   const uint64_t* in;       // [B][n1+1]
   const void* const* ptrs;  // optional: ptrs[b] = L1 LWE input of item b
+  const uint16_t* st16;     // [B][n1] rounded + offset states (ks_tc_states_kernel)
   const uint4* bfrag;       // [n_tiles][k_steps][32 lanes][4] : per lane 8 planes x (b0, b1)
   const uint64_t* colsum;   // [chunks][n0+1]: sum over the chunk's (i, t) of ksk, chunk = c * L + t
   int batch, n1, n0, radix_log, count;
@@ -683,6 +684,20 @@ __global__ void ks_tc_colsum_kernel(uint64_t* colsum, const uint64_t* ksk, int n
   colsum[(size_t)chunk * cols + col] = acc;
 }
 
+// st16[b][i] = round(a_i of input b) + radix_offset: the digit source of K4t, computed once per
+// launch instead of once per column block
+__global__ void ks_tc_states_kernel(uint16_t* st16, const uint64_t* in, const void* const* ptrs, int batch, int n1,
+                                    int radix_log, int count) {
+  const uint32_t off = (uint32_t)radix_offset(radix_log, count);
+  const size_t total = (size_t)batch * n1;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = e / n1;
+    const int i = (int)(e % n1);
+    const uint64_t* src = ptrs ? static_cast<const uint64_t*>(ptrs[b]) : in + b * (size_t)(n1 + 1);
+    st16[e] = (uint16_t)((uint32_t)radix_round(src[i], radix_log, count) + off);
+  }
+}
+
 __device__ __forceinline__ void imma_16832_u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
@@ -713,14 +728,12 @@ __global__ void __launch_bounds__(256, 1) keyswitch_tc_kernel(KsTcBatch P) {
     const int c = kc / L, t = kc % L;  // chunk order: mask-element chunk outer, digit level inner
     if (c != staged_c) {
       __syncthreads();  // previous chunk's fragments have been read
-      for (int idx = threadIdx.x; idx < kKtM * kKtIC; idx += blockDim.x) {
-        const int b = idx / kKtIC, i = idx % kKtIC;
-        uint32_t v = off;  // padding rows: all digits B/2 (their outputs are never stored)
-        if (b0 + b < P.batch) {
-          const uint64_t* src = P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + b]) : P.in + (size_t)(b0 + b) * (P.n1 + 1);
-          v += (uint32_t)radix_round(src[c * kKtIC + i], P.radix_log, L);
-        }
-        st[b * kKtRow + i] = (uint16_t)v;
+      // 128 rows x 1 KiB: 16 bytes per thread and step, rows beyond the batch get all digits = B/2
+      for (int idx = threadIdx.x; idx < kKtM * (kKtIC / 8); idx += blockDim.x) {
+        const int b = idx / (kKtIC / 8), i8 = idx % (kKtIC / 8);
+        uint4 v = make_uint4(off * 0x00010001u, off * 0x00010001u, off * 0x00010001u, off * 0x00010001u);
+        if (b0 + b < P.batch) v = __ldg(reinterpret_cast<const uint4*>(P.st16 + (size_t)(b0 + b) * P.n1 + c * kKtIC) + i8);
+        *reinterpret_cast<uint4*>(st + b * kKtRow + 8 * i8) = v;
       }
       __syncthreads();
       staged_c = c;

@@ -69,7 +69,10 @@ ksk_bytes = keys.ksk.nbytes
 alg = ksk_bytes + B * (ev.len_lwe_l1 + ev.len_lwe_l0) * 8
 rows.append({"op": "keyswitch_l1_l0", "batch": B, "ms": ms, "ops_per_s": B / ms * 1e3, "algorithmic_gb_s": alg / ms / 1e6,
              "hbm_frac": alg / ms / 1e6 / hbm, "u64_mad_per_s": B * 2048 * 6 * 638 / ms * 1e3,
-             "note": "integer MAD bound for large batches: the KSK is swept once per 16 ciphertexts from L2"})
+             "int8_tmac_per_s": B * 2048 * 6 * 640 * 8 / ms / 1e9, "imma_peak_tmac_per_s": 572.0,
+             "tensor_frac": B * 2048 * 6 * 640 * 8 / ms / 1e9 / 572.0,
+             "note": "8 u8 x u8 -> s32 byte-plane GEMMs on mma.sync m16n8k32 (IMMA); peak = measured IMMA.16832 rate "
+                     "on this part (build/imma_probe.cu: 572 T MAC/s)"})
 # ---- sample extract ----
 g = rand_u64(B, ev.len_glwe)
 l1o = torch.empty(B * ev.len_lwe_l1, dtype=torch.int64, device=dev)
