@@ -192,6 +192,10 @@ int spf_b200_graph_run(spf_b200_graph *graph);
 void spf_b200_graph_destroy(spf_b200_graph *graph);
 int spf_b200_graph_levels(const spf_b200_graph *graph);
 uint64_t spf_b200_graph_launches(const spf_b200_graph *graph); /* kernel launches of the last run */
+/* Re-points the host buffer of an Input* / Output* node of a built graph: one validated, levelised,
+ * device-resident graph then serves every invocation of the same instruction shape (the reference
+ * rebuilds and re-levelises the MUX circuit per instruction dispatch, fhe_circuit.rs:473-494). */
+int spf_b200_graph_set_io(spf_b200_graph *graph, size_t node, void *io);
 /* build + run + destroy */
 int spf_b200_run_graph(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes);
 

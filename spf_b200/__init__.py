@@ -392,6 +392,7 @@ ABI.update({
     "spf_b200_graph_levels": [_vp],
     "spf_b200_graph_launches": [_vp],
     "spf_b200_run_graph": [_vp, C.POINTER(_Node), _sz],
+    "spf_b200_graph_set_io": [_vp, _sz, _vp],
     "spf_b200_graph_build_sharded": [_vp, C.POINTER(_Node), _sz, C.c_int, C.POINTER(_vp)],
     "spf_b200_graph_run_sharded": [_vp, C.c_int, C.c_int, _vp, _vp],
 })
@@ -483,6 +484,15 @@ class CompiledGraph:
         if self._cb_error is not None:
             raise self._cb_error
         self.ev._check(rc)
+
+    def set_io(self, node: int, buf: np.ndarray) -> None:
+        """Re-point an Input*/Output* node at another host buffer (same ciphertext kind): a compiled graph
+        is reusable across invocations of the same instruction shape."""
+        if not isinstance(buf, np.ndarray) or not buf.flags["C_CONTIGUOUS"]:
+            raise SpfError(-1, "io buffers must be C-contiguous numpy arrays")
+        self.ev._check(lib().spf_b200_graph_set_io(self._h, node, buf.ctypes.data))
+        self._bound = getattr(self, "_bound", {})
+        self._bound[node] = buf  # keep alive
 
     @property
     def levels(self) -> int:

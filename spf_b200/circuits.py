@@ -111,3 +111,36 @@ def add_then_greater_than(a_bits, b_bits, c_bits, out_sum, out_gt, programs: int
         ss = [_refresh(c, n) for n in s]
         c.add("OutputGlwe1", _greater_than_node(c, ss, sc), io=out_gt[p])
     return c
+
+
+class InstructionCache:
+    """Graph-generation cache: one compiled, levelised, device-resident graph per
+    (instruction, width), re-bound to the operands of each invocation with CompiledGraph.set_io
+    instead of rebuilding the MUX circuit and re-levelising it per dispatch as
+    FheCircuit::insert_mux_circuit_and_connect_inputs (fhe_circuit.rs:473-494) does."""
+
+    def __init__(self, evaluation):
+        from . import CompiledGraph
+
+        self._ev, self._compile, self._cache = evaluation, CompiledGraph, {}
+        self.hits = self.misses = 0
+
+    def add(self, a_bits, b_bits, out_bits):
+        """out = a + b (w-bit operands as L1 GLWE bit ciphertexts, w + 1 result bits), blocking."""
+        w = len(a_bits)
+        key = ("add", w)
+        if key not in self._cache:
+            self.misses += 1
+            c = ripple_carry_adder(list(a_bits), list(b_bits), list(out_bits))
+            ins = [i for i, n in enumerate(c.nodes) if n[0] == 2]    # InputGlwe1, in a then b order
+            outs = [i for i, n in enumerate(c.nodes) if n[0] == 7]   # OutputGlwe1, sum bits then carry
+            self._cache[key] = (self._compile(self._ev, c), ins, outs)
+        else:
+            self.hits += 1
+        g, ins, outs = self._cache[key]
+        for node, buf in zip(ins, list(a_bits) + list(b_bits)):
+            g.set_io(node, buf)
+        for node, buf in zip(outs, out_bits):
+            g.set_io(node, buf)
+        g.run()
+        return g

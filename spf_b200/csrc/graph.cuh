@@ -486,6 +486,18 @@ int spf_b200_graph_run(spf_b200_graph* g) {
   return spf_b200_graph_run_sharded(g, 0, 1, nullptr, nullptr);
 }
 
+// Re-points the host buffer of an Input*/Output* node, so that one built (validated, levelised, device-
+// resident) graph serves every invocation of the same instruction shape: the reference rebuilds the
+// MUX circuit and re-levelises on every instruction dispatch (fhe_circuit.rs:473-494).
+int spf_b200_graph_set_io(spf_b200_graph* g, size_t node, void* io) {
+  if (!g) return SPF_E_INVALID;
+  if (node >= g->nodes.size() || g->nodes[node].op > SPF_OP_OUTPUT_GLEV1)
+    return fail(g->ctx, SPF_E_INVALID, "set_io: node " + std::to_string(node) + " is not an Input*/Output* node");
+  if (!io) return fail(g->ctx, SPF_E_INVALID, "set_io: io pointer is NULL");
+  g->nodes[node].io = io;
+  return 0;
+}
+
 int spf_b200_graph_levels(const spf_b200_graph* g) { return g ? g->n_levels : -1; }
 uint64_t spf_b200_graph_launches(const spf_b200_graph* g) { return g ? g->launches_per_run : 0; }
 

@@ -228,3 +228,22 @@ def test_sharded_run_emulated_on_one_gpu(keys, client, evaluation):
     assert spf_b200.lib().spf_b200_graph_run(graphs[0]._h) == -1
     for g in graphs:
         g.close()
+
+
+def test_instruction_cache_reuses_compiled_graph(keys, client, evaluation):
+    """one compiled graph per (instruction, width), re-bound per invocation."""
+    import spf_b200
+    from spf_b200.circuits import InstructionCache
+
+    cache = InstructionCache(evaluation)
+    w = 5
+    for a, b in ((3, 9), (31, 31), (0, 17)):
+        ab = [client.encrypt_glwe_l1([(a >> i) & 1]) for i in range(w)]
+        bb = [client.encrypt_glwe_l1([(b >> i) & 1]) for i in range(w)]
+        outs = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w + 1)]
+        cache.add(ab, bb, outs)
+        assert sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(outs)) == a + b
+    assert (cache.misses, cache.hits) == (1, 2)
+    g = cache._cache[("add", w)][0]
+    with pytest.raises(spf_b200.SpfError):
+        g.set_io(10 ** 6, np.zeros(4, dtype=np.uint64))  # not a node
