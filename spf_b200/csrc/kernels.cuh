@@ -31,10 +31,12 @@ __device__ __forceinline__ void load_tables(C2* sT1, C2* sT2, const DevTables& t
 constexpr int kTableBytes = (kT1Elems + kT2Elems) * 16;  // 17472
 
 // ------------------------------------------------------------------------------------------
-// K3: batched programmable bootstrap (blind rotation).  3 ciphertexts per CTA, each owned by a
-// PAIR of teams (128 threads, see pbs_pair_team), one CTA per SM: 12 warps, <= 168 registers.
-// Every pair walks the 637 BSK rows in order, so a row is fetched from HBM once per sweep and
-// then served from L2 to all resident CTAs.
+// K3: batched programmable bootstrap (blind rotation), throughput mode.  3 ciphertexts per CTA,
+// each owned by a PAIR of teams (128 threads, see pbs_pair_team), one persistent CTA per SM:
+// 12 warps, <= 168 registers.  Resident pairs walk the 637 BSK rows roughly in step, so a row is
+// fetched from HBM once per sweep and then served from L2 to all CTAs.  The per-thread constants
+// and parked values of a pair live in TENSOR MEMORY (tcgen05.ld/st): the switches below exist for
+// A/B measurements (DESIGN.md section 7 lists what each is worth).
 // ------------------------------------------------------------------------------------------
 constexpr int kPbsPairs = 3;
 constexpr int kPbsPairBytes = 2 * kN * 8 + 2 * kXBuf * 16;            // acc + 2 exchange buffers = 66048
