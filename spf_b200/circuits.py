@@ -144,3 +144,22 @@ class InstructionCache:
             g.set_io(node, buf)
         g.run()
         return g
+
+
+# ---- packing front end --------------------------------------------------------
+def pack(c: FheCircuit, bit_nodes: list[int]) -> int:
+    """DynamicGenericIntGraphNodes::pack (parasol_runtime/src/fluent/dynamic_generic_int_graph_nodes.rs:
+    139-205): bit i (an L1 GLWE with the bit in coefficient 0) is multiplied by X^i (MulXN) and the shifted
+    ciphertexts are summed by a GlweAdd tree, so bit i ends up in coefficient i of ONE GLWE."""
+    assert len(bit_nodes) > 0
+    level = [n if i == 0 else c.add("MulXN", n, arg=i) for i, n in enumerate(bit_nodes)]
+    while len(level) > 1:
+        nxt = [c.add("GlweAdd", level[i], level[i + 1]) if i + 1 < len(level) else level[i] for i in range(0, len(level), 2)]
+        level = nxt
+    return level[0]
+
+
+def unpack(c: FheCircuit, packed_node: int, bit_len: int) -> list[int]:
+    """PackedDynamicGenericIntGraphNode::unpack (fluent/packed_dynamic_generic_int_graph_node.rs:24-38):
+    SampleExtract(i) of the packed GLWE gives bit i as an L1 LWE."""
+    return [c.add("SampleExtract", packed_node, arg=i) for i in range(bit_len)]

@@ -247,3 +247,30 @@ def test_instruction_cache_reuses_compiled_graph(keys, client, evaluation):
     g = cache._cache[("add", w)][0]
     with pytest.raises(spf_b200.SpfError):
         g.set_io(10 ** 6, np.zeros(4, dtype=np.uint64))  # not a node
+
+
+def test_pack_unpack_roundtrip(oracle, keys, client, proc):
+    """the fluent layer's pack (MulXN + GlweAdd tree) and unpack (SampleExtract(i)) graph
+    shapes on the executor; the unpacked bits are refreshed through keyswitch + CBS and used as selectors."""
+    import spf_b200
+    from spf_b200.circuits import pack, unpack
+
+    value, w = 0b1011001, 7
+    bits = [(value >> i) & 1 for i in range(w)]
+    c = spf_b200.FheCircuit()
+    ins = [c.add("InputGlwe1", io=client.encrypt_glwe_l1([b])) for b in bits]
+    packed = pack(c, ins)
+    packed_out = np.zeros(keys.glwe_len, dtype=np.uint64)
+    c.add("OutputGlwe1", packed, io=packed_out)
+    lwes = unpack(c, packed, w)
+    l1_out = [np.zeros(keys.lwe1_len, dtype=np.uint64) for _ in range(w)]
+    zero, one = c.add("ZeroGlwe1"), c.add("OneGlwe1")
+    mux_out = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w)]
+    for i, n in enumerate(lwes):
+        c.add("OutputLwe1", n, io=l1_out[i])
+        sel = c.add("CircuitBootstrap", c.add("KeyswitchL1toL0", n))
+        c.add("OutputGlwe1", c.add("CMux", sel, zero, one), io=mux_out[i])
+    proc.run_graph_blocking(c)
+    assert client.decrypt_glwe_l1(packed_out)[:w].tolist() == bits          # bit i sits in coefficient i
+    assert [client.decrypt_lwe_l1(x) for x in l1_out] == bits
+    assert [int(client.decrypt_glwe_l1(x)[0]) for x in mux_out] == bits
