@@ -24,6 +24,9 @@
  *                      void*, NULL = the context's own stream).  Device-resident FFT-domain
  *                      ciphertexts (GGSW) carry a 2^-10 scale factor; they only
  *                      ever travel between spf_b200_dev_* calls.
+ *  - Device-pointer ops of one context share grow-only device scratch (PBS outputs, keyswitch digit
+ *    states): issue them on ONE stream at a time, or serialise streams with events; independent
+ *    pipelines use independent contexts.
  *  - A context is bound to one CUDA device and may be used from one thread at a time (the
  *    reference allows only one dispatching thread as well: CircuitProcessor methods take
  *    &mut self, circuit_processor/mod.rs:125-130).
