@@ -174,14 +174,14 @@ struct DevPairCx {
   }
   __device__ __forceinline__ void own_load(uint64_t (&own)[32], const uint64_t* pa) const {
 #if SPF_PBS_TMEM_OWN
+    uint32_t r[4][16];
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      uint32_t r[16];
-      tmem_ld16(r, own_taddr + 16 * c);
-      tmem_wait_ld();
+    for (int c = 0; c < 4; c++) tmem_ld16(r[c], own_taddr + 16 * c);
+    tmem_wait_ld();  // one wait for all four loads
 #pragma unroll
-      for (int i = 0; i < 8; i++) own[8 * c + i] = ((uint64_t)r[2 * i + 1] << 32) | r[2 * i];
-    }
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) own[8 * c + i] = ((uint64_t)r[c][2 * i + 1] << 32) | r[c][2 * i];
 #else
 #pragma unroll
     for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
