@@ -94,6 +94,7 @@ struct spf_b200_graph {
   int n_levels = 0;
   uint64_t launches_per_run = 0;
   int world = 1;  // CircuitBootstrap groups are laid out as `world` equal chunks (spf_b200_graph_build_sharded)
+  std::vector<void*> pinned;  // io buffers page-locked by this graph (cudaHostRegister), so that their copies are true DMAs
 };
 
 namespace {
@@ -134,6 +135,14 @@ int ensure_constants(spf_b200_ctx* ctx) {
 }
 
 int graph_fail(spf_b200_ctx* ctx, const std::string& msg) { return fail(ctx, SPF_E_GRAPH, msg); }
+
+// Page-lock a host ciphertext buffer for the lifetime of the graph (best effort: a buffer that cannot
+// be registered -- already pinned by the caller, read-only mapping -- is simply copied as pageable).
+void pin_io(spf_b200_graph* g, void* p, size_t bytes) {
+  if (!p || getenv("SPF_B200_NO_PIN")) return;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) g->pinned.push_back(p);
+  else cudaGetLastError();  // clear the sticky-free error
+}
 
 // Items per rank of a sharded CircuitBootstrap group: equal chunks (the last ones may be short or
 // empty) so that one all-gather of world * chunk items puts every GGSW on every rank.
@@ -368,8 +377,11 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
         default:
           if (G.out_base) g->dptr[id] = G.out_base + k * ct_bytes(p, oi.out);
       }
-      if (G.op <= SPF_OP_INPUT_GLEV1) g->inputs.push_back(id);
-      if (G.op >= SPF_OP_OUTPUT_LWE0 && G.op <= SPF_OP_OUTPUT_GLEV1) g->outputs.push_back(id);
+      if (G.op <= SPF_OP_INPUT_GLEV1) { g->inputs.push_back(id); pin_io(g.get(), g->nodes[id].io, ct_host_bytes(p, g->type[id])); }
+      if (G.op >= SPF_OP_OUTPUT_LWE0 && G.op <= SPF_OP_OUTPUT_GLEV1) {
+        g->outputs.push_back(id);
+        pin_io(g.get(), g->nodes[id].io, ct_host_bytes(p, g->type[g->nodes[id].in[0]]));
+      }
     }
   }
   std::vector<void*> h_ptrs(std::max<size_t>(n_ptrs, 1), nullptr);
@@ -477,6 +489,7 @@ void spf_b200_graph_destroy(spf_b200_graph* g) {
   cudaFree(g->d_ptrs);
   cudaFree(g->d_u32);
   cudaFree(g->d_out_stage);
+  for (void* q : g->pinned) cudaHostUnregister(q);
   delete g;
 }
 
@@ -494,7 +507,14 @@ int spf_b200_graph_set_io(spf_b200_graph* g, size_t node, void* io) {
   if (node >= g->nodes.size() || g->nodes[node].op > SPF_OP_OUTPUT_GLEV1)
     return fail(g->ctx, SPF_E_INVALID, "set_io: node " + std::to_string(node) + " is not an Input*/Output* node");
   if (!io) return fail(g->ctx, SPF_E_INVALID, "set_io: io pointer is NULL");
+  void* old = g->nodes[node].io;
+  if (old == io) return 0;
+  auto it = std::find(g->pinned.begin(), g->pinned.end(), old);
+  if (it != g->pinned.end()) { cudaHostUnregister(old); g->pinned.erase(it); }
   g->nodes[node].io = io;
+  const uint32_t op = g->nodes[node].op;
+  const CtType t = op <= SPF_OP_INPUT_GLEV1 ? g->type[node] : g->type[g->nodes[node].in[0]];
+  pin_io(g, io, ct_host_bytes(&g->ctx->p, t));
   return 0;
 }
 
