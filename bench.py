@@ -450,11 +450,12 @@ def run_gpu(args):
         client = O.Client(keys)
         if args.check > 0:
             if result_host is None:
-                tmp = torch.empty(args.check * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
-                ev.dev_fft_rescale(tmp.data_ptr(), d_out.data_ptr(), args.check * ev.len_ggsw, to_device=False, stream=stream)
+                nchk = min(args.check, B)
+                tmp = torch.empty(nchk * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
+                ev.dev_fft_rescale(tmp.data_ptr(), d_out.data_ptr(), nchk * ev.len_ggsw, to_device=False, stream=stream)
                 torch.cuda.synchronize()
-                sample_out = tmp.cpu().numpy().view(np.complex128).reshape(args.check, ev.len_ggsw)
-                idx = list(range(args.check))
+                sample_out = tmp.cpu().numpy().view(np.complex128).reshape(nchk, ev.len_ggsw)
+                idx = list(range(nchk))
             else:
                 idx = np.linspace(0, B - 1, args.check).astype(int).tolist()
                 sample_out = result_host[idx]

@@ -149,6 +149,10 @@ struct HostQuadCx {
   pthread_barrier_t* bar_quad;
   void sync() { pthread_barrier_wait(bar_team); }
   void quad_sync() { pthread_barrier_wait(bar_quad); }
+  // the device stages the next BSK row in shared memory with a bulk copy; the host reads the key directly
+  void row_prefetch(const C2*) {}
+  const C2* row_wait(int, const C2* row) { return row; }
+  C2 row_load(const C2* p) { return *p; }
   template <bool CONJ>
   void t1_mul(C2 (&v)[16], const C2* T1) {
     for (int k1 = 0; k1 < 16; k1++) v[k1] = CONJ ? cmul_conj(v[k1], T1[k1 * 64 + u]) : cmul(v[k1], T1[k1 * 64 + u]);
@@ -280,7 +284,10 @@ void emu_pbs_quad(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lu
   std::vector<C2> xbuf(4 * kXBuf);
   std::vector<uint64_t> acc(2 * kN);
   PbsArgs A{lwe_in, lut, glwe_out, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count};
-  run_quad([&](HostQuadCx& cx) { pbs_quad_team(cx, A, acc.data(), xbuf.data(), t.T1.data(), t.T2.data()); });
+  run_quad([&](HostQuadCx& cx) {
+    int executed = 0;
+    pbs_quad_team(cx, A, acc.data(), xbuf.data(), t.T1.data(), t.T2.data(), executed);
+  });
 }
 
 // trace / CBS tail for one level.  mode: 0 CBS pre-process + trace (+SS), 1 plain trace, 2 SS only.

@@ -294,13 +294,48 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
 // K3q: latency mode of the blind rotation, one ciphertext per CTA on 4 teams (pbs_quad_team);
 // chosen by launch_pbs when the batch has at most one ciphertext per SM.
 // ------------------------------------------------------------------------------------------
-constexpr int kQuadSmem = kTableBytes + 2 * kN * 8 + 4 * kXBuf * 16;  // 116800
+// smem: pass-2 twiddles | GLWE accumulator | 4 exchange buffers | one staged BSK row (128 KiB) | mbarrier.
+// The pass-1 twiddles are only needed to fill tensor memory at start-up and borrow the row buffer.
+constexpr int kQuadT2Bytes = kT2Elems * 16;                                         // 1088
+constexpr int kQuadRowBytes = 8 * kM * 16;                                           // 131072: one GGSW of the BSK
+constexpr int kQuadSmem = kQuadT2Bytes + 2 * kN * 8 + 4 * kXBuf * 16 + kQuadRowBytes + 16;  // 231504
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 struct DevQuadCx {
   int u, h, t;
   uint32_t t1_taddr;
+  C2* row;          // staged BSK row
+  uint64_t* mbar;   // completes when the bulk copy into `row` has landed
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(1 + 2 * h + t) : "memory"); }
   __device__ __forceinline__ void quad_sync() const { __syncthreads(); }
+  // one thread of the CTA starts the bulk copy (TMA) of the next step's 128 KiB BSK row
+  __device__ __forceinline__ void row_prefetch(const C2* src) const {
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"((uint32_t)kQuadRowBytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(row)), "l"(src), "r"((uint32_t)kQuadRowBytes), "r"(smem_u32(mbar)) : "memory");
+    }
+  }
+  // k-th completed copy: mbarrier phase parity k & 1
+  __device__ __forceinline__ const C2* row_wait(int k, const C2*) const {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "ROW_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra ROW_DONE;\n\t"
+        "bra ROW_WAIT;\n\t"
+        "ROW_DONE:\n\t"
+        "}" ::"r"(smem_u32(mbar)), "r"((uint32_t)(k & 1)) : "memory");
+    return row;
+  }
+  __device__ __forceinline__ C2 row_load(const C2* p) const {
+    C2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(smem_u32(p)) : "memory");
+    return r;
+  }
   template <bool CONJ>
   __device__ __forceinline__ void t1_mul(C2 (&v)[16], const C2* T1) const {
 #pragma unroll
@@ -329,15 +364,23 @@ struct DevQuadCx {
 
 __global__ void __launch_bounds__(4 * kTeam, 1) pbs_quad_kernel(PbsBatch P, DevTables tabs) {
   extern __shared__ __align__(16) unsigned char smem[];
-  C2* sT1 = reinterpret_cast<C2*>(smem);
-  C2* sT2 = sT1 + kT1Elems;
+  C2* sT2 = reinterpret_cast<C2*>(smem);
+  uint64_t* acc = reinterpret_cast<uint64_t*>(smem + kQuadT2Bytes);
+  C2* xb = reinterpret_cast<C2*>(smem + kQuadT2Bytes + 2 * kN * 8);
+  C2* row = reinterpret_cast<C2*>(smem + kQuadT2Bytes + 2 * kN * 8 + 4 * kXBuf * 16);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kQuadT2Bytes + 2 * kN * 8 + 4 * kXBuf * 16 + kQuadRowBytes);
+  C2* sT1 = row;  // borrowed until tensor memory holds the pass-1 twiddles
   load_tables(sT1, sT2, tabs);
   uint32_t tmem_alloc;
   const uint32_t t1_taddr = pair_tmem_init(sT1, sT2, tmem_alloc);
-  uint64_t* acc = reinterpret_cast<uint64_t*>(smem + kTableBytes);
-  C2* xb = reinterpret_cast<C2*>(smem + kTableBytes + 2 * kN * 8);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   const int team = threadIdx.x / kTeam;
-  DevQuadCx cx{(int)(threadIdx.x % kTeam), team >> 1, team & 1, t1_taddr};
+  DevQuadCx cx{(int)(threadIdx.x % kTeam), team >> 1, team & 1, t1_taddr, row, mbar};
+  int copies = 0;  // bulk copies completed so far on this CTA's mbarrier (phase parity bookkeeping)
   for (int c = blockIdx.x; c < P.batch; c += gridDim.x) {
     PbsArgs A;
     A.lwe_in = P.ptrs ? static_cast<const uint64_t*>(P.ptrs[c]) : P.lwe_in + (size_t)c * (P.lwe_n + 1);
@@ -349,7 +392,7 @@ __global__ void __launch_bounds__(4 * kTeam, 1) pbs_quad_kernel(PbsBatch P, DevT
     A.log_v = P.log_v;
     A.cbs_radix_log = P.cbs_radix_log;
     A.cbs_count = P.cbs_count;
-    pbs_quad_team(cx, A, acc, xb, sT1, sT2);
+    pbs_quad_team(cx, A, acc, xb, sT1, sT2, copies);
     cx.quad_sync();
   }
   pair_tmem_free(tmem_alloc);

@@ -501,8 +501,9 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
 // instead of two + two + one; the arithmetic per coefficient is identical to pbs_pair_team.
 //   cx.u, cx.h, cx.t;  cx.sync(): team barrier;  cx.quad_sync(): the ciphertext's 256 threads
 //   xb: 4 exchange buffers, team (h, t) owns xb + (2 h + t) * kXBuf.
+//   executed: running count of executed steps on this CTA (phase bookkeeping of the staged-row barrier)
 template <class Cx>
-SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const C2* T1, const C2* T2) {
+SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const C2* T1, const C2* T2, int& executed) {
   const int u = cx.u, h = cx.h, t = cx.t, g = 2 * h + t;
   const int k1 = u & 15, q = u >> 4;
   const int n = A.lwe_n;
@@ -534,6 +535,18 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
   uint64_t own[32];
 #pragma unroll
   for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
+  // The BSK row of the NEXT executed step is staged in shared memory by a bulk copy (device: TMA,
+  // cp.async.bulk + mbarrier) while the current step's inverse transform and the next forward
+  // transform run, so the multiply-accumulate phase never waits for L2.
+  auto next_executed = [&](int from) {  // first step >= from whose rotation is not the identity
+    int j = from;
+    while (j < n && modulus_switch(ldg_u64(A.lwe_in + j), A.log_chi, A.log_v, log2n) == 0) j++;
+    return j;
+  };
+  {
+    const int j0 = next_executed(0);
+    if (j0 < n) cx.row_prefetch(A.bsk + (size_t)j0 * 8 * kM);
+  }
 #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const int at = (int)modulus_switch(a_next, A.log_chi, A.log_v, log2n);
@@ -566,17 +579,19 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     }
     cx.quad_sync();
     // MAD: team g owns the bins u + 64 (g + 4 k3) of every polynomial
+    const C2* staged = cx.row_wait(executed, ggsw);  // this step's BSK row (device: in shared memory)
+    executed++;
     C2 f[2][4];
 #pragma unroll
     for (int b = 0; b < 4; b++) {  // spectrum of team b = (hb, tb): digit tb <-> GLEV level 1 - tb
-      const C2* grow = ggsw + (size_t)(((b >> 1) * 2 + (1 - (b & 1))) * 2) * kM;
+      const C2* grow = staged + (size_t)(((b >> 1) * 2 + (1 - (b & 1))) * 2) * kM;
       C2 d[4], g0[4], g1[4];
 #pragma unroll
       for (int qp = 0; qp < 4; qp++) d[qp] = xb[b * kXBuf + k1 * kXPad + qp + 4 * q + 16 * g];
 #pragma unroll
       for (int k3 = 0; k3 < 4; k3++) {
-        g0[k3] = ldg_c2_pinned(grow + u + 64 * (g + 4 * k3));
-        g1[k3] = ldg_c2_pinned(grow + kM + u + 64 * (g + 4 * k3));
+        g0[k3] = cx.row_load(grow + u + 64 * (g + 4 * k3));
+        g1[k3] = cx.row_load(grow + kM + u + 64 * (g + 4 * k3));
       }
       bfly4<false>(d[0], d[1], d[2], d[3]);
 #pragma unroll
@@ -593,6 +608,10 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       for (int qp = 0; qp < 4; qp++) xb[2 * p * kXBuf + k1 * kXPad + qp + 4 * q + 16 * g] = f[p][qp];
     }
     cx.quad_sync();
+    {  // every thread is done with the staged row: fetch the one of the next executed step
+      const int jn = next_executed(i + 1);
+      if (jn < n) cx.row_prefetch(A.bsk + (size_t)jn * 8 * kM);
+    }
     if (t == 0) {
       C2 w[16];
       double ws[16];
