@@ -253,3 +253,17 @@ def test_kernel_selection_thresholds(oracle, keys, client, evaluation):
         assert oracle.torus_distance(want, bulk[i]).max() <= 2.0 ** -30
         assert oracle.torus_distance(want, wide[i]).max() <= 2.0 ** -30
         assert client.decrypt_glwe_l1(wide[i])[:2].tolist() == ([1, 1] if bits[i] else [0, 1])
+
+
+def test_short_lwe_through_every_kernel():
+    """tools/sanitizer_probe.py: DEFAULT_128 rings with a 16-step blind rotation through every kernel
+    (quad and pair-team PBS, trace / scheme switch, wide and bulk CMUX, tensor-core and IMAD keyswitch);
+    also exercises a non-default l0 dimension end to end."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitizer_probe.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "sanitizer probe: ok" in r.stdout, r.stdout + r.stderr
