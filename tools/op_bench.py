@@ -87,6 +87,28 @@ cts = torch.from_numpy(encrypt_lwe0_numpy(keys.lwe0_sk, bits, keys.params.lwe_st
 ggsw = torch.empty(B * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
 ms = timed(lambda: ev.dev_circuit_bootstrap(ggsw.data_ptr(), cts.data_ptr(), B, reference_scale=False, stream=s), reps=2)
 rows.append({"op": "circuit_bootstrap", "batch": B, "ms": ms, "ops_per_s": B / ms * 1e3, "fp64_tflops": 293.3e6 * B / ms / 1e9})
+# ---- PBS alone (device resident) ----
+from bench import cbs_lut
+lut = torch.from_numpy(cbs_lut().view(np.int64)).to(dev)
+glwe_o = torch.empty(B * ev.len_glwe, dtype=torch.int64, device=dev)
+ms = timed(lambda: ev.dev_programmable_bootstrap(glwe_o.data_ptr(), cts.data_ptr(), lut.data_ptr(), 0, 2, B, stream=s), reps=2)
+rows.append({"op": "programmable_bootstrap", "batch": B, "ms": ms, "ops_per_s": B / ms * 1e3, "fp64_tflops": 263.5e6 * B / ms / 1e9})
+del ggsw, glwe_o
+# ---- GLEV cmux and scheme switch: host-pointer API only (copies inside the timed call) ----
+nb = min(B, 512)
+torch.cuda.synchronize()
+glev_a = rng.integers(0, 1 << 63, (nb, ev.len_glev), dtype=np.uint64)
+glev_b = rng.integers(0, 1 << 63, (nb, ev.len_glev), dtype=np.uint64)
+sel_h = np.broadcast_to(np.ascontiguousarray(one), (nb, ev.len_ggsw)).copy()
+ev.glev_cmux(sel_h[:4], glev_a[:4], glev_b[:4])
+t0 = time.perf_counter(); ev.glev_cmux(sel_h, glev_a, glev_b); dt = time.perf_counter() - t0
+rows.append({"op": "glev_cmux (host pointers, copies inside)", "batch": nb, "ms": 1e3 * dt, "ops_per_s": nb / dt})
+glev_in = np.stack([client.encrypt_glev_l1([1])] * 8 + [client.encrypt_glev_l1([0])] * 8)
+glev_in = np.ascontiguousarray(np.tile(glev_in, (nb // 16, 1)))
+ev.scheme_switch(glev_in[:4])
+t0 = time.perf_counter(); ss = ev.scheme_switch(glev_in); dt = time.perf_counter() - t0
+rows.append({"op": "scheme_switch (host pointers, copies inside)", "batch": len(glev_in), "ms": 1e3 * dt, "ops_per_s": len(glev_in) / dt,
+             "decrypt_ok": bool(client.decrypt_ggsw_l1(ss[0]) == 1 and client.decrypt_ggsw_l1(ss[8]) == 0)})
 for r in rows:
     print(json.dumps(r), flush=True)
 # ---- CPU port, single thread, one op each (the reference's bench measures exactly these) ----
@@ -97,4 +119,8 @@ l1c = O.sample_extract(keys, g1, 0)
 t0 = time.perf_counter(); O.sample_extract(keys, g1, 0); cpu["sample_extract_ms"] = 1e3 * (time.perf_counter() - t0)
 t0 = time.perf_counter(); l0c = O.keyswitch_lwe(keys, l1c); cpu["keyswitch_ms"] = 1e3 * (time.perf_counter() - t0)
 t0 = time.perf_counter(); O.circuit_bootstrap(keys, l0c); cpu["circuit_bootstrap_ms"] = 1e3 * (time.perf_counter() - t0)
+t0 = time.perf_counter(); O.cbs_pbs_stage(keys, l0c); cpu["programmable_bootstrap_ms"] = 1e3 * (time.perf_counter() - t0)
+ge = client.encrypt_glev_l1([1])
+t0 = time.perf_counter(); O.glev_cmux(keys, ge, ge, one); cpu["glev_cmux_ms"] = 1e3 * (time.perf_counter() - t0)
+t0 = time.perf_counter(); O.scheme_switch(keys, ge); cpu["scheme_switch_ms"] = 1e3 * (time.perf_counter() - t0)
 print(json.dumps({"cpu_port_single_thread": cpu}), flush=True)
