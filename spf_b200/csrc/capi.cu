@@ -38,6 +38,7 @@ struct spf_b200_ctx {
   uint64_t* ksk_colsum = nullptr;  // keyswitch_kernel's per-block column sums of the KSK
   uint4* ks_bfrag = nullptr;       // keyswitch_tc_kernel: KSK byte planes in mma B-fragment order (nullptr: shape unsupported)
   uint64_t* ks_tc_colsum = nullptr;  // keyswitch_tc_kernel: per-(chunk, level) column sums
+  uint8_t* ks_btiles = nullptr;      // keyswitch_umma_kernel: KSK byte planes as canonical K-major UMMA tiles
   C2 *T1 = nullptr, *T2 = nullptr;
   uint32_t* kinv = nullptr;
   cudaStream_t stream[2] = {nullptr, nullptr};
@@ -231,6 +232,13 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
       ks_tc_colsum_kernel<<<dim3((cols + 127) / 128, chunks), 128, 0, ctx->stream[0]>>>(ctx->ks_tc_colsum, ctx->ksk, n1, L, cols);
       CUB(cudaGetLastError());
       CUB(cudaFuncSetAttribute(keyswitch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKtSmem));
+      // tcgen05 keyswitch (K4u): the same planes as canonical K-major UMMA tiles, 16 KiB per (column block, k-step)
+      const int n_blocks = (cols + kKuN - 1) / kKuN;
+      const size_t tile_bytes = (size_t)n_blocks * ks_total * kKuBTile;
+      CUB(cudaMalloc(&ctx->ks_btiles, tile_bytes));
+      ks_umma_prepare_kernel<<<(unsigned)((tile_bytes / 16 + 255) / 256), 256, 0, ctx->stream[0]>>>(ctx->ks_btiles, ctx->ksk, n1, L, cols, n_blocks);
+      CUB(cudaGetLastError());
+      CUB(cudaFuncSetAttribute(keyswitch_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKuSmem));
     }
   }
   CUB(cudaStreamSynchronize(ctx->stream[0]));
@@ -344,6 +352,20 @@ int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, s
     ks_tc_states_kernel<<<std::min<int>((int)((batch * (size_t)P.n1 + 255) / 256), ctx->sm_count * 8), 256, 0, s>>>(
         (uint16_t*)st16.p, d_in, ptrs, P.batch, P.n1, P.radix_log, P.count);
     if (int rc = check_launch(ctx, "ks_tc_states_kernel")) return rc;
+    const char* impl = getenv("SPF_B200_KS_IMPL");  // "mma": legacy mma.sync kernel (K4t), default: tcgen05 (K4u)
+    if (!(impl && !strcmp(impl, "mma"))) {
+      KsUBatch U;
+      U.out = d_out; U.in = d_in; U.ptrs = ptrs; U.st16 = (const uint16_t*)st16.p; U.btiles = ctx->ks_btiles; U.colsum = ctx->ks_tc_colsum;
+      U.batch = P.batch; U.n1 = P.n1; U.n0 = P.n0; U.radix_log = P.radix_log; U.count = P.count;
+      const int ux = (int)((batch + kKuM - 1) / kKuM), uy = (P.n0 + 1 + kKuN - 1) / kKuN;
+      const int chunks = P.n1 / kKtIC * P.count;
+      int z = std::max(1, std::min(chunks, (ctx->sm_count + ux * uy - 1) / (ux * uy)));  // split K until every SM has a CTA
+      U.chunks_per_cta = (chunks + z - 1) / z;
+      z = (chunks + U.chunks_per_cta - 1) / U.chunks_per_cta;
+      if (z > 1) CU(cudaMemsetAsync(d_out, 0, batch * (size_t)(P.n0 + 1) * 8, s));
+      keyswitch_umma_kernel<<<dim3(ux, uy, z), 192, kKuSmem, s>>>(U);
+      return check_launch(ctx, "keyswitch_umma_kernel");
+    }
     T.out = d_out; T.in = d_in; T.ptrs = ptrs; T.st16 = (const uint16_t*)st16.p; T.bfrag = ctx->ks_bfrag; T.colsum = ctx->ks_tc_colsum;
     T.batch = P.batch; T.n1 = P.n1; T.n0 = P.n0; T.radix_log = P.radix_log; T.count = P.count;
     const int gx = (int)((batch + kKtM - 1) / kKtM), gy = (P.n0 + 1 + kKtN - 1) / kKtN;
@@ -532,7 +554,7 @@ void spf_b200_destroy(spf_b200_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
-  cudaFree(ctx->bsk); cudaFree(ctx->ak); cudaFree(ctx->ssk); cudaFree(ctx->ksk); cudaFree(ctx->ksk_colsum); cudaFree(ctx->ks_bfrag); cudaFree(ctx->ks_tc_colsum);
+  cudaFree(ctx->bsk); cudaFree(ctx->ak); cudaFree(ctx->ssk); cudaFree(ctx->ksk); cudaFree(ctx->ksk_colsum); cudaFree(ctx->ks_bfrag); cudaFree(ctx->ks_tc_colsum); cudaFree(ctx->ks_btiles);
   cudaFree(ctx->T1); cudaFree(ctx->T2); cudaFree(ctx->kinv); cudaFree(ctx->consts);
   for (int i = 0; i < 2; i++) {
     for (DevBuf& b : ctx->scratch[i]) cudaFree(b.p);

@@ -845,6 +845,209 @@ __global__ void __launch_bounds__(256, 1) keyswitch_tc_kernel(KsTcBatch P) {
 }
 
 // ------------------------------------------------------------------------------------------
+// K4u: the keyswitch contraction on the 5th-generation tensor cores (tcgen05.mma kind::i8, TMEM
+// accumulators), same mathematics as K4t: eight exact u8 x u8 -> s32 byte-plane GEMMs.
+// CTA tile 128 ciphertexts x 64 columns x 8 planes = 8 accumulators of 64 TMEM columns (all 512).
+// Per k-step (32 digits): the 16 KiB of B (8 planes x 64 columns x 32 bytes, stored by
+// ks_umma_prepare_kernel in the canonical K-major core-matrix layout) arrive by ONE bulk copy
+// (cp.async.bulk -> mbarrier), the 4 KiB A tile is cut out of the u16 digit states by 128 producer
+// threads (thread = ciphertext row), one thread issues the 8 MMAs and commits them to the stage's
+// "empty" barrier.  4-stage ring; warps 0-3 produce A and run the epilogue (TMEM lane = row),
+// warp 4 feeds B, warp 5 issues the MMAs.  Epilogue: recombine the planes with shifts, remove the
+// digit offset (per-key column sums), subtract from (0, body); grid.z splits K (u64 atomics).
+// ------------------------------------------------------------------------------------------
+constexpr int kKuM = 128, kKuN = 64, kKuStages = 4;
+constexpr int kKuATile = kKuM * 32, kKuBPlane = kKuN * 32, kKuBTile = 8 * kKuBPlane;   // 4096, 2048, 16384
+constexpr int kKuSmem = kKuStages * (kKuATile + kKuBTile) + 1024;                      // + barriers, surplus table
+
+struct KsUBatch {
+  uint64_t* out;
+  const uint64_t* in;
+  const void* const* ptrs;
+  const uint16_t* st16;     // [B][n1] rounded + offset states
+  const uint8_t* btiles;    // [n_blocks][k_steps][8 planes][2 kc][8 col-groups][8 cols][16 B]
+  const uint64_t* colsum;   // [chunks][n0+1], chunk = c * L + t  (as K4t)
+  int batch, n1, n0, radix_log, count;
+  int chunks_per_cta;
+};
+
+// One thread per 16-byte row piece: btiles[...][col % 8] = bytes of plane j of KSK for 16 consecutive k
+__global__ void ks_umma_prepare_kernel(uint8_t* btiles, const uint64_t* ksk, int n1, int levels, int cols, int n_blocks) {
+  const int ks_total = n1 * levels / 32;
+  const size_t slot = blockIdx.x * (size_t)blockDim.x + threadIdx.x;  // (nb, ks, j, kc, cg, cr)
+  const size_t total = (size_t)n_blocks * ks_total * 8 * 2 * 8 * 8;
+  if (slot >= total) return;
+  const int cr = (int)(slot & 7), cg = (int)((slot >> 3) & 7), kc = (int)((slot >> 6) & 1), j = (int)((slot >> 7) & 7);
+  const int ks = (int)((slot >> 10) % ks_total), nb = (int)((slot >> 10) / ks_total);
+  const int col = nb * kKuN + cg * 8 + cr;
+  uint32_t w[4] = {0, 0, 0, 0};
+  if (col < cols) {
+    for (int e = 0; e < 16; e++) {
+      const int k = ks * 32 + kc * 16 + e, t = k / n1, i = k % n1;  // digit t <-> KSK level levels-1-t
+      const uint64_t v = ksk[((size_t)i * levels + (levels - 1 - t)) * cols + col];
+      w[e >> 2] |= (uint32_t)((v >> (8 * j)) & 0xFF) << (8 * (e & 3));
+    }
+  }
+  reinterpret_cast<uint4*>(btiles)[slot] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // K-major, no swizzle: ((8, n), 2) : ((16 B, SBO), LBO); version 1 (cute/arch/mma_sm100_desc.hpp layout)
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "KU_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra KU_DONE;\n\t"
+      "bra KU_WAIT;\n\t"
+      "KU_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) keyswitch_umma_kernel(KsUBatch P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sA = smem;                                  // [stage][4096]
+  unsigned char* sB = smem + kKuStages * kKuATile;           // [stage][16384]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKuStages * (kKuATile + kKuBTile));  // full[4], empty[4], done
+  uint64_t* surplus = bars + 16;                             // [64]
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int L = P.count, chunks_per_t = P.n1 / kKtIC, total_chunks = chunks_per_t * L;
+  const int ks_per_t = P.n1 / 32, ks_total = ks_per_t * L, ks_per_chunk = kKtIC / 32;
+  const int kc_begin = blockIdx.z * P.chunks_per_cta, kc_end = min(kc_begin + P.chunks_per_cta, total_chunks);
+  const int n_ksteps = (kc_end - kc_begin) * ks_per_chunk;
+  const int b0 = blockIdx.x * kKuM, cols = P.n0 + 1;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kKuStages), done = smem_u32(bars + 2 * kKuStages);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kKuStages; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * s), "r"(kKuM + 1) : "memory");  // 128 A producers + the TMA thread
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(empty0 + 8 * s) : "memory");
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(done) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < kKuN) {  // (B/2) * sum of the KSK rows this CTA covers, per column
+    const int col = blockIdx.y * kKuN + tid;
+    uint64_t sp = 0;
+    if (col < cols)
+      for (int kc = kc_begin; kc < kc_end; kc++) sp += P.colsum[(size_t)kc * cols + col];
+    surplus[tid] = sp << (P.radix_log - 1);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tacc = tmem_base;
+
+  if (warp < 4) {
+    // ===== A producers: thread = ciphertext row =====
+    const int r = tid;
+    const bool live = b0 + r < P.batch;
+    const uint32_t off = (uint32_t)radix_offset(P.radix_log, L);
+    const uint32_t dmask = ((1u << P.radix_log) - 1) * 0x00010001u;
+    const uint16_t* row = P.st16 + (size_t)(live ? b0 + r : 0) * P.n1;
+    const uint32_t a_dst = smem_u32(sA) + (r / 8) * 128 + (r % 8) * 16;
+    for (int it = 0; it < n_ksteps; it++) {
+      const int kc = kc_begin + it / ks_per_chunk, c = kc / L, t = kc % L, kk = it % ks_per_chunk;
+      const int stage = it % kKuStages;
+      const uint4* src = reinterpret_cast<const uint4*>(row + c * kKtIC + kk * 32);
+      uint4 w[4];
+#pragma unroll
+      for (int x = 0; x < 4; x++) w[x] = live ? __ldg(src + x) : make_uint4(off * 0x00010001u, off * 0x00010001u, off * 0x00010001u, off * 0x00010001u);
+      const int shift = P.radix_log * t;
+      uint32_t o[8];
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        o[2 * x] = __byte_perm((w[x].x >> shift) & dmask, (w[x].y >> shift) & dmask, 0x6420);
+        o[2 * x + 1] = __byte_perm((w[x].z >> shift) & dmask, (w[x].w >> shift) & dmask, 0x6420);
+      }
+      if (it >= kKuStages) mbar_wait(empty0 + 8 * stage, ((it / kKuStages) - 1) & 1);  // the MMAs that read this stage are done
+      const uint32_t dst = a_dst + stage * kKuATile;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (kKuM / 8) * 128), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * stage) : "memory");
+    }
+    // ===== epilogue: TMEM lane = row =====
+    mbar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const bool split = gridDim.z > 1;
+    const uint64_t* inrow = live ? (P.ptrs ? static_cast<const uint64_t*>(P.ptrs[b0 + r]) : P.in + (size_t)(b0 + r) * (P.n1 + 1)) : nullptr;
+    for (int cc = 0; cc < kKuN / 8; cc++) {
+      uint32_t v[8][8];
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[j][0]), "=r"(v[j][1]), "=r"(v[j][2]), "=r"(v[j][3]), "=r"(v[j][4]), "=r"(v[j][5]), "=r"(v[j][6]), "=r"(v[j][7])
+                     : "r"(tacc + ((uint32_t)(warp * 32) << 16) + j * kKuN + cc * 8));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (live) {
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+          const int col = blockIdx.y * kKuN + cc * 8 + x;
+          if (col < cols) {
+            uint64_t sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) sum += (uint64_t)v[j][x] << (8 * j);
+            uint64_t body = (col == P.n0 && blockIdx.z == 0) ? inrow[P.n1] : 0;
+            const uint64_t val = body - (sum - surplus[cc * 8 + x]);
+            uint64_t* o = P.out + (size_t)(b0 + r) * cols + col;
+            if (split) atomicAdd(reinterpret_cast<unsigned long long*>(o), (unsigned long long)val);
+            else *o = val;
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ===== B producer: one bulk copy of 16 KiB per k-step =====
+    if ((tid & 31) == 0) {
+      for (int it = 0; it < n_ksteps; it++) {
+        const int kc = kc_begin + it / ks_per_chunk, c = kc / L, t = kc % L, kk = it % ks_per_chunk;
+        const int stage = it % kKuStages;
+        const size_t ksg = (size_t)t * ks_per_t + (size_t)c * ks_per_chunk + kk;
+        const uint8_t* src = P.btiles + ((size_t)blockIdx.y * ks_total + ksg) * kKuBTile;
+        if (it >= kKuStages) mbar_wait(empty0 + 8 * stage, ((it / kKuStages) - 1) & 1);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8 * stage), "r"((uint32_t)kKuBTile) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sB) + stage * kKuBTile), "l"(src), "r"((uint32_t)kKuBTile), "r"(full0 + 8 * stage) : "memory");
+      }
+    }
+  } else {
+    // ===== MMA issuer =====
+    if ((tid & 31) == 0) {
+      const uint32_t idesc = (2u << 4) | ((uint32_t)(kKuN >> 3) << 17) | ((uint32_t)(kKuM >> 4) << 24);  // s32 += u8 x u8, K-major
+      for (int it = 0; it < n_ksteps; it++) {
+        const int stage = it % kKuStages;
+        mbar_wait(full0 + 8 * stage, (it / kKuStages) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = umma_smem_desc(smem_u32(sA) + stage * kKuATile, (kKuM / 8) * 128, 128);
+        const uint32_t acc = it > 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const uint64_t db = umma_smem_desc(smem_u32(sB) + stage * kKuBTile + j * kKuBPlane, (kKuN / 8) * 128, 128);
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+              "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+              ::"r"(tacc + j * kKuN), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * stage) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(done) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tacc) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // K7: small integer ops
 // ------------------------------------------------------------------------------------------
 // sample_extract (ops/ciphertext/glwe_ciphertext_ops.rs:31-76), k = 1
