@@ -852,11 +852,11 @@ __global__ void __launch_bounds__(256, 1) keyswitch_tc_kernel(KsTcBatch P) {
 // ks_umma_prepare_kernel in the canonical K-major core-matrix layout) arrive by ONE bulk copy
 // (cp.async.bulk -> mbarrier), the 4 KiB A tile is cut out of the u16 digit states by 128 producer
 // threads (thread = ciphertext row), one thread issues the 8 MMAs and commits them to the stage's
-// "empty" barrier.  4-stage ring; warps 0-3 produce A and run the epilogue (TMEM lane = row),
+// "empty" barrier.  6-stage ring; warps 0-3 produce A and run the epilogue (TMEM lane = row),
 // warp 4 feeds B, warp 5 issues the MMAs.  Epilogue: recombine the planes with shifts, remove the
 // digit offset (per-key column sums), subtract from (0, body); grid.z splits K (u64 atomics).
 // ------------------------------------------------------------------------------------------
-constexpr int kKuM = 128, kKuN = 64, kKuStages = 4;
+constexpr int kKuM = 128, kKuN = 64, kKuStages = 6;
 constexpr int kKuATile = kKuM * 32, kKuBPlane = kKuN * 32, kKuBTile = 8 * kKuBPlane;   // 4096, 2048, 16384
 constexpr int kKuSmem = kKuStages * (kKuATile + kKuBTile) + 1024;                      // + barriers, surplus table
 
@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(192, 1) keyswitch_umma_kernel(KsUBatch P) {
   unsigned char* sA = smem;                                  // [stage][4096]
   unsigned char* sB = smem + kKuStages * kKuATile;           // [stage][16384]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKuStages * (kKuATile + kKuBTile));  // full[4], empty[4], done
-  uint64_t* surplus = bars + 16;                             // [64]
+  uint64_t* surplus = bars + 16;                             // [64] (after 2 * stages + 1 barriers)
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int L = P.count, chunks_per_t = P.n1 / kKtIC, total_chunks = chunks_per_t * L;
@@ -954,13 +954,19 @@ __global__ void __launch_bounds__(192, 1) keyswitch_umma_kernel(KsUBatch P) {
     const uint32_t dmask = ((1u << P.radix_log) - 1) * 0x00010001u;
     const uint16_t* row = P.st16 + (size_t)(live ? b0 + r : 0) * P.n1;
     const uint32_t a_dst = smem_u32(sA) + (r / 8) * 128 + (r % 8) * 16;
-    for (int it = 0; it < n_ksteps; it++) {
-      const int kc = kc_begin + it / ks_per_chunk, c = kc / L, t = kc % L, kk = it % ks_per_chunk;
-      const int stage = it % kKuStages;
+    const uint4 pad = make_uint4(off * 0x00010001u, off * 0x00010001u, off * 0x00010001u, off * 0x00010001u);
+    auto load_states = [&](int it, uint4 (&w)[4]) {  // the 32 states of this row for k-step `it`
+      const int kc = kc_begin + it / ks_per_chunk, c = kc / L, kk = it % ks_per_chunk;
       const uint4* src = reinterpret_cast<const uint4*>(row + c * kKtIC + kk * 32);
-      uint4 w[4];
 #pragma unroll
-      for (int x = 0; x < 4; x++) w[x] = live ? __ldg(src + x) : make_uint4(off * 0x00010001u, off * 0x00010001u, off * 0x00010001u, off * 0x00010001u);
+      for (int x = 0; x < 4; x++) w[x] = live ? __ldg(src + x) : pad;
+    };
+    uint4 w[4], wn[4];
+    if (n_ksteps > 0) load_states(0, w);
+    for (int it = 0; it < n_ksteps; it++) {
+      const int kc = kc_begin + it / ks_per_chunk, t = kc % L;
+      const int stage = it % kKuStages;
+      if (it + 1 < n_ksteps) load_states(it + 1, wn);  // one k-step ahead: the L2 latency stays off the ring's critical path
       const int shift = P.radix_log * t;
       uint32_t o[8];
 #pragma unroll
@@ -974,6 +980,8 @@ __global__ void __launch_bounds__(192, 1) keyswitch_umma_kernel(KsUBatch P) {
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (kKuM / 8) * 128), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * stage) : "memory");
+#pragma unroll
+      for (int x = 0; x < 4; x++) w[x] = wn[x];
     }
     // ===== epilogue: TMEM lane = row =====
     mbar_wait(done, 0);
