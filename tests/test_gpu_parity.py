@@ -35,7 +35,7 @@ def test_keyswitch_bit_exact(oracle, keys, client, evaluation):
     assert [client.decrypt_lwe_l0(x) for x in got] == bits
 
 
-@pytest.mark.parametrize("batch", [1, 15, 16, 17, 33])
+@pytest.mark.parametrize("batch", [1, 15, 16, 17, 33, 129, 300])
 def test_keyswitch_ragged_batches(oracle, keys, evaluation, batch):
     rng = np.random.default_rng(batch)
     l1 = rng.integers(0, 1 << 64, (batch, keys.lwe1_len), dtype=np.uint64)
