@@ -222,7 +222,9 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
     CUB(cudaGetLastError());
     // tensor-core keyswitch (kernels.cuh K4t): KSK byte planes in fragment order + per-chunk column sums
     const int L = (int)params->ks.count, lb = (int)params->ks.radix_log;
-    if (n1 % kKtIC == 0 && L * lb + 1 <= 16 && lb <= 8) {
+    // byte-plane GEMMs accumulate in s32: (B - 1) * 255 per term, n1 * L terms
+    const bool s32_ok = (uint64_t)n1 * L * ((1u << lb) - 1) * 255ull < (1ull << 31);
+    if (n1 % kKtIC == 0 && L * lb + 1 <= 16 && lb <= 8 && s32_ok) {
       const int n_tiles = (cols + kKtN - 1) / kKtN * (kKtN / 8), ks_total = n1 * L / 32, chunks = n1 / kKtIC * L;
       const size_t slots = (size_t)n_tiles * ks_total * 32;
       CUB(cudaMalloc(&ctx->ks_bfrag, slots * 4 * sizeof(uint4)));
