@@ -22,6 +22,9 @@ struct HostCx {
   int u;
   pthread_barrier_t* bar;
   void sync() { pthread_barrier_wait(bar); }
+  uint64_t rp_stash[32];  // device: the thread's tensor-memory columns
+  void rp_store(const uint64_t (&rp)[32]) { memcpy(rp_stash, rp, sizeof(rp_stash)); }
+  void rp_load(uint64_t (&rp)[32]) { memcpy(rp, rp_stash, sizeof(rp_stash)); }
 };
 
 // pair of teams (pbs_pair_team): 128 host threads, one barrier per half and one for the pair
@@ -99,7 +102,7 @@ void run_team(Body body) {
   std::vector<pthread_t> th(kTeam);
   for (int u = 0; u < kTeam; u++) {
     ls[u].body = &body;
-    ls[u].cx = HostCx{u, &bar};
+    ls[u].cx = HostCx{u, &bar, {}};
     pthread_create(&th[u], nullptr, Launch<Body>::run, &ls[u]);
   }
   for (int u = 0; u < kTeam; u++) pthread_join(th[u], nullptr);

@@ -9,11 +9,37 @@
 namespace spf {
 
 // One team = 2 warps.  Team-private named barrier ids 1..15 (0 is __syncthreads).
+__device__ __forceinline__ void tmem_ld16(uint32_t (&r)[16], uint32_t taddr);
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]);
+__device__ __forceinline__ void tmem_wait_ld();
+__device__ __forceinline__ void tmem_wait_st();
+
 struct DevCx {
   int u;
   int bar;
+  uint32_t rp_taddr;  // 64 private tensor-memory columns of this warp (trace / scheme-switch kernel only)
   __device__ __forceinline__ void sync() const {
     asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory");
+  }
+  __device__ __forceinline__ void rp_store(const uint64_t (&rp)[32]) const {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      uint32_t r[16];
+#pragma unroll
+      for (int i = 0; i < 8; i++) { r[2 * i] = (uint32_t)rp[8 * c + i]; r[2 * i + 1] = (uint32_t)(rp[8 * c + i] >> 32); }
+      tmem_st16(rp_taddr + 16 * c, r);
+    }
+    tmem_wait_st();
+  }
+  __device__ __forceinline__ void rp_load(uint64_t (&rp)[32]) const {
+    uint32_t r[4][16];
+#pragma unroll
+    for (int c = 0; c < 4; c++) tmem_ld16(r[c], rp_taddr + 16 * c);
+    tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) rp[8 * c + i] = ((uint64_t)r[c][2 * i + 1] << 32) | r[c][2 * i];
   }
 };
 
@@ -423,34 +449,50 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(TraceSsBa
   C2* sT1 = reinterpret_cast<C2*>(smem);
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
+  // tensor memory: 64 columns per warp for the parked decomposition states (warps w and w + 4 share a lane quarter)
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(&tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_alloc = tmem_base;
   const int team = threadIdx.x / kTeam;
   const int item = blockIdx.x * (blockDim.x / kTeam) + team;
-  if (item >= P.batch * P.levels) return;
-  const int c = item / P.levels, level = item % P.levels;
-  unsigned char* base = smem + kTableBytes + team * kTrTeamBytes;
-  uint64_t* g = reinterpret_cast<uint64_t*>(base);
-  C2* xbuf = reinterpret_cast<C2*>(base + 2 * kN * 8);
-  DevCx cx{(int)(threadIdx.x % kTeam), team + 1};
-  TraceSsArgs A;
-  const size_t glwe = 2 * kN;
-  if (P.ptrs) A.glwe_in = static_cast<const uint64_t*>(P.ptrs[c]) + (P.mode == 2 ? (size_t)level * glwe : 0);
-  else if (P.mode == 0) A.glwe_in = P.glwe_in + (size_t)c * glwe;
-  else A.glwe_in = P.glwe_in + (size_t)item * glwe;
-  A.glev_out = P.glev_out ? P.glev_out + (size_t)item * glwe : nullptr;
-  A.ggsw_out = P.ggsw_out ? P.ggsw_out + (size_t)c * 2 * P.cbs_count * 2 * kM : nullptr;
-  A.ak = P.ak;
-  A.ssk = P.ssk;
-  A.kinv = P.kinv;
-  A.level = level;
-  A.mode = P.mode;
-  A.cbs_radix_log = P.cbs_radix_log;
-  A.cbs_count = P.cbs_count;
-  A.tr_radix_log = P.tr_radix_log;
-  A.tr_count = P.tr_count;
-  A.ss_radix_log = P.ss_radix_log;
-  A.ss_count = P.ss_count;
-  A.out_scale = P.out_scale;
-  trace_ss_team(cx, A, g, xbuf, sT1, sT2);
+  if (item < P.batch * P.levels) {  // no early return: every thread must reach the deallocation barrier
+    const int c = item / P.levels, level = item % P.levels;
+    unsigned char* base = smem + kTableBytes + team * kTrTeamBytes;
+    uint64_t* g = reinterpret_cast<uint64_t*>(base);
+    C2* xbuf = reinterpret_cast<C2*>(base + 2 * kN * 8);
+    DevCx cx{(int)(threadIdx.x % kTeam), team + 1, tmem_alloc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 64};
+    TraceSsArgs A;
+    const size_t glwe = 2 * kN;
+    if (P.ptrs) A.glwe_in = static_cast<const uint64_t*>(P.ptrs[c]) + (P.mode == 2 ? (size_t)level * glwe : 0);
+    else if (P.mode == 0) A.glwe_in = P.glwe_in + (size_t)c * glwe;
+    else A.glwe_in = P.glwe_in + (size_t)item * glwe;
+    A.glev_out = P.glev_out ? P.glev_out + (size_t)item * glwe : nullptr;
+    A.ggsw_out = P.ggsw_out ? P.ggsw_out + (size_t)c * 2 * P.cbs_count * 2 * kM : nullptr;
+    A.ak = P.ak;
+    A.ssk = P.ssk;
+    A.kinv = P.kinv;
+    A.level = level;
+    A.mode = P.mode;
+    A.cbs_radix_log = P.cbs_radix_log;
+    A.cbs_count = P.cbs_count;
+    A.tr_radix_log = P.tr_radix_log;
+    A.tr_count = P.tr_count;
+    A.ss_radix_log = P.ss_radix_log;
+    A.ss_count = P.ss_count;
+    A.out_scale = P.out_scale;
+    trace_ss_team(cx, A, g, xbuf, sT1, sT2);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_alloc) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------

@@ -147,22 +147,32 @@ SPF_HD void gadget_mad(Cx& cx, C2 (&acc)[2][16], uint64_t* st, C2* xbuf, const C
 }
 
 // Stateless variant: the digits of level t are read straight out of the bit fields of
-// round(coef(j)) + radix_offset (no carry chain, so no per-coefficient state to keep between levels);
-// coef is re-evaluated per level.  Frees the 16 KiB state array: one more team fits on an SM.
+// r' = round(coef(j)) + radix_offset (no carry chain, so nothing to update between levels).  r' is
+// evaluated ONCE per product (the automorphism gather and the 64-bit rounding are the expensive part)
+// and parked with cx.rp_store: tensor-memory columns of the thread on the device, so neither the
+// 16 KiB shared-memory state array of gadget_mad nor 64 registers are needed.
 template <class Cx, class F>
 SPF_HD void gadget_mad_stateless(Cx& cx, C2 (&acc)[2][16], F coef, C2* xbuf, const C2* T1, const C2* T2, const C2* glev,
                                  int radix_log, int count) {
   const uint64_t off = radix_offset(radix_log, count);
   const uint64_t dmask = (1ull << radix_log) - 1;
   const int32_t half = 1 << (radix_log - 1);
+  {
+    uint64_t rp[32];
+#pragma unroll
+    for (int i2 = 0; i2 < 32; i2++) rp[i2] = radix_round(coef(cx.u + 64 * i2), radix_log, count) + off;
+    cx.rp_store(rp);
+  }
   for (int t = 0; t < count; t++) {
     C2 v[16];
+    {
+      uint64_t rp[32];
+      cx.rp_load(rp);
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-      const uint64_t r0 = radix_round(coef(cx.u + 64 * m), radix_log, count) + off;
-      const uint64_t r1 = radix_round(coef(cx.u + 64 * m + kM), radix_log, count) + off;
-      v[m].x = i32_to_f64((int32_t)((r0 >> (t * radix_log)) & dmask) - half);
-      v[m].y = i32_to_f64((int32_t)((r1 >> (t * radix_log)) & dmask) - half);
+      for (int m = 0; m < 16; m++) {
+        v[m].x = i32_to_f64((int32_t)((rp[m] >> (t * radix_log)) & dmask) - half);
+        v[m].y = i32_to_f64((int32_t)((rp[m + 16] >> (t * radix_log)) & dmask) - half);
+      }
     }
     team_fft_fwd(cx, v, xbuf, T1, T2);
     mad_glwe(acc, v, glev + (size_t)(count - 1 - t) * 2 * kM, cx.u);
