@@ -10,8 +10,12 @@ HDRS := $(CSRC)/fft16.cuh $(CSRC)/fft_consts.h $(CSRC)/team_ops.cuh $(CSRC)/kern
 
 all: spf_b200/libspf_b200.so $(CSRC)/libspf_emu.so oracle
 
-spf_b200/libspf_b200.so: $(CSRC)/capi.cu $(HDRS)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/capi.cu 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
+# muxgen.cpp is host-only (MUX-circuit generator); it is linked into the product library
+$(CSRC)/muxgen.o: $(CSRC)/muxgen.cpp include/spf_b200.h
+	$(CXX) -O2 -std=c++17 -fPIC -Wall -c -o $@ $(CSRC)/muxgen.cpp
+
+spf_b200/libspf_b200.so: $(CSRC)/capi.cu $(CSRC)/muxgen.o $(HDRS)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/capi.cu $(CSRC)/muxgen.o 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
 
 $(CSRC)/libspf_emu.so: $(CSRC)/emu.cpp $(HDRS)
 	$(CXX) -O2 -march=x86-64-v3 -std=c++17 -fPIC -shared -Wall -Wno-unknown-pragmas -o $@ $(CSRC)/emu.cpp -lpthread
@@ -20,7 +24,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f spf_b200/libspf_b200.so $(CSRC)/libspf_emu.so $(CSRC)/ptxas.log
+	rm -f spf_b200/libspf_b200.so $(CSRC)/muxgen.o $(CSRC)/libspf_emu.so $(CSRC)/ptxas.log
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

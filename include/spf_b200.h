@@ -248,6 +248,36 @@ int spf_b200_parse_ciphertext(const spf_params *params, int kind, const uint8_t 
 int spf_b200_write_ciphertext(const spf_params *params, int kind, const uint64_t *data, uint8_t *out, size_t cap,
                               size_t *written);
 
+/* ---- MUX-circuit generation (the step before the path) -------------------------
+ * A Parasol instruction becomes a FheCircuit by expanding a multiplexer circuit derived from reduced
+ * ordered BDDs (mux_circuits/src/{add,sub,neg,comparisons,and,or,mul}.rs; MuxCircuit::from(&[Bdd]),
+ * mux_circuits/src/lib.rs:355-451).  spf_b200_mux_circuit builds the same Boolean functions over the
+ * same input order with its own shared-ROBDD manager (host code, no GPU, no context) and returns a
+ * flat node list in topological order: node 0 = Zero, node 1 = One, nodes 2..2+inputs = Variable(i),
+ * then Mux nodes (sel = a Variable node; output = low when the selector is 0, high when 1,
+ * lib.rs:66-76), then one Output(i) node per result bit whose `low` is the node it forwards.
+ * Tags equal MuxOp's bincode variant indices (lib.rs:54-94). */
+typedef enum { SPF_MUX_ONE = 0, SPF_MUX_ZERO = 1, SPF_MUX_MUX = 2, SPF_MUX_VARIABLE = 3, SPF_MUX_OUTPUT = 4 } spf_mux_op;
+typedef struct {
+  uint32_t op;  /* spf_mux_op */
+  uint32_t arg; /* Variable / Output index */
+  int32_t sel, low, high; /* producer node indices, -1 = none */
+} spf_mux_node;
+typedef enum {
+  SPF_MUX_RIPPLE_CARRY_ADDER = 0, /* add.rs:13-56; n, m operand widths; flags bit0 = carry-in first */
+  SPF_MUX_FULL_SUBTRACTOR = 1,    /* sub.rs:12-49; flags bit0 = borrow-in first */
+  SPF_MUX_NEGATOR = 2,            /* neg.rs:7-27 */
+  SPF_MUX_COMPARE = 3,            /* comparisons.rs:127-181; flags bit0 = greater (else less), bit1 = or-equal */
+  SPF_MUX_COMPARE_SIGNED = 4,     /* comparisons.rs:79-117; same flags */
+  SPF_MUX_COMPARE_EQUAL = 5,      /* comparisons.rs:19-72; flags bit0 = not-equal */
+  SPF_MUX_BITWISE = 6,            /* and.rs / or.rs; flags bit0 = or (else and) */
+  SPF_MUX_UNSIGNED_MULTIPLIER = 7,/* mul.rs:30-141, n x m -> n + m bits; inputs a[0..n) then b[0..m) */
+  SPF_MUX_GRADESCHOOL_REDUCE = 8  /* mul.rs:428-586; inputs ordered by encode_gradeschool_reduction */
+} spf_mux_kind;
+/* *out is malloc'ed; release with spf_b200_mux_free.  SPF_E_INVALID for bad sizes. */
+int spf_b200_mux_circuit(uint32_t kind, uint32_t n, uint32_t m, uint32_t flags, spf_mux_node **out, size_t *count);
+void spf_b200_mux_free(spf_mux_node *nodes);
+
 /* FP64 peak probe used by bench.py for the roofline denominator: runs a dependent-free DFMA
  * loop on every SM and returns achieved TFLOP/s (2 flops per DFMA). */
 int spf_b200_fp64_peak(spf_b200_ctx *ctx, double *tflops_out);

@@ -396,6 +396,18 @@ ABI.update({
     "spf_b200_graph_build_sharded": [_vp, C.POINTER(_Node), _sz, C.c_int, C.POINTER(_vp)],
     "spf_b200_graph_run_sharded": [_vp, C.c_int, C.c_int, _vp, _vp],
 })
+
+
+class _MuxNode(C.Structure):
+    """spf_mux_node (include/spf_b200.h): one node of a generated MUX circuit."""
+    _fields_ = [("op", C.c_uint32), ("arg", C.c_uint32), ("sel", C.c_int32), ("low", C.c_int32), ("high", C.c_int32)]
+
+
+ABI.update({
+    "spf_b200_mux_circuit": [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.POINTER(_MuxNode)), C.POINTER(_sz)],
+    "spf_b200_mux_free": [C.POINTER(_MuxNode)],
+})
+_RESTYPES["spf_b200_mux_free"] = None
 # spf_exchange_fn(user, d_buf, chunk_bytes, world, stream) -> int
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
 _RESTYPES.update({"spf_b200_graph_destroy": None, "spf_b200_graph_launches": C.c_uint64})

@@ -1,0 +1,204 @@
+"""MUX-circuit generator (spf_b200/csrc/muxgen.cpp through the C ABI) and its expansion into
+FheCircuit graphs: the reference's own test strategy for mux_circuits (random operands against plain
+integer arithmetic, mux_circuits/src/{add,sub,neg,comparisons,mul}.rs `mod tests`), the multiplexer
+counts of the reference's shipped pre-generated circuits as golden values, and the serialized
+MuxCircuit format.  No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+from spf_b200 import FheCircuit, OP, SpfError
+from spf_b200 import mux_circuits as M
+
+REF_DATA = "/root/reference/mux_circuits/src/data"
+
+
+def bits(v, w):
+    return [(v >> i) & 1 for i in range(w)]
+
+
+def value(b):
+    return sum(int(x) << i for i, x in enumerate(b))
+
+
+def rand(rng, w):
+    return int.from_bytes(rng.bytes(16), "little") % (1 << w)
+
+
+@pytest.mark.parametrize("n,m,cin", [(8, 8, False), (8, 8, True), (5, 9, False), (9, 5, True), (32, 32, False), (1, 1, True)])
+def test_ripple_carry_adder(n, m, cin):
+    c = M.ripple_carry_adder(n, m, cin)
+    assert c.metrics()["inputs"] == n + m + cin and c.metrics()["outputs"] == max(n, m) + 1
+    rng = np.random.default_rng(n * 100 + m)
+    lo = min(n, m)
+    for _ in range(50):
+        a, b, ci = rand(rng, n), rand(rng, m), int(rng.integers(0, 2)) if cin else 0
+        ab, bb = bits(a, n), bits(b, m)
+        inp = ([ci] if cin else []) + [x for p in zip(ab[:lo], bb[:lo]) for x in p] + (ab[lo:] if n > m else bb[lo:])
+        assert value(c.evaluate(inp)) == a + b + ci
+
+
+@pytest.mark.parametrize("n,bin_", [(8, False), (8, True), (32, False)])
+def test_full_subtractor(n, bin_):
+    c = M.full_subtractor(n, bin_)
+    rng = np.random.default_rng(n)
+    for _ in range(50):
+        a, b, bi = rand(rng, n), rand(rng, n), int(rng.integers(0, 2)) if bin_ else 0
+        inp = ([bi] if bin_ else []) + [x for p in zip(bits(a, n), bits(b, n)) for x in p]
+        out = c.evaluate(inp)
+        assert value(out[:n]) == (a - b - bi) % (1 << n) and out[n] == int(a - b - bi < 0)
+
+
+def test_negator():
+    c = M.negator(16)
+    for a in (0, 1, 2, 0x8000, 0xFFFF, 12345):
+        assert value(c.evaluate(bits(a, 16))) == (-a) % (1 << 16)
+
+
+@pytest.mark.parametrize("greater", [False, True])
+@pytest.mark.parametrize("or_equal", [False, True])
+def test_comparisons(greater, or_equal):
+    n = 8
+    cu, cs = M.compare_or_maybe_equal(n, greater, or_equal), M.compare_or_maybe_equal_signed(n, greater, or_equal)
+    rng = np.random.default_rng(3)
+    cases = [(rand(rng, n), rand(rng, n)) for _ in range(100)] + [(7, 7), (0, 255), (255, 0), (128, 127)]
+    for a, b in cases:
+        inp = [x for p in zip(bits(a, n), bits(b, n)) for x in p]
+        want = (a > b if greater else a < b) or (or_equal and a == b)
+        assert cu.evaluate(inp) == [int(want)]
+        sa, sb = a - 256 * (a >> 7), b - 256 * (b >> 7)
+        want = (sa > sb if greater else sa < sb) or (or_equal and sa == sb)
+        assert cs.evaluate(inp) == [int(want)]
+
+
+def test_equality_and_bitwise():
+    n = 8
+    eq, ne, an, orr = M.compare_equal(n), M.compare_not_equal(n), M.make_and_circuit(n), M.make_or_circuit(n)
+    rng = np.random.default_rng(4)
+    for a, b in [(rand(rng, n), rand(rng, n)) for _ in range(50)] + [(9, 9), (0, 0)]:
+        inp = [x for p in zip(bits(a, n), bits(b, n)) for x in p]
+        assert eq.evaluate(inp) == [int(a == b)] and ne.evaluate(inp) == [int(a != b)]
+        assert value(an.evaluate(inp)) == a & b and value(orr.evaluate(inp)) == a | b
+
+
+# multiplexer counts of the circuits the reference ships pre-generated (mux_circuits/src/data/
+# multiplier-n8-m8, multiplier-n16-m16, gradeschool-reduction-n64-m64, loaded by mul.rs:62-68,393-400)
+GOLDEN_MUX_GATES = {("unsigned_multiplier", 8, 8): 3228, ("unsigned_multiplier", 16, 16): 29500,
+                    ("gradeschool_reduce", 64, 64): 36888}
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (4, 4), (5, 3), (3, 7), (8, 8), (16, 16)])
+def test_unsigned_multiplier(n, m):
+    c = M.unsigned_multiplier(n, m)
+    assert c.metrics()["inputs"] == n + m and c.metrics()["outputs"] == n + m
+    if ("unsigned_multiplier", n, m) in GOLDEN_MUX_GATES:
+        assert c.metrics()["mux_gates"] == GOLDEN_MUX_GATES[("unsigned_multiplier", n, m)]
+    rng = np.random.default_rng(n * 64 + m)
+    cases = [(rand(rng, n), rand(rng, m)) for _ in range(20 if n < 16 else 6)] + [((1 << n) - 1, (1 << m) - 1), (0, 1)]
+    for a, b in cases:
+        assert value(c.evaluate(bits(a, n) + bits(b, m))) == a * b
+
+
+@pytest.mark.parametrize("n,m", [(32, 32), (64, 64), (40, 24), (20, 18)])
+def test_gradeschool_reduce(n, m):
+    c = M.gradeschool_reduce(n, m)
+    assert c.metrics()["inputs"] == 2 * (n + m) and c.metrics()["outputs"] == n + m
+    if ("gradeschool_reduce", n, m) in GOLDEN_MUX_GATES:
+        assert c.metrics()["mux_gates"] == GOLDEN_MUX_GATES[("gradeschool_reduce", n, m)]
+    (a_lo, a_hi), (b_lo, b_hi) = M.partition_integer(n), M.partition_integer(m)
+    rng = np.random.default_rng(n)
+    for x, y in [(rand(rng, n), rand(rng, m)) for _ in range(8)] + [((1 << n) - 1, (1 << m) - 1)]:
+        xl, xh, yl, yh = x & ((1 << a_lo) - 1), x >> a_lo, y & ((1 << b_lo) - 1), y >> b_lo
+        inp = M.encode_gradeschool_reduction(n, m, bits(xl * yl, a_lo + b_lo), bits(xl * yh, a_lo + b_hi),
+                                             bits(xh * yl, a_hi + b_lo), bits(xh * yh, a_hi + b_hi))
+        assert value(c.evaluate(inp)) == x * y
+
+
+def test_generator_rejects_bad_sizes():
+    for args in [("unsigned_multiplier", 0, 4), ("unsigned_multiplier", 4, 0), ("unsigned_multiplier", 256, 256),
+                 ("gradeschool_reduce", 16, 32), ("ripple_carry_adder", 4, 0)]:
+        with pytest.raises(SpfError):
+            M.MuxCircuit.generate(*args)
+
+
+def test_bincode_round_trip_and_errors():
+    c = M.unsigned_multiplier(4, 4)
+    blob = c.to_bincode()
+    d = M.MuxCircuit.from_bincode(blob)
+    assert d.metrics() == c.metrics()
+    for a, b in [(3, 5), (15, 15), (9, 0)]:
+        assert value(d.evaluate(bits(a, 4) + bits(b, 4))) == a * b
+    with pytest.raises(SpfError):
+        M.MuxCircuit.from_bincode(blob[:-3])
+    with pytest.raises(SpfError):
+        M.MuxCircuit.from_bincode(b"\xff" * 8 + blob[8:])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DATA), reason="reference checkout not present (GPU box)")
+@pytest.mark.parametrize("name,kind,n,m", [("multiplier-n8-m8", "unsigned_multiplier", 8, 8),
+                                           ("multiplier-n16-m16", "unsigned_multiplier", 16, 16),
+                                           ("gradeschool-reduction-n64-m64", "gradeschool_reduce", 64, 64)])
+def test_reference_shipped_circuits_load_and_agree(name, kind, n, m):
+    """The reference's pre-generated circuits parse with from_bincode, have the golden multiplexer
+    counts, and compute the same function as the generated circuit on random inputs."""
+    ref = M.MuxCircuit.from_bincode(open(os.path.join(REF_DATA, name), "rb").read())
+    gen = M.MuxCircuit.generate(kind, n, m)
+    assert ref.metrics() == gen.metrics()
+    assert ref.metrics()["mux_gates"] == GOLDEN_MUX_GATES[(kind, n, m)]
+    rng = np.random.default_rng(11)
+    for _ in range(4):
+        inp = rng.integers(0, 2, len(ref.inputs)).tolist()
+        assert ref.evaluate(inp) == gen.evaluate(inp)
+
+
+def _plain_run(c: FheCircuit, ggsw_bits: dict[int, int]) -> dict[int, int]:
+    """Evaluate the Boolean skeleton of a FheCircuit (CMux / constants / conversions) on plaintext bits."""
+    val = {}
+    for i, (op, arg, ins, io) in enumerate(c.nodes):
+        if i in ggsw_bits:
+            val[i] = ggsw_bits[i]
+        elif op == OP["CMux"]:
+            val[i] = val[ins[2]] if val[ins[0]] else val[ins[1]]
+        elif op in (OP["ZeroGlwe1"], OP["ZeroGgsw1"]):
+            val[i] = 0
+        elif op in (OP["OneGlwe1"], OP["OneGgsw1"]):
+            val[i] = 1
+        elif op in (OP["SampleExtract"], OP["KeyswitchL1toL0"], OP["CircuitBootstrap"]):
+            val[i] = val[ins[0]]
+    return val
+
+
+@pytest.mark.parametrize("w", [8, 32, 24])
+def test_append_uint_multiply_structure(w):
+    """circuits/mul.rs: a w x w product expands to 16x16 blocks + one reduction behind a bootstrap
+    level (w > 16) or a single block (w <= 16); the graph's Boolean skeleton multiplies."""
+    c = FheCircuit()
+    a = [c.add("OneGgsw1") for _ in range(w)]   # stand-ins for the operands' GGSW producers
+    b = [c.add("OneGgsw1") for _ in range(w)]
+    lo, hi = M.append_uint_multiply(c, a, b)
+    assert len(lo) == w and len(hi) == w
+    n_cbs = sum(1 for n in c.nodes if n[0] == OP["CircuitBootstrap"])
+    assert n_cbs == (0 if w <= 16 else 4 * w)
+    rng = np.random.default_rng(w)
+    for x, y in [(rand(rng, w), rand(rng, w)), ((1 << w) - 1, (1 << w) - 1)]:
+        assign = {n: bt for n, bt in zip(a + b, bits(x, w) + bits(y, w))}
+        val = _plain_run(c, assign)
+        assert value([val[n] for n in lo + hi]) == x * y
+    pruned, ren = M.prune(c, lo)
+    assert len(pruned.nodes) < len(c.nodes)
+    x, y = rand(rng, w), rand(rng, w)
+    # inputs that survive pruning keep their meaning
+    assign = {ren[n]: bt for n, bt in zip(a + b, bits(x, w) + bits(y, w)) if n in ren}
+    val = _plain_run(pruned, assign)
+    assert value([val[ren[n]] for n in lo]) == (x * y) % (1 << w)
+
+
+def test_insert_mux_circuit_validates_inputs():
+    c = FheCircuit()
+    z = c.add("ZeroGlwe1")
+    with pytest.raises(SpfError):
+        M.insert_mux_circuit(c, M.make_and_circuit(1), [z, z])
+    g = c.add("OneGgsw1")
+    with pytest.raises(SpfError):
+        M.insert_mux_circuit(c, M.make_and_circuit(1), [g])
