@@ -1,11 +1,11 @@
-"""Test/bench helper circuits.  The reference derives its MUX trees from BDDs
-(mux_circuits/src/add.rs:13-56, biodivine-lib-bdd) above the drop-in boundary; that generator is out
-of scope here, so this module hand-builds a functionally equivalent
-ripple-carry adder MUX tree with the same front end as FheCircuit::insert_mux_circuit_and_connect_
-inputs (fhe_circuit.rs:473-494): per input bit InputGlwe1 -> SampleExtract(0) -> KeyswitchL1toL0 ->
-CircuitBootstrap, then CMux / Not / ZeroGlwe1 / OneGlwe1 nodes and one OutputGlwe1 per result bit.
-It is NOT node-for-node the reference's graph (the BDD may share sub-terms differently); its
-decryptions are identical."""
+"""Program-level circuits.  Two families:
+* hand-built ripple MUX chains (ripple_carry_adder, add_then_greater_than): compact adders/comparators
+  with the same front end as FheCircuit::insert_mux_circuit_and_connect_inputs (fhe_circuit.rs:473-494):
+  per input bit InputGlwe1 -> SampleExtract(0) -> KeyswitchL1toL0 -> CircuitBootstrap, then CMux / Not /
+  ZeroGlwe1 / OneGlwe1 nodes and one OutputGlwe1 per result bit; functionally equivalent to, but not
+  node-for-node, the reference's BDD-derived trees;
+* BDD-derived circuits through spf_b200.mux_circuits (multiply_then_greater_than): the reference's own
+  constructions (mux_circuits/src/*.rs), generated natively."""
 from __future__ import annotations
 
 import numpy as np
@@ -111,6 +111,33 @@ def add_then_greater_than(a_bits, b_bits, c_bits, out_sum, out_gt, programs: int
         ss = [_refresh(c, n) for n in s]
         c.add("OutputGlwe1", _greater_than_node(c, ss, sc), io=out_gt[p])
     return c
+
+
+def multiply_then_greater_than(a_bits, b_bits, c_bits, out_prod, out_gt, programs: int = 1) -> FheCircuit:
+    """BASELINE config 4's program: p = a * b (w-bit operands, low w bits of the product, the ISA `Mul`
+    of parasol_cpu/src/proc/ops/mul.rs:75-117), then p > c (`CmpGt`, ops/comparisons.rs:62-98 with
+    compare_or_maybe_equal(w, greater, !or_equal)).  The MUX circuits are the BDD-derived ones of
+    spf_b200.mux_circuits (16x16 multiplier blocks + grade-school reduction for w > 16), the high word is
+    pruned as the reference does (mul.rs:106-108).  Dependency levels of circuit bootstraps for w = 32:
+    3w inputs | the partial-product bits entering the reduction | w product bits entering the compare.
+    a_bits/b_bits/c_bits: [programs][w] L1 GLWE inputs; out_prod [programs][w], out_gt [programs]."""
+    from . import mux_circuits as M
+
+    c = FheCircuit()
+    keep = []
+    for p in range(programs):
+        w = len(a_bits[p])
+        sa = [_front(c, x) for x in a_bits[p]]
+        sb = [_front(c, x) for x in b_bits[p]]
+        sc = [_front(c, x) for x in c_bits[p]]
+        lo, _hi = M.append_uint_multiply(c, sa, sb)
+        for i in range(w):
+            keep.append(c.add("OutputGlwe1", lo[i], io=out_prod[p][i]))
+        sp = [_refresh(c, n) for n in lo]
+        cmp_inputs = [x for pair in zip(sp, sc) for x in pair]  # a0 b0 a1 b1 ... (comparisons.rs:127-141)
+        (gt,) = M.insert_mux_circuit(c, M.compare_or_maybe_equal(w, True, False), cmp_inputs)
+        keep.append(c.add("OutputGlwe1", gt, io=out_gt[p]))
+    return M.prune(c, keep)[0]
 
 
 class InstructionCache:

@@ -323,13 +323,29 @@ int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const 
   P.radix_log = (int)ctx->p.cbs.radix_log;
   P.count = (int)ctx->p.cbs.count;
   // few outputs (a level of a ripple MUX chain): one CTA of 8 teams per output, 3-5x lower latency
+  // Programmatic dependent launch: consecutive levels of a MUX tree are back-to-back CMUX kernels; each
+  // loads its tables (and prefetches its selector) while the previous level drains (kernels.cuh, pdl_wait).
+  static const bool pdl = !getenv("SPF_B200_NO_PDL");
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const DevTables T = tabs(ctx);
   if (n_glwe <= (size_t)ctx->sm_count && P.count == 4) {
-    cmux_wide_kernel<<<(int)n_glwe, kWideTeams * kTeam, kWideSmem, s>>>(P, tabs(ctx));
+    cfg.gridDim = dim3((unsigned)n_glwe);
+    cfg.blockDim = dim3(kWideTeams * kTeam);
+    cfg.dynamicSmemBytes = kWideSmem;
+    cudaLaunchKernelEx(&cfg, cmux_wide_kernel, P, T);
     return check_launch(ctx, "cmux_wide_kernel");
   }
   const int per = per_cta(ctx, n_glwe, kCmuxTeams);
-  const int grid = (int)((n_glwe + per - 1) / per);
-  cmux_kernel<<<grid, per * kTeam, kTableBytes + per * kCmuxTeamBytes, s>>>(P, tabs(ctx));
+  cfg.gridDim = dim3((unsigned)((n_glwe + per - 1) / per));
+  cfg.blockDim = dim3(per * kTeam);
+  cfg.dynamicSmemBytes = kTableBytes + per * kCmuxTeamBytes;
+  cudaLaunchKernelEx(&cfg, cmux_kernel, P, T);
   return check_launch(ctx, "cmux_kernel");
 }
 

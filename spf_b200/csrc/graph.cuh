@@ -455,8 +455,19 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
                                 spf_b200_len_ggsw_l1(p), 1.0 / 1024.0, s))
         return rc;
   }
+  // SPF_B200_GRAPH_TIMING=1: CUDA events around every group, per-op totals on stderr (diagnostics only;
+  // the events serialise nothing but do defeat the programmatic overlap between CMUX levels)
+  static const bool timing = getenv("SPF_B200_GRAPH_TIMING") != nullptr;
+  std::vector<cudaEvent_t> ev;
+  if (timing) {
+    ev.resize(g->groups.size() + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], s);
+  }
+  size_t gi = 0;
   for (const Group& G : g->groups) {
     if (int rc = run_group(g, G, s, rank, world)) return rc;
+    if (timing) cudaEventRecord(ev[++gi], s);
     if (world > 1 && G.op == SPF_OP_CIRCUIT_BOOTSTRAP) {
       const size_t chunk_bytes = cbs_chunk_items(G.ids.size(), world) * ct_bytes(p, T_GGSW1);
       if (int rc = exchange(user, G.out_base, chunk_bytes, world, s))
@@ -478,6 +489,20 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
     CU(cudaMemcpyAsync(g->nodes[id].io, from, ct_host_bytes(p, t), cudaMemcpyDeviceToHost, s));
   }
   CU(cudaStreamSynchronize(s));
+  if (timing) {
+    std::map<uint32_t, std::pair<double, size_t>> per_op;
+    std::map<uint32_t, size_t> groups_of;
+    for (size_t k = 0; k < g->groups.size(); k++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[k], ev[k + 1]);
+      per_op[g->groups[k].op].first += ms;
+      per_op[g->groups[k].op].second += g->groups[k].ids.size();
+      groups_of[g->groups[k].op]++;
+    }
+    for (auto& kv : per_op)
+      fprintf(stderr, "[spf_b200 graph] %-18s %6zu groups %8zu nodes %9.3f ms\n", kOpNames[kv.first], groups_of[kv.first], kv.second.second, kv.second.first);
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
   g->launches_per_run = ctx->launches.load() - l0;
   return 0;
 }

@@ -56,6 +56,16 @@ __device__ __forceinline__ void load_tables(C2* sT1, C2* sT2, const DevTables& t
 
 constexpr int kTableBytes = (kT1Elems + kT2Elems) * 16;  // 17472
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor in the stream is still running; everything
+// before pdl_wait() must therefore touch only data no earlier kernel of the stream writes (twiddle
+// tables, the pointer tables uploaded at graph build) -- pdl_wait() returns once the predecessor has
+// completed and its writes are visible.  pdl_launch_dependents() lets the successor's CTAs be
+// scheduled as soon as every CTA of this grid has passed it.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ------------------------------------------------------------------------------------------
 // K3: batched programmable bootstrap (blind rotation), throughput mode.  3 ciphertexts per CTA,
 // each owned by a PAIR of teams (128 threads, see pbs_pair_team), one persistent CTA per SM:
@@ -518,7 +528,9 @@ __global__ void __launch_bounds__(kCmuxTeams * kTeam, 1) cmux_kernel(CmuxBatch P
   extern __shared__ __align__(16) unsigned char smem[];
   C2* sT1 = reinterpret_cast<C2*>(smem);
   C2* sT2 = sT1 + kT1Elems;
+  pdl_launch_dependents();
   load_tables(sT1, sT2, tabs);
+  pdl_wait();  // the ciphertexts come from earlier kernels of the stream
   const int team = threadIdx.x / kTeam;
   const int c = blockIdx.x * (blockDim.x / kTeam) + team;
   if (c >= P.batch) return;
@@ -544,7 +556,12 @@ __global__ void __launch_bounds__(kCmuxTeams * kTeam, 1) cmux_kernel(CmuxBatch P
 // K2w: latency-oriented CMUX, one CTA of 8 teams per GLWE output (cmux_wide); chosen by
 // launch_cmux when there are fewer outputs than SMs (the ripple MUX chain of a Parasol program).
 // ------------------------------------------------------------------------------------------
-constexpr int kWideSmem = kTableBytes + kWideTeams * kXBuf * 16;  // 150592
+// Both GLWE inputs (2 x 32 KiB) are staged in shared memory by two bulk copies (TMA): the four teams
+// that decompose the same polynomial would otherwise each pull it through L2 (256 KiB per CMUX instead
+// of 64 KiB, which made the load phase L2->SM bandwidth bound: 6.9 k of the kernel's 22 k clocks).
+constexpr int kWideGlweBytes = 2 * kN * 8;
+constexpr int kWideSmem = kTableBytes + kWideTeams * kXBuf * 16 + 2 * kWideGlweBytes + 16;  // 216144
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity);
 
 struct DevWideCx {
   int u, team;
@@ -556,21 +573,41 @@ __global__ void __launch_bounds__(kWideTeams * kTeam, 1) cmux_wide_kernel(CmuxBa
   extern __shared__ __align__(16) unsigned char smem[];
   C2* sT1 = reinterpret_cast<C2*>(smem);
   C2* sT2 = sT1 + kT1Elems;
-  load_tables(sT1, sT2, tabs);
-  C2* xb = reinterpret_cast<C2*>(smem + kTableBytes);
-  DevWideCx cx{(int)(threadIdx.x % kTeam), (int)(threadIdx.x / kTeam)};
+  pdl_launch_dependents();
   const int c = blockIdx.x;
-  const size_t glwe = 2 * kN;
-  if (P.ptrs) {
-    const int item = c / P.glwe_per_item;
-    const size_t off = (size_t)(c % P.glwe_per_item) * glwe;
-    const uint64_t* d0 = static_cast<const uint64_t*>(P.ptrs[3 * item + 1]);
-    cmux_wide(cx, P.out + (size_t)c * glwe, d0 ? d0 + off : nullptr, static_cast<const uint64_t*>(P.ptrs[3 * item + 2]) + off,
-              static_cast<const C2*>(P.ptrs[3 * item]), xb, sT1, sT2, P.radix_log, P.count);
-  } else {
-    cmux_wide(cx, P.out + (size_t)c * glwe, P.d0 ? P.d0 + (size_t)c * glwe : nullptr, P.d1 + (size_t)c * glwe,
-              P.ggsw + (size_t)(c / P.glwe_per_item) * P.ggsw_stride, xb, sT1, sT2, P.radix_log, P.count);
+  {  // the selector GGSW (256 KiB) is pulled towards L2 while the predecessor level still runs
+    const C2* gg = P.ptrs ? static_cast<const C2*>(P.ptrs[3 * (c / P.glwe_per_item)]) : P.ggsw + (size_t)(c / P.glwe_per_item) * P.ggsw_stride;
+    const char* q = reinterpret_cast<const char*>(gg);
+    for (int i = threadIdx.x; i < (int)(2 * 2 * 4 * kM * sizeof(C2) / 128) && P.count == 4; i += blockDim.x) prefetch_l2(q + (size_t)i * 128);
   }
+  C2* xb = reinterpret_cast<C2*>(smem + kTableBytes);
+  uint64_t* sd1 = reinterpret_cast<uint64_t*>(smem + kTableBytes + kWideTeams * kXBuf * 16);
+  uint64_t* sd0 = sd1 + 2 * kN;
+  uint64_t* mbar = sd0 + 2 * kN;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  load_tables(sT1, sT2, tabs);  // ends with a CTA barrier: the mbarrier is initialised for everyone
+  const size_t glwe = 2 * kN;
+  const int item = c / P.glwe_per_item;
+  const size_t off = P.ptrs ? (size_t)(c % P.glwe_per_item) * glwe : (size_t)c * glwe;
+  const uint64_t* d0 = P.ptrs ? static_cast<const uint64_t*>(P.ptrs[3 * item + 1]) : P.d0;
+  const uint64_t* d1 = P.ptrs ? static_cast<const uint64_t*>(P.ptrs[3 * item + 2]) : P.d1;
+  const C2* ggsw = P.ptrs ? static_cast<const C2*>(P.ptrs[3 * item]) : P.ggsw + (size_t)item * P.ggsw_stride;
+  pdl_wait();  // the GLWE inputs come from earlier kernels of the stream
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = d0 ? 2 * kWideGlweBytes : kWideGlweBytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sd1)), "l"(d1 + off), "r"((uint32_t)kWideGlweBytes), "r"(smem_u32(mbar)) : "memory");
+    if (d0)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(sd0)), "l"(d0 + off), "r"((uint32_t)kWideGlweBytes), "r"(smem_u32(mbar)) : "memory");
+  }
+  mbar_wait(smem_u32(mbar), 0);
+  DevWideCx cx{(int)(threadIdx.x % kTeam), (int)(threadIdx.x / kTeam)};
+  cmux_wide(cx, P.out + (size_t)c * glwe, d0 ? sd0 : nullptr, sd1, ggsw, xb, sT1, sT2, P.radix_log, P.count);
 }
 
 // ------------------------------------------------------------------------------------------

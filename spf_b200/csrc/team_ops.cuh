@@ -780,34 +780,62 @@ SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2
 //   cx.u / cx.team: thread in team, team 0..7;  cx.sync(): team barrier;  cx.cta_sync(): all 512
 //   xb: 8 exchange buffers.  count must be 4 (k = 1): 2 polynomials x 4 levels = 8 teams.
 constexpr int kWideTeams = 8;
+#if defined(SPF_WIDE_TRACE) && defined(__CUDA_ARCH__)
+#define SPF_WT(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) wt[k] = clock64(); } while (0)
+#else
+#define SPF_WT(k) do { } while (0)
+#endif
 template <class Cx>
 SPF_HD void cmux_wide(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t* d1, const C2* ggsw, C2* xb,
                       const C2* T1, const C2* T2, int radix_log, int count) {
   const int u = cx.u, team = cx.team;
   const int r = team / count, t = team % count;
   C2* xown = xb + team * kXBuf;
+#if defined(SPF_WIDE_TRACE) && defined(__CUDA_ARCH__)
+  long long wt[8];
+#endif
+  SPF_WT(0);
   {
     const uint64_t off = radix_offset(radix_log, count);
     const uint64_t dmask = (1ull << radix_log) - 1;
     const int32_t half = 1 << (radix_log - 1);
     C2 v[16];
+    const int shift = 64 - radix_log * count;
+    if (shift >= 33) {
+      // All digits and the rounding bit lie in the high word (cbs_radix: 16 bits): digit_t is a bit field of
+      // hi(x) + round + offset, 32-bit arithmetic only (the general form below costs ~2.5x the integer work).
+      const uint32_t c1 = (1u << (shift - 33)) + ((uint32_t)off << (shift - 32));
+      const int sh = shift - 32 + t * radix_log;
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-      const int j = r * kN + u + 64 * m;
-      const uint64_t x0 = d0 ? ldg_u64(d1 + j) - ldg_u64(d0 + j) : ldg_u64(d1 + j);
-      const uint64_t x1 = d0 ? ldg_u64(d1 + j + kM) - ldg_u64(d0 + j + kM) : ldg_u64(d1 + j + kM);
-      const uint64_t r0 = radix_round(x0, radix_log, count) + off, r1 = radix_round(x1, radix_log, count) + off;
-      v[m].x = i32_to_f64((int32_t)((r0 >> (t * radix_log)) & dmask) - half);
-      v[m].y = i32_to_f64((int32_t)((r1 >> (t * radix_log)) & dmask) - half);
+      for (int m = 0; m < 16; m++) {
+        const int j = r * kN + u + 64 * m;
+        const uint64_t x0 = d0 ? d1[j] - d0[j] : d1[j];  // d0 / d1 may be shared-memory copies (cmux_wide_kernel)
+        const uint64_t x1 = d0 ? d1[j + kM] - d0[j + kM] : d1[j + kM];
+        v[m].x = i32_to_f64((int32_t)((((uint32_t)(x0 >> 32) + c1) >> sh) & (uint32_t)dmask) - half);
+        v[m].y = i32_to_f64((int32_t)((((uint32_t)(x1 >> 32) + c1) >> sh) & (uint32_t)dmask) - half);
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const int j = r * kN + u + 64 * m;
+        const uint64_t x0 = d0 ? d1[j] - d0[j] : d1[j];
+        const uint64_t x1 = d0 ? d1[j + kM] - d0[j + kM] : d1[j + kM];
+        const uint64_t r0 = radix_round(x0, radix_log, count) + off, r1 = radix_round(x1, radix_log, count) + off;
+        v[m].x = i32_to_f64((int32_t)((r0 >> (t * radix_log)) & dmask) - half);
+        v[m].y = i32_to_f64((int32_t)((r1 >> (t * radix_log)) & dmask) - half);
+      }
     }
+    SPF_WT(1);
     fwd_pass1(v, u, T1);
     fwd_x1_write(v, xown, u);
     cx.sync();
+    SPF_WT(2);
     fwd_x1_read(v, xown, u);
     fwd_pass2(v, u, T2);
     fwd_x2_write(v, xown, u);  // in place
   }
   cx.cta_sync();
+  SPF_WT(3);
   // ---- MAD: thread (p, k1, k2) owns bins k1 + 16 k2 + 256 k3, k3 = 0..3, of output polynomial p ----
   const int tid = team * kTeam + u;
   const int p = tid >> 8, k1 = tid & 15, k2 = (tid >> 4) & 15;
@@ -835,10 +863,12 @@ SPF_HD void cmux_wide(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t*
     }
   }
   bfly4<true>(f[0], f[1], f[2], f[3]);
+  SPF_WT(4);
   cx.cta_sync();  // every spectrum has been consumed: buffers 0 and 1 take the two outputs
 #pragma unroll
   for (int qp = 0; qp < 4; qp++) xb[p * kXBuf + k1 * kXPad + qp + 4 * k2] = f[qp];
   cx.cta_sync();
+  SPF_WT(5);
   if (team < 2) {  // team p finishes the inverse transform of output polynomial p
     C2 w[16];
     double ws[16];
@@ -846,18 +876,25 @@ SPF_HD void cmux_wide(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t*
     inv_pass2(w, u, T2);
     inv_x1_write(w, xown, u);  // in place
     cx.sync();
+    SPF_WT(6);
     inv_x1_read(w, xown, u);
 #pragma unroll
     for (int k1i = 0; k1i < 16; k1i++) w[k1i] = cmul_conj(w[k1i], T1[k1i * 64 + u]);
     inv_pass1_core_s(w, ws);
+    SPF_WT(7);
 #pragma unroll
     for (int m = 0; m < 16; m++) {
       const int j = team * kN + u + 64 * m;
       uint64_t re = f64_to_torus_s(w[m].x, ws[m]), im = f64_to_torus_s(w[m].y, ws[m]);
-      if (d0) { re += ldg_u64(d0 + j); im += ldg_u64(d0 + j + kM); }
+      if (d0) { re += d0[j]; im += d0[j + kM]; }
       out[j] = re;
       out[j + kM] = im;
     }
+#if defined(SPF_WIDE_TRACE) && defined(__CUDA_ARCH__)
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+      printf("WT load %lld p1 %lld p2 %lld mad %lld sync %lld inv2 %lld inv1 %lld store %lld total %lld\n", wt[1] - wt[0], wt[2] - wt[1],
+             wt[3] - wt[2], wt[4] - wt[3], wt[5] - wt[4], wt[6] - wt[5], wt[7] - wt[6], clock64() - wt[7], clock64() - wt[0]);
+#endif
   }
 }
 

@@ -274,3 +274,48 @@ def test_pack_unpack_roundtrip(oracle, keys, client, proc):
     assert client.decrypt_glwe_l1(packed_out)[:w].tolist() == bits          # bit i sits in coefficient i
     assert [client.decrypt_lwe_l1(x) for x in l1_out] == bits
     assert [int(client.decrypt_glwe_l1(x)[0]) for x in mux_out] == bits
+
+
+def _multiply_program(client, keys, w, vals):
+    from spf_b200.circuits import multiply_then_greater_than
+
+    enc = lambda v: [client.encrypt_glwe_l1([(v >> i) & 1]) for i in range(w)]
+    a, b, c = ([enc(v[k]) for v in vals] for k in range(3))
+    out_prod = [[np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w)] for _ in vals]
+    out_gt = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in vals]
+    return multiply_then_greater_than(a, b, c, out_prod, out_gt, len(vals)), out_prod, out_gt
+
+
+def _check_multiply(client, vals, w, out_prod, out_gt):
+    for (a, b, c), p_bits, gt in zip(vals, out_prod, out_gt):
+        p = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(p_bits))
+        assert p == (a * b) % (1 << w), (a, b, p)
+        assert int(client.decrypt_glwe_l1(gt)[0]) == int(p > c)
+
+
+def test_multiply_then_compare_8bit(keys, client, proc):
+    """The ISA's unsigned multiply (parasol_cpu/src/proc/tests/mul.rs) on 8-bit operands: one BDD-derived
+    8x8 multiplier block (the low word keeps 639 of its 3228 multiplexers after pruning), then CmpGt on the
+    refreshed product bits."""
+    w = 8
+    vals = [(13, 11, 100), (255, 255, 0), (0, 77, 0)]
+    circ, out_prod, out_gt = _multiply_program(client, keys, w, vals)
+    g = proc.compile(circ)
+    g.run()
+    _check_multiply(client, vals, w, out_prod, out_gt)
+    g.close()
+
+
+def test_multiply_then_compare_32bit(keys, client, proc):
+    """BASELINE config 4's program on one GPU: 32-bit multiply (four 16x16 blocks + grade-school reduction,
+    45 k CMUX nodes over ~600 dependency levels, three circuit-bootstrap levels of 96 / 64 / 32) then
+    greater-than; decrypts to the plain product and comparison."""
+    w = 32
+    rng = np.random.default_rng(21)
+    vals = [(int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w))), (0xFFFFFFFF, 0xFFFFFFFF, 0)]
+    for v in vals:
+        circ, out_prod, out_gt = _multiply_program(client, keys, w, [v])
+        g = proc.compile(circ)
+        g.run()
+        _check_multiply(client, [v], w, out_prod, out_gt)
+        g.close()

@@ -1,7 +1,8 @@
-"""Run `programs` two-level encrypted programs (32-bit add, then greater-than) as ONE graph sharded
-over the GPUs of a box (BASELINE config 4's execution model) and report latency.
+"""Run `programs` multi-level encrypted programs -- add then greater-than, or (kind = mul) BASELINE
+config 4's multiply then greater-than -- as ONE graph sharded over the GPUs of a box
+and report latency.
 launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port P tools/sharded_graph_run.py [width] [programs] [runs]"""
+        --master-port P tools/sharded_graph_run.py [width] [programs] [runs] [add|mul]"""
 import json
 import os
 import sys
@@ -14,12 +15,13 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle as O  # key / input generation and decryption only
 import spf_b200
-from spf_b200.circuits import add_then_greater_than
+from spf_b200.circuits import add_then_greater_than, multiply_then_greater_than
 from spf_b200.multi import NcclExchange, broadcast_compute_key
 
 w = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 programs = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 runs = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+kind = sys.argv[4] if len(sys.argv) > 4 else "add"
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -43,9 +45,13 @@ enc = lambda v: [client.encrypt_glwe_l1([(v >> i) & 1]) for i in range(w)]
 a, b, c = ([enc(v[k]) for v in vals] for k in range(3))
 out_sum = [[np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w)] for _ in range(programs)]
 out_gt = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(programs)]
-circ = add_then_greater_than(a, b, c, out_sum, out_gt, programs)
+t0 = time.perf_counter()
+circ = (multiply_then_greater_than if kind == "mul" else add_then_greater_than)(a, b, c, out_sum, out_gt, programs)
+build_ms = 1e3 * (time.perf_counter() - t0)
 ex = NcclExchange(rank) if world > 1 else None
+t0 = time.perf_counter()
 g = spf_b200.CompiledGraph(ev, circ, world=world, rank=rank, exchange=ex)
+compile_ms = 1e3 * (time.perf_counter() - t0)
 times = []
 for _ in range(runs + 1):
     if world > 1:
@@ -57,15 +63,17 @@ for _ in range(runs + 1):
 ok = True
 for (x, y, z), s_bits, gt in zip(vals, out_sum, out_gt):
     s = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(s_bits))
-    ok &= s == (x + y) % (1 << w) and int(client.decrypt_glwe_l1(gt)[0]) == int(s > z)
+    ok &= s == ((x * y) if kind == "mul" else (x + y)) % (1 << w) and int(client.decrypt_glwe_l1(gt)[0]) == int(s > z)
 t = torch.tensor([min(times[1:])], dtype=torch.float64, device="cuda")
 oks = torch.tensor([int(ok)], device="cuda")
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(oks, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(json.dumps({"workload": f"{programs} x (add{w} then greater-than) in one graph", "n_gpus": world,
-                      "cbs_per_level": [3 * w * programs, w * programs], "levels": g.levels, "launches": g.launches,
+    n_op = lambda name: sum(1 for n in circ.nodes if n[0] == spf_b200.OP[name])
+    print(json.dumps({"workload": f"{programs} x ({kind}{w} then greater-than) in one graph", "n_gpus": world,
+                      "nodes": len(circ.nodes), "cmux": n_op("CMux"), "circuit_bootstraps": n_op("CircuitBootstrap"),
+                      "host_graph_build_ms": build_ms, "compile_ms": compile_ms, "levels": g.levels, "launches": g.launches,
                       "graph_ms_max_over_ranks": float(t.item()), "correct_on_all_ranks": bool(oks.item()),
                       "key_broadcast_ms": bcast_ms, "exchanges_per_run": (ex.calls // (runs + 1)) if ex else 0,
                       "exchange_bytes_per_run": (ex.bytes // (runs + 1)) if ex else 0}))
