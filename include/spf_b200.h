@@ -204,16 +204,25 @@ int spf_b200_run_graph(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes)
 
 /* ---- the same graph sharded over the GPUs of one box ---------------------------
  * One process per GPU; every rank builds the same graph over the same inputs and a replica of the
- * compute key.  Each CircuitBootstrap group (a dependency level's ready batch -- the only expensive
- * ops) is laid out as `world` equal chunks; rank r bootstraps chunk r and then calls `exchange`,
- * which must complete the buffer on every rank (an in-place all-gather: on entry chunk r of
- * d_buf[world][chunk_bytes] is valid on rank r, on return -- in stream order -- all chunks are valid
- * everywhere).  spf_b200/multi.py provides the NCCL implementation.  All other ops run replicated.
+ * compute key.  Work is split two ways:
+ *  - each CircuitBootstrap group (a dependency level's ready batch) is laid out as `world` equal
+ *    chunks; rank r bootstraps chunk r;
+ *  - the ops between two bootstrap levels (CMux / Not / GlweAdd / MulXN trees and the SampleExtract ->
+ *    KeyswitchL1toL0 chains behind them) are partitioned by connected component of their data edges:
+ *    one instruction's MUX tree runs on ONE rank, trees are spread over the ranks by size.
+ * After every CircuitBootstrap group (GGSWs, 256 KiB each) and every KeyswitchL1toL0 group (L0 LWEs,
+ * 5 KB each) the run calls `exchange`, which must complete the buffer on every rank (an in-place
+ * all-gather: on entry chunk r of d_buf[world][chunk_bytes] is valid on rank r, on return -- in stream
+ * order -- all chunks are valid everywhere).  spf_b200/multi.py provides the NCCL implementation.
+ * Output* nodes fed by a MUX tree are written on the owning rank only (spf_b200_graph_output_rank);
+ * everything else is written on every rank.
  * Returns nonzero from `exchange` abort the run with SPF_E_GRAPH. */
 typedef int (*spf_exchange_fn)(void *user, void *d_buf, size_t chunk_bytes, int world, void *stream);
 int spf_b200_graph_build_sharded(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes, int world,
                                  spf_b200_graph **out);
 int spf_b200_graph_run_sharded(spf_b200_graph *graph, int rank, int world, spf_exchange_fn exchange, void *user);
+/* Rank that writes Output* node `node` in a sharded run; -1 = every rank; -2 = not an Output* node. */
+int spf_b200_graph_output_rank(const spf_b200_graph *graph, size_t node);
 
 /* ---- serialized keys and ciphertexts ------------------------------------------
  * The reference serialises with bincode 1.3.3 (Cargo.lock:244-245), fixed-width little-endian

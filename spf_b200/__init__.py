@@ -395,6 +395,7 @@ ABI.update({
     "spf_b200_graph_set_io": [_vp, _sz, _vp],
     "spf_b200_graph_build_sharded": [_vp, C.POINTER(_Node), _sz, C.c_int, C.POINTER(_vp)],
     "spf_b200_graph_run_sharded": [_vp, C.c_int, C.c_int, _vp, _vp],
+    "spf_b200_graph_output_rank": [_vp, _sz],
 })
 
 
@@ -505,6 +506,14 @@ class CompiledGraph:
         self.ev._check(lib().spf_b200_graph_set_io(self._h, node, buf.ctypes.data))
         self._bound = getattr(self, "_bound", {})
         self._bound[node] = buf  # keep alive
+
+    def output_rank(self, node: int) -> int:
+        """Rank whose run() writes Output* node `node` (-1: every rank).  In a sharded run the outputs of
+        a MUX tree are delivered on the rank that owns the tree."""
+        r = int(lib().spf_b200_graph_output_rank(self._h, node))
+        if r == -2:
+            raise SpfError(-1, f"node {node} is not an Output* node")
+        return r
 
     @property
     def levels(self) -> int:

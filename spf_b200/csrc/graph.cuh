@@ -69,11 +69,17 @@ size_t ct_host_bytes(const spf_params* p, CtType t) { return ct_bytes(p, t); }
 struct Group {
   uint32_t op;
   int level;
-  std::vector<int> ids;
+  std::vector<int> ids;   // slot k of the group's output buffer holds node ids[k]; -1 = padding slot
   size_t ptr_off = 0;   // offset (entries) into the device pointer table
   size_t u32_off = 0;   // offset into the device u32 table
   char* out_base = nullptr;
   char* scratch = nullptr;  // CBS: PBS outputs
+  // Sharded layout (world > 1): slots [all_start, all_start + all_cnt) are computed by every rank,
+  // slots [r_start[r], r_start[r] + r_cnt[r]) by rank r only.  `gather_chunk` > 0: the first
+  // world * gather_chunk slots are `world` equal chunks completed by an all-gather after the group.
+  size_t all_start = 0, all_cnt = 0;
+  std::vector<size_t> r_start, r_cnt;
+  size_t gather_chunk = 0;
 };
 
 }  // namespace
@@ -94,6 +100,7 @@ struct spf_b200_graph {
   int n_levels = 0;
   uint64_t launches_per_run = 0;
   int world = 1;  // CircuitBootstrap groups are laid out as `world` equal chunks (spf_b200_graph_build_sharded)
+  std::vector<int> owner;  // rank that computes the node's ciphertext, -1 = every rank holds it
   std::vector<void*> pinned;  // io buffers page-locked by this graph (cudaHostRegister), so that their copies are true DMAs
 };
 
@@ -148,45 +155,53 @@ void pin_io(spf_b200_graph* g, void* p, size_t bytes) {
 // empty) so that one all-gather of world * chunk items puts every GGSW on every rank.
 size_t cbs_chunk_items(size_t n, int world) { return (n + (size_t)world - 1) / (size_t)world; }
 
-int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s, int rank = 0, int world = 1) {
+// Runs slots [start, start + n) of a group.
+int run_group_range(spf_b200_graph* g, const Group& G, cudaStream_t s, size_t start, size_t n) {
   spf_b200_ctx* ctx = g->ctx;
-  const size_t n = G.ids.size();
-  const void* const* ptrs = reinterpret_cast<const void* const*>(g->d_ptrs + G.ptr_off);
+  if (n == 0) return 0;
+  const spf_params* p = &ctx->p;
+  const size_t out_bytes = ct_bytes(p, op_info(G.op).out);
+  char* out = G.out_base ? G.out_base + start * out_bytes : nullptr;
+  const void* const* base = reinterpret_cast<const void* const*>(g->d_ptrs + G.ptr_off);
+  const void* const* p1 = base + start;
+  const void* const* p2 = base + 2 * start;
+  const void* const* p3 = base + 3 * start;
+  const uint32_t* u32 = g->d_u32 + G.u32_off + start;
   switch (G.op) {
     case SPF_OP_SAMPLE_EXTRACT:
-      return launch_sample_extract(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, g->d_u32 + G.u32_off, 0, n, s, ptrs);
+      return launch_sample_extract(ctx, reinterpret_cast<uint64_t*>(out), nullptr, u32, 0, n, s, p1);
     case SPF_OP_KEYSWITCH_L1_TO_L0:
-      return launch_keyswitch(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, n, s, ptrs);
+      return launch_keyswitch(ctx, reinterpret_cast<uint64_t*>(out), nullptr, n, s, p1);
     case SPF_OP_NOT:
-      return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, 1, 0, n, s, ptrs);
+      return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, 1, 0, n, s, p2);
     case SPF_OP_GLWE_ADD:
-      return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, 0, 0, n, s, ptrs);
+      return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, 0, 0, n, s, p2);
     case SPF_OP_MUL_XN:
-      return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, 2, 0, n, s, ptrs,
-                                g->d_u32 + G.u32_off);
+      return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, 2, 0, n, s, p2, u32);
     case SPF_OP_CMUX:
     case SPF_OP_MULTIPLY_GGSW_GLWE:
-      return launch_cmux(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, nullptr, 0, 1, n, s, ptrs);
+      return launch_cmux(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, nullptr, 0, 1, n, s, p3);
     case SPF_OP_GLEV_CMUX:
-      return launch_cmux(ctx, reinterpret_cast<uint64_t*>(G.out_base), nullptr, nullptr, nullptr, 0, (int)ctx->p.cbs.count,
-                         n * ctx->p.cbs.count, s, ptrs);
+      return launch_cmux(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, nullptr, 0, (int)p->cbs.count, n * p->cbs.count, s, p3);
     case SPF_OP_CIRCUIT_BOOTSTRAP: {
-      // sharded run: this rank bootstraps only its chunk; the caller's exchange fills in the rest
-      const size_t chunk = cbs_chunk_items(n, world);
-      const size_t start = std::min(n, chunk * (size_t)rank), cnt = std::min(n - start, chunk);
-      if (cnt == 0) return 0;
-      const size_t glwe = ct_bytes(&ctx->p, T_GLWE1), ggsw = ct_bytes(&ctx->p, T_GGSW1);
+      const size_t glwe = ct_bytes(p, T_GLWE1);
       if (int rc = launch_pbs(ctx, reinterpret_cast<uint64_t*>(G.scratch + start * glwe), nullptr, nullptr, true, 0,
-                              cbs_log_v(&ctx->p), cnt, s, ptrs + start))
+                              cbs_log_v(p), n, s, p1))
         return rc;
       return launch_trace_ss(ctx, reinterpret_cast<const uint64_t*>(G.scratch + start * glwe), nullptr,
-                             reinterpret_cast<C2*>(G.out_base + start * ggsw), 0, (int)ctx->p.cbs.count, 1.0, cnt, s);
+                             reinterpret_cast<C2*>(out), 0, (int)p->cbs.count, 1.0, n, s);
     }
     case SPF_OP_SCHEME_SWITCH:
-      return launch_trace_ss(ctx, nullptr, nullptr, reinterpret_cast<C2*>(G.out_base), 2, (int)ctx->p.cbs.count, 1.0, n, s, ptrs);
+      return launch_trace_ss(ctx, nullptr, nullptr, reinterpret_cast<C2*>(out), 2, (int)p->cbs.count, 1.0, n, s, p1);
     default:
       return 0;
   }
+}
+
+// This rank's share of a group: the replicated slots, then its own slots.
+int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s, int rank) {
+  if (int rc = run_group_range(g, G, s, G.all_start, G.all_cnt)) return rc;
+  return run_group_range(g, G, s, G.r_start[rank], G.r_cnt[rank]);
 }
 
 }  // namespace
@@ -195,6 +210,7 @@ extern "C" {
 
 void spf_b200_graph_destroy(spf_b200_graph* g);
 int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user);
+int spf_b200_graph_output_rank(const spf_b200_graph* g, size_t node);
 
 int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, int world, spf_b200_graph** out) {
   if (!ctx) return SPF_E_INVALID;
@@ -270,11 +286,11 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   // bootstraps back to back.  Nodes of those three ops that have the same number of circuit
   // bootstraps upstream (their "stage") are therefore delayed to the level of the latest one, so
   // that a stage bootstraps as ONE batch; delaying a node is always legal, consumers are re-levelled.
+  std::vector<int> stage(n, 0);
   {
     std::vector<int> order(n);
     for (size_t i = 0; i < n; i++) order[i] = (int)i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return g->level[a] < g->level[b]; });  // topological
-    std::vector<int> stage(n, 0);
     for (int v : order) {
       const OpInfo oi = op_info(g->nodes[v].op);
       for (int k = 0; k < oi.n_in; k++) {
@@ -312,6 +328,68 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   }
   for (size_t i = 0; i < n; i++) g->n_levels = std::max(g->n_levels, g->level[i] + 1);
   if (int rc = ensure_constants(ctx)) return rc;
+  // ---- ownership (sharded graphs) ----
+  // The ops between two bootstrap levels (the MUX trees and the sample-extract / keyswitch chains behind
+  // them) are partitioned by connected component of their data edges: a component -- one instruction's
+  // tree -- runs on ONE rank ("run each instruction's tree on one GPU and shard across
+  // trees"), components are spread over the ranks stage by stage by size.  Keyswitch outputs (5 KB) are
+  // all-gathered, so every circuit-bootstrap level can still be split evenly whatever produced its inputs.
+  // A component whose ciphertexts are consumed by an op outside this scheme stays replicated.
+  g->owner.assign(n, -1);
+  if (world > 1) {
+    auto local = [](uint32_t op) {
+      return op == SPF_OP_CMUX || op == SPF_OP_GLEV_CMUX || op == SPF_OP_MULTIPLY_GGSW_GLWE || op == SPF_OP_NOT ||
+             op == SPF_OP_GLWE_ADD || op == SPF_OP_MUL_XN || op == SPF_OP_SAMPLE_EXTRACT || op == SPF_OP_KEYSWITCH_L1_TO_L0;
+    };
+    std::vector<int> parent(n);
+    for (size_t i = 0; i < n; i++) parent[i] = (int)i;
+    auto find = [&](int v) {
+      while (parent[v] != v) { parent[v] = parent[parent[v]]; v = parent[v]; }
+      return v;
+    };
+    std::vector<char> replicated(n, 0);
+    for (size_t v = 0; v < n; v++) {
+      const uint32_t op = g->nodes[v].op;
+      const OpInfo oi = op_info(op);
+      const bool is_output = op >= SPF_OP_OUTPUT_LWE0 && op <= SPF_OP_OUTPUT_GLEV1;
+      for (int e = 0; e < oi.n_in; e++) {
+        const int w = g->nodes[v].in[e];
+        if (!local(g->nodes[w].op)) continue;
+        if (local(op)) parent[find((int)v)] = find(w);
+        else if (!is_output && g->nodes[w].op != SPF_OP_KEYSWITCH_L1_TO_L0) replicated[w] = 1;
+      }
+    }
+    struct Comp { int root, stage, first; size_t weight; bool replicated; };
+    std::map<int, Comp> comps;
+    for (size_t v = 0; v < n; v++) {
+      if (!local(g->nodes[v].op)) continue;
+      const int r = find((int)v);
+      auto it = comps.find(r);
+      if (it == comps.end()) it = comps.emplace(r, Comp{r, 0, (int)v, 0, false}).first;
+      it->second.weight++;
+      it->second.stage = std::max(it->second.stage, stage[v]);
+      it->second.replicated |= replicated[v] != 0;
+    }
+    std::vector<Comp> list;
+    for (auto& kv : comps) list.push_back(kv.second);
+    std::sort(list.begin(), list.end(), [](const Comp& a, const Comp& b) {
+      if (a.stage != b.stage) return a.stage < b.stage;
+      if (a.weight != b.weight) return a.weight > b.weight;
+      return a.first < b.first;
+    });
+    std::map<int, int> rank_of;
+    std::vector<size_t> load(world, 0);
+    int cur_stage = -1;
+    for (const Comp& c : list) {
+      if (c.stage != cur_stage) { cur_stage = c.stage; std::fill(load.begin(), load.end(), 0); }
+      if (c.replicated) { rank_of[c.root] = -1; continue; }
+      const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      load[r] += c.weight;
+      rank_of[c.root] = r;
+    }
+    for (size_t v = 0; v < n; v++)
+      if (local(g->nodes[v].op)) g->owner[v] = rank_of[find((int)v)];
+  }
   // ---- groups, arena layout, pointer tables ----
   std::vector<std::vector<int>> by_level(g->n_levels);
   for (size_t i = 0; i < n; i++) by_level[g->level[i]].push_back((int)i);
@@ -327,16 +405,46 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
       Group G;
       G.op = op;
       G.level = lv;
-      G.ids = kv.second;
+      G.r_start.assign(world, 0);
+      G.r_cnt.assign(world, 0);
       const OpInfo oi = op_info(op);
       const bool is_const = op >= SPF_OP_ZERO_LWE0 && op <= SPF_OP_ONE_GLEV1;
       const bool is_output = op >= SPF_OP_OUTPUT_LWE0 && op <= SPF_OP_OUTPUT_GLEV1;
+      if (world == 1 || is_const || is_output || op <= SPF_OP_INPUT_GLEV1) {
+        G.ids = kv.second;  // computed (or simply present) on every rank
+        G.all_cnt = G.ids.size();
+      } else if (op == SPF_OP_CIRCUIT_BOOTSTRAP) {
+        // `world` equal chunks by index (the last ones may be short or empty), completed by an all-gather
+        G.ids = kv.second;
+        G.gather_chunk = cbs_chunk_items(G.ids.size(), world);
+        for (int r = 0; r < world; r++) {
+          G.r_start[r] = std::min(G.ids.size(), G.gather_chunk * (size_t)r);
+          G.r_cnt[r] = std::min(G.ids.size() - G.r_start[r], G.gather_chunk);
+        }
+        G.ids.resize(G.gather_chunk * (size_t)world, -1);
+      } else {
+        std::vector<std::vector<int>> by_rank(world);
+        std::vector<int> everyone;
+        for (int id : kv.second) (g->owner[id] < 0 ? everyone : by_rank[g->owner[id]]).push_back(id);
+        size_t widest = 0;
+        for (auto& v : by_rank) widest = std::max(widest, v.size());
+        // keyswitch outputs are all-gathered: pad every rank's share to the widest one
+        const bool gather = op == SPF_OP_KEYSWITCH_L1_TO_L0 && widest > 0;
+        if (gather) G.gather_chunk = widest;
+        for (int r = 0; r < world; r++) {
+          G.r_start[r] = G.ids.size();
+          G.r_cnt[r] = by_rank[r].size();
+          G.ids.insert(G.ids.end(), by_rank[r].begin(), by_rank[r].end());
+          if (gather) G.ids.resize(G.r_start[r] + widest, -1);
+        }
+        G.all_start = G.ids.size();
+        G.all_cnt = everyone.size();
+        G.ids.insert(G.ids.end(), everyone.begin(), everyone.end());
+      }
       size_t o = (size_t)-1, sc = (size_t)-1;
       if (!is_const && !is_output) {
         o = arena;
-        // CircuitBootstrap outputs are padded to `world` equal chunks (in-place all-gather layout)
-        const size_t slots = op == SPF_OP_CIRCUIT_BOOTSTRAP ? cbs_chunk_items(G.ids.size(), world) * (size_t)world : G.ids.size();
-        arena = align(arena + ct_bytes(p, oi.out) * slots);
+        arena = align(arena + ct_bytes(p, oi.out) * G.ids.size());
         if (op == SPF_OP_CIRCUIT_BOOTSTRAP) { sc = arena; arena = align(arena + ct_bytes(p, T_GLWE1) * G.ids.size()); }
       }
       if (op == SPF_OP_OUTPUT_GGSW1) out_stage += ct_bytes(p, T_GGSW1) * G.ids.size();
@@ -365,6 +473,7 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
     if (scratch_off[gi] != (size_t)-1) G.scratch = g->arena + scratch_off[gi];
     for (size_t k = 0; k < G.ids.size(); k++) {
       const int id = G.ids[k];
+      if (id < 0) continue;  // padding slot
       switch (G.op) {
         case SPF_OP_ZERO_LWE0: g->dptr[id] = ctx->c_lwe0[0]; break;
         case SPF_OP_ONE_LWE0: g->dptr[id] = ctx->c_lwe0[1]; break;
@@ -389,6 +498,7 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   for (Group& G : g->groups) {
     const OpInfo oi = op_info(G.op);
     for (size_t k = 0; k < G.ids.size(); k++) {
+      if (G.ids[k] < 0) continue;  // padding slot
       const spf_node& nd = g->nodes[G.ids[k]];
       switch (G.op) {
         case SPF_OP_CMUX:
@@ -466,10 +576,10 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
   }
   size_t gi = 0;
   for (const Group& G : g->groups) {
-    if (int rc = run_group(g, G, s, rank, world)) return rc;
+    if (int rc = run_group(g, G, s, rank)) return rc;
     if (timing) cudaEventRecord(ev[++gi], s);
-    if (world > 1 && G.op == SPF_OP_CIRCUIT_BOOTSTRAP) {
-      const size_t chunk_bytes = cbs_chunk_items(G.ids.size(), world) * ct_bytes(p, T_GGSW1);
+    if (world > 1 && G.gather_chunk > 0) {  // circuit-bootstrap outputs (GGSW) and keyswitch outputs (L0 LWE)
+      const size_t chunk_bytes = G.gather_chunk * ct_bytes(p, op_info(G.op).out);
       if (int rc = exchange(user, G.out_base, chunk_bytes, world, s))
         return fail(ctx, SPF_E_GRAPH, "exchange callback failed with status " + std::to_string(rc));
     }
@@ -477,6 +587,7 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
   size_t stage = 0;
   for (int id : g->outputs) {
     const int src = g->nodes[id].in[0];
+    if (spf_b200_graph_output_rank(g, (size_t)id) >= 0 && spf_b200_graph_output_rank(g, (size_t)id) != rank) continue;  // lives on its owner
     const CtType t = g->type[src];
     const char* from = g->dptr[src];
     if (t == T_GGSW1) {
@@ -541,6 +652,17 @@ int spf_b200_graph_set_io(spf_b200_graph* g, size_t node, void* io) {
   const CtType t = op <= SPF_OP_INPUT_GLEV1 ? g->type[node] : g->type[g->nodes[node].in[0]];
   pin_io(g, io, ct_host_bytes(&g->ctx->p, t));
   return 0;
+}
+
+// Rank on which a sharded run delivers the ciphertext of Output* node `node`: -1 = on every rank (the
+// producer is replicated or all-gathered: inputs, constants, circuit bootstraps, keyswitches), else the rank
+// that owns the producing MUX tree.  -2 for a bad argument.
+int spf_b200_graph_output_rank(const spf_b200_graph* g, size_t node) {
+  if (!g || node >= g->nodes.size()) return -2;
+  const uint32_t op = g->nodes[node].op;
+  if (op < SPF_OP_OUTPUT_LWE0 || op > SPF_OP_OUTPUT_GLEV1) return -2;
+  const int src = g->nodes[node].in[0];
+  return g->nodes[src].op == SPF_OP_KEYSWITCH_L1_TO_L0 ? -1 : g->owner[src];
 }
 
 int spf_b200_graph_levels(const spf_b200_graph* g) { return g ? g->n_levels : -1; }

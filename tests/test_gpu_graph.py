@@ -189,9 +189,10 @@ def test_add_then_compare_two_level_program(keys, client, proc):
 
 def test_sharded_run_emulated_on_one_gpu(keys, client, evaluation):
     """spf_b200_graph_run_sharded with world = 2, both ranks emulated on this GPU: rank r computes
-    only chunk r of every CircuitBootstrap level; the exchange callback parks the rank's own chunk
-    and fills in the peer's chunk from the peer's previous pass.  After (levels + 1) alternating
-    passes every level has seen correct peer data, and rank 0's outputs must decrypt correctly."""
+    chunk r of every CircuitBootstrap level and the MUX trees it owns; the exchange callback parks the
+    rank's own chunk and fills in the peer's chunk from the peer's previous pass.  After (exchanges + 1)
+    alternating passes every exchange has seen correct peer data; every output is written by its owning
+    rank into the shared host buffers, which must then decrypt correctly."""
     import ctypes as C
 
     import spf_b200
@@ -218,12 +219,17 @@ def test_sharded_run_emulated_on_one_gpu(keys, client, evaluation):
         return exchange
 
     graphs = [spf_b200.CompiledGraph(evaluation, circ, world=world, rank=r, exchange=make_exchange(r)) for r in range(world)]
-    for _ in range(3):  # two bootstrap levels -> correct after three alternating passes
+    for _ in range(5):  # four dependent exchanges -> correct after five alternating passes
         for r in (1, 0):
             counter["i"] = 0
             graphs[r].run()
-    assert counter["i"] == 2  # one exchange per circuit-bootstrap level
+    assert counter["i"] == 4  # per bootstrap level: keyswitch outputs, then the GGSWs
     _check_program(client, vals, w, out_sum, out_gt)
+    out_nodes = [i for i, nd in enumerate(circ.nodes) if nd[0] == spf_b200.OP["OutputGlwe1"]]
+    ranks = {graphs[0].output_rank(i) for i in out_nodes}
+    assert ranks <= {0, 1} and all(graphs[0].output_rank(i) == graphs[1].output_rank(i) for i in out_nodes)
+    with pytest.raises(spf_b200.SpfError):
+        graphs[0].output_rank(0)
     # a graph laid out for a sharded run refuses the unsharded entry point
     assert spf_b200.lib().spf_b200_graph_run(graphs[0]._h) == -1
     for g in graphs:

@@ -60,21 +60,31 @@ for _ in range(runs + 1):
     t0 = time.perf_counter()
     g.run()
     times.append(1e3 * (time.perf_counter() - t0))
-ok = True
-for (x, y, z), s_bits, gt in zip(vals, out_sum, out_gt):
-    s = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(s_bits))
-    ok &= s == ((x * y) if kind == "mul" else (x + y)) % (1 << w) and int(client.decrypt_glwe_l1(gt)[0]) == int(s > z)
+# every output is checked on the rank that holds it (a MUX tree's outputs live on the tree's owner)
+out_nodes = [i for i, nd in enumerate(circ.nodes) if nd[0] == spf_b200.OP["OutputGlwe1"]]
+assert len(out_nodes) == programs * (w + 1)
+ok, checked = True, 0
+for p_, (x, y, z) in enumerate(vals):
+    want = ((x * y) if kind == "mul" else (x + y)) % (1 << w)
+    bufs = out_sum[p_] + [out_gt[p_]]
+    wants = [(want >> i) & 1 for i in range(w)] + [int(want > z)]
+    for node, buf, bit in zip(out_nodes[p_ * (w + 1):(p_ + 1) * (w + 1)], bufs, wants):
+        if g.output_rank(node) in (-1, rank):
+            ok &= int(client.decrypt_glwe_l1(buf)[0]) == bit
+            checked += 1
 t = torch.tensor([min(times[1:])], dtype=torch.float64, device="cuda")
 oks = torch.tensor([int(ok)], device="cuda")
+n_checked = torch.tensor([checked], device="cuda")
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+    dist.all_reduce(n_checked, op=dist.ReduceOp.SUM)
 if rank == 0:
     n_op = lambda name: sum(1 for n in circ.nodes if n[0] == spf_b200.OP[name])
     print(json.dumps({"workload": f"{programs} x ({kind}{w} then greater-than) in one graph", "n_gpus": world,
                       "nodes": len(circ.nodes), "cmux": n_op("CMux"), "circuit_bootstraps": n_op("CircuitBootstrap"),
                       "host_graph_build_ms": build_ms, "compile_ms": compile_ms, "levels": g.levels, "launches": g.launches,
-                      "graph_ms_max_over_ranks": float(t.item()), "correct_on_all_ranks": bool(oks.item()),
+                      "graph_ms_max_over_ranks": float(t.item()), "correct_on_all_ranks": bool(oks.item()), "outputs_checked_over_ranks": int(n_checked.item()), "outputs": len(out_nodes),
                       "key_broadcast_ms": bcast_ms, "exchanges_per_run": (ex.calls // (runs + 1)) if ex else 0,
                       "exchange_bytes_per_run": (ex.bytes // (runs + 1)) if ex else 0}))
 if world > 1:
