@@ -221,6 +221,12 @@ typedef int (*spf_exchange_fn)(void *user, void *d_buf, size_t chunk_bytes, int 
 int spf_b200_graph_build_sharded(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes, int world,
                                  spf_b200_graph **out);
 int spf_b200_graph_run_sharded(spf_b200_graph *graph, int rank, int world, spf_exchange_fn exchange, void *user);
+/* Host-only planning (no GPU, no context): validates the graph exactly as spf_b200_graph_build does and returns,
+ * per node, its dependency level (after bootstrap-stage alignment) and the rank that computes it in a run sharded
+ * over `world` ranks (-1 = every rank).  level_out / owner_out may be NULL.  Malformed graphs: SPF_E_GRAPH with
+ * the message in spf_b200_last_error(NULL). */
+int spf_b200_graph_plan(const spf_params *params, const spf_node *nodes, size_t n_nodes, int world,
+                        int32_t *level_out, int32_t *owner_out);
 /* Rank that writes Output* node `node` in a sharded run; -1 = every rank; -2 = not an Output* node. */
 int spf_b200_graph_output_rank(const spf_b200_graph *graph, size_t node);
 

@@ -396,6 +396,7 @@ ABI.update({
     "spf_b200_graph_build_sharded": [_vp, C.POINTER(_Node), _sz, C.c_int, C.POINTER(_vp)],
     "spf_b200_graph_run_sharded": [_vp, C.c_int, C.c_int, _vp, _vp],
     "spf_b200_graph_output_rank": [_vp, _sz],
+    "spf_b200_graph_plan": [C.POINTER(Params), C.POINTER(_Node), _sz, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
 })
 
 
@@ -438,6 +439,20 @@ class FheCircuit:
                 arr[i].inp[e] = ins[e]
             arr[i].io = io.ctypes.data if io is not None else None
         return arr
+
+
+def plan_graph(circuit: "FheCircuit", world: int = 1, params: Params | None = None) -> tuple[np.ndarray, np.ndarray]:
+    """Host-only schedule of a graph (no GPU): (level, owner) per node -- the dependency level after
+    bootstrap-stage alignment and, for a run sharded over `world` ranks, the rank that computes the node
+    (-1: every rank).  Raises SpfError(-4, ...) for malformed graphs like CircuitProcessor.run_graph_blocking."""
+    p = params or default_128()
+    n = len(circuit.nodes)
+    level, owner = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+    rc = lib().spf_b200_graph_plan(C.byref(p), circuit._pack(), n, world, level.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   owner.ctypes.data_as(C.POINTER(C.c_int32)))
+    if rc:
+        raise SpfError(rc, (lib().spf_b200_last_error(None) or b"").decode())
+    return level[:n], owner[:n]
 
 
 class CircuitProcessor:

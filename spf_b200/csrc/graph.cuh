@@ -204,53 +204,40 @@ int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s, int rank) {
   return run_group_range(g, G, s, G.r_start[rank], G.r_cnt[rank]);
 }
 
-}  // namespace
-
-extern "C" {
-
-void spf_b200_graph_destroy(spf_b200_graph* g);
-int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user);
-int spf_b200_graph_output_rank(const spf_b200_graph* g, size_t node);
-
-int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, int world, spf_b200_graph** out) {
-  if (!ctx) return SPF_E_INVALID;
-  if (!out || (!nodes && n)) return fail(ctx, SPF_E_INVALID, "NULL argument");
-  if (world < 1 || world > 1024) return fail(ctx, SPF_E_INVALID, "world must be in 1..1024");
-  *out = nullptr;
-  const spf_params* p = &ctx->p;
-  std::unique_ptr<spf_b200_graph, void (*)(spf_b200_graph*)> g(new spf_b200_graph(), spf_b200_graph_destroy);
-  g->ctx = ctx;
-  g->world = world;
-  g->nodes.assign(nodes, nodes + n);
+// Host-only part of a graph build: validation, levelisation with bootstrap-stage alignment and (world > 1) the
+// ownership partition.  Fills g->type / level / owner / n_levels; needs no GPU.  Errors go to `ectx` (may be NULL:
+// then they are readable through spf_b200_last_error(NULL)).
+int plan_graph(spf_b200_ctx* ectx, const spf_params* p, spf_b200_graph* g, int world, std::vector<int>& stage) {
+  const size_t n = g->nodes.size();
   g->type.resize(n);
   g->level.assign(n, -1);
   g->dptr.assign(n, nullptr);
   // ---- validation (Task::validate_inputs / validate_op, task.rs:24-179) ----
   for (size_t i = 0; i < n; i++) {
     const spf_node& nd = g->nodes[i];
-    if (nd.op > SPF_OP_MUL_XN) return graph_fail(ctx, "node " + std::to_string(i) + ": unknown op " + std::to_string(nd.op));
+    if (nd.op > SPF_OP_MUL_XN) return graph_fail(ectx, "node " + std::to_string(i) + ": unknown op " + std::to_string(nd.op));
     const OpInfo oi = op_info(nd.op);
     g->type[i] = oi.out;
     for (int e = 0; e < 3; e++) {
       const int src = nd.in[e];
       if (e < oi.n_in) {
         if (src < 0 || (size_t)src >= n)
-          return graph_fail(ctx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): missing ciphertext input on edge " + std::to_string(e));
+          return graph_fail(ectx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): missing ciphertext input on edge " + std::to_string(e));
       } else if (src >= 0 && nd.op != SPF_OP_RETIRE && nd.op != SPF_OP_NOP) {
-        return graph_fail(ctx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): unexpected extra input edge");
+        return graph_fail(ectx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): unexpected extra input edge");
       }
     }
     if (nd.op == SPF_OP_SAMPLE_EXTRACT && nd.arg >= p->glwe_n)
-      return graph_fail(ctx, "illegal sample extract index " + std::to_string(nd.arg));
+      return graph_fail(ectx, "illegal sample extract index " + std::to_string(nd.arg));
     const bool is_io = nd.op <= SPF_OP_OUTPUT_GLEV1;
-    if (is_io && !nd.io) return graph_fail(ctx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): io pointer is NULL");
+    if (is_io && !nd.io) return graph_fail(ectx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): io pointer is NULL");
   }
   for (size_t i = 0; i < n; i++) {
     const spf_node& nd = g->nodes[i];
     const OpInfo oi = op_info(nd.op);
     for (int e = 0; e < oi.n_in; e++) {
       if (g->type[nd.in[e]] != oi.in[e])
-        return graph_fail(ctx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): input " + std::to_string(e) +
+        return graph_fail(ectx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): input " + std::to_string(e) +
                                    " from node " + std::to_string(nd.in[e]) + " (" + kOpNames[g->nodes[nd.in[e]].op] + ") has the wrong ciphertext kind");
     }
   }
@@ -267,7 +254,7 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
         const OpInfo oi = op_info(g->nodes[v].op);
         if (e < oi.n_in) {
           const int w = g->nodes[v].in[e++];
-          if (state[w] == 1) return graph_fail(ctx, "graph has a cycle through node " + std::to_string(w));
+          if (state[w] == 1) return graph_fail(ectx, "graph has a cycle through node " + std::to_string(w));
           if (state[w] == 0) { state[w] = 1; stack.push_back({w, 0}); }
         } else {
           int lv = 0;
@@ -286,7 +273,7 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   // bootstraps back to back.  Nodes of those three ops that have the same number of circuit
   // bootstraps upstream (their "stage") are therefore delayed to the level of the latest one, so
   // that a stage bootstraps as ONE batch; delaying a node is always legal, consumers are re-levelled.
-  std::vector<int> stage(n, 0);
+  stage.assign(n, 0);
   {
     std::vector<int> order(n);
     for (size_t i = 0; i < n; i++) order[i] = (int)i;
@@ -327,7 +314,6 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
     }
   }
   for (size_t i = 0; i < n; i++) g->n_levels = std::max(g->n_levels, g->level[i] + 1);
-  if (int rc = ensure_constants(ctx)) return rc;
   // ---- ownership (sharded graphs) ----
   // The ops between two bootstrap levels (the MUX trees and the sample-extract / keyswitch chains behind
   // them) are partitioned by connected component of their data edges: a component -- one instruction's
@@ -390,6 +376,30 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
     for (size_t v = 0; v < n; v++)
       if (local(g->nodes[v].op)) g->owner[v] = rank_of[find((int)v)];
   }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void spf_b200_graph_destroy(spf_b200_graph* g);
+int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user);
+int spf_b200_graph_output_rank(const spf_b200_graph* g, size_t node);
+
+int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, int world, spf_b200_graph** out) {
+  if (!ctx) return SPF_E_INVALID;
+  if (!out || (!nodes && n)) return fail(ctx, SPF_E_INVALID, "NULL argument");
+  if (world < 1 || world > 1024) return fail(ctx, SPF_E_INVALID, "world must be in 1..1024");
+  *out = nullptr;
+  const spf_params* p = &ctx->p;
+  std::unique_ptr<spf_b200_graph, void (*)(spf_b200_graph*)> g(new spf_b200_graph(), spf_b200_graph_destroy);
+  g->ctx = ctx;
+  g->world = world;
+  g->nodes.assign(nodes, nodes + n);
+  std::vector<int> stage;
+  if (int rc = plan_graph(ctx, p, g.get(), world, stage)) return rc;
+  if (int rc = ensure_constants(ctx)) return rc;
   // ---- groups, arena layout, pointer tables ----
   std::vector<std::vector<int>> by_level(g->n_levels);
   for (size_t i = 0; i < n; i++) by_level[g->level[i]].push_back((int)i);
@@ -663,6 +673,23 @@ int spf_b200_graph_output_rank(const spf_b200_graph* g, size_t node) {
   if (op < SPF_OP_OUTPUT_LWE0 || op > SPF_OP_OUTPUT_GLEV1) return -2;
   const int src = g->nodes[node].in[0];
   return g->nodes[src].op == SPF_OP_KEYSWITCH_L1_TO_L0 ? -1 : g->owner[src];
+}
+
+// Host-only planning (no GPU, no context): the validation, levelisation and ownership partition of
+// spf_b200_graph_build_sharded, for hosts that want to inspect or test a schedule.
+int spf_b200_graph_plan(const spf_params* params, const spf_node* nodes, size_t n, int world, int32_t* level_out, int32_t* owner_out) {
+  if (!params || (!nodes && n)) return fail(nullptr, SPF_E_INVALID, "NULL argument");
+  if (world < 1 || world > 1024) return fail(nullptr, SPF_E_INVALID, "world must be in 1..1024");
+  spf_b200_graph g;
+  g.world = world;
+  g.nodes.assign(nodes, nodes + n);
+  std::vector<int> stage;
+  if (int rc = plan_graph(nullptr, params, &g, world, stage)) return rc;
+  for (size_t i = 0; i < n; i++) {
+    if (level_out) level_out[i] = g.level[i];
+    if (owner_out) owner_out[i] = g.owner[i];
+  }
+  return 0;
 }
 
 int spf_b200_graph_levels(const spf_b200_graph* g) { return g ? g->n_levels : -1; }

@@ -1,0 +1,117 @@
+"""The host-only half of the graph executor (spf_b200_graph_plan): validation as Task::validate
+(parasol_runtime/src/circuit_processor/task.rs:24-179, tests/faults.rs), levelisation with bootstrap-stage
+alignment, and the ownership partition of a run sharded over several GPUs.  No GPU needed."""
+import collections
+
+import numpy as np
+import pytest
+
+import spf_b200
+from spf_b200 import OP, FheCircuit, SpfError, plan_graph
+from spf_b200.circuits import add_then_greater_than, multiply_then_greater_than
+
+LOCAL = {OP[k] for k in ("CMux", "GlevCMux", "MultiplyGgswGlwe", "Not", "GlweAdd", "MulXN", "SampleExtract", "KeyswitchL1toL0")}
+
+
+def _bufs(programs, w):
+    buf = lambda: np.zeros(4096, np.uint64)
+    mk = lambda: [[buf() for _ in range(w)] for _ in range(programs)]
+    return mk(), mk(), mk(), mk(), [buf() for _ in range(programs)]
+
+
+def _check_partition(c, level, owner, world):
+    for v, (op, arg, ins, io) in enumerate(c.nodes):
+        if op not in LOCAL:
+            assert owner[v] == -1, (v, op)
+            continue
+        assert -1 <= owner[v] < world
+        for e, src in enumerate(ins):
+            if src < 0:
+                continue
+            assert level[src] < level[v]
+            if c.nodes[src][0] in LOCAL:   # data edge inside a tree: same rank
+                assert owner[src] == owner[v], (v, src)
+
+
+def test_levels_and_stage_alignment():
+    a, b, c_, out_sum, out_gt = _bufs(1, 8)
+    c = add_then_greater_than(a, b, c_, out_sum, out_gt, 1)
+    level, owner = plan_graph(c, 1)
+    assert (owner == -1).all()
+    cbs = [v for v, nd in enumerate(c.nodes) if nd[0] == OP["CircuitBootstrap"]]
+    by_level = collections.Counter(int(level[v]) for v in cbs)
+    assert sorted(by_level.values()) == [8, 24]   # the refresh of the 8 sum bits bootstraps as ONE batch
+    for v, (op, arg, ins, io) in enumerate(c.nodes):
+        assert all(level[s] < level[v] for s in ins if s >= 0)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_ownership_of_adder_program(world):
+    programs, w = 8, 8
+    a, b, c_, out_sum, out_gt = _bufs(programs, w)
+    c = add_then_greater_than(a, b, c_, out_sum, out_gt, programs)
+    level, owner = plan_graph(c, world)
+    _check_partition(c, level, owner, world)
+    cmux_per_rank = collections.Counter(int(owner[v]) for v, nd in enumerate(c.nodes) if nd[0] == OP["CMux"])
+    assert set(cmux_per_rank) == set(range(world))               # every rank owns trees
+    assert max(cmux_per_rank.values()) <= 2 * min(cmux_per_rank.values())
+
+
+def test_ownership_of_multiply_program_is_balanced():
+    programs, w = 2, 32
+    a, b, c_, out_p, out_gt = _bufs(programs, w)
+    c = multiply_then_greater_than(a, b, c_, out_p, out_gt, programs)
+    level, owner = plan_graph(c, 2)
+    _check_partition(c, level, owner, 2)
+    per_rank = collections.Counter(int(o) for o in owner if o >= 0)
+    assert abs(per_rank[0] - per_rank[1]) <= 0.1 * per_rank[0]
+    assert level.max() + 1 > 600   # 510-deep 16x16 blocks + reduction + compare
+
+
+def test_single_tree_has_one_owner():
+    a, b, c_, out_sum, out_gt = _bufs(1, 8)
+    c = add_then_greater_than(a, b, c_, out_sum, out_gt, 1)
+    level, owner = plan_graph(c, 4)
+    adder = {int(owner[v]) for v, nd in enumerate(c.nodes) if nd[0] in (OP["CMux"], OP["Not"])}
+    assert len(adder) <= 2 and -1 not in adder   # the adder tree and the comparison tree: one rank each
+
+
+def test_tree_feeding_a_scheme_switch_stays_replicated():
+    glev = np.zeros(16384, np.uint64)
+    ggsw = np.zeros(16384, np.complex128)
+    c = FheCircuit()
+    sel = c.add("InputGgsw1", io=ggsw)
+    x = c.add("GlevCMux", sel, c.add("InputGlev1", io=glev), c.add("OneGlev1"))
+    ss = c.add("SchemeSwitch", x)
+    c.add("OutputGgsw1", ss, io=np.zeros(16384, np.complex128))
+    level, owner = plan_graph(c, 2)
+    assert owner[x] == -1 and owner[ss] == -1
+
+
+def test_malformed_graphs_are_rejected_without_a_gpu():
+    """circuit_processor/tests/faults.rs: wrong ciphertext kind, missing input, illegal sample-extract index; plus a cycle."""
+    glwe, lwe0 = np.zeros(4096, np.uint64), np.zeros(638, np.uint64)
+
+    def expect(c, text):
+        with pytest.raises(SpfError) as e:
+            plan_graph(c)
+        assert e.value.code == -4 and text in str(e.value)
+
+    c = FheCircuit()
+    c.add("KeyswitchL1toL0", c.add("InputLwe0", io=lwe0))
+    expect(c, "wrong ciphertext kind")
+    c = FheCircuit()
+    c.add("CMux", c.add("ZeroGgsw1"), c.add("ZeroGlwe1"))
+    expect(c, "missing ciphertext input")
+    c = FheCircuit()
+    c.add("SampleExtract", c.add("InputGlwe1", io=glwe), arg=2048)
+    expect(c, "illegal sample extract index")
+    c = FheCircuit()
+    c.add("Not", 1)
+    c.add("Not", 0)
+    expect(c, "cycle")
+    c = FheCircuit()
+    c.nodes.append((99, 0, (-1, -1, -1), None))
+    expect(c, "unknown op")
+    with pytest.raises(SpfError):
+        plan_graph(FheCircuit(), world=0)
