@@ -415,7 +415,10 @@ __global__ void __launch_bounds__(4 * kTeam, 1) pbs_quad_kernel(PbsBatch P, DevT
   }
   __syncthreads();
   const int team = threadIdx.x / kTeam;
-  DevQuadCx cx{(int)(threadIdx.x % kTeam), team >> 1, team & 1, t1_taddr, row, mbar};
+  // team w = (h, t) with h = w & 1, t = w >> 1: the two teams that run the inverse transforms (t = 0) are warps
+  // 0..3, one per SM sub-partition (warp % 4) -- with h = w >> 1 they were warps 0,1,4,5, i.e. the FP64-issue-bound
+  // inverse phase ran on two of the four sub-partitions.
+  DevQuadCx cx{(int)(threadIdx.x % kTeam), team & 1, team >> 1, t1_taddr, row, mbar};
   int copies = 0;  // bulk copies completed so far on this CTA's mbarrier (phase parity bookkeeping)
   for (int c = blockIdx.x; c < P.batch; c += gridDim.x) {
     PbsArgs A;

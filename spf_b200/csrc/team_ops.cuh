@@ -521,6 +521,12 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
   const int log2n = 12;  // log2(2N)
   uint64_t* pa = acc + h * kN;
   C2* xown = xb + g * kXBuf;
+#if defined(SPF_QUAD_TRACE) && defined(__CUDA_ARCH__)
+  long long qt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, qc = 0, qn = 0;
+#define SPF_QT(k) do { const long long now_ = clock64(); qt[k] += now_ - qc; qc = now_; } while (0)
+#else
+#define SPF_QT(k) do { } while (0)
+#endif
   // 1. acc = LUT * X^{-b~}: team (h, t) fills half t of polynomial h
   {
     uint64_t b = ldg_u64(A.lwe_in + n);
@@ -563,6 +569,9 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     if (i + 1 < n) a_next = ldg_u64(A.lwe_in + i + 1);
     if (at == 0) continue;
     const C2* ggsw = A.bsk + (size_t)i * 8 * kM;
+#if defined(SPF_QUAD_TRACE) && defined(__CUDA_ARCH__)
+    qc = clock64(); qn++;
+#endif
     {
       C2 v[16];
       const int base = (u - at) & (2 * kN - 1);
@@ -578,19 +587,24 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         const double d = t ? digit_hi16_to_f64(w + 0x8000u) : digit_lo16_to_f64(w);
         if (i2 < 16) v[i2].x = d; else v[i2 - 16].y = d;
       }
+      SPF_QT(0);
       fwd_pass1_core(v);
       cx.template t1_mul<false>(v, T1);
       fwd_x1_write(v, xown, u);
       cx.sync();
+      SPF_QT(1);
       fwd_x1_read(v, xown, u);
       dft16<false>(v);
       cx.template t2_mul<false>(v, T2);
       fwd_x2_write(v, xown, u);  // in place
+      SPF_QT(2);
     }
     cx.quad_sync();
+    SPF_QT(3);
     // MAD: team g owns the bins u + 64 (g + 4 k3) of every polynomial
     const C2* staged = cx.row_wait(executed, ggsw);  // this step's BSK row (device: in shared memory)
     executed++;
+    SPF_QT(4);
     C2 f[2][4];
 #pragma unroll
     for (int b = 0; b < 4; b++) {  // spectrum of team b = (hb, tb): digit tb <-> GLEV level 1 - tb
@@ -617,7 +631,9 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
 #pragma unroll
       for (int qp = 0; qp < 4; qp++) xb[2 * p * kXBuf + k1 * kXPad + qp + 4 * q + 16 * g] = f[p][qp];
     }
+    SPF_QT(5);
     cx.quad_sync();
+    SPF_QT(6);
     {  // every thread is done with the staged row: fetch the one of the next executed step
       const int jn = next_executed(i + 1);
       if (jn < n) cx.row_prefetch(A.bsk + (size_t)jn * 8 * kM);
@@ -630,9 +646,11 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       dft16<true>(w);
       inv_x1_write(w, xown, u);  // in place
       cx.sync();
+      SPF_QT(7);
       inv_x1_read(w, xown, u);
       cx.template t1_mul<true>(w, T1);
       inv_pass1_core_s(w, ws);
+      SPF_QT(8);
 #pragma unroll
       for (int m = 0; m < 16; m++) {
         const int j = u + 64 * m;
@@ -642,12 +660,18 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         pa[j + kM] = own[m + 16];
       }
     }
+    SPF_QT(9);
     cx.quad_sync();
     if (t == 1) {
 #pragma unroll
       for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
     }
   }
+#if defined(SPF_QUAD_TRACE) && defined(__CUDA_ARCH__)
+  if (threadIdx.x == 0 && blockIdx.x == 0 && qn > 0)
+    printf("QT digits %lld p1 %lld p2 %lld qsync1 %lld rowwait %lld mad %lld qsync2 %lld inv2 %lld inv1 %lld store %lld steps %lld\n", qt[0] / qn, qt[1] / qn,
+           qt[2] / qn, qt[3] / qn, qt[4] / qn, qt[5] / qn, qt[6] / qn, qt[7] / qn, qt[8] / qn, qt[9] / qn, qn);
+#endif
   // 3. result: team (h, t) stores half t of polynomial h
   for (int i = 16 * t; i < 16 * t + 16; i++) {
     const int j = u + 64 * i;

@@ -14,7 +14,7 @@ import tempfile
 def sass_lines(so, kernel):
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(so)], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
+    cubin = max((f for f in os.listdir(tmp) if f.endswith('.cubin')), key=lambda f: os.path.getsize(os.path.join(tmp, f)))
     txt = subprocess.run(['nvdisasm', '-g', os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
     start = txt.index('.text.' + kernel + ':')
     end = txt.find('//--------------------- .', start)
