@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="CBS in the CPU baseline sample (0 = about 10 s of work on all host threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-add", action="store_true", help="skip the Parasol 8/32-bit add latency measurement")
+    ap.add_argument("--no-add", action="store_true", help="skip the Parasol program latency measurements (8/32-bit add, mul32 + compare)")
     ap.add_argument("--check", type=int, default=8, help="outputs decrypted with the oracle after the run (checker only)")
     return ap.parse_args()
 
@@ -226,6 +226,110 @@ def cpu_add_latency(keys, a_bits, b_bits, nthreads):
         ncarry = O.glwe_not(keys, carry)
     outs.append(carry)
     return time.perf_counter() - t0, outs
+
+
+def cpu_run_graph(keys, circ, nthreads):
+    """Any FheCircuit on the CPU port with the reference's execution model (circuit_processor/mod.rs:130-253):
+    every ready op is one single-threaded task, the independent tasks of a dependency level are spread over
+    the host threads.  Levels come from the host-only planner; the arithmetic is the oracle's.  Returns seconds."""
+    import ctypes as C
+
+    import oracle as O
+    import spf_b200
+    from spf_b200 import OPS
+
+    l = O.lib()
+    p = keys.params
+    level, _ = spf_b200.plan_graph(circ, 1)
+    groups = {}
+    for v in np.argsort(level, kind="stable").tolist():
+        groups.setdefault((int(level[v]), circ.nodes[v][0]), []).append(v)
+    zero = np.zeros(keys.glwe_len, dtype=np.uint64)
+    one = zero.copy()
+    one[p.glwe_k * p.glwe_n] = np.uint64(1 << 63)
+    val = {}
+    t0 = time.perf_counter()
+    for (lv, opc), ids in sorted(groups.items()):
+        op = OPS[opc]
+        ins = [circ.nodes[v][2] for v in ids]
+        if op == "InputGlwe1":
+            for v in ids:
+                val[v] = circ.nodes[v][3]
+        elif op in ("ZeroGlwe1", "OneGlwe1"):
+            for v in ids:
+                val[v] = zero if op == "ZeroGlwe1" else one
+        elif op == "SampleExtract":
+            for v, i in zip(ids, ins):
+                val[v] = O.sample_extract(keys, val[i[0]], circ.nodes[v][1])
+        elif op == "KeyswitchL1toL0":
+            out = np.zeros((len(ids), keys.lwe0_len), dtype=np.uint64)
+            l.orc_keyswitch_lwe_batch(out, np.stack([val[i[0]] for i in ins]), len(ids), keys.ksk, C.byref(p), min(nthreads, len(ids)))
+            for k, v in enumerate(ids):
+                val[v] = out[k]
+        elif op == "CircuitBootstrap":
+            out = O.circuit_bootstrap_batch(keys, np.stack([val[i[0]] for i in ins]), min(nthreads, len(ids)))
+            for k, v in enumerate(ids):
+                val[v] = out[k]
+        elif op == "CMux":
+            out = np.zeros((len(ids), keys.glwe_len), dtype=np.uint64)
+            tab = lambda arrs: (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+            l.orc_cmux_batch_ptrs(tab([out[k] for k in range(len(ids))]), tab([val[i[1]] for i in ins]), tab([val[i[2]] for i in ins]),
+                                  tab([val[i[0]] for i in ins]), len(ids), C.byref(p), min(nthreads, len(ids)))
+            for k, v in enumerate(ids):
+                val[v] = out[k]
+        elif op == "Not":
+            for v, i in zip(ids, ins):
+                val[v] = O.glwe_not(keys, val[i[0]])
+        elif op == "OutputGlwe1":
+            for v, i in zip(ids, ins):
+                circ.nodes[v][3][:] = val[i[0]]
+        else:
+            raise ValueError(f"cpu_run_graph: op {op} not needed by the benchmark programs")
+    return time.perf_counter() - t0
+
+
+def measure_program_latency(ev, keys, args):
+    """BASELINE config 4's program on this GPU: 32-bit multiply (low word) then greater-than, BDD-derived MUX
+    circuits (spf_b200.mux_circuits), 45 k CMUX + 192 circuit bootstraps over ~630 dependency levels; wall clock of
+    CompiledGraph.run() including the H2D of the 96 input and D2H of the 33 output ciphertexts."""
+    import oracle as O  # client-side encrypt/decrypt + the CPU baseline; never on the measured path
+
+    import spf_b200
+    from spf_b200.circuits import multiply_then_greater_than
+
+    client = O.Client(keys)
+    w, a, b, c = 32, 0xDEADBEEF, 0x12345679, 0x40000000
+    enc = lambda v: [client.encrypt_glwe_l1([(v >> i) & 1]) for i in range(w)]
+    ab, bb, cb = enc(a), enc(b), enc(c)
+    mk_out = lambda: ([[np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w)]], [np.zeros(keys.glwe_len, dtype=np.uint64)])
+
+    def check(out_prod, out_gt):
+        prod = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(out_prod[0]))
+        return prod == (a * b) % (1 << w) and int(client.decrypt_glwe_l1(out_gt[0])[0]) == int(prod > c)
+
+    out_prod, out_gt = mk_out()
+    t0 = time.perf_counter()
+    circ = multiply_then_greater_than([ab], [bb], [cb], out_prod, out_gt, 1)
+    build_ms = 1e3 * (time.perf_counter() - t0)
+    g = spf_b200.CircuitProcessor(ev).compile(circ)
+    g.run()
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        g.run()
+        ts.append(time.perf_counter() - t0)
+    n_op = lambda name: sum(1 for nd in circ.nodes if nd[0] == spf_b200.OP[name])
+    res = {"program": "mul32 (low word) then greater-than", "cmux": n_op("CMux"), "circuit_bootstraps": n_op("CircuitBootstrap"),
+           "levels": g.levels, "launches": g.launches, "gpu_ms": 1e3 * float(np.median(ts)), "gpu_ms_min": 1e3 * min(ts),
+           "host_graph_build_ms": build_ms, "correct": check(out_prod, out_gt)}
+    g.close()
+    if not args.no_cpu_baseline:
+        nt = O.hw_threads()
+        out_prod, out_gt = mk_out()
+        ccirc = multiply_then_greater_than([ab], [bb], [cb], out_prod, out_gt, 1)
+        dt = cpu_run_graph(keys, ccirc, nt)
+        res.update({"cpu_port_ms": 1e3 * dt, "cpu_threads": nt, "cpu_correct": check(out_prod, out_gt)})
+    return res
 
 
 def measure_add_latency(ev, keys, args):
@@ -475,9 +579,10 @@ def run_gpu(args):
 
     # ---- Parasol add latency (the metric's second half): encrypted w-bit add through the graph
     #      executor (16/64 x SampleExtract -> Keyswitch -> CBS, then the ripple-carry MUX tree) ------
-    add_latency = None
+    add_latency = program_latency = None
     if rank == 0 and world == 1 and not args.no_add:
         add_latency = measure_add_latency(ev, keys, args)
+        program_latency = measure_program_latency(ev, keys, args)  # BASELINE config 4's program on one GPU
 
     if rank == 0:
         line = {
@@ -492,7 +597,7 @@ def run_gpu(args):
                        "key_broadcast_ms": key_bcast_ms},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "check": check, "wall_s_timed_region": wall,
-            "parasol_add_latency": add_latency,
+            "parasol_add_latency": add_latency, "parasol_mul32_cmp_latency": program_latency,
         }
         print(json.dumps(line))
     ev.close()

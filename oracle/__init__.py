@@ -123,6 +123,8 @@ def _declare(l):
     l.orc_circuit_bootstrap_batch.argtypes = [_c64p, _u64p, sz, _c64p, _c64p, _c64p, _PP, C.c_int]
     l.orc_cmux_batch.argtypes = [_u64p, _u64p, _u64p, _c64p, sz, _PP, C.c_int]
     l.orc_keyswitch_lwe_batch.argtypes = [_u64p, _u64p, sz, _u64p, _PP, C.c_int]
+    l.orc_cmux_batch_ptrs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, sz, _PP, C.c_int]
+    l.orc_cmux_batch_ptrs.restype = None
     l.orc_rng_seed.argtypes = [C.POINTER(Rng), C.c_uint64]
     l.orc_rng_u64.argtypes = [C.POINTER(Rng)]
     l.orc_rng_u64.restype = C.c_uint64

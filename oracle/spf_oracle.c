@@ -630,6 +630,10 @@ static void *batch_worker(void *arg) {
       orc_cmux((u64 *)j->out + b * g, (const u64 *)j->in0 + b * g, (const u64 *)j->in1 + b * g,
                (const c64 *)j->in2 + b * orc_size_ggsw_fft(p, p->cbs), p, p->cbs);
     } break;
+    case 3: /* pointer tables: one (out, low, high, selector) quadruple per item */
+      orc_cmux(((u64 **)j->out)[b], ((const u64 *const *)j->in0)[b], ((const u64 *const *)j->in1)[b],
+               ((const c64 *const *)j->in2)[b], p, p->cbs);
+      break;
     case 2:
       orc_keyswitch_lwe((u64 *)j->out + b * orc_size_lwe(p->lwe_n),
                         (const u64 *)j->in0 + b * orc_size_lwe(p->glwe_k * p->glwe_n), j->k0, p);
@@ -658,6 +662,13 @@ void orc_circuit_bootstrap_batch(c64 *out, const u64 *lwe_in, size_t batch, cons
 void orc_cmux_batch(u64 *c, const u64 *d0, const u64 *d1, const c64 *ggsw, size_t batch,
                     const orc_params *p, int nthreads) {
   batch_job j = {0}; j.kind = 1; j.batch = batch; j.p = p; j.out = c; j.in0 = d0; j.in1 = d1; j.in2 = ggsw;
+  run_batch(j, nthreads);
+}
+/* The same, operands given by pointer tables (a dependency level of a MUX tree: the reference runs every
+ * ready CMux as one single-threaded task on its rayon pool, circuit_processor/mod.rs:201-223). */
+void orc_cmux_batch_ptrs(u64 *const *c, const u64 *const *d0, const u64 *const *d1, const c64 *const *ggsw,
+                         size_t batch, const orc_params *p, int nthreads) {
+  batch_job j = {0}; j.kind = 3; j.batch = batch; j.p = p; j.out = (void *)c; j.in0 = d0; j.in1 = d1; j.in2 = ggsw;
   run_batch(j, nthreads);
 }
 void orc_keyswitch_lwe_batch(u64 *out, const u64 *in, size_t batch, const u64 *ksk, const orc_params *p,

@@ -110,6 +110,8 @@ void orc_circuit_bootstrap_batch(orc_c64 *ggsw_out, const uint64_t *lwe_in, size
                                  const orc_c64 *ssk_fft, const orc_params *p, int nthreads);
 void orc_cmux_batch(uint64_t *c, const uint64_t *d0, const uint64_t *d1, const orc_c64 *ggsw_fft,
                     size_t batch, const orc_params *p, int nthreads);
+void orc_cmux_batch_ptrs(uint64_t *const *c, const uint64_t *const *d0, const uint64_t *const *d1,
+                         const orc_c64 *const *ggsw_fft, size_t batch, const orc_params *p, int nthreads);
 void orc_keyswitch_lwe_batch(uint64_t *lwe0_out, const uint64_t *lwe1_in, size_t batch,
                              const uint64_t *ksk, const orc_params *p, int nthreads);
 
