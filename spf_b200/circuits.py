@@ -152,25 +152,74 @@ class InstructionCache:
         self._ev, self._compile, self._cache = evaluation, CompiledGraph, {}
         self.hits = self.misses = 0
 
-    def add(self, a_bits, b_bits, out_bits):
-        """out = a + b (w-bit operands as L1 GLWE bit ciphertexts, w + 1 result bits), blocking."""
-        w = len(a_bits)
-        key = ("add", w)
+    def _run(self, key, build, in_bufs, out_bufs):
         if key not in self._cache:
             self.misses += 1
-            c = ripple_carry_adder(list(a_bits), list(b_bits), list(out_bits))
-            ins = [i for i, n in enumerate(c.nodes) if n[0] == 2]    # InputGlwe1, in a then b order
-            outs = [i for i, n in enumerate(c.nodes) if n[0] == 7]   # OutputGlwe1, sum bits then carry
+            c = build()
+            ins = [i for i, n in enumerate(c.nodes) if n[0] == 2]    # InputGlwe1, in operand order
+            outs = [i for i, n in enumerate(c.nodes) if n[0] == 7]   # OutputGlwe1, in result-bit order
+            assert len(ins) == len(in_bufs) and len(outs) == len(out_bufs)
             self._cache[key] = (self._compile(self._ev, c), ins, outs)
         else:
             self.hits += 1
         g, ins, outs = self._cache[key]
-        for node, buf in zip(ins, list(a_bits) + list(b_bits)):
-            g.set_io(node, buf)
-        for node, buf in zip(outs, out_bits):
+        for node, buf in zip(ins + outs, list(in_bufs) + list(out_bufs)):
             g.set_io(node, buf)
         g.run()
         return g
+
+    def add(self, a_bits, b_bits, out_bits):
+        """out = a + b (w-bit operands as L1 GLWE bit ciphertexts, w + 1 result bits), blocking."""
+        a_bits, b_bits, out_bits = list(a_bits), list(b_bits), list(out_bits)
+        return self._run(("add", len(a_bits)), lambda: ripple_carry_adder(a_bits, b_bits, out_bits), a_bits + b_bits, out_bits)
+
+    def _mux_instruction(self, key, mux_builder, operands, out_bits, interleave):
+        """One ISA instruction = front end (fhe_circuit.rs:473-494) + one BDD-derived MUX circuit + outputs."""
+        from . import mux_circuits as M
+
+        def build():
+            c = FheCircuit()
+            sels = [[_front(c, x) for x in op] for op in operands]
+            order = [x for grp in zip(*sels) for x in grp] if interleave else [x for op in sels for x in op]
+            for node, buf in zip(M.insert_mux_circuit(c, mux_builder(), order), out_bits):
+                c.add("OutputGlwe1", node, io=buf)
+            return M.prune(c, [i for i, n in enumerate(c.nodes) if n[0] == 7])[0]
+
+        return self._run(key, build, [x for op in operands for x in op], out_bits)
+
+    def multiply(self, a_bits, b_bits, out_bits):
+        """out = low w bits of a * b, w <= 16 (one multiplier block, parasol_cpu/src/proc/ops/mul.rs:75-117)."""
+        from . import mux_circuits as M
+
+        a_bits, b_bits, out_bits = list(a_bits), list(b_bits), list(out_bits)
+        w = len(a_bits)
+        if w > M.CIRCUIT_CUTOFF or len(b_bits) != w or len(out_bits) != w:
+            raise ValueError("InstructionCache.multiply: equal widths up to 16 bits (wider products span two bootstrap levels: "
+                             "use circuits.multiply_then_greater_than / mux_circuits.append_uint_multiply)")
+        full = lambda: M.unsigned_multiplier(w, w)
+        low = lambda: _keep_outputs(full(), w)
+        return self._mux_instruction(("mul", w), low, [a_bits, b_bits], out_bits, interleave=False)
+
+    def greater_than(self, a_bits, b_bits, out_bit):
+        """out = (a > b), unsigned (comparisons.rs:62-98 with compare_or_maybe_equal(w, true, false))."""
+        from . import mux_circuits as M
+
+        a_bits, b_bits = list(a_bits), list(b_bits)
+        w = len(a_bits)
+        return self._mux_instruction(("gt", w), lambda: M.compare_or_maybe_equal(w, True, False), [a_bits, b_bits], [out_bit], interleave=True)
+
+
+def _keep_outputs(mux, n_outputs: int):
+    """The first n_outputs outputs of a MUX circuit (the unreferenced multiplexers are pruned after expansion)."""
+    from . import mux_circuits as M
+
+    keep = mux.op != M.OUTPUT
+    keep[mux.outputs[:n_outputs]] = True
+    idx = np.flatnonzero(keep)
+    new = np.full(len(mux.op), -1, np.int32)
+    new[idx] = np.arange(len(idx), dtype=np.int32)
+    ren = lambda x: np.where(x[idx] >= 0, new[np.maximum(x[idx], 0)], -1)
+    return M.MuxCircuit(mux.op[idx], mux.arg[idx], ren(mux.sel), ren(mux.low), ren(mux.high))
 
 
 # ---- packing front end (SURVEY.md 8(f).4) --------------------------------------------------------

@@ -255,6 +255,26 @@ def test_instruction_cache_reuses_compiled_graph(keys, client, evaluation):
         g.set_io(10 ** 6, np.zeros(4, dtype=np.uint64))  # not a node
 
 
+def test_instruction_cache_multiply_and_compare(keys, client, evaluation):
+    """The cached ISA instructions built from BDD-derived MUX circuits: 6-bit unsigned multiply (low word)
+    and greater-than, two invocations each on ONE compiled graph."""
+    from spf_b200.circuits import InstructionCache
+
+    cache = InstructionCache(evaluation)
+    w = 6
+    enc = lambda v: [client.encrypt_glwe_l1([(v >> i) & 1]) for i in range(w)]
+    for a, b in ((13, 11), (63, 63)):
+        outs = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w)]
+        cache.multiply(enc(a), enc(b), outs)
+        assert sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(outs)) == (a * b) % (1 << w)
+        gt = np.zeros(keys.glwe_len, dtype=np.uint64)
+        cache.greater_than(enc(a), enc(b), gt)
+        assert int(client.decrypt_glwe_l1(gt)[0]) == int(a > b)
+    assert (cache.misses, cache.hits) == (2, 2)
+    with pytest.raises(ValueError):
+        cache.multiply(enc(1) * 4, enc(1) * 4, [np.zeros(keys.glwe_len, dtype=np.uint64)] * (4 * w))
+
+
 def test_pack_unpack_roundtrip(oracle, keys, client, proc):
     """the fluent layer's pack (MulXN + GlweAdd tree) and unpack (SampleExtract(i)) graph
     shapes on the executor; the unpacked bits are refreshed through keyswitch + CBS and used as selectors."""

@@ -202,3 +202,14 @@ def test_insert_mux_circuit_validates_inputs():
     g = c.add("OneGgsw1")
     with pytest.raises(SpfError):
         M.insert_mux_circuit(c, M.make_and_circuit(1), [g])
+
+
+def test_low_word_of_a_multiplier():
+    """circuits._keep_outputs: the ISA Mul keeps the low word only (parasol_cpu/src/proc/ops/mul.rs:106-108)."""
+    from spf_b200.circuits import _keep_outputs
+
+    w = 6
+    c = _keep_outputs(M.unsigned_multiplier(w, w), w)
+    assert c.metrics()["outputs"] == w and c.metrics()["inputs"] == 2 * w
+    for a, b in [(13, 11), (63, 63), (0, 5), (32, 2)]:
+        assert value(c.evaluate(bits(a, w) + bits(b, w))) == (a * b) % (1 << w)
