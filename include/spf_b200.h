@@ -221,6 +221,21 @@ typedef int (*spf_exchange_fn)(void *user, void *d_buf, size_t chunk_bytes, int 
 int spf_b200_graph_build_sharded(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes, int world,
                                  spf_b200_graph **out);
 int spf_b200_graph_run_sharded(spf_b200_graph *graph, int rank, int world, spf_exchange_fn exchange, void *user);
+/* ---- peer-memory exchange for sharded runs (no NCCL on the data path) --------------------------------
+ * With the arenas of all ranks mapped into every process, spf_b200_graph_run_sharded(graph, rank, world, NULL, NULL)
+ * replaces the exchange callback by direct P2P traffic over NVLink: the scheme-switch kernel stores every GGSW it
+ * produces at the same offset into the arena of every rank while it computes the next one (the all-gather is fused
+ * into the kernel that produces the data), keyswitch outputs are broadcast by a small copy kernel, and dependency
+ * levels are separated by a flag barrier through peer memory (a rank that never arrives makes the run fail with
+ * SPF_E_GRAPH after a 5 s device-side timeout instead of hanging).  Every rank must build the same graph with the
+ * same `world`.  One process per GPU: export with spf_b200_graph_ipc_handle (a 64-byte cudaIpcMemHandle_t), gather
+ * the handles on the host, import with spf_b200_graph_open_peers.  Several ranks inside one process (tests):
+ * spf_b200_graph_set_peers with the arena addresses. */
+void *spf_b200_graph_arena(const spf_b200_graph *graph);
+int spf_b200_graph_ipc_handle(spf_b200_graph *graph, uint8_t *handle_out /* 64 bytes */);
+int spf_b200_graph_open_peers(spf_b200_graph *graph, int rank, int world, const uint8_t *handles /* world x 64 */);
+int spf_b200_graph_set_peers(spf_b200_graph *graph, int rank, int world, void *const *arenas);
+
 /* Host-only planning (no GPU, no context): validates the graph exactly as spf_b200_graph_build does and returns,
  * per node, its dependency level (after bootstrap-stage alignment) and the rank that computes it in a run sharded
  * over `world` ranks (-1 = every rank).  level_out / owner_out may be NULL.  Malformed graphs: SPF_E_GRAPH with

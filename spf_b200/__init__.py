@@ -396,6 +396,10 @@ ABI.update({
     "spf_b200_graph_build_sharded": [_vp, C.POINTER(_Node), _sz, C.c_int, C.POINTER(_vp)],
     "spf_b200_graph_run_sharded": [_vp, C.c_int, C.c_int, _vp, _vp],
     "spf_b200_graph_output_rank": [_vp, _sz],
+    "spf_b200_graph_arena": [_vp],
+    "spf_b200_graph_ipc_handle": [_vp, _vp],
+    "spf_b200_graph_open_peers": [_vp, C.c_int, C.c_int, _vp],
+    "spf_b200_graph_set_peers": [_vp, C.c_int, C.c_int, C.POINTER(_vp)],
     "spf_b200_graph_plan": [C.POINTER(Params), C.POINTER(_Node), _sz, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
 })
 
@@ -412,7 +416,7 @@ ABI.update({
 _RESTYPES["spf_b200_mux_free"] = None
 # spf_exchange_fn(user, d_buf, chunk_bytes, world, stream) -> int
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
-_RESTYPES.update({"spf_b200_graph_destroy": None, "spf_b200_graph_launches": C.c_uint64})
+_RESTYPES.update({"spf_b200_graph_destroy": None, "spf_b200_graph_launches": C.c_uint64, "spf_b200_graph_arena": _vp})
 
 
 class FheCircuit:
@@ -490,6 +494,7 @@ class CompiledGraph:
         ev._check(lib().spf_b200_graph_build_sharded(ev.handle, arr, len(circuit.nodes), self.world, C.byref(self._h)))
         self._exchange = exchange
         self._cb_error = None
+        self._peers = False
 
         def _cb(user, d_buf, chunk_bytes, world_, stream):
             try:
@@ -506,7 +511,10 @@ class CompiledGraph:
             self.ev._check(lib().spf_b200_graph_run(self._h))
             return
         if self._cb is None:
-            raise SpfError(-1, "a sharded graph needs an exchange callable")
+            if not self._peers:
+                raise SpfError(-1, "a sharded graph needs an exchange callable or opened peer arenas")
+            self.ev._check(lib().spf_b200_graph_run_sharded(self._h, self.rank, self.world, None, None))
+            return
         self._cb_error = None
         rc = lib().spf_b200_graph_run_sharded(self._h, self.rank, self.world, C.cast(self._cb, _vp), None)
         if self._cb_error is not None:
@@ -521,6 +529,31 @@ class CompiledGraph:
         self.ev._check(lib().spf_b200_graph_set_io(self._h, node, buf.ctypes.data))
         self._bound = getattr(self, "_bound", {})
         self._bound[node] = buf  # keep alive
+
+    # ---- peer-memory exchange (no exchange callable): every rank maps every other rank's arena ----
+    @property
+    def arena(self) -> int:
+        return int(lib().spf_b200_graph_arena(self._h) or 0)
+
+    def ipc_handle(self) -> bytes:
+        """64-byte cudaIpcMemHandle_t of this graph's arena, to be gathered over all ranks."""
+        buf = (C.c_uint8 * 64)()
+        self.ev._check(lib().spf_b200_graph_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def open_peers(self, handles: list[bytes]) -> None:
+        """handles[r] = rank r's ipc_handle(); afterwards run() exchanges over peer memory (NVLink P2P)."""
+        if len(handles) != self.world or any(len(h) != 64 for h in handles):
+            raise SpfError(-1, "open_peers: one 64-byte handle per rank")
+        blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        self.ev._check(lib().spf_b200_graph_open_peers(self._h, self.rank, self.world, blob))
+        self._peers = True
+
+    def set_peers(self, arenas: list[int]) -> None:
+        """Same-process variant (tests): arenas[r] = CompiledGraph.arena of rank r's graph."""
+        arr = (_vp * self.world)(*arenas)
+        self.ev._check(lib().spf_b200_graph_set_peers(self._h, self.rank, self.world, arr))
+        self._peers = True
 
     def output_rank(self, node: int) -> int:
         """Rank whose run() writes Output* node `node` (-1: every rank).  In a sharded run the outputs of

@@ -281,9 +281,12 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
 }
 
 int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_glev_out, C2* d_ggsw_out, int mode,
-                    int levels, double out_scale, size_t batch, cudaStream_t s, const void* const* ptrs = nullptr) {
+                    int levels, double out_scale, size_t batch, cudaStream_t s, const void* const* ptrs = nullptr,
+                    const PeerOffsets* peers = nullptr) {
   if (batch == 0) return 0;
   TraceSsBatch P;
+  if (peers) P.peers = *peers;
+  else P.peers.n = 0;
   P.glwe_in = d_glwe_in;
   P.glev_out = d_glev_out;
   P.ggsw_out = d_ggsw_out;

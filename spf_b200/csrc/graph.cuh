@@ -101,10 +101,19 @@ struct spf_b200_graph {
   uint64_t launches_per_run = 0;
   int world = 1;  // CircuitBootstrap groups are laid out as `world` equal chunks (spf_b200_graph_build_sharded)
   std::vector<int> owner;  // rank that computes the node's ciphertext, -1 = every rank holds it
+  // peer-memory exchange of a sharded run (spf_b200_graph_open_peers / set_peers): the first kArenaHeader bytes of
+  // every arena hold the level-barrier flags (u64 per rank) and an error word
+  PeerOffsets peers = {};
+  bool peers_set = false;
+  int peer_rank = -1;
+  unsigned long long epoch = 0;
+  std::vector<void*> ipc_opened;
   std::vector<void*> pinned;  // io buffers page-locked by this graph (cudaHostRegister), so that their copies are true DMAs
 };
 
 namespace {
+
+constexpr size_t kArenaHeader = 4096;  // flags[world] at 0, error word at 2048
 
 // Device constants for Zero*/One* nodes (mod.rs:95-105,475-506).  ZeroGgsw1/OneGgsw1 are real CBS
 // outputs of the trivial LWE 0/1, exactly as Evaluation::new computes them (evaluation.rs:161-197).
@@ -156,7 +165,7 @@ void pin_io(spf_b200_graph* g, void* p, size_t bytes) {
 size_t cbs_chunk_items(size_t n, int world) { return (n + (size_t)world - 1) / (size_t)world; }
 
 // Runs slots [start, start + n) of a group.
-int run_group_range(spf_b200_graph* g, const Group& G, cudaStream_t s, size_t start, size_t n) {
+int run_group_range(spf_b200_graph* g, const Group& G, cudaStream_t s, size_t start, size_t n, const PeerOffsets* peers = nullptr) {
   spf_b200_ctx* ctx = g->ctx;
   if (n == 0) return 0;
   const spf_params* p = &ctx->p;
@@ -189,7 +198,7 @@ int run_group_range(spf_b200_graph* g, const Group& G, cudaStream_t s, size_t st
                               cbs_log_v(p), n, s, p1))
         return rc;
       return launch_trace_ss(ctx, reinterpret_cast<const uint64_t*>(G.scratch + start * glwe), nullptr,
-                             reinterpret_cast<C2*>(out), 0, (int)p->cbs.count, 1.0, n, s);
+                             reinterpret_cast<C2*>(out), 0, (int)p->cbs.count, 1.0, n, s, nullptr, peers);
     }
     case SPF_OP_SCHEME_SWITCH:
       return launch_trace_ss(ctx, nullptr, nullptr, reinterpret_cast<C2*>(out), 2, (int)p->cbs.count, 1.0, n, s, p1);
@@ -199,9 +208,17 @@ int run_group_range(spf_b200_graph* g, const Group& G, cudaStream_t s, size_t st
 }
 
 // This rank's share of a group: the replicated slots, then its own slots.
-int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s, int rank) {
+int run_group(spf_b200_graph* g, const Group& G, cudaStream_t s, int rank, const PeerOffsets* peers = nullptr) {
   if (int rc = run_group_range(g, G, s, G.all_start, G.all_cnt)) return rc;
-  return run_group_range(g, G, s, G.r_start[rank], G.r_cnt[rank]);
+  return run_group_range(g, G, s, G.r_start[rank], G.r_cnt[rank], peers);
+}
+
+// One level barrier over peer memory (peer_barrier_kernel); epochs only grow, so flags never need resetting.
+int peer_barrier(spf_b200_graph* g, cudaStream_t s) {
+  g->epoch++;
+  peer_barrier_kernel<<<1, 32, 0, s>>>(reinterpret_cast<unsigned long long*>(g->arena), g->peers, g->peer_rank, g->epoch,
+                                       reinterpret_cast<int*>(g->arena + 2048), 5000000000ull);
+  return check_launch(g->ctx, "peer_barrier_kernel");
 }
 
 // Host-only part of a graph build: validation, levelisation with bootstrap-stage alignment and (world > 1) the
@@ -403,7 +420,7 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   // ---- groups, arena layout, pointer tables ----
   std::vector<std::vector<int>> by_level(g->n_levels);
   for (size_t i = 0; i < n; i++) by_level[g->level[i]].push_back((int)i);
-  size_t arena = 0, n_ptrs = 0, n_u32 = 0, out_stage = 0;
+  size_t arena = kArenaHeader, n_ptrs = 0, n_u32 = 0, out_stage = 0;
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   std::vector<size_t> out_off, scratch_off;
   for (int lv = 0; lv < g->n_levels; lv++) {
@@ -472,6 +489,7 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   CU(cudaSetDevice(ctx->device));
   g->arena_bytes = std::max<size_t>(arena, 256);
   CU(cudaMalloc(&g->arena, g->arena_bytes));
+  CU(cudaMemset(g->arena, 0, kArenaHeader));
   CU(cudaMalloc(&g->d_ptrs, std::max<size_t>(n_ptrs, 1) * sizeof(void*)));
   CU(cudaMalloc(&g->d_u32, std::max<size_t>(n_u32, 1) * 4));
   if (out_stage) CU(cudaMalloc(&g->d_out_stage, out_stage));
@@ -562,11 +580,15 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
   spf_b200_ctx* ctx = g->ctx;
   if (world != g->world || rank < 0 || rank >= world)
     return fail(ctx, SPF_E_INVALID, "rank/world do not match the graph's sharded layout");
-  if (world > 1 && !exchange) return fail(ctx, SPF_E_INVALID, "a sharded run needs an exchange callback");
+  const bool peer_mode = world > 1 && !exchange;
+  if (peer_mode && (!g->peers_set || g->peer_rank != rank))
+    return fail(ctx, SPF_E_INVALID, "a sharded run needs an exchange callback or opened peer arenas (spf_b200_graph_open_peers)");
   const spf_params* p = &ctx->p;
   CU(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream[0];
   const uint64_t l0 = ctx->launches.load();
+  // every rank has finished its previous run before anyone stores into its arena again
+  if (peer_mode) if (int rc = peer_barrier(g, s)) return rc;
   for (int id : g->inputs) {
     const CtType t = g->type[id];
     CU(cudaMemcpyAsync(g->dptr[id], g->nodes[id].io, ct_host_bytes(p, t), cudaMemcpyHostToDevice, s));
@@ -586,12 +608,23 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
   }
   size_t gi = 0;
   for (const Group& G : g->groups) {
-    if (int rc = run_group(g, G, s, rank)) return rc;
+    // peer mode: the scheme-switch kernel stores its GGSWs into every rank's arena while it computes them
+    if (int rc = run_group(g, G, s, rank, peer_mode && G.op == SPF_OP_CIRCUIT_BOOTSTRAP ? &g->peers : nullptr)) return rc;
     if (timing) cudaEventRecord(ev[++gi], s);
     if (world > 1 && G.gather_chunk > 0) {  // circuit-bootstrap outputs (GGSW) and keyswitch outputs (L0 LWE)
-      const size_t chunk_bytes = G.gather_chunk * ct_bytes(p, op_info(G.op).out);
-      if (int rc = exchange(user, G.out_base, chunk_bytes, world, s))
-        return fail(ctx, SPF_E_GRAPH, "exchange callback failed with status " + std::to_string(rc));
+      const size_t item_bytes = ct_bytes(p, op_info(G.op).out);
+      if (!peer_mode) {
+        if (int rc = exchange(user, G.out_base, G.gather_chunk * item_bytes, world, s))
+          return fail(ctx, SPF_E_GRAPH, "exchange callback failed with status " + std::to_string(rc));
+      } else {
+        if (G.op == SPF_OP_KEYSWITCH_L1_TO_L0 && G.r_cnt[rank] > 0) {
+          const size_t n16 = G.r_cnt[rank] * item_bytes / 16;
+          peer_bcast_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 4 * (size_t)ctx->sm_count), 256, 0, s>>>(
+              reinterpret_cast<const uint4*>(G.out_base + G.r_start[rank] * item_bytes), n16, g->peers);
+          if (int rc = check_launch(ctx, "peer_bcast_kernel")) return rc;
+        }
+        if (int rc = peer_barrier(g, s)) return rc;
+      }
     }
   }
   size_t stage = 0;
@@ -610,6 +643,14 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
     CU(cudaMemcpyAsync(g->nodes[id].io, from, ct_host_bytes(p, t), cudaMemcpyDeviceToHost, s));
   }
   CU(cudaStreamSynchronize(s));
+  if (peer_mode) {
+    int err = 0;
+    CU(cudaMemcpy(&err, g->arena + 2048, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) {
+      CU(cudaMemset(g->arena + 2048, 0, sizeof(int)));
+      return fail(ctx, SPF_E_GRAPH, "peer barrier timed out: a rank of the sharded run did not arrive");
+    }
+  }
   if (timing) {
     std::map<uint32_t, std::pair<double, size_t>> per_op;
     std::map<uint32_t, size_t> groups_of;
@@ -631,6 +672,7 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
 void spf_b200_graph_destroy(spf_b200_graph* g) {
   if (!g) return;
   cudaSetDevice(g->ctx->device);
+  for (void* q : g->ipc_opened) cudaIpcCloseMemHandle(q);
   cudaFree(g->arena);
   cudaFree(g->d_ptrs);
   cudaFree(g->d_u32);
@@ -673,6 +715,61 @@ int spf_b200_graph_output_rank(const spf_b200_graph* g, size_t node) {
   if (op < SPF_OP_OUTPUT_LWE0 || op > SPF_OP_OUTPUT_GLEV1) return -2;
   const int src = g->nodes[node].in[0];
   return g->nodes[src].op == SPF_OP_KEYSWITCH_L1_TO_L0 ? -1 : g->owner[src];
+}
+
+// ---- peer-memory exchange: the arenas of all ranks mapped into every process (CUDA IPC over NVLink) ----
+void* spf_b200_graph_arena(const spf_b200_graph* g) { return g ? g->arena : nullptr; }
+
+int spf_b200_graph_ipc_handle(spf_b200_graph* g, uint8_t* handle_out) {
+  if (!g) return SPF_E_INVALID;
+  if (!handle_out) return fail(g->ctx, SPF_E_INVALID, "NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  spf_b200_ctx* ctx = g->ctx;
+  CU(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, g->arena));
+  memcpy(handle_out, &h, 64);
+  return 0;
+}
+
+// arenas[r] = rank r's arena as addressable from THIS process (arenas[rank] is ignored); all ranks must have built
+// the same graph with the same `world`, so that a ciphertext sits at the same offset in every arena.
+int spf_b200_graph_set_peers(spf_b200_graph* g, int rank, int world, void* const* arenas) {
+  if (!g) return SPF_E_INVALID;
+  if (!arenas || world != g->world || rank < 0 || rank >= world || world - 1 > kMaxPeers)
+    return fail(g->ctx, SPF_E_INVALID, "set_peers: rank/world do not match the graph (at most 8 ranks)");
+  g->peers.n = 0;
+  for (int r = 0; r < world; r++) {
+    if (r == rank) continue;
+    if (!arenas[r]) return fail(g->ctx, SPF_E_INVALID, "set_peers: NULL arena");
+    g->peers.rank_of[g->peers.n] = r;
+    g->peers.off[g->peers.n] = (long long)(static_cast<char*>(arenas[r]) - g->arena);
+    g->peers.n++;
+  }
+  g->peer_rank = rank;
+  g->peers_set = true;
+  return 0;
+}
+
+// handles: world x 64 bytes, handles[r] = spf_b200_graph_ipc_handle of rank r's graph (gathered by the host, e.g.
+// with torch.distributed.all_gather_object); opens every peer arena with peer access enabled.
+int spf_b200_graph_open_peers(spf_b200_graph* g, int rank, int world, const uint8_t* handles) {
+  if (!g) return SPF_E_INVALID;
+  if (!handles || world != g->world || rank < 0 || rank >= world || world - 1 > kMaxPeers)
+    return fail(g->ctx, SPF_E_INVALID, "open_peers: rank/world do not match the graph (at most 8 ranks)");
+  spf_b200_ctx* ctx = g->ctx;
+  CU(cudaSetDevice(ctx->device));
+  std::vector<void*> arenas(world, nullptr);
+  for (int r = 0; r < world; r++) {
+    if (r == rank) { arenas[r] = g->arena; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    void* q = nullptr;
+    CU(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+    g->ipc_opened.push_back(q);
+    arenas[r] = q;
+  }
+  return spf_b200_graph_set_peers(g, rank, world, arenas.data());
 }
 
 // Host-only planning (no GPU, no context): the validation, levelisation and ownership partition of

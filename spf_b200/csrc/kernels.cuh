@@ -444,6 +444,15 @@ constexpr int kTrTeams = 4;
 constexpr int kTrTeamBytes = 2 * kN * 8 + kXBuf * 16;                 // g + xbuf = 49408 (digits are stateless)
 constexpr int kTrSmem = kTableBytes + kTrTeams * kTrTeamBytes;        // 215104
 
+// Peer arenas of a sharded graph (graph.cuh): byte offsets from this rank's arena to the arenas of the other
+// ranks as mapped into this process (CUDA IPC), and the ranks they belong to.
+constexpr int kMaxPeers = 7;
+struct PeerOffsets {
+  int n;
+  int rank_of[kMaxPeers];
+  long long off[kMaxPeers];
+};
+
 struct TraceSsBatch {
   const uint64_t* glwe_in;  // mode 0: [B][2][2048] PBS outputs; mode 1: [B][...] GLWEs; mode 2: [B][l][2][2048] GLEVs
   uint64_t* glev_out;       // optional [B][levels][2][2048] (mode 0/1)
@@ -455,9 +464,10 @@ struct TraceSsBatch {
   int batch, levels, mode;
   int cbs_radix_log, cbs_count, tr_radix_log, tr_count, ss_radix_log, ss_count;
   double out_scale;
+  PeerOffsets peers;       // n = 0: GGSWs are stored locally only
 };
 
-__global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(TraceSsBatch P, DevTables tabs) {
+__global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(const __grid_constant__ TraceSsBatch P, DevTables tabs) {
   extern __shared__ __align__(16) unsigned char smem[];
   C2* sT1 = reinterpret_cast<C2*>(smem);
   C2* sT2 = sT1 + kT1Elems;
@@ -501,11 +511,49 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(TraceSsBa
     A.ss_radix_log = P.ss_radix_log;
     A.ss_count = P.ss_count;
     A.out_scale = P.out_scale;
+    A.n_peers = P.peers.n;
+    A.peer_off = P.peers.off;
     trace_ss_team(cx, A, g, xbuf, sT1, sT2);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_alloc) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Peer-memory level barrier and broadcast of a sharded graph run (no NCCL on the data path).
+// flags[world] (u64) sit at the start of every rank's arena: flags[src] on rank dst = the last epoch rank src
+// has signalled to dst.  One warp: thread i signals peer i (after a system-scope fence that orders the P2P stores
+// of the preceding kernels before the flag), then waits for peer i's signal.  A rank that never arrives trips the
+// timeout and sets *err instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------
+__global__ void peer_barrier_kernel(unsigned long long* flags, PeerOffsets peers, int rank, unsigned long long epoch, int* err,
+                                    unsigned long long timeout_ns) {
+  const int i = threadIdx.x;
+  __threadfence_system();
+  if (i < peers.n) {
+    volatile unsigned long long* theirs = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(flags) + peers.off[i]) + rank;
+    *theirs = epoch;
+    __threadfence_system();
+    volatile unsigned long long* mine = flags + peers.rank_of[i];
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*mine < epoch) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) { atomicExch(err, 1); break; }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+
+// dst_r[i] = src[i] for every peer r (the keyswitch outputs of this rank's trees: 5 KB each)
+__global__ void peer_bcast_kernel(const uint4* src, size_t n16, PeerOffsets peers) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = src[i];
+    for (int r = 0; r < peers.n; r++)
+      *reinterpret_cast<uint4*>(reinterpret_cast<char*>(const_cast<uint4*>(src + i)) + peers.off[r]) = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

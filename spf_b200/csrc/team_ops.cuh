@@ -696,7 +696,16 @@ struct TraceSsArgs {
   int tr_radix_log, tr_count;
   int ss_radix_log, ss_count;
   double out_scale;         // 1.0: GGSW stays device-resident (2^-10 convention); 1024.0: reference scale
+  // Sharded graphs, peer-memory exchange: every GGSW element is also stored at the same offset in the arenas of
+  // the other ranks (P2P over NVLink), peer_off[r] = byte distance from the local arena to peer r's arena.
+  int n_peers;
+  const long long* peer_off;
 };
+
+SPF_HD void ggsw_store(const TraceSsArgs& A, C2* p, C2 v) {
+  *p = v;
+  for (int r = 0; r < A.n_peers; r++) *reinterpret_cast<C2*>(reinterpret_cast<char*>(p) + A.peer_off[r]) = v;
+}
 
 // y[j] of sigma_k(p): polynomial_pow_k (ops/polynomial/mod.rs:62-87) as a gather.
 SPF_HD uint64_t automorph_coeff(const uint64_t* p, int j, uint32_t kinv) {
@@ -779,17 +788,17 @@ SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2
     // FFT(x.b): row 1 b-slot, and the a-slot of row 0 (update_encrypted_secret_key_component_fft)
     team_poly_fft(cx, f[0], [&](int j) { return g[kN + j]; }, xbuf, T1, T2);
 #pragma unroll
-    for (int s = 0; s < 16; s++) { row1[kM + bin_of(u, s)] = cscale(f[0][s], A.out_scale); f[1][s] = C2{0.0, 0.0}; }
+    for (int s = 0; s < 16; s++) { ggsw_store(A, row1 + kM + bin_of(u, s), cscale(f[0][s], A.out_scale)); f[1][s] = C2{0.0, 0.0}; }
     gadget_mad_stateless(cx, f, [&](int j) { return g[j]; }, xbuf, T1, T2, A.ssk, A.ss_radix_log, A.ss_count);
 #pragma unroll
     for (int s = 0; s < 16; s++) {
-      row0[bin_of(u, s)] = cscale(f[0][s], A.out_scale);
-      row0[kM + bin_of(u, s)] = cscale(f[1][s], A.out_scale);
+      ggsw_store(A, row0 + bin_of(u, s), cscale(f[0][s], A.out_scale));
+      ggsw_store(A, row0 + kM + bin_of(u, s), cscale(f[1][s], A.out_scale));
     }
     // row 1 a-slot: FFT(x.a)
     team_poly_fft(cx, f[0], [&](int j) { return g[j]; }, xbuf, T1, T2);
 #pragma unroll
-    for (int s = 0; s < 16; s++) row1[bin_of(u, s)] = cscale(f[0][s], A.out_scale);
+    for (int s = 0; s < 16; s++) ggsw_store(A, row1 + bin_of(u, s), cscale(f[0][s], A.out_scale));
   }
 }
 

@@ -98,3 +98,16 @@ class NcclExchange:
             all_gather_chunks(buf, chunk_bytes, world, self.rank, self.group)
         self.calls += 1
         self.bytes += world * chunk_bytes
+
+
+def open_peer_arenas(graph, group=None) -> None:
+    """Peer-memory exchange for a sharded CompiledGraph (one process per GPU): all-gathers the CUDA IPC handles
+    of the ranks' arenas over torch.distributed (host side, once per graph) and maps them; afterwards graph.run()
+    needs no exchange callable -- GGSWs are stored into every rank's arena by the scheme-switch kernel itself
+    (NVLink P2P) and levels are separated by flag barriers through peer memory."""
+    import torch.distributed as dist
+
+    handles = [None] * graph.world
+    dist.all_gather_object(handles, graph.ipc_handle(), group=group)
+    graph.open_peers(handles)
+    dist.barrier(group=group)  # nobody runs before every rank has mapped every arena

@@ -302,6 +302,49 @@ def test_pack_unpack_roundtrip(oracle, keys, client, proc):
     assert [int(client.decrypt_glwe_l1(x)[0]) for x in mux_out] == bits
 
 
+def test_peer_memory_exchange_two_ranks_on_one_gpu(keys, client, evaluation):
+    """The fused exchange of a sharded run (spf_b200_graph_set_peers): two ranks as two contexts on this GPU, run
+    concurrently from two host threads; the scheme-switch kernel of each rank stores its GGSWs into both arenas,
+    keyswitch outputs are broadcast, levels are separated by the peer-memory flag barrier.  Each output is written
+    by its owner rank into the shared host buffers."""
+    import threading
+
+    import spf_b200
+
+    ev1 = spf_b200.Evaluation(keys.bsk_fft, keys.ksk, keys.ssk_fft, keys.ak_fft, device=0)
+    rng = np.random.default_rng(31)
+    w, world = 4, 2
+    vals, circ, out_sum, out_gt = _two_level_program(client, keys, w, 2, rng)
+    graphs = [spf_b200.CompiledGraph(e, circ, world=world, rank=r) for r, e in enumerate((evaluation, ev1))]
+    with pytest.raises(spf_b200.SpfError):
+        graphs[0].run()  # neither an exchange callable nor peers
+    arenas = [g.arena for g in graphs]
+    assert all(arenas) and arenas[0] != arenas[1]
+    for g in graphs:
+        g.set_peers(arenas)
+    for _ in range(2):  # twice: the start-of-run barrier orders run k + 1 after every rank's run k
+        for buf in [b for p_ in out_sum for b in p_] + out_gt:
+            buf[:] = 0
+        errs = []
+
+        def go(g):
+            try:
+                g.run()
+            except Exception as e:  # surfaced below
+                errs.append(e)
+
+        ths = [threading.Thread(target=go, args=(g,)) for g in graphs]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        assert not errs, errs
+        _check_program(client, vals, w, out_sum, out_gt)
+    for g in graphs:
+        g.close()
+    ev1.close()
+
+
 def _multiply_program(client, keys, w, vals):
     from spf_b200.circuits import multiply_then_greater_than
 

@@ -2,7 +2,9 @@
 config 4's multiply then greater-than -- as ONE graph sharded over the GPUs of a box
 and report latency.
 launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port P tools/sharded_graph_run.py [width] [programs] [runs] [add|mul]"""
+        --master-port P tools/sharded_graph_run.py [width] [programs] [runs] [add|mul] [nccl|peer]
+exchange: nccl = all-gathers between levels (NcclExchange); peer = P2P stores from the producing kernels into every
+rank's arena + flag barriers (spf_b200_graph_open_peers)."""
 import json
 import os
 import sys
@@ -16,12 +18,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle as O  # key / input generation and decryption only
 import spf_b200
 from spf_b200.circuits import add_then_greater_than, multiply_then_greater_than
-from spf_b200.multi import NcclExchange, broadcast_compute_key
+from spf_b200.multi import NcclExchange, broadcast_compute_key, open_peer_arenas
 
 w = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 programs = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 runs = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 kind = sys.argv[4] if len(sys.argv) > 4 else "add"
+xmode = sys.argv[5] if len(sys.argv) > 5 else "nccl"
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -48,10 +51,12 @@ out_gt = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(programs)]
 t0 = time.perf_counter()
 circ = (multiply_then_greater_than if kind == "mul" else add_then_greater_than)(a, b, c, out_sum, out_gt, programs)
 build_ms = 1e3 * (time.perf_counter() - t0)
-ex = NcclExchange(rank) if world > 1 else None
+ex = NcclExchange(rank) if world > 1 and xmode == "nccl" else None
 t0 = time.perf_counter()
 g = spf_b200.CompiledGraph(ev, circ, world=world, rank=rank, exchange=ex)
 compile_ms = 1e3 * (time.perf_counter() - t0)
+if world > 1 and xmode == "peer":
+    open_peer_arenas(g)
 times = []
 for _ in range(runs + 1):
     if world > 1:
@@ -81,7 +86,7 @@ if world > 1:
     dist.all_reduce(n_checked, op=dist.ReduceOp.SUM)
 if rank == 0:
     n_op = lambda name: sum(1 for n in circ.nodes if n[0] == spf_b200.OP[name])
-    print(json.dumps({"workload": f"{programs} x ({kind}{w} then greater-than) in one graph", "n_gpus": world,
+    print(json.dumps({"workload": f"{programs} x ({kind}{w} then greater-than) in one graph", "n_gpus": world, "exchange": xmode if world > 1 else None,
                       "nodes": len(circ.nodes), "cmux": n_op("CMux"), "circuit_bootstraps": n_op("CircuitBootstrap"),
                       "host_graph_build_ms": build_ms, "compile_ms": compile_ms, "levels": g.levels, "launches": g.launches,
                       "graph_ms_max_over_ranks": float(t.item()), "correct_on_all_ranks": bool(oks.item()), "outputs_checked_over_ranks": int(n_checked.item()), "outputs": len(out_nodes),
