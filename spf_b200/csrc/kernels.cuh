@@ -74,7 +74,10 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // and parked values of a pair live in TENSOR MEMORY (tcgen05.ld/st): the switches below exist for
 // A/B measurements (DESIGN.md section 7 lists what each is worth).
 // ------------------------------------------------------------------------------------------
-constexpr int kPbsPairs = 3;
+#ifndef SPF_PBS_PAIRS
+#define SPF_PBS_PAIRS 3
+#endif
+constexpr int kPbsPairs = SPF_PBS_PAIRS;
 constexpr int kPbsPairBytes = 2 * kN * 8 + 2 * kXBuf * 16;            // acc + 2 exchange buffers = 66048
 constexpr int kPbsSmem = kTableBytes + kPbsPairs * kPbsPairBytes;      // 215616
 
