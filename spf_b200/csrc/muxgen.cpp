@@ -190,6 +190,43 @@ Fns build_bitwise(BddManager& M, uint32_t n, bool is_or) {
   return out;
 }
 
+// bitshift (bitshift.rs:49-157): barrel shifter of 2:1 multiplexers.  Inputs are BIG-endian: variables
+// 0..inputs are the value (index 0 = most significant bit), then shift_size shift-amount bits, most
+// significant first; the low ceil(log2(inputs)) of them drive the stages, any higher one set clears the
+// result (logical) or fills it with the sign (arithmetic).  mode: 0 logical, 1 rotation, 2 arithmetic.
+Fns build_bitshift(BddManager& M, uint32_t inputs, uint32_t shift_size, bool right, uint32_t mode) {
+  uint32_t used = 0;
+  while ((1u << used) < inputs) used++;
+  if (used == 0) used = 1;
+  auto ite = [&](uint32_t c, uint32_t a, uint32_t b) { return M.bor(M.band(c, a), M.and_not(b, c)); };
+  Fns result(inputs);
+  for (uint32_t i = 0; i < inputs; i++) result[i] = M.var(i);
+  const uint32_t old_msb = result[0];
+  for (uint32_t i = 0; i < used; i++) {
+    const uint32_t shift = 1u << (used - 1 - i);
+    const uint32_t select = M.var(inputs + (shift_size - used) + i);
+    const uint32_t k = shift % inputs;
+    Fns inter(inputs);
+    for (uint32_t j = 0; j < inputs; j++) inter[j] = right ? result[(j + inputs - k) % inputs] : result[(j + k) % inputs];
+    Fns next(inputs);
+    for (uint32_t j = 0; j < inputs; j++) {
+      uint32_t shifted;
+      if (mode == 0) shifted = (right ? j < shift : j + shift >= inputs) ? 0u : inter[j];
+      else if (mode == 1) shifted = inter[j];
+      else shifted = j < shift ? old_msb : inter[j];
+      next[j] = ite(select, shifted, result[j]);
+    }
+    result.swap(next);
+  }
+  if (mode != 1) {
+    uint32_t clear = 0;
+    for (uint32_t x = 0; x < shift_size - used; x++) clear = M.bor(clear, M.var(inputs + x));
+    const uint32_t fill = mode == 0 ? 0u : old_msb;
+    for (uint32_t j = 0; j < inputs; j++) result[j] = ite(clear, fill, result[j]);
+  }
+  return result;
+}
+
 // mul_bdd_encode (mul.rs:149-179): the order in which the n*m (x, y) variable pairs appear, walking
 // the anti-diagonals of the partial-product array from the most significant one; returns for every
 // duplicated BDD variable the operand bit it stands for (x bits are 0..n, y bits n..n+m).
@@ -405,6 +442,17 @@ int spf_b200_mux_circuit(uint32_t kind, uint32_t n, uint32_t m, uint32_t flags, 
     case SPF_MUX_BITWISE: {
       BddManager M(2 * n);
       return emit(M, build_bitwise(M, n, f0), 2 * n, nullptr, out, count);
+    }
+    case SPF_MUX_BITSHIFT: {  // n = value width, m = shift-amount width; flags bit0 = right, bits 1-2 = mode
+      const uint32_t mode = (flags >> 1) & 3;
+      uint32_t used = 0;
+      while ((1u << used) < n) used++;
+      if (used == 0) used = 1;
+      if (m < used || mode > 2) return SPF_E_INVALID;                       // bitshift.rs:57-60
+      if (mode == 1 && (n & (n - 1)) != 0) return SPF_E_INVALID;            // rotation: power-of-two widths only (:64-66)
+      if (mode == 2 && !f0) return SPF_E_INVALID;                           // arithmetic shifts are right shifts (:68-70)
+      BddManager M(n + m);
+      return emit(M, build_bitshift(M, n, m, f0, mode), n + m, nullptr, out, count);
     }
     case SPF_MUX_UNSIGNED_MULTIPLIER: {
       if (m == 0 || (uint64_t)n * m * 2 >= (1u << 16)) return SPF_E_INVALID;  // mul.rs:36 (u16 variable ids)

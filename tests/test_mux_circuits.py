@@ -213,3 +213,45 @@ def test_low_word_of_a_multiplier():
     assert c.metrics()["outputs"] == w and c.metrics()["inputs"] == 2 * w
     for a, b in [(13, 11), (63, 63), (0, 5), (32, 2)]:
         assert value(c.evaluate(bits(a, w) + bits(b, w))) == (a * b) % (1 << w)
+
+
+@pytest.mark.parametrize("right,mode", [(False, "logical"), (True, "logical"), (True, "arithmetic"), (False, "rotation"), (True, "rotation")])
+def test_bitshift(right, mode):
+    """mux_circuits/src/bitshift.rs tests: every value/shift pair of an 8-bit barrel shifter (big-endian inputs)."""
+    w = 8
+    c = M.bitshift(w, w, right, mode)
+    be = lambda v: [(v >> (w - 1 - i)) & 1 for i in range(w)]
+    from_be = lambda b: sum(int(x) << (w - 1 - i) for i, x in enumerate(b))
+    for v in (0x00, 0x01, 0x80, 0xA5, 0xFF, 0x3C):
+        for sh in list(range(0, 10)) + [16, 255]:
+            got = from_be(c.evaluate(be(v) + be(sh)))
+            if mode == "rotation":
+                k = sh % w
+                want = ((v >> k) | (v << (w - k))) & 0xFF if right else ((v << k) | (v >> (w - k))) & 0xFF
+            elif mode == "logical":
+                want = 0 if sh >= w else ((v >> sh) if right else (v << sh) & 0xFF)
+            else:
+                sv = v - 256 * (v >> 7)
+                want = (sv >> min(sh, w - 1)) & 0xFF
+            assert got == want, (v, sh, got, want)
+
+
+def test_bitshift_rejects_what_the_reference_panics_on():
+    for args in [(6, 6, False, "rotation"), (8, 8, False, "arithmetic"), (8, 2, True, "logical")]:
+        with pytest.raises(SpfError):
+            M.bitshift(*args)
+
+
+def test_small_circuits_exhaustively():
+    """Every input of a 3 x 3 multiplier, a 3 + 3 adder with carry-in and the 3-bit comparisons."""
+    mul, add = M.unsigned_multiplier(3, 3), M.ripple_carry_adder(3, 3, True)
+    for a in range(8):
+        for b in range(8):
+            assert value(mul.evaluate(bits(a, 3) + bits(b, 3))) == a * b
+            inter = [x for p in zip(bits(a, 3), bits(b, 3)) for x in p]
+            for cin in (0, 1):
+                assert value(add.evaluate([cin] + inter)) == a + b + cin
+            for greater in (False, True):
+                for or_eq in (False, True):
+                    want = (a > b if greater else a < b) or (or_eq and a == b)
+                    assert M.compare_or_maybe_equal(3, greater, or_eq).evaluate(inter) == [int(want)]
