@@ -510,7 +510,8 @@ def run_gpu(args):
             "hbm": {"achieved": alg_bytes / (pbs_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes / (pbs_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
                     "peak_source": hbm_src},
-            "traffic": ncu_traffic(B),
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch (bytes), from the committed ncu capture
+            "traffic": (ncu_traffic(B) or {}).get("bytes_per_launch"), "traffic_detail": ncu_traffic(B),
         }
         del d_rot, d_glwe, lut
 
