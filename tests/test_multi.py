@@ -117,3 +117,53 @@ def test_level_exchange_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+class _FakeGraph:
+    """Stands in for a sharded CompiledGraph: records what open_peer_arenas hands to open_peers."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world, self.opened = rank, world, None
+
+    def ipc_handle(self):
+        return bytes([self.rank]) * 64
+
+    def open_peers(self, handles):
+        self.opened = list(handles)
+
+
+def _peer_worker(rank, world, port, out_q):
+    import torch.distributed as dist
+
+    from spf_b200.multi import open_peer_arenas
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = _FakeGraph(rank, world)
+        open_peer_arenas(g)
+        out_q.put((rank, g.opened == [bytes([r]) * 64 for r in range(world)]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_arena_handles_are_gathered_world2_gloo():
+    """Host plumbing of the peer-memory exchange: every rank ends up with every rank's 64-byte IPC handle, in
+    rank order (the CUDA side -- cudaIpcOpenMemHandle, P2P stores, flag barriers -- is covered by the GPU tests)."""
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
