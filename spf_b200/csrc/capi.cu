@@ -325,7 +325,7 @@ int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const 
   P.glwe_per_item = glwe_per_item;
   P.radix_log = (int)ctx->p.cbs.radix_log;
   P.count = (int)ctx->p.cbs.count;
-  // few outputs (a level of a ripple MUX chain): one CTA of 8 teams per output, 3-5x lower latency
+  // few outputs (a level of a MUX tree): one CTA of 8 teams per output, 3-5x lower latency
   // Programmatic dependent launch: consecutive levels of a MUX tree are back-to-back CMUX kernels; each
   // loads its tables (and prefetches its selector) while the previous level drains (kernels.cuh, pdl_wait).
   static const bool pdl = !getenv("SPF_B200_NO_PDL");
@@ -337,7 +337,11 @@ int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const 
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   const DevTables T = tabs(ctx);
-  if (n_glwe <= (size_t)ctx->sm_count && P.count == 4) {
+  static const char* wide_env = getenv("SPF_B200_CMUX_WIDE_MAX");  // A/B: largest batch served by the wide kernel
+  // two waves of the wide kernel still beat one team per output (cold L2: 49 vs 59 us at 296 outputs; 4 x mul32 in one
+  // graph 45.2 -> 42.2 ms); from three waves on the throughput kernel wins (profiles/r1_w_cmux_kernel_choice.json)
+  const size_t wide_max = wide_env ? (size_t)atoll(wide_env) : 2 * (size_t)ctx->sm_count;
+  if (n_glwe <= wide_max && P.count == 4) {
     cfg.gridDim = dim3((unsigned)n_glwe);
     cfg.blockDim = dim3(kWideTeams * kTeam);
     cfg.dynamicSmemBytes = kWideSmem;

@@ -229,9 +229,9 @@ def test_large_batch_cbs_sampled(oracle, keys, client, evaluation):
 
 
 def test_kernel_selection_thresholds(oracle, keys, client, evaluation):
-    """launch_pbs / launch_cmux switch kernels at one item per SM (148): the latency kernels
-    (pbs_quad_kernel, cmux_wide_kernel) below, the throughput kernels (pair teams, one team per CMUX)
-    above.  Both sides must decrypt correctly; within a kernel, results do not depend on the batch."""
+    """launch_pbs switches kernels at one ciphertext per SM (148), launch_cmux at two outputs per SM (296): the
+    latency kernels (pbs_quad_kernel, cmux_wide_kernel) below, the throughput kernels (pair teams, one team per
+    CMUX) above.  Both sides must decrypt correctly; within a kernel, results do not depend on the batch."""
     rng = np.random.default_rng(21)
     bits = rng.integers(0, 2, 300)
     cts = client.encrypt_lwe_l0_batch(bits.tolist())
@@ -242,12 +242,14 @@ def test_kernel_selection_thresholds(oracle, keys, client, evaluation):
     for i in (0, 77, 147):
         assert client.decrypt_ggsw_l1(quad[i]) == bits[i] == client.decrypt_ggsw_l1(pair[i])
     assert client.decrypt_ggsw_l1(pair2[299]) == bits[299]
-    # CMUX: the same 149 ops through the bulk kernel, the first 148 through the wide kernel
+    # CMUX: 297 ops through the bulk kernel, the first 148 and the first 296 through the wide kernel
     a, b = client.encrypt_glwe_l1([0, 1]), client.encrypt_glwe_l1([1, 1])
-    sel = np.stack([quad[i] for i in range(148)] + [pair[148]])
-    A, B = np.stack([a] * 149), np.stack([b] * 149)
+    sel = np.stack([quad[i % 148] for i in range(297)])
+    A, B = np.stack([a] * 297), np.stack([b] * 297)
     bulk = evaluation.cmux(sel, A, B)
     wide = evaluation.cmux(sel[:148], A[:148], B[:148])
+    wide2 = evaluation.cmux(sel[:296], A[:296], B[:296])
+    assert np.array_equal(wide2[:148], wide)
     for i in (0, 5, 100, 147):
         want = oracle.cmux(keys, a, b, sel[i])
         assert oracle.torus_distance(want, bulk[i]).max() <= 2.0 ** -30
