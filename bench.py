@@ -299,9 +299,16 @@ def measure_program_latency(ev, keys, args):
 
     client = O.Client(keys)
     w, a, b, c = 32, 0xDEADBEEF, 0x12345679, 0x40000000
-    enc = lambda v: [client.encrypt_glwe_l1([(v >> i) & 1]) for i in range(w)]
+    slab = iter(spf_b200.pinned_zeros((3 * w + 2 * (w + 1), keys.glwe_len)))  # one page-locked slab for all buffers
+
+    def enc(v):
+        out = [next(slab) for _ in range(w)]
+        for i, r in enumerate(out):
+            r[:] = client.encrypt_glwe_l1([(v >> i) & 1])
+        return out
+
     ab, bb, cb = enc(a), enc(b), enc(c)
-    mk_out = lambda: ([[np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w)]], [np.zeros(keys.glwe_len, dtype=np.uint64)])
+    mk_out = lambda: ([[next(slab) for _ in range(w)]], [next(slab)])
 
     def check(out_prod, out_gt):
         prod = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(out_prod[0]))
@@ -343,9 +350,11 @@ def measure_add_latency(ev, keys, args):
     res = {"graph": "hand-built ripple-carry MUX tree (functionally equivalent to mux_circuits' BDD adder, not "
                     "node-for-node; SURVEY.md section 7)", "includes": "H2D of 2w GLWE inputs + D2H of w+1 GLWE outputs"}
     for w, a, b in ((8, 2, 7), (32, 0xDEADBEEF, 0x12345679)):
-        ab = [client.encrypt_glwe_l1([(a >> i) & 1]) for i in range(w)]
-        bb = [client.encrypt_glwe_l1([(b >> i) & 1]) for i in range(w)]
-        outs = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w + 1)]
+        slab = spf_b200.pinned_zeros((3 * w + 1, keys.glwe_len))  # one page-locked slab for all 3w + 1 buffers
+        ab, bb, outs = list(slab[:w]), list(slab[w:2 * w]), list(slab[2 * w:])
+        for i in range(w):
+            ab[i][:] = client.encrypt_glwe_l1([(a >> i) & 1])
+            bb[i][:] = client.encrypt_glwe_l1([(b >> i) & 1])
         g = proc.compile(ripple_carry_adder(ab, bb, outs))
         g.run()
         ts = []

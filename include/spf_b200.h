@@ -199,6 +199,11 @@ uint64_t spf_b200_graph_launches(const spf_b200_graph *graph); /* kernel launche
  * device-resident graph then serves every invocation of the same instruction shape (the reference
  * rebuilds and re-levelises the MUX circuit per instruction dispatch, fhe_circuit.rs:473-494). */
 int spf_b200_graph_set_io(spf_b200_graph *graph, size_t node, void *io);
+/* Page-locked host memory for ciphertext buffers.  Input and Output node buffers that are already page-locked (this
+ * allocator, cudaHostAlloc, a cudaHostRegister done by the caller) are used as they are; any other buffer is registered
+ * by the graph on first use, which is slow when there are hundreds of them (allocate ONE slab and slice it). */
+int spf_b200_host_alloc(void **out, size_t bytes);
+int spf_b200_host_free(void *p);
 /* build + run + destroy */
 int spf_b200_run_graph(spf_b200_ctx *ctx, const spf_node *nodes, size_t n_nodes);
 

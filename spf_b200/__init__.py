@@ -396,6 +396,8 @@ ABI.update({
     "spf_b200_graph_build_sharded": [_vp, C.POINTER(_Node), _sz, C.c_int, C.POINTER(_vp)],
     "spf_b200_graph_run_sharded": [_vp, C.c_int, C.c_int, _vp, _vp],
     "spf_b200_graph_output_rank": [_vp, _sz],
+    "spf_b200_host_alloc": [C.POINTER(_vp), _sz],
+    "spf_b200_host_free": [_vp],
     "spf_b200_graph_arena": [_vp],
     "spf_b200_graph_ipc_handle": [_vp, _vp],
     "spf_b200_graph_open_peers": [_vp, C.c_int, C.c_int, _vp],
@@ -443,6 +445,23 @@ class FheCircuit:
                 arr[i].inp[e] = ins[e]
             arr[i].io = io.ctypes.data if io is not None else None
         return arr
+
+
+def pinned_zeros(shape, dtype=np.uint64) -> np.ndarray:
+    """A zeroed numpy array in page-locked host memory (ONE slab: slice it into ciphertext buffers).  Graph IO
+    from such buffers is a DMA without per-buffer registration; the memory is released with the array."""
+    import weakref
+
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = _vp()
+    rc = lib().spf_b200_host_alloc(C.byref(ptr), max(nbytes, 1))
+    if rc:
+        raise SpfError(rc, (lib().spf_b200_last_error(None) or b"").decode())
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
+    weakref.finalize(buf, lib().spf_b200_host_free, ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    arr[...] = 0
+    return arr
 
 
 def plan_graph(circuit: "FheCircuit", world: int = 1, params: Params | None = None) -> tuple[np.ndarray, np.ndarray]:

@@ -154,8 +154,14 @@ int graph_fail(spf_b200_ctx* ctx, const std::string& msg) { return fail(ctx, SPF
 
 // Page-lock a host ciphertext buffer for the lifetime of the graph (best effort: a buffer that cannot
 // be registered -- already pinned by the caller, read-only mapping -- is simply copied as pageable).
+// Buffers that are page-locked already (spf_b200_host_alloc, cudaHostAlloc, a caller's own registration) are left
+// alone: cudaHostRegister costs 0.4 ms per 32 KiB buffer and grows with the number of registrations (5 s for the 516
+// buffers of four mul32 programs), so hosts should carve their ciphertext buffers out of ONE pinned slab.
 void pin_io(spf_b200_graph* g, void* p, size_t bytes) {
   if (!p || getenv("SPF_B200_NO_PIN")) return;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return;
+  cudaGetLastError();
   if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) g->pinned.push_back(p);
   else cudaGetLastError();  // clear the sticky-free error
 }
@@ -414,9 +420,14 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   g->ctx = ctx;
   g->world = world;
   g->nodes.assign(nodes, nodes + n);
+  static const bool build_timing = getenv("SPF_B200_GRAPH_TIMING") != nullptr;
+  auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now_ms();
   std::vector<int> stage;
   if (int rc = plan_graph(ctx, p, g.get(), world, stage)) return rc;
+  const double t_plan = now_ms();
   if (int rc = ensure_constants(ctx)) return rc;
+  const double t_consts = now_ms();
   // ---- groups, arena layout, pointer tables ----
   std::vector<std::vector<int>> by_level(g->n_levels);
   for (size_t i = 0; i < n; i++) by_level[g->level[i]].push_back((int)i);
@@ -488,8 +499,10 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   }
   CU(cudaSetDevice(ctx->device));
   g->arena_bytes = std::max<size_t>(arena, 256);
+  const double t_layout = now_ms();
   CU(cudaMalloc(&g->arena, g->arena_bytes));
   CU(cudaMemset(g->arena, 0, kArenaHeader));
+  const double t_malloc = now_ms();
   CU(cudaMalloc(&g->d_ptrs, std::max<size_t>(n_ptrs, 1) * sizeof(void*)));
   CU(cudaMalloc(&g->d_u32, std::max<size_t>(n_u32, 1) * 4));
   if (out_stage) CU(cudaMalloc(&g->d_out_stage, out_stage));
@@ -521,6 +534,7 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
       }
     }
   }
+  const double t_pin = now_ms();
   std::vector<void*> h_ptrs(std::max<size_t>(n_ptrs, 1), nullptr);
   std::vector<uint32_t> h_u32(std::max<size_t>(n_u32, 1), 0);
   for (Group& G : g->groups) {
@@ -559,6 +573,10 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   }
   CU(cudaMemcpy(g->d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(g->d_u32, h_u32.data(), h_u32.size() * 4, cudaMemcpyHostToDevice));
+  if (build_timing)
+    fprintf(stderr, "[spf_b200 graph build] %zu nodes: plan %.1f ms, constants %.1f, layout %.1f, cudaMalloc of %.2f GB %.1f, addresses + page-locking %zu io buffers %.1f, tables %.1f\n",
+            n, t_plan - t_start, t_consts - t_plan, t_layout - t_consts, g->arena_bytes / 1e9, t_malloc - t_layout, g->inputs.size() + g->outputs.size(),
+            t_pin - t_malloc, now_ms() - t_pin);
   *out = g.release();
   return 0;
 }
@@ -715,6 +733,21 @@ int spf_b200_graph_output_rank(const spf_b200_graph* g, size_t node) {
   if (op < SPF_OP_OUTPUT_LWE0 || op > SPF_OP_OUTPUT_GLEV1) return -2;
   const int src = g->nodes[node].in[0];
   return g->nodes[src].op == SPF_OP_KEYSWITCH_L1_TO_L0 ? -1 : g->owner[src];
+}
+
+// Page-locked host memory for ciphertext buffers (one slab for many ciphertexts): graph IO from such memory is a
+// true DMA without per-buffer registration.  No context needed; errors through spf_b200_last_error(NULL).
+int spf_b200_host_alloc(void** out, size_t bytes) {
+  if (!out || !bytes) return fail(nullptr, SPF_E_INVALID, "host_alloc: NULL / empty");
+  *out = nullptr;
+  const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) return fail(nullptr, SPF_E_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return 0;
+}
+int spf_b200_host_free(void* p) {
+  if (!p) return 0;
+  const cudaError_t e = cudaFreeHost(p);
+  return e == cudaSuccess ? 0 : fail(nullptr, SPF_E_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
 }
 
 // ---- peer-memory exchange: the arenas of all ranks mapped into every process (CUDA IPC over NVLink) ----

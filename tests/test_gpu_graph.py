@@ -275,6 +275,27 @@ def test_instruction_cache_multiply_and_compare(keys, client, evaluation):
         cache.multiply(enc(1) * 4, enc(1) * 4, [np.zeros(keys.glwe_len, dtype=np.uint64)] * (4 * w))
 
 
+def test_pinned_slab_buffers(keys, client, proc):
+    """spf_b200_host_alloc: ciphertext buffers sliced from one page-locked slab work as graph IO (and are not
+    registered again); the slab is released with the array."""
+    import spf_b200
+
+    slab = spf_b200.pinned_zeros((3, keys.glwe_len))
+    assert slab.flags["C_CONTIGUOUS"] and not slab.any()
+    slab[0][:] = client.encrypt_glwe_l1([1, 0, 1])
+    c = spf_b200.FheCircuit()
+    x = c.add("InputGlwe1", io=slab[0])
+    c.add("OutputGlwe1", x, io=slab[1])
+    c.add("OutputGlwe1", c.add("Not", x), io=slab[2])
+    g = proc.compile(c)
+    g.run()
+    assert np.array_equal(slab[1], slab[0])
+    assert client.decrypt_glwe_l1(slab[2])[:3].tolist() == [0, 0, 1]   # Not adds a trivial one: only coefficient 0 flips
+    g.close()
+    with pytest.raises(spf_b200.SpfError):
+        spf_b200.pinned_zeros((1 << 50,), np.uint8)
+
+
 def test_pack_unpack_roundtrip(oracle, keys, client, proc):
     """the fluent layer's pack (MulXN + GlweAdd tree) and unpack (SampleExtract(i)) graph
     shapes on the executor; the unpacked bits are refreshed through keyswitch + CBS and used as selectors."""

@@ -44,10 +44,23 @@ ev = spf_b200.Evaluation(*[t.data_ptr() for t in kt], device=local, on_device=Tr
 
 rng = np.random.default_rng(2024)
 vals = [(int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w))) for _ in range(programs)]
-enc = lambda v: [client.encrypt_glwe_l1([(v >> i) & 1]) for i in range(w)]
+# every ciphertext buffer is a row of ONE page-locked slab (spf_b200_host_alloc): graph IO is plain DMA
+slab = spf_b200.pinned_zeros((programs * (4 * w + 1), keys.glwe_len))
+rows = iter(slab)
+
+
+def enc(v):
+    out = []
+    for i in range(w):
+        r = next(rows)
+        r[:] = client.encrypt_glwe_l1([(v >> i) & 1])
+        out.append(r)
+    return out
+
+
 a, b, c = ([enc(v[k]) for v in vals] for k in range(3))
-out_sum = [[np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(w)] for _ in range(programs)]
-out_gt = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(programs)]
+out_sum = [[next(rows) for _ in range(w)] for _ in range(programs)]
+out_gt = [next(rows) for _ in range(programs)]
 t0 = time.perf_counter()
 circ = (multiply_then_greater_than if kind == "mul" else add_then_greater_than)(a, b, c, out_sum, out_gt, programs)
 build_ms = 1e3 * (time.perf_counter() - t0)
