@@ -313,9 +313,11 @@ int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_gl
 }
 
 int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const uint64_t* d_d1, const C2* d_ggsw,
-                size_t ggsw_stride, int glwe_per_item, size_t n_glwe, cudaStream_t s, const void* const* ptrs = nullptr) {
+                size_t ggsw_stride, int glwe_per_item, size_t n_glwe, cudaStream_t s, const void* const* ptrs = nullptr,
+                void* const* out_ptrs = nullptr) {
   if (n_glwe == 0) return 0;
   CmuxBatch P;
+  P.out_ptrs = out_ptrs;
   P.out = d_out;
   P.d0 = d_d0;
   P.d1 = d_d1;

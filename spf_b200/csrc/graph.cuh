@@ -80,6 +80,7 @@ struct Group {
   size_t all_start = 0, all_cnt = 0;
   std::vector<size_t> r_start, r_cnt;
   size_t gather_chunk = 0;
+  bool slot_outputs = false;  // CMux / MultiplyGgswGlwe: every output has its own recycled GLWE slot (out pointer table)
 };
 
 }  // namespace
@@ -101,6 +102,8 @@ struct spf_b200_graph {
   uint64_t launches_per_run = 0;
   int world = 1;  // CircuitBootstrap groups are laid out as `world` equal chunks (spf_b200_graph_build_sharded)
   std::vector<int> owner;  // rank that computes the node's ciphertext, -1 = every rank holds it
+  std::vector<int> slot;   // CMux outputs: index of the node's GLWE slot in the recycled pool, -1 otherwise
+  size_t pool_slots = 0;   // size of that pool: the largest number of CMux outputs alive at once
   // peer-memory exchange of a sharded run (spf_b200_graph_open_peers / set_peers): the first kArenaHeader bytes of
   // every arena hold the level-barrier flags (u64 per rank) and an error word
   PeerOffsets peers = {};
@@ -194,8 +197,9 @@ int run_group_range(spf_b200_graph* g, const Group& G, cudaStream_t s, size_t st
     case SPF_OP_MUL_XN:
       return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, 2, 0, n, s, p2, u32);
     case SPF_OP_CMUX:
-    case SPF_OP_MULTIPLY_GGSW_GLWE:
-      return launch_cmux(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, nullptr, 0, 1, n, s, p3);
+    case SPF_OP_MULTIPLY_GGSW_GLWE:  // pointer table: 3 inputs per slot for all slots, then one output pointer per slot
+      return launch_cmux(ctx, nullptr, nullptr, nullptr, nullptr, 0, 1, n, s, p3,
+                         reinterpret_cast<void* const*>(g->d_ptrs + G.ptr_off + 3 * G.ids.size() + start));
     case SPF_OP_GLEV_CMUX:
       return launch_cmux(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, nullptr, 0, (int)p->cbs.count, n * p->cbs.count, s, p3);
     case SPF_OP_CIRCUIT_BOOTSTRAP: {
@@ -434,9 +438,34 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   size_t arena = kArenaHeader, n_ptrs = 0, n_u32 = 0, out_stage = 0;
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   std::vector<size_t> out_off, scratch_off;
+  // CMux / MultiplyGgswGlwe outputs (the bulk of a MUX tree: 45 k of the 46 k nodes of a 32-bit multiply) do not get
+  // a buffer each: they take a GLWE slot from a pool and give it back once the last level that reads them has
+  // run.  last_use = the highest level of a consumer; ciphertexts that feed an Output node stay until the end.
+  // Levels run in stream order (a programmatically launched CMUX level writes only after griddepcontrol.wait),
+  // and no other rank ever stores into these slots, so a slot freed after level L can be rewritten at level L + 1.
+  auto pooled = [](uint32_t op) { return op == SPF_OP_CMUX || op == SPF_OP_MULTIPLY_GGSW_GLWE; };
+  g->slot.assign(n, -1);
+  std::vector<int> last_use(n, -1);
+  for (size_t v = 0; v < n; v++) {
+    const OpInfo oi = op_info(g->nodes[v].op);
+    const bool is_out = g->nodes[v].op >= SPF_OP_OUTPUT_LWE0 && g->nodes[v].op <= SPF_OP_OUTPUT_GLEV1;
+    for (int e = 0; e < oi.n_in; e++) {
+      const int w = g->nodes[v].in[e];
+      last_use[w] = std::max(last_use[w], is_out ? g->n_levels : g->level[v]);
+    }
+  }
+  std::vector<std::vector<int>> release_at(g->n_levels + 2);
+  std::vector<int> free_slots;
   for (int lv = 0; lv < g->n_levels; lv++) {
+    for (int v : release_at[lv]) free_slots.push_back(g->slot[v]);  // last read at level lv - 1
     std::map<uint32_t, std::vector<int>> ops;
     for (int id : by_level[lv]) ops[g->nodes[id].op].push_back(id);
+    for (int id : by_level[lv]) {
+      if (!pooled(g->nodes[id].op)) continue;
+      if (free_slots.empty()) g->slot[id] = (int)g->pool_slots++;
+      else { g->slot[id] = free_slots.back(); free_slots.pop_back(); }
+      release_at[std::min(std::max(last_use[id], lv) + 1, g->n_levels + 1)].push_back(id);
+    }
     for (auto& kv : ops) {
       const uint32_t op = kv.first;
       if (op == SPF_OP_RETIRE || op == SPF_OP_NOP) continue;
@@ -480,7 +509,8 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
         G.ids.insert(G.ids.end(), everyone.begin(), everyone.end());
       }
       size_t o = (size_t)-1, sc = (size_t)-1;
-      if (!is_const && !is_output) {
+      G.slot_outputs = pooled(op);
+      if (!is_const && !is_output && !G.slot_outputs) {
         o = arena;
         arena = align(arena + ct_bytes(p, oi.out) * G.ids.size());
         if (op == SPF_OP_CIRCUIT_BOOTSTRAP) { sc = arena; arena = align(arena + ct_bytes(p, T_GLWE1) * G.ids.size()); }
@@ -488,7 +518,8 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
       if (op == SPF_OP_OUTPUT_GGSW1) out_stage += ct_bytes(p, T_GGSW1) * G.ids.size();
       G.ptr_off = n_ptrs;
       G.u32_off = n_u32;
-      if (op == SPF_OP_CMUX || op == SPF_OP_GLEV_CMUX || op == SPF_OP_MULTIPLY_GGSW_GLWE) n_ptrs += 3 * G.ids.size();
+      if (G.slot_outputs) n_ptrs += 4 * G.ids.size();  // {sel, low, high} per slot, then the output pointers
+      else if (op == SPF_OP_GLEV_CMUX) n_ptrs += 3 * G.ids.size();
       else if (op == SPF_OP_NOT || op == SPF_OP_GLWE_ADD || op == SPF_OP_MUL_XN) n_ptrs += 2 * G.ids.size();
       else if (oi.n_in == 1 && !is_output) n_ptrs += G.ids.size();
       if (op == SPF_OP_SAMPLE_EXTRACT || op == SPF_OP_MUL_XN) n_u32 += G.ids.size();
@@ -498,6 +529,8 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
     }
   }
   CU(cudaSetDevice(ctx->device));
+  const size_t pool_off = arena;
+  arena = align(arena + g->pool_slots * ct_bytes(p, T_GLWE1));
   g->arena_bytes = std::max<size_t>(arena, 256);
   const double t_layout = now_ms();
   CU(cudaMalloc(&g->arena, g->arena_bytes));
@@ -525,7 +558,8 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
         case SPF_OP_ZERO_GLEV1: g->dptr[id] = ctx->c_glev[0]; break;
         case SPF_OP_ONE_GLEV1: g->dptr[id] = ctx->c_glev[1]; break;
         default:
-          if (G.out_base) g->dptr[id] = G.out_base + k * ct_bytes(p, oi.out);
+          if (G.slot_outputs) g->dptr[id] = g->arena + pool_off + (size_t)g->slot[id] * ct_bytes(p, T_GLWE1);
+          else if (G.out_base) g->dptr[id] = G.out_base + k * ct_bytes(p, oi.out);
       }
       if (G.op <= SPF_OP_INPUT_GLEV1) { g->inputs.push_back(id); pin_io(g.get(), g->nodes[id].io, ct_host_bytes(p, g->type[id])); }
       if (G.op >= SPF_OP_OUTPUT_LWE0 && G.op <= SPF_OP_OUTPUT_GLEV1) {
@@ -548,11 +582,13 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
           h_ptrs[G.ptr_off + 3 * k + 0] = g->dptr[nd.in[0]];
           h_ptrs[G.ptr_off + 3 * k + 1] = g->dptr[nd.in[1]];
           h_ptrs[G.ptr_off + 3 * k + 2] = g->dptr[nd.in[2]];
+          if (G.slot_outputs) h_ptrs[G.ptr_off + 3 * G.ids.size() + k] = g->dptr[G.ids[k]];
           break;
         case SPF_OP_MULTIPLY_GGSW_GLWE:  // in[0] = Glwe, in[1] = Ggsw
           h_ptrs[G.ptr_off + 3 * k + 0] = g->dptr[nd.in[1]];
           h_ptrs[G.ptr_off + 3 * k + 1] = nullptr;
           h_ptrs[G.ptr_off + 3 * k + 2] = g->dptr[nd.in[0]];
+          h_ptrs[G.ptr_off + 3 * G.ids.size() + k] = g->dptr[G.ids[k]];
           break;
         case SPF_OP_NOT:
         case SPF_OP_MUL_XN:
@@ -574,8 +610,8 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   CU(cudaMemcpy(g->d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(g->d_u32, h_u32.data(), h_u32.size() * 4, cudaMemcpyHostToDevice));
   if (build_timing)
-    fprintf(stderr, "[spf_b200 graph build] %zu nodes: plan %.1f ms, constants %.1f, layout %.1f, cudaMalloc of %.2f GB %.1f, addresses + page-locking %zu io buffers %.1f, tables %.1f\n",
-            n, t_plan - t_start, t_consts - t_plan, t_layout - t_consts, g->arena_bytes / 1e9, t_malloc - t_layout, g->inputs.size() + g->outputs.size(),
+    fprintf(stderr, "[spf_b200 graph build] %zu nodes: plan %.1f ms, constants %.1f, layout %.1f, cudaMalloc of %.2f GB (%zu recycled CMux slots) %.1f, addresses + page-locking %zu io buffers %.1f, tables %.1f\n",
+            n, t_plan - t_start, t_consts - t_plan, t_layout - t_consts, g->arena_bytes / 1e9, g->pool_slots, t_malloc - t_layout, g->inputs.size() + g->outputs.size(),
             t_pin - t_malloc, now_ms() - t_pin);
   *out = g.release();
   return 0;

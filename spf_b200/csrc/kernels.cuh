@@ -573,6 +573,7 @@ struct CmuxBatch {
   const C2* ggsw;         // 2^-10 scaled
   size_t ggsw_stride;     // elements between consecutive items' GGSWs (0 = shared)
   const void* const* ptrs;  // optional device table, 3 per item: {ggsw, d0 (may be null), d1} (graph executor)
+  void* const* out_ptrs;    // optional device table: out_ptrs[c] = output of GLWE c (recycled slots of the graph arena)
   int batch;              // number of GLWE outputs
   int glwe_per_item;      // 1 for cmux, l_cbs for glev_cmux (GLWEs sharing one GGSW)
   int radix_log, count;
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(kCmuxTeams * kTeam, 1) cmux_kernel(CmuxBatch P
     const int item = c / P.glwe_per_item;
     const size_t off = (size_t)(c % P.glwe_per_item) * glwe;
     const uint64_t* d0 = static_cast<const uint64_t*>(P.ptrs[3 * item + 1]);
-    cmux_team(cx, P.out + (size_t)c * glwe, d0 ? d0 + off : nullptr,
+    cmux_team(cx, P.out_ptrs ? static_cast<uint64_t*>(P.out_ptrs[c]) : P.out + (size_t)c * glwe, d0 ? d0 + off : nullptr,
               static_cast<const uint64_t*>(P.ptrs[3 * item + 2]) + off, static_cast<const C2*>(P.ptrs[3 * item]), st,
               xbuf, sT1, sT2, P.radix_log, P.count);
     return;
@@ -661,7 +662,8 @@ __global__ void __launch_bounds__(kWideTeams * kTeam, 1) cmux_wide_kernel(CmuxBa
   }
   mbar_wait(smem_u32(mbar), 0);
   DevWideCx cx{(int)(threadIdx.x % kTeam), (int)(threadIdx.x / kTeam)};
-  cmux_wide(cx, P.out + (size_t)c * glwe, d0 ? sd0 : nullptr, sd1, ggsw, xb, sT1, sT2, P.radix_log, P.count);
+  cmux_wide(cx, P.out_ptrs ? static_cast<uint64_t*>(P.out_ptrs[c]) : P.out + (size_t)c * glwe, d0 ? sd0 : nullptr, sd1, ggsw, xb, sT1, sT2,
+            P.radix_log, P.count);
 }
 
 // ------------------------------------------------------------------------------------------
