@@ -98,6 +98,11 @@ struct spf_b200_graph {
   void** d_ptrs = nullptr;
   uint32_t* d_u32 = nullptr;
   char* d_out_stage = nullptr;  // rescaled GGSW outputs
+  // non-GGSW outputs are gathered (gather_outputs_kernel) into d_gather in g->outputs order before they are copied out
+  char* d_gather = nullptr;
+  void* d_gather_tab = nullptr;  // [src pointers | word offsets | word counts]
+  std::vector<size_t> gather_off;  // byte offset of output k in d_gather, (size_t)-1 for GGSW outputs
+  size_t gather_items = 0;
   int n_levels = 0;
   uint64_t launches_per_run = 0;
   int world = 1;  // CircuitBootstrap groups are laid out as `world` equal chunks (spf_b200_graph_build_sharded)
@@ -609,6 +614,33 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   }
   CU(cudaMemcpy(g->d_ptrs, h_ptrs.data(), h_ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(g->d_u32, h_u32.data(), h_u32.size() * 4, cudaMemcpyHostToDevice));
+  {  // gather tables for the outputs
+    std::vector<void*> src;
+    std::vector<unsigned long long> off16;
+    std::vector<unsigned> n16;
+    size_t total = 0;
+    g->gather_off.assign(g->outputs.size(), (size_t)-1);
+    for (size_t k = 0; k < g->outputs.size(); k++) {
+      const int from = g->nodes[g->outputs[k]].in[0];
+      if (g->type[from] == T_GGSW1) continue;
+      const size_t bytes = ct_bytes(p, g->type[from]);
+      g->gather_off[k] = total;
+      src.push_back(g->dptr[from]);
+      off16.push_back(total / 8);
+      n16.push_back((unsigned)(bytes / 8));
+      total += bytes;
+    }
+    g->gather_items = src.size();
+    if (g->gather_items) {
+      const size_t n_it = g->gather_items;
+      CU(cudaMalloc(&g->d_gather, total));
+      CU(cudaMalloc(&g->d_gather_tab, n_it * (sizeof(void*) + sizeof(unsigned long long) + sizeof(unsigned))));
+      char* t = static_cast<char*>(g->d_gather_tab);
+      CU(cudaMemcpy(t, src.data(), n_it * sizeof(void*), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(t + n_it * sizeof(void*), off16.data(), n_it * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(t + n_it * (sizeof(void*) + sizeof(unsigned long long)), n16.data(), n_it * sizeof(unsigned), cudaMemcpyHostToDevice));
+    }
+  }
   if (build_timing)
     fprintf(stderr, "[spf_b200 graph build] %zu nodes: plan %.1f ms, constants %.1f, layout %.1f, cudaMalloc of %.2f GB (%zu recycled CMux slots) %.1f, addresses + page-locking %zu io buffers %.1f, tables %.1f\n",
             n, t_plan - t_start, t_consts - t_plan, t_layout - t_consts, g->arena_bytes / 1e9, g->pool_slots, t_malloc - t_layout, g->inputs.size() + g->outputs.size(),
@@ -643,9 +675,20 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
   const uint64_t l0 = ctx->launches.load();
   // every rank has finished its previous run before anyone stores into its arena again
   if (peer_mode) if (int rc = peer_barrier(g, s)) return rc;
+  // inputs whose host buffers AND device buffers are consecutive (rows of one host slab, in node order) go up as one copy
+  for (size_t i = 0; i < g->inputs.size();) {
+    const int id0 = g->inputs[i];
+    size_t bytes = ct_host_bytes(p, g->type[id0]), j = i + 1;
+    while (j < g->inputs.size() && g->dptr[g->inputs[j]] == g->dptr[id0] + bytes &&
+           static_cast<char*>(g->nodes[g->inputs[j]].io) == static_cast<char*>(g->nodes[id0].io) + bytes) {
+      bytes += ct_host_bytes(p, g->type[g->inputs[j]]);
+      j++;
+    }
+    CU(cudaMemcpyAsync(g->dptr[id0], g->nodes[id0].io, bytes, cudaMemcpyHostToDevice, s));
+    i = j;
+  }
   for (int id : g->inputs) {
     const CtType t = g->type[id];
-    CU(cudaMemcpyAsync(g->dptr[id], g->nodes[id].io, ct_host_bytes(p, t), cudaMemcpyHostToDevice, s));
     if (t == T_GGSW1)
       if (int rc = launch_scale(ctx, reinterpret_cast<C2*>(g->dptr[id]), reinterpret_cast<const C2*>(g->dptr[id]),
                                 spf_b200_len_ggsw_l1(p), 1.0 / 1024.0, s))
@@ -681,20 +724,45 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
       }
     }
   }
+  if (g->gather_items) {
+    const size_t n_it = g->gather_items;
+    const char* t = static_cast<const char*>(g->d_gather_tab);
+    gather_outputs_kernel<<<dim3(4, (unsigned)n_it), 256, 0, s>>>(
+        reinterpret_cast<unsigned long long*>(g->d_gather), reinterpret_cast<const void* const*>(t),
+        reinterpret_cast<const unsigned long long*>(t + n_it * sizeof(void*)),
+        reinterpret_cast<const unsigned*>(t + n_it * (sizeof(void*) + sizeof(unsigned long long))));
+    if (int rc = check_launch(ctx, "gather_outputs_kernel")) return rc;
+  }
+  auto mine = [&](size_t k) {  // outputs of a MUX tree live on the tree's owner
+    const int r = spf_b200_graph_output_rank(g, (size_t)g->outputs[k]);
+    return r < 0 || r == rank;
+  };
   size_t stage = 0;
-  for (int id : g->outputs) {
+  for (size_t k = 0; k < g->outputs.size();) {
+    const int id = g->outputs[k];
     const int src = g->nodes[id].in[0];
-    if (spf_b200_graph_output_rank(g, (size_t)id) >= 0 && spf_b200_graph_output_rank(g, (size_t)id) != rank) continue;  // lives on its owner
     const CtType t = g->type[src];
-    const char* from = g->dptr[src];
     if (t == T_GGSW1) {
       char* tmp = g->d_out_stage + stage;
       stage += ct_bytes(p, T_GGSW1);
-      if (int rc = launch_scale(ctx, reinterpret_cast<C2*>(tmp), reinterpret_cast<const C2*>(from), spf_b200_len_ggsw_l1(p), 1024.0, s))
-        return rc;
-      from = tmp;
+      if (mine(k)) {
+        if (int rc = launch_scale(ctx, reinterpret_cast<C2*>(tmp), reinterpret_cast<const C2*>(g->dptr[src]), spf_b200_len_ggsw_l1(p), 1024.0, s))
+          return rc;
+        CU(cudaMemcpyAsync(g->nodes[id].io, tmp, ct_host_bytes(p, t), cudaMemcpyDeviceToHost, s));
+      }
+      k++;
+      continue;
     }
-    CU(cudaMemcpyAsync(g->nodes[id].io, from, ct_host_bytes(p, t), cudaMemcpyDeviceToHost, s));
+    if (!mine(k)) { k++; continue; }
+    // consecutive outputs whose host buffers are consecutive too leave in one copy
+    size_t bytes = ct_host_bytes(p, t), j = k + 1;
+    while (j < g->outputs.size() && g->gather_off[j] == g->gather_off[k] + bytes && mine(j) &&
+           static_cast<char*>(g->nodes[g->outputs[j]].io) == static_cast<char*>(g->nodes[id].io) + bytes) {
+      bytes += ct_host_bytes(p, g->type[g->nodes[g->outputs[j]].in[0]]);
+      j++;
+    }
+    CU(cudaMemcpyAsync(g->nodes[id].io, g->d_gather + g->gather_off[k], bytes, cudaMemcpyDeviceToHost, s));
+    k = j;
   }
   CU(cudaStreamSynchronize(s));
   if (peer_mode) {
@@ -731,6 +799,8 @@ void spf_b200_graph_destroy(spf_b200_graph* g) {
   cudaFree(g->d_ptrs);
   cudaFree(g->d_u32);
   cudaFree(g->d_out_stage);
+  cudaFree(g->d_gather);
+  cudaFree(g->d_gather_tab);
   for (void* q : g->pinned) cudaHostUnregister(q);
   delete g;
 }

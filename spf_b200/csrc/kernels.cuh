@@ -550,6 +550,16 @@ __global__ void peer_barrier_kernel(unsigned long long* flags, PeerOffsets peers
   __threadfence_system();
 }
 
+// Gathers the ciphertexts behind a graph's Output nodes into one contiguous staging buffer, so that they leave
+// the device in as few copies as their host buffers allow: item k = n8[k] 8-byte words from src[k] to dst + off8[k]
+// (every ciphertext is a whole number of u64 words; an L1 LWE is 2049 of them).
+__global__ void gather_outputs_kernel(unsigned long long* dst, const void* const* src, const unsigned long long* off8, const unsigned* n8) {
+  const int k = blockIdx.y;
+  const unsigned long long* s = static_cast<const unsigned long long*>(src[k]);
+  unsigned long long* d = dst + off8[k];
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n8[k]; i += gridDim.x * blockDim.x) d[i] = s[i];
+}
+
 // dst_r[i] = src[i] for every peer r (the keyswitch outputs of this rank's trees: 5 KB each)
 __global__ void peer_bcast_kernel(const uint4* src, size_t n16, PeerOffsets peers) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
