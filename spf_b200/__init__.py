@@ -427,24 +427,99 @@ class FheCircuit:
     (left, right); CMux / GlevCMux take (sel, low, high); MultiplyGgswGlwe takes (glwe, ggsw).
     Input / Output nodes carry the numpy buffer they read from / write into."""
 
+    _DT = np.dtype([("op", "<u4"), ("arg", "<u4"), ("inp", "<i4", (3,)), ("pad", "<u4"), ("io", "<u8")])  # spf_node
+
     def __init__(self):
-        self.nodes: list[tuple[int, int, tuple[int, int, int], np.ndarray | None]] = []
+        self._n = 0
+        self._buf = np.zeros(64, dtype=self._DT)   # node table in the C ABI's layout, grown geometrically
+        self._buf["inp"] = -1
+        self._io: dict[int, np.ndarray] = {}      # node -> host buffer (kept alive here)
+
+    def __len__(self) -> int:
+        return self._n
+
+    def _reserve(self, extra: int) -> None:
+        if self._n + extra > len(self._buf):
+            grown = np.zeros(max(2 * len(self._buf), self._n + extra), dtype=self._DT)
+            grown["inp"] = -1
+            grown[:self._n] = self._buf[:self._n]
+            self._buf = grown
 
     def add(self, op: str, *inputs: int, arg: int = 0, io: np.ndarray | None = None) -> int:
-        ins = tuple(inputs) + (-1,) * (3 - len(inputs))
+        return self._append(OP[op], int(arg), tuple(inputs) + (-1,) * (3 - len(inputs)), io)
+
+    def _append(self, opc: int, arg: int, ins, io) -> int:
         if io is not None and not io.flags["C_CONTIGUOUS"]:
             raise SpfError(-1, "io buffers must be C-contiguous")
-        self.nodes.append((OP[op], int(arg), ins, io))
-        return len(self.nodes) - 1
+        self._reserve(1)
+        i = self._n
+        row = self._buf[i]
+        row["op"], row["arg"], row["inp"] = opc, arg, ins
+        if io is not None:
+            self._io[i] = io
+        self._n += 1
+        return i
+
+    def add_block(self, opcodes: np.ndarray, ins: np.ndarray) -> np.ndarray:
+        """Append len(opcodes) nodes at once (opcodes: op codes, ins: [m, 3] producer indices, -1 = none) and
+        return their indices -- the bulk path MUX-circuit expansion uses (tens of thousands of CMux nodes)."""
+        m = len(opcodes)
+        self._reserve(m)
+        blk = self._buf[self._n:self._n + m]
+        blk["op"], blk["arg"], blk["inp"] = opcodes, 0, ins
+        self._n += m
+        return np.arange(self._n - m, self._n, dtype=np.int64)
+
+    @property
+    def nodes(self) -> "_NodesView":
+        """Sequence view of the nodes as (op code, arg, (in0, in1, in2), io buffer) tuples."""
+        return _NodesView(self)
+
+    @property
+    def ops(self) -> np.ndarray:
+        return self._buf["op"][:self._n]
+
+    @property
+    def inputs_of(self) -> np.ndarray:
+        return self._buf["inp"][:self._n]
 
     def _pack(self):
-        arr = (_Node * max(len(self.nodes), 1))()
-        for i, (op, arg, ins, io) in enumerate(self.nodes):
-            arr[i].op, arr[i].arg = op, arg
-            for e in range(3):
-                arr[i].inp[e] = ins[e]
-            arr[i].io = io.ctypes.data if io is not None else None
-        return arr
+        """The node table as the C ABI wants it (spf_node[]); io pointers are filled in here."""
+        arr = self._buf[:max(self._n, 1)].copy()
+        arr["io"] = 0
+        for i, io in self._io.items():
+            arr["io"][i] = io.ctypes.data
+        self._packed = arr  # keeps the memory alive for the duration of the call
+        return arr.ctypes.data_as(C.POINTER(_Node))
+
+
+class _NodesView:
+    """list-like read view (plus append) over a FheCircuit's node table."""
+
+    def __init__(self, c: FheCircuit):
+        self._c = c
+
+    def __len__(self):
+        return self._c._n
+
+    def __getitem__(self, i: int):
+        c = self._c
+        if i < 0:
+            i += c._n
+        if not 0 <= i < c._n:
+            raise IndexError(i)
+        row = c._buf[i]
+        return int(row["op"]), int(row["arg"]), tuple(int(x) for x in row["inp"]), c._io.get(i)
+
+    def __iter__(self):
+        c = self._c
+        ops, args, ins = c._buf["op"][:c._n].tolist(), c._buf["arg"][:c._n].tolist(), c._buf["inp"][:c._n].tolist()
+        for i in range(c._n):
+            yield ops[i], args[i], tuple(ins[i]), c._io.get(i)
+
+    def append(self, node) -> None:
+        opc, arg, ins, io = node
+        self._c._append(int(opc), int(arg), tuple(ins), io)
 
 
 def pinned_zeros(shape, dtype=np.uint64) -> np.ndarray:
