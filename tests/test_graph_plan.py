@@ -115,3 +115,32 @@ def test_malformed_graphs_are_rejected_without_a_gpu():
     expect(c, "unknown op")
     with pytest.raises(SpfError):
         plan_graph(FheCircuit(), world=0)
+
+
+def test_fhe_circuit_node_table_matches_the_c_struct():
+    """FheCircuit stores nodes in spf_node's layout; the list-like view, bulk append and the hand-over agree."""
+    import ctypes as C
+
+    from spf_b200 import _Node
+
+    assert FheCircuit._DT.itemsize == C.sizeof(_Node) == 32
+    assert FheCircuit._DT.fields["io"][1] == _Node.io.offset and FheCircuit._DT.fields["inp"][1] == _Node.inp.offset
+    buf = np.zeros(4096, np.uint64)
+    c = FheCircuit()
+    x = c.add("InputGlwe1", io=buf)
+    s = c.add("SampleExtract", x, arg=7)
+    blk = c.add_block(np.full(100, OP["Not"], np.uint32), np.stack([np.full(100, x), np.full(100, -1), np.full(100, -1)], axis=1))
+    assert blk.tolist() == list(range(2, 102)) and len(c) == len(c.nodes) == 102
+    assert c.nodes[1] == (OP["SampleExtract"], 7, (x, -1, -1), None) and c.nodes[-1][0] == OP["Not"]
+    assert c.nodes[0][3] is buf
+    assert [n[0] for n in c.nodes][:3] == [OP["InputGlwe1"], OP["SampleExtract"], OP["Not"]]
+    c.nodes.append((OP["OutputGlwe1"], 0, (blk[-1], -1, -1), buf))
+    arr = c._pack()
+    assert (arr[0].op, arr[1].arg, arr[1].inp[0], arr[102].inp[0]) == (OP["InputGlwe1"], 7, x, 101)
+    assert arr[0].io == arr[102].io == buf.ctypes.data and not arr[1].io
+    with pytest.raises(IndexError):
+        c.nodes[103]
+    with pytest.raises(SpfError):
+        c.add("InputGlwe1", io=np.zeros((4, 4), np.uint64)[:, 0])   # not C-contiguous
+    level, owner = plan_graph(c)
+    assert level[x] == 0 and level[102] == 2
