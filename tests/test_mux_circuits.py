@@ -255,3 +255,23 @@ def test_small_circuits_exhaustively():
                 for or_eq in (False, True):
                     want = (a > b if greater else a < b) or (or_eq and a == b)
                     assert M.compare_or_maybe_equal(3, greater, or_eq).evaluate(inter) == [int(want)]
+
+
+def test_random_widths_property():
+    """hypothesis: for random small widths the generated adder / subtractor / multiplier agree with integer arithmetic."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 6), st.integers(1, 6), st.integers(0, 2 ** 12 - 1), st.integers(0, 2 ** 12 - 1))
+    def check(n, m, x, y):
+        a, b = x % (1 << n), y % (1 << m)
+        assert value(M.unsigned_multiplier(n, m).evaluate(bits(a, n) + bits(b, m))) == a * b
+        lo = min(n, m)
+        ab, bb = bits(a, n), bits(b, m)
+        inp = [v for p in zip(ab[:lo], bb[:lo]) for v in p] + (ab[lo:] if n > m else bb[lo:])
+        assert value(M.ripple_carry_adder(n, m).evaluate(inp)) == a + b
+        b2 = y % (1 << n)
+        out = M.full_subtractor(n).evaluate([v for p in zip(bits(a, n), bits(b2, n)) for v in p])
+        assert value(out[:n]) == (a - b2) % (1 << n) and out[n] == int(a < b2)
+
+    check()
