@@ -232,7 +232,8 @@ int spf_b200_graph_run_sharded(spf_b200_graph *graph, int rank, int world, spf_e
  * produces at the same offset into the arena of every rank while it computes the next one (the all-gather is fused
  * into the kernel that produces the data), keyswitch outputs are broadcast by a small copy kernel, and dependency
  * levels are separated by a flag barrier through peer memory (a rank that never arrives makes the run fail with
- * SPF_E_GRAPH after a 5 s device-side timeout instead of hanging).  Every rank must build the same graph with the
+ * SPF_E_GRAPH after a 5 s device-side timeout instead of hanging; the epochs of the ranks then disagree, so the
+ * graphs must be rebuilt before another sharded run).  Every rank must build the same graph with the
  * same `world`.  One process per GPU: export with spf_b200_graph_ipc_handle (a 64-byte cudaIpcMemHandle_t), gather
  * the handles on the host, import with spf_b200_graph_open_peers.  Several ranks inside one process (tests):
  * spf_b200_graph_set_peers with the arena addresses. */

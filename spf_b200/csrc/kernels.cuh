@@ -534,6 +534,7 @@ __global__ void peer_barrier_kernel(unsigned long long* flags, PeerOffsets peers
                                     unsigned long long timeout_ns) {
   const int i = threadIdx.x;
   __threadfence_system();
+  if (*reinterpret_cast<volatile int*>(err)) return;  // an earlier barrier of this run timed out: do not wait again
   if (i < peers.n) {
     volatile unsigned long long* theirs = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(flags) + peers.off[i]) + rank;
     *theirs = epoch;

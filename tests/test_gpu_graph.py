@@ -366,6 +366,27 @@ def test_peer_memory_exchange_two_ranks_on_one_gpu(keys, client, evaluation):
     ev1.close()
 
 
+def test_peer_barrier_times_out_instead_of_hanging(keys, client, evaluation):
+    """A rank that never arrives: the peer-memory barrier gives up after its device-side timeout (5 s) and the run
+    fails with SPF_E_GRAPH -- the GPU is not left spinning."""
+    import time
+
+    import spf_b200
+
+    rng = np.random.default_rng(33)
+    vals, circ, out_sum, out_gt = _two_level_program(client, keys, 2, 1, rng)
+    graphs = [spf_b200.CompiledGraph(evaluation, circ, world=2, rank=r) for r in range(2)]
+    for g in graphs:
+        g.set_peers([x.arena for x in graphs])
+    t0 = time.perf_counter()
+    with pytest.raises(spf_b200.SpfError) as e:
+        graphs[0].run()   # rank 1 never runs
+    assert "peer barrier timed out" in str(e.value) and e.value.code == -4
+    assert 4.0 < time.perf_counter() - t0 < 12.0   # one timeout, not one per barrier
+    for g in graphs:
+        g.close()
+
+
 def _multiply_program(client, keys, w, vals):
     from spf_b200.circuits import multiply_then_greater_than
 
