@@ -456,6 +456,7 @@ int spf_b200_mux_circuit(uint32_t kind, uint32_t n, uint32_t m, uint32_t flags, 
     }
     case SPF_MUX_UNSIGNED_MULTIPLIER: {
       if (m == 0 || (uint64_t)n * m * 2 >= (1u << 16)) return SPF_E_INVALID;  // mul.rs:36 (u16 variable ids)
+      if ((uint64_t)n * m * 2 > 16384) return SPF_E_UNSUPPORTED;  // apply() recurses once per variable: bound the stack
       BddManager M(2 * n * m);
       const Fns f = build_multiplier(M, n, m);
       const std::vector<uint32_t> map = multiplier_variable_map(n, m);
