@@ -275,6 +275,32 @@ def test_instruction_cache_multiply_and_compare(keys, client, evaluation):
         cache.multiply(enc(1) * 4, enc(1) * 4, [np.zeros(keys.glwe_len, dtype=np.uint64)] * (4 * w))
 
 
+def test_glev_round_trip_then_mux_circuit(keys, client, proc):
+    """The reference's ciphertext conversions in a graph (fhe_circuit.rs:562-619): selectors go GGSW -> GLEV
+    (GlevCMux(sel, ZeroGlev1, OneGlev1)) -> GGSW (SchemeSwitch, no circuit bootstrap) and then drive a BDD-derived
+    2-bit AND with a second operand.  (Deeper GLEV-mode trees are outside the noise budget of DEFAULT_128: one
+    CMux with cbs_radix (l = 4, logB = 4) leaves ~2^-13 of decomposition noise, which already swamps the two finest
+    GLEV levels -- `tools/glev_debug.py` shows the levels decoding to garbage after two GlevCMux.)"""
+    import spf_b200
+    from spf_b200 import mux_circuits as M
+
+    for a, b in ((0b11, 0b01), (0b10, 0b11), (0b00, 0b10)):
+        c = spf_b200.FheCircuit()
+        front = lambda v: [M.insert_ciphertext_conversion(c, c.add("InputGlwe1", io=client.encrypt_glwe_l1([(v >> i) & 1])), "glwe", "ggsw")
+                           for i in range(2)]
+        sa, sb = front(a), front(b)
+        sa_rt = [M.insert_ciphertext_conversion(c, M.insert_ciphertext_conversion(c, x, "ggsw", "glev"), "glev", "ggsw") for x in sa]
+        and_out = M.insert_mux_circuit(c, M.make_and_circuit(2), [sa_rt[0], sb[0], sa_rt[1], sb[1]])
+        outs = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(2)]
+        for n, buf in zip(and_out, outs):
+            c.add("OutputGlwe1", n, io=buf)
+        ops = [spf_b200.OPS[n[0]] for n in c.nodes]
+        assert ops.count("CircuitBootstrap") == 4 and ops.count("SchemeSwitch") == 2 and ops.count("GlevCMux") == 2
+        proc.run_graph_blocking(c)
+        got = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(outs))
+        assert got == a & b, (a, b, got)
+
+
 def test_pinned_slab_buffers(keys, client, proc):
     """spf_b200_host_alloc: ciphertext buffers sliced from one page-locked slab work as graph IO (and are not
     registered again); the slab is released with the array."""

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from spf_b200 import FheCircuit, OP, SpfError
+from spf_b200 import OPS as spf_b200_ops
 from spf_b200 import mux_circuits as M
 
 REF_DATA = "/root/reference/mux_circuits/src/data"
@@ -275,3 +276,27 @@ def test_random_widths_property():
         assert value(out[:n]) == (a - b2) % (1 << n) and out[n] == int(a < b2)
 
     check()
+
+
+def test_ciphertext_conversions_and_glev_mode():
+    """insert_ciphertext_conversion (fhe_circuit.rs:562-619) chains and MuxMode::Glev expansion; the planner accepts
+    the result (kinds line up)."""
+    from spf_b200 import plan_graph
+
+    c = FheCircuit()
+    g = c.add("OneGgsw1")
+    assert M.insert_ciphertext_conversion(c, g, "ggsw", "ggsw") == g
+    l0 = M.insert_ciphertext_conversion(c, g, "ggsw", "lwe0")      # MultiplyGgswGlwe -> SampleExtract -> Keyswitch
+    back = M.insert_ciphertext_conversion(c, l0, "lwe0", "glev")   # CircuitBootstrap -> GlevCMux
+    again = M.insert_ciphertext_conversion(c, back, "glev", "glwe")  # SchemeSwitch -> MultiplyGgswGlwe
+    names = [spf_b200_ops[n[0]] for n in c.nodes]
+    assert names == ["OneGgsw1", "OneGlwe1", "MultiplyGgswGlwe", "SampleExtract", "KeyswitchL1toL0", "CircuitBootstrap",
+                     "ZeroGlev1", "OneGlev1", "GlevCMux", "SchemeSwitch", "OneGlwe1", "MultiplyGgswGlwe"]
+    assert again == len(c) - 1
+    outs = M.insert_mux_circuit(c, M.make_and_circuit(2), [g, g, g, g], mux_mode="glev")
+    sel = [M.insert_ciphertext_conversion(c, o, "glev", "ggsw") for o in outs]
+    M.insert_mux_circuit(c, M.make_or_circuit(1), sel)
+    level, owner = plan_graph(c, 2)   # validates the kinds of every edge
+    assert sum(1 for n in c.nodes if spf_b200_ops[n[0]] == "GlevCMux") >= 3
+    with pytest.raises(SpfError):
+        M.insert_ciphertext_conversion(c, g, "ggsw", "nonsense")
