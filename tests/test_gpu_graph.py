@@ -275,7 +275,6 @@ def test_instruction_cache_multiply_and_compare(keys, client, evaluation):
         cache.multiply(enc(1) * 4, enc(1) * 4, [np.zeros(keys.glwe_len, dtype=np.uint64)] * (4 * w))
 
 
-@pytest.mark.xfail(reason="added while the GPU pool was unavailable: not yet run on a B200", strict=False)
 def test_glev_round_trip_then_mux_circuit(keys, client, proc):
     """The reference's ciphertext conversions in a graph (fhe_circuit.rs:562-619): selectors go GGSW -> GLEV
     (GlevCMux(sel, ZeroGlev1, OneGlev1)) -> GGSW (SchemeSwitch, no circuit bootstrap) and then drive a BDD-derived
