@@ -443,7 +443,13 @@ __global__ void __launch_bounds__(4 * kTeam, 1) pbs_quad_kernel(PbsBatch P, DevT
 // ------------------------------------------------------------------------------------------
 // K5+K6: trace (+ CBS pre-processing) and scheme switch, one team per (ciphertext, level).
 // ------------------------------------------------------------------------------------------
-constexpr int kTrTeams = 4;
+#ifndef SPF_TR_TEAMS
+#define SPF_TR_TEAMS 4
+#endif
+#ifndef SPF_TR_MIN_BLOCKS
+#define SPF_TR_MIN_BLOCKS 1
+#endif
+constexpr int kTrTeams = SPF_TR_TEAMS;
 constexpr int kTrTeamBytes = 2 * kN * 8 + kXBuf * 16;                 // g + xbuf = 49408 (digits are stateless)
 constexpr int kTrSmem = kTableBytes + kTrTeams * kTrTeamBytes;        // 215104
 
@@ -470,7 +476,7 @@ struct TraceSsBatch {
   PeerOffsets peers;       // n = 0: GGSWs are stored locally only
 };
 
-__global__ void __launch_bounds__(kTrTeams * kTeam, 1) trace_ss_kernel(const __grid_constant__ TraceSsBatch P, DevTables tabs) {
+__global__ void __launch_bounds__(kTrTeams * kTeam, SPF_TR_MIN_BLOCKS) trace_ss_kernel(const __grid_constant__ TraceSsBatch P, DevTables tabs) {
   extern __shared__ __align__(16) unsigned char smem[];
   C2* sT1 = reinterpret_cast<C2*>(smem);
   C2* sT2 = sT1 + kT1Elems;
