@@ -301,6 +301,26 @@ def test_glev_round_trip_then_mux_circuit(keys, client, proc):
         assert got == a & b, (a, b, got)
 
 
+def test_signed_multiply_4bit(keys, client, proc):
+    """append_int_multiply (parasol_runtime/src/circuits/mul.rs:19-73) on encrypted 4-bit two's-complement operands:
+    abs -> unsigned multiplier -> conditional negate, three bootstrap levels; the 8 product bits decrypt to a * b."""
+    import spf_b200
+    from spf_b200 import mux_circuits as M
+
+    w = 4
+    for a, b in ((-3, 5), (-8, -8), (7, -1)):
+        c = spf_b200.FheCircuit()
+        front = lambda v: [M.insert_ciphertext_conversion(c, c.add("InputGlwe1", io=client.encrypt_glwe_l1([(v >> i) & 1])), "glwe", "ggsw")
+                           for i in range(w)]
+        lo, hi = M.append_int_multiply(c, front(a & 0xF), front(b & 0xF))
+        outs = [np.zeros(keys.glwe_len, dtype=np.uint64) for _ in range(2 * w)]
+        for n, buf in zip(lo + hi, outs):
+            c.add("OutputGlwe1", n, io=buf)
+        proc.run_graph_blocking(c)
+        got = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(outs))
+        assert got == (a * b) % 256, (a, b, got)
+
+
 def test_pinned_slab_buffers(keys, client, proc):
     """spf_b200_host_alloc: ciphertext buffers sliced from one page-locked slab work as graph IO (and are not
     registered again); the slab is released with the array."""

@@ -167,6 +167,8 @@ def _plain_run(c: FheCircuit, ggsw_bits: dict[int, int]) -> dict[int, int]:
             val[i] = 1
         elif op in (OP["SampleExtract"], OP["KeyswitchL1toL0"], OP["CircuitBootstrap"]):
             val[i] = val[ins[0]]
+        elif op == OP["MultiplyGgswGlwe"]:   # in[0] = Glwe, in[1] = Ggsw
+            val[i] = val[ins[0]] & val[ins[1]]
     return val
 
 
@@ -300,3 +302,19 @@ def test_ciphertext_conversions_and_glev_mode():
     assert sum(1 for n in c.nodes if spf_b200_ops[n[0]] == "GlevCMux") >= 3
     with pytest.raises(SpfError):
         M.insert_ciphertext_conversion(c, g, "ggsw", "nonsense")
+
+
+@pytest.mark.parametrize("w", [4, 6])
+def test_append_int_multiply_structure(w):
+    """circuits/mul.rs:19-73: the signed product's Boolean skeleton over every pair of w-bit two's-complement values."""
+    c = FheCircuit()
+    a = [c.add("OneGgsw1") for _ in range(w)]
+    b = [c.add("OneGgsw1") for _ in range(w)]
+    lo, hi = M.append_int_multiply(c, a, b)
+    assert len(lo) == w and len(hi) == w
+    signed = lambda v: v - (1 << w) * (v >> (w - 1))
+    step = 1 if w == 4 else 5
+    for x in range(0, 1 << w, step):
+        for y in range(0, 1 << w, step):
+            val = _plain_run(c, {n: bt for n, bt in zip(a + b, bits(x, w) + bits(y, w))})
+            assert value([val[n] for n in lo + hi]) == (signed(x) * signed(y)) % (1 << (2 * w)), (x, y)
