@@ -86,3 +86,24 @@ def test_create_fails_loudly_without_gpu_or_with_bad_args(oracle):
         rc = l.spf_b200_create(C.byref(p), dummy.ctypes.data, n[0], dummy.ctypes.data, n[1], dummy.ctypes.data, n[2],
                                dummy.ctypes.data, n[3], 0, C.byref(h))
         assert rc == -3 and b"no CPU fallback" in l.spf_b200_last_error(None)
+
+
+def test_plain_c_consumer(tmp_path):
+    """The boundary is a C ABI: a plain C11 program includes include/spf_b200.h, links libspf_b200.so and uses the
+    host-only entry points (MUX-circuit generator, graph planner, error reporting) without Python or a GPU."""
+    import shutil
+    import subprocess
+
+    import spf_b200
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    lib_dir = os.path.dirname(spf_b200.LIB_PATH)
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.check_call([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", lib_dir,
+                           "-l:" + os.path.basename(spf_b200.LIB_PATH), "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "c abi ok: 3228 multiplexers" in out.stdout
