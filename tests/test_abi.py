@@ -107,3 +107,46 @@ def test_plain_c_consumer(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "c abi ok: 3228 multiplexers" in out.stdout
+
+
+def test_cpp_host_mirror(tmp_path):
+    """include/spf_b200.hpp (the C++ host side above the C ABI: Evaluation / FheCircuit / CircuitProcessor /
+    MuxCircuit with the reference's names) compiles with -Wall -Wextra -Werror, links, and its host-only parts run."""
+    import shutil
+    import subprocess
+
+    import spf_b200
+
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if cxx is None:
+        pytest.skip("no C++ compiler")
+    lib_dir = os.path.dirname(spf_b200.LIB_PATH)
+    exe = str(tmp_path / "hpp_smoke")
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "hpp_smoke.cpp"), "-o", exe, "-L", lib_dir,
+                           "-l:" + os.path.basename(spf_b200.LIB_PATH), "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "hpp ok: 2 + 7 = 9" in out.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_host_mirror_gpu_path(tmp_path):
+    """The same program with the argument "gpu": Evaluation::circuit_bootstrap / cmux, CircuitProcessor::
+    run_graph_blocking and a CompiledGraph through the C++ wrapper on cuda:0 (all-zero keys: the calls, not the
+    cryptography)."""
+    import shutil
+    import subprocess
+
+    import spf_b200
+
+    cxx = shutil.which("g++") or shutil.which("c++")
+    if cxx is None:
+        pytest.skip("no C++ compiler")
+    lib_dir = os.path.dirname(spf_b200.LIB_PATH)
+    exe = str(tmp_path / "hpp_smoke")
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "hpp_smoke.cpp"),
+                           "-o", exe, "-L", lib_dir, "-l:" + os.path.basename(spf_b200.LIB_PATH), "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "gpu path ok" in out.stdout
