@@ -375,6 +375,24 @@ def measure_add_latency(ev, keys, args):
             cgot = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(couts))
             entry.update({"cpu_port_ms": 1e3 * dt, "cpu_threads": nt, "cpu_correct": cgot == a + b})
         res[f"add{w}"] = entry
+        # the same add with the reference's own BDD-derived adder circuit (mux_circuits::add::ripple_carry_adder):
+        # more multiplexers (O(w^2): every sum bit carries its own copy of the carry chain), the same depth
+        from spf_b200.circuits import bdd_adder
+
+        for o in outs:
+            o[:] = 0
+        circ = bdd_adder(ab, bb, outs)
+        g = proc.compile(circ)
+        g.run()
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            g.run()
+            ts.append(time.perf_counter() - t0)
+        got = sum(int(client.decrypt_glwe_l1(o)[0]) << i for i, o in enumerate(outs))
+        res[f"add{w}_bdd_circuit"] = {"gpu_ms": 1e3 * float(np.median(ts)), "levels": g.levels, "launches": g.launches,
+                                      "cmux": int((circ.ops == spf_b200.OP["CMux"]).sum()), "correct": got == a + b}
+        g.close()
     return res
 
 

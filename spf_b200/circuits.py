@@ -46,6 +46,23 @@ def ripple_carry_adder(a_bits: list[np.ndarray], b_bits: list[np.ndarray], out_b
     return c
 
 
+def bdd_adder(a_bits: list[np.ndarray], b_bits: list[np.ndarray], out_bits: list[np.ndarray]) -> FheCircuit:
+    """The same add with the reference's own MUX circuit: mux_circuits::add::ripple_carry_adder(w, w, false)
+    (add.rs:13-56, inputs interleaved a0 b0 a1 b1 ...) expanded by insert_mux_circuit, behind the front end of
+    FheCircuit::insert_mux_circuit_and_connect_inputs (fhe_circuit.rs:473-494) -- what parasol_cpu's Add dispatches."""
+    from . import mux_circuits as M
+
+    w = len(a_bits)
+    assert len(b_bits) == w and len(out_bits) == w + 1
+    c = FheCircuit()
+    sa = [_front(c, x) for x in a_bits]
+    sb = [_front(c, x) for x in b_bits]
+    outs = M.insert_mux_circuit(c, M.ripple_carry_adder(w, w, False), [x for pair in zip(sa, sb) for x in pair])
+    for node, buf in zip(outs, out_bits):
+        c.add("OutputGlwe1", node, io=buf)
+    return c
+
+
 def _front(c: FheCircuit, ct):
     """InputGlwe1 -> SampleExtract(0) -> KeyswitchL1toL0 -> CircuitBootstrap (fhe_circuit.rs:473-494)."""
     x = c.add("InputGlwe1", io=ct)
