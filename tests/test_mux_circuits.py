@@ -318,3 +318,40 @@ def test_append_int_multiply_structure(w):
         for y in range(0, 1 << w, step):
             val = _plain_run(c, {n: bt for n, bt in zip(a + b, bits(x, w) + bits(y, w))})
             assert value([val[n] for n in lo + hi]) == (signed(x) * signed(y)) % (1 << (2 * w)), (x, y)
+
+
+def test_program_graph_skeletons():
+    """circuits.{bdd_adder, ripple_carry_adder, multiply_then_greater_than}: the Boolean skeletons of the program graphs
+    (front ends passed through) compute a + b and (a * b mod 2^w, > c) on plaintext bits."""
+    from spf_b200.circuits import bdd_adder, multiply_then_greater_than, ripple_carry_adder
+
+    def run(c, in_bits):
+        ins = [i for i, n in enumerate(c.nodes) if n[0] == OP["InputGlwe1"]]
+        assert len(ins) == len(in_bits)
+        val = {}
+        for i, (op, arg, src, io) in enumerate(c.nodes):
+            if op == OP["InputGlwe1"]:
+                val[i] = in_bits[ins.index(i)]
+            elif op == OP["CMux"]:
+                val[i] = val[src[2]] if val[src[0]] else val[src[1]]
+            elif op == OP["Not"]:
+                val[i] = 1 - val[src[0]]
+            elif op == OP["ZeroGlwe1"]:
+                val[i] = 0
+            elif op == OP["OneGlwe1"]:
+                val[i] = 1
+            elif op != OP["OutputGlwe1"]:
+                val[i] = val[src[0]]
+        return [val[src[0]] for op, arg, src, io in c.nodes if op == OP["OutputGlwe1"]]
+
+    buf = lambda: np.zeros(4096, np.uint64)
+    w = 6
+    for build in (bdd_adder, ripple_carry_adder):
+        c = build([buf() for _ in range(w)], [buf() for _ in range(w)], [buf() for _ in range(w + 1)])
+        for a, b in ((13, 50), (63, 63), (0, 0), (32, 31)):
+            assert value(run(c, bits(a, w) + bits(b, w))) == a + b, build.__name__
+    mk = lambda: [[buf() for _ in range(w)]]
+    c = multiply_then_greater_than(mk(), mk(), mk(), mk(), [buf()], 1)
+    for a, b, d in ((13, 11, 9), (63, 63, 0), (7, 9, 63), (0, 5, 0)):
+        out = run(c, bits(a, w) + bits(b, w) + bits(d, w))
+        assert value(out[:w]) == (a * b) % (1 << w) and out[w] == int((a * b) % (1 << w) > d)
