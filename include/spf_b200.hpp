@@ -13,6 +13,7 @@
 #pragma once
 
 #include <cstdint>
+#include <initializer_list>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -244,6 +245,7 @@ class MuxCircuit {
   // mux_circuits::{add::ripple_carry_adder, mul::unsigned_multiplier, comparisons::compare_or_maybe_equal, ...}
   static MuxCircuit ripple_carry_adder(std::uint32_t n, std::uint32_t m, bool cin = false) { return generate(SPF_MUX_RIPPLE_CARRY_ADDER, n, m, cin); }
   static MuxCircuit unsigned_multiplier(std::uint32_t n, std::uint32_t m) { return generate(SPF_MUX_UNSIGNED_MULTIPLIER, n, m); }
+  static MuxCircuit gradeschool_reduce(std::uint32_t n, std::uint32_t m) { return generate(SPF_MUX_GRADESCHOOL_REDUCE, n, m); }
   static MuxCircuit compare_or_maybe_equal(std::uint32_t n, bool greater, bool or_equal) {
     return generate(SPF_MUX_COMPARE, n, 0, (greater ? 1u : 0u) | (or_equal ? 2u : 0u));
   }
@@ -295,6 +297,57 @@ inline std::vector<int> insert_mux_circuit(FheCircuit& c, const MuxCircuit& mux,
     }
   }
   return outs;
+}
+
+// insert_ciphertext_conversion(L1Glwe -> L1Ggsw) (fhe_circuit.rs:562-619): SampleExtract(0) -> KeyswitchL1toL0 -> CircuitBootstrap
+inline int glwe_to_ggsw(FheCircuit& c, int node) {
+  return c.add(SPF_OP_CIRCUIT_BOOTSTRAP, c.add(SPF_OP_KEYSWITCH_L1_TO_L0, c.add(SPF_OP_SAMPLE_EXTRACT, node)));
+}
+
+// mux_circuits::mul::partition_integer (mul.rs:263-273), CIRCUIT_CUTOFF = 16: (low, high) word widths
+inline std::pair<std::size_t, std::size_t> partition_integer(std::size_t n) {
+  return n <= 16 ? std::make_pair(n, std::size_t{0}) : std::make_pair(n - n / 2, n / 2);
+}
+
+// circuits/mul.rs:91-199 (mul_impl): recursive grade-school multiplication of GGSW-encrypted operands (LSB first):
+// blocks of at most 16 x 16 bits from the multiplier MUX circuit, then -- behind one bootstrap level -- the 4-way
+// reduction circuit fed in the order of encode_gradeschool_reduction (mul.rs:289-387).  Returns the GLWE nodes of the
+// len(a) + len(b) product bits.
+inline std::vector<int> append_uint_multiply(FheCircuit& c, std::vector<int> a, std::vector<int> b) {
+  if (a.size() < b.size()) std::swap(a, b);
+  const auto [a_lo, a_hi] = partition_integer(a.size());
+  const auto [b_lo, b_hi] = partition_integer(b.size());
+  const std::vector<int> al(a.begin(), a.begin() + a_lo), ah(a.begin() + a_lo, a.end());
+  const std::vector<int> bl(b.begin(), b.begin() + b_lo), bh(b.begin() + b_lo, b.end());
+  if (a_hi == 0 && b_hi == 0) {
+    std::vector<int> in = a;
+    in.insert(in.end(), b.begin(), b.end());
+    return insert_mux_circuit(c, MuxCircuit::unsigned_multiplier((std::uint32_t)a.size(), (std::uint32_t)b.size()), in);
+  }
+  if (b_hi == 0) {  // a_lo * b + ((a_hi * b) << a_lo): the low word passes through, the rest goes through an adder
+    const std::vector<int> ll = append_uint_multiply(c, al, bl), hl = append_uint_multiply(c, ah, bl);
+    std::vector<int> in;
+    for (std::size_t i = 0; i < b_lo; i++) { in.push_back(glwe_to_ggsw(c, ll[a_lo + i])); in.push_back(glwe_to_ggsw(c, hl[i])); }
+    for (std::size_t i = b_lo; i < hl.size(); i++) in.push_back(glwe_to_ggsw(c, hl[i]));
+    const std::vector<int> sum = insert_mux_circuit(c, MuxCircuit::ripple_carry_adder((std::uint32_t)b_lo, (std::uint32_t)(a_hi + b_lo)), in);
+    std::vector<int> out(ll.begin(), ll.begin() + a_lo);
+    out.insert(out.end(), sum.begin(), sum.end());
+    return out;
+  }
+  const std::vector<int> ll = append_uint_multiply(c, al, bl), lh = append_uint_multiply(c, al, bh);
+  const std::vector<int> hl = append_uint_multiply(c, ah, bl), hh = append_uint_multiply(c, ah, bh);
+  const std::vector<int>* src[4] = {&ll, &hl, &lh, &hh};
+  std::size_t pos[4] = {0, 0, 0, 0};
+  std::vector<int> bits;
+  auto take = [&](std::initializer_list<int> which, std::size_t run) {
+    for (std::size_t i = 0; i < run; i++)
+      for (int w : which) bits.push_back((*src[w])[pos[w] + i]);
+    for (int w : which) pos[w] += run;
+  };
+  take({0}, b_lo); take({0, 2}, a_lo - b_lo); take({0, 1, 2}, b_lo); take({1, 2, 3}, b_hi); take({1, 3}, a_hi - b_hi); take({3}, b_hi);
+  std::vector<int> sel;
+  for (int n : bits) sel.push_back(glwe_to_ggsw(c, n));
+  return insert_mux_circuit(c, MuxCircuit::gradeschool_reduce((std::uint32_t)a.size(), (std::uint32_t)b.size()), sel);
 }
 
 }  // namespace spf

@@ -75,6 +75,42 @@ int main(int argc, char** argv) {
     if (e.code != SPF_E_INVALID) return fail(8, e.what());
   }
 
+  // circuits/mul.rs mul_impl in C++: an 18 x 18 product = four 9 x 9 blocks + the 4-way reduction behind one bootstrap
+  // level; its Boolean skeleton (conversions passed through) multiplies
+  {
+    spf::FheCircuit m;
+    std::vector<int> ma, mb;
+    for (int i = 0; i < 18; i++) ma.push_back(m.add(SPF_OP_ONE_GGSW1));
+    for (int i = 0; i < 18; i++) mb.push_back(m.add(SPF_OP_ONE_GGSW1));
+    const std::vector<int> prod = spf::append_uint_multiply(m, ma, mb);
+    if (prod.size() != 36) return fail(9, "product width");
+    const unsigned long long x = 0x2F1A7ull & 0x3FFFF, y = 0x31C59ull & 0x3FFFF;
+    std::vector<int> val(m.size(), 0);
+    std::size_t n_cbs = 0;
+    for (std::size_t i = 0; i < m.size(); i++) {
+      const spf_node& n = m.nodes()[i];
+      switch (n.op) {
+        case SPF_OP_ONE_GGSW1: {
+          std::size_t k = 0;
+          while (k < 18 && ma[k] != (int)i) k++;
+          if (k < 18) { val[i] = (x >> k) & 1; break; }
+          k = 0;
+          while (mb[k] != (int)i) k++;
+          val[i] = (y >> k) & 1;
+        } break;
+        case SPF_OP_ONE_GLWE1: val[i] = 1; break;
+        case SPF_OP_ZERO_GLWE1: val[i] = 0; break;
+        case SPF_OP_CMUX: val[i] = val[n.in[0]] ? val[n.in[2]] : val[n.in[1]]; break;
+        case SPF_OP_CIRCUIT_BOOTSTRAP: n_cbs++; val[i] = val[n.in[0]]; break;
+        default: val[i] = val[n.in[0]]; break;
+      }
+    }
+    unsigned long long got = 0;
+    for (std::size_t i = 0; i < prod.size(); i++) got |= (unsigned long long)val[prod[i]] << i;
+    if (got != x * y || n_cbs != 4 * 18) return fail(10, "append_uint_multiply skeleton");
+    m.plan(p, 4);  // kinds line up, no cycle
+  }
+
   if (argc > 1 && std::string(argv[1]) == "gpu") {
     std::vector<double> bsk(2 * spf_b200_len_bsk(&p)), ssk(2 * spf_b200_len_ssk(&p)), ak(2 * spf_b200_len_ak(&p));
     std::vector<std::uint64_t> ksk(spf_b200_len_ksk(&p)), io(2 * 4096, 0);
