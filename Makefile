@@ -4,7 +4,7 @@
 #   oracle/libspf_oracle.so      CPU oracle (test infrastructure)
 NVCC ?= nvcc
 CXX ?= g++
-NVFLAGS ?= -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v
+NVFLAGS ?= -std=c++17 -O3 -fmad=false -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v
 CSRC := spf_b200/csrc
 HDRS := $(CSRC)/fft16.cuh $(CSRC)/fft_consts.h $(CSRC)/team_ops.cuh $(CSRC)/kernels.cuh $(CSRC)/tables.h $(CSRC)/graph.cuh $(CSRC)/serial.inl include/spf_b200.h
 
@@ -18,7 +18,7 @@ spf_b200/libspf_b200.so: $(CSRC)/capi.cu $(CSRC)/muxgen.o $(HDRS)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/capi.cu $(CSRC)/muxgen.o 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; false)
 
 $(CSRC)/libspf_emu.so: $(CSRC)/emu.cpp $(HDRS)
-	$(CXX) -O2 -march=x86-64-v3 -std=c++17 -fPIC -shared -Wall -Wno-unknown-pragmas -o $@ $(CSRC)/emu.cpp -lpthread
+	$(CXX) -O2 -march=x86-64-v3 -ffp-contract=off -std=c++17 -fPIC -shared -Wall -Wno-unknown-pragmas -o $@ $(CSRC)/emu.cpp -lpthread
 
 oracle:
 	$(MAKE) -C oracle

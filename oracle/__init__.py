@@ -309,6 +309,17 @@ class Client:
                 out[r, lv] = self.decrypt_glwe_l1(g[r, lv], (lv + 1) * p.cbs.radix_log)
         return out
 
+    def ggsw_phases(self, ggsw_fft: np.ndarray) -> np.ndarray:
+        """Raw phases b - a.s of every (row, level) GLWE of a GGSW-FFT: array [rows, levels, N] of torus
+        elements (used to state GPU-vs-oracle distances at the ciphertext level)."""
+        l = lib()
+        p = self.p
+        ggsw = np.zeros(l.orc_size_ggsw(C.byref(p), p.cbs), dtype=np.uint64)
+        l.orc_ggsw_ifft(ggsw, np.ascontiguousarray(ggsw_fft), C.byref(p), p.cbs)
+        rows, levels = p.glwe_k + 1, p.cbs.count
+        g = ggsw.reshape(rows, levels, self.k.glwe_len)
+        return np.stack([np.stack([self.decrypt_glwe_l1_raw(g[r, lv]) for lv in range(levels)]) for r in range(rows)])
+
     def ggsw_expected_messages(self, bit: int) -> np.ndarray:
         """Plaintext every (row, level) GLWE of a fresh GGSW(bit) decodes to: row k: bit at
         coeff 0; rows j<k: -(bit * s_j) -- all at plaintext_bits=(level+1)*logB where the

@@ -277,7 +277,7 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
   }
   const int per = per_cta(ctx, batch, kPbsPairs);
   const int grid = (int)std::min<size_t>((batch + per - 1) / per, (size_t)ctx->sm_count);  // persistent pairs
-  pbs_kernel<<<grid, per * 2 * kTeam, kTableBytes + per * kPbsPairBytes, s>>>(P, tabs(ctx));
+  pbs_kernel<<<grid, per * 2 * kTeam, kPbsSmem, s>>>(P, tabs(ctx));
   return check_launch(ctx, "pbs_kernel");
 }
 

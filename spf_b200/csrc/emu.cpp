@@ -27,8 +27,12 @@ struct HostCx {
   void rp_load(uint64_t (&rp)[32]) { memcpy(rp, rp_stash, sizeof(rp_stash)); }
 };
 
-// pair of teams (pbs_pair_team): 128 host threads, one barrier per half and one for the pair
-struct HostPairCx {
+// pair of teams (pbs_pair_team): 128 host threads, one barrier per half and one for the pair.  TR / CH select the
+// same code paths as the device builds (accumulator image in the exchange buffer; chunked own-coefficient access).
+template <bool TR, bool CH>
+struct HostPairCxT {
+  static constexpr bool kTransient = TR;
+  static constexpr bool kChunked = CH;
   int u, h;
   pthread_barrier_t* bar_half;
   pthread_barrier_t* bar_pair;
@@ -45,18 +49,21 @@ struct HostPairCx {
     for (int k2 = 1; k2 < 16; k2++) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
   }
   // the device keeps a private copy of the thread's own accumulator coefficients in tensor memory
-  void own_load(uint64_t (&own)[32], const uint64_t* pa) {
-    for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
-  }
-  void own_store(const uint64_t (&)[32]) {}
+  uint64_t own_stash[32];
+  void own_load(uint64_t (&own)[32], const uint64_t*) { memcpy(own, own_stash, sizeof(own_stash)); }
+  void own_store(const uint64_t (&own)[32]) { memcpy(own_stash, own, sizeof(own_stash)); }
+  void own_ld8(uint64_t (&o)[8], int c) { memcpy(o, own_stash + 8 * c, 64); }
+  void own_ld4x2(uint64_t (&o)[8], int m4) { memcpy(o, own_stash + m4, 32); memcpy(o + 4, own_stash + m4 + 16, 32); }
+  void own_st4x2(const uint64_t (&o)[8], int m4) { memcpy(own_stash + m4, o, 32); memcpy(own_stash + m4 + 16, o + 4, 32); }
+  void own_st_wait() {}
   void f_store(const C2 (&)[2][8]) {}  // device: accumulators parked in tensor memory between digit levels
   void f_load(C2 (&)[2][8]) {}
 };
 
-template <class Body>
+template <class Cx, class Body>
 struct PairLaunch {
   Body* body;
-  HostPairCx cx;
+  Cx cx;
   static void* run(void* p) {
     PairLaunch* l = (PairLaunch*)p;
     (*l->body)(l->cx);
@@ -64,18 +71,21 @@ struct PairLaunch {
   }
 };
 
-template <class Body>
+template <class Cx, class Body>
 void run_pair(Body body) {
   pthread_barrier_t half[2], pair;
   pthread_barrier_init(&half[0], nullptr, kTeam);
   pthread_barrier_init(&half[1], nullptr, kTeam);
   pthread_barrier_init(&pair, nullptr, 2 * kTeam);
-  std::vector<PairLaunch<Body>> ls(2 * kTeam);
+  std::vector<PairLaunch<Cx, Body>> ls(2 * kTeam);
   std::vector<pthread_t> th(2 * kTeam);
   for (int t = 0; t < 2 * kTeam; t++) {
     ls[t].body = &body;
-    ls[t].cx = HostPairCx{t % kTeam, t / kTeam, &half[t / kTeam], &pair};
-    pthread_create(&th[t], nullptr, PairLaunch<Body>::run, &ls[t]);
+    ls[t].cx.u = t % kTeam;
+    ls[t].cx.h = t / kTeam;
+    ls[t].cx.bar_half = &half[t / kTeam];
+    ls[t].cx.bar_pair = &pair;
+    pthread_create(&th[t], nullptr, PairLaunch<Cx, Body>::run, &ls[t]);
   }
   for (int t = 0; t < 2 * kTeam; t++) pthread_join(th[t], nullptr);
   pthread_barrier_destroy(&half[0]);
@@ -204,6 +214,18 @@ const Tables& tables() {
   return t;
 }
 
+// generalized PBS; bsk in device scale (2^-10).  lut may be null (CBS mode).  transient / chunked select the code
+// paths of the device builds (SPF_PBS_TRANSIENT, 4 pairs per CTA); the arithmetic is the same in all four.
+template <bool TR, bool CH>
+void emu_pbs_t(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, const C2* bsk_dev, int lwe_n,
+                      int log_chi, int log_v, int cbs_radix_log, int cbs_count) {
+  const Tables& t = tables();
+  std::vector<C2> xbuf(2 * kXBuf);
+  std::vector<uint64_t> acc(2 * kN);
+  PbsArgs A{lwe_in, lut, glwe_out, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count};
+  using Cx = HostPairCxT<TR, CH>;
+  run_pair<Cx>([&](Cx& cx) { pbs_pair_team(cx, A, acc.data(), xbuf.data(), t.T1.data(), t.T2.data()); });
+}
 }  // namespace
 
 extern "C" {
@@ -268,16 +290,15 @@ void emu_cmux_wide(uint64_t* out, const uint64_t* d0, const uint64_t* d1, const 
   });
 }
 
-// generalized PBS; bsk in device scale (2^-10).  lut may be null (CBS mode).
+void emu_pbs_variant(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, const C2* bsk_dev, int lwe_n,
+                     int log_chi, int log_v, int cbs_radix_log, int cbs_count, int transient, int chunked) {
+  auto fn = transient ? (chunked ? emu_pbs_t<true, true> : emu_pbs_t<true, false>)
+                      : (chunked ? emu_pbs_t<false, true> : emu_pbs_t<false, false>);
+  fn(glwe_out, lwe_in, lut, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count);
+}
 void emu_pbs(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, const C2* bsk_dev, int lwe_n,
              int log_chi, int log_v, int cbs_radix_log, int cbs_count) {
-  const Tables& t = tables();
-  std::vector<C2> xbuf(2 * kXBuf);
-  std::vector<uint64_t> acc(2 * kN);
-  PbsArgs A{lwe_in, lut, glwe_out, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count};
-  run_pair([&](HostPairCx& cx) {
-    pbs_pair_team(cx, A, acc.data(), xbuf.data(), t.T1.data(), t.T2.data());
-  });
+  emu_pbs_t<true, false>(glwe_out, lwe_in, lut, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count);
 }
 
 // the latency-mode (four-team) blind rotation

@@ -56,12 +56,10 @@ SPF_HD constexpr int bin_of(int u, int s) { return u + 64 * slot_row(s); }
 
 SPF_HD C2 cadd(C2 a, C2 b) { return C2{a.x + b.x, a.y + b.y}; }
 SPF_HD C2 csub(C2 a, C2 b) { return C2{a.x - b.x, a.y - b.y}; }
-// a * (c + i s)
-SPF_HD C2 cmul_cs(C2 a, double c, double s) { return C2{a.x * c - a.y * s, a.x * s + a.y * c}; }
-SPF_HD C2 cmul(C2 a, C2 b) { return C2{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
-SPF_HD C2 cmul_conj(C2 a, C2 b) { return C2{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }  // a * conj(b)
-// acc += a * b as four chained FMAs (written out: `acc += a.x*b.x - a.y*b.y` compiles to
-// DMUL + DFMA + DADD per component because floating-point adds are not reassociated)
+// Every multiply-add of the hot path is an EXPLICIT fma: the library is compiled with -fmad=false and
+// the host emulator with -ffp-contract=off, so neither compiler chooses which product of
+// `a*b - c*d` to fuse and the GPU and the emulator produce bit-identical doubles
+// (tests/test_gpu_parity.py::test_pbs_bit_exact_vs_emulator).
 SPF_HD double spf_fma(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)
   return fma(a, b, c);
@@ -69,6 +67,11 @@ SPF_HD double spf_fma(double a, double b, double c) {
   return __builtin_fma(a, b, c);
 #endif
 }
+// a * (c + i s)
+SPF_HD C2 cmul_cs(C2 a, double c, double s) { return C2{spf_fma(a.x, c, -(a.y * s)), spf_fma(a.x, s, a.y * c)}; }
+SPF_HD C2 cmul(C2 a, C2 b) { return C2{spf_fma(a.x, b.x, -(a.y * b.y)), spf_fma(a.x, b.y, a.y * b.x)}; }
+SPF_HD C2 cmul_conj(C2 a, C2 b) { return C2{spf_fma(a.x, b.x, a.y * b.y), spf_fma(a.y, b.x, -(a.x * b.y))}; }  // a * conj(b)
+// acc += a * b as four chained FMAs
 SPF_HD void cmad(C2& acc, C2 a, C2 b) {
   acc.x = spf_fma(-a.y, b.y, spf_fma(a.x, b.x, acc.x));
   acc.y = spf_fma(a.y, b.x, spf_fma(a.x, b.y, acc.y));

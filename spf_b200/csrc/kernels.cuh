@@ -77,9 +77,18 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #ifndef SPF_PBS_PAIRS
 #define SPF_PBS_PAIRS 3
 #endif
+#ifndef SPF_PBS_TRANSIENT
+#define SPF_PBS_TRANSIENT 1  // accumulator image in the exchange buffer (pbs_pair_team, Cx::kTransient): 33 KB per pair
+#endif
 constexpr int kPbsPairs = SPF_PBS_PAIRS;
-constexpr int kPbsPairBytes = 2 * kN * 8 + 2 * kXBuf * 16;            // acc + 2 exchange buffers = 66048
-constexpr int kPbsSmem = kTableBytes + kPbsPairs * kPbsPairBytes;      // 215616
+constexpr int kPbsPairBytes = (SPF_PBS_TRANSIENT ? 0 : 2 * kN * 8) + 2 * kXBuf * 16;  // [acc +] 2 exchange buffers
+// tensor-memory columns: [0,64) T1 | own coefficients 64 per pair | parked accumulators 64 per pair while they fit
+// in the 512 columns (| T2 block when SPF_PBS_TMEM_T2); pairs beyond that park their accumulators in shared memory
+constexpr int kPbsTmemOwn0 = 64;
+constexpr int kPbsTmemF0 = kPbsTmemOwn0 + 64 * kPbsPairs;
+constexpr int kPbsTmemFPairs = (512 - kPbsTmemF0) / 64 < kPbsPairs ? (512 - kPbsTmemF0) / 64 : kPbsPairs;
+constexpr int kPbsFParkBytes = (kPbsPairs - kPbsTmemFPairs) * 2 * kTeam * 16 * 16;  // 32 KiB per pair parked in smem
+constexpr int kPbsSmem = kTableBytes + kPbsPairs * kPbsPairBytes + kPbsFParkBytes;
 
 #ifndef SPF_PBS_TMEM_T1
 #define SPF_PBS_TMEM_T1 1   // pass-1 twiddles (per thread) in tensor memory
@@ -110,9 +119,17 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// TMEM columns: [0,64) T1, [64,128) T2 (shared by the three warps of a lane quarter, which have
-// the same thread-in-team index), [128 + 64 p, +64) own coefficients of pair p's warps.
 constexpr int kPbsTmemCols = 512;
+__device__ __forceinline__ void tmem_ld8(uint32_t (&r)[8], uint32_t taddr) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -121,11 +138,19 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+static_assert(!SPF_PBS_TRANSIENT || SPF_PBS_TMEM_OWN, "the transient accumulator image needs the tensor-memory own copy");
+#ifndef SPF_PBS_CHUNKED
+#define SPF_PBS_CHUNKED (SPF_PBS_PAIRS > 3)  // 128-register build: own coefficients / twiddles fetched in small chunks
+#endif
 struct DevPairCx {
+  static constexpr bool kTransient = SPF_PBS_TRANSIENT != 0;
+  static constexpr bool kChunked = SPF_PBS_CHUNKED != 0;
   int u, h;
   int bar_half, bar_pair;
-  uint32_t t1_taddr;   // this warp's lane quarter, column 0 of the T1 block (T2 block at +64)
-  uint32_t own_taddr;  // this warp's private 64 columns (accumulator stash: +192)
+  uint32_t t1_taddr;   // this warp's lane quarter, column 0 of the T1 block
+  uint32_t own_taddr;  // this warp's private 64 columns (own coefficients)
+  uint32_t f_taddr;    // this warp's 64 columns for the parked accumulators (unused when fpark != nullptr)
+  C2* fpark;           // shared-memory parking [16][128] of a pair whose accumulators do not fit in tensor memory
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar_half) : "memory"); }
   __device__ __forceinline__ void pair_sync() const { asm volatile("bar.sync %0, 128;" ::"r"(bar_pair) : "memory"); }
   // v[k1] *= T1[k1][u] (or its conjugate).  The 16 twiddles of a thread never change, so they sit
@@ -134,7 +159,20 @@ struct DevPairCx {
   // LSU pipe does not see.
   template <bool CONJ>
   __device__ __forceinline__ void t1_mul(C2 (&v)[16], const C2* T1) const {
-#if SPF_PBS_TMEM_T1
+#if SPF_PBS_TMEM_T1 && SPF_PBS_CHUNKED
+#pragma unroll
+    for (int g = 0; g < 4; g++) {  // 4 twiddles (16 registers) at a time
+      uint32_t r[16];
+      tmem_ld16(r, t1_taddr + 16 * g);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const C2 w{__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2])};
+        const int k = 4 * g + i;
+        v[k] = CONJ ? cmul_conj(v[k], w) : cmul(v[k], w);
+      }
+    }
+#elif SPF_PBS_TMEM_T1
 #pragma unroll
     for (int half = 0; half < 2; half++) {
       uint32_t r0[16], r1[16];
@@ -162,8 +200,8 @@ struct DevPairCx {
 #pragma unroll
     for (int half = 0; half < 2; half++) {
       uint32_t r0[16], r1[16];
-      tmem_ld16(r0, t1_taddr + 64 + 32 * half);
-      tmem_ld16(r1, t1_taddr + 64 + 32 * half + 16);
+      tmem_ld16(r0, t1_taddr + 448 + 32 * half);
+      tmem_ld16(r1, t1_taddr + 448 + 32 * half + 16);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -182,6 +220,11 @@ struct DevPairCx {
   }
   __device__ __forceinline__ void f_store(const C2 (&f)[2][8]) const {
 #if SPF_PBS_TMEM_F
+    if (fpark) {
+#pragma unroll
+      for (int c = 0; c < 16; c++) fpark[c * 2 * kTeam + h * kTeam + u] = f[c >> 3][c & 7];
+      return;
+    }
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       uint32_t r[16];
@@ -191,16 +234,21 @@ struct DevPairCx {
         r[4 * i] = (uint32_t)__double2loint(x.x); r[4 * i + 1] = (uint32_t)__double2hiint(x.x);
         r[4 * i + 2] = (uint32_t)__double2loint(x.y); r[4 * i + 3] = (uint32_t)__double2hiint(x.y);
       }
-      tmem_st16(own_taddr + 192 + 16 * c, r);
+      tmem_st16(f_taddr + 16 * c, r);
     }
     tmem_wait_st();
 #endif
   }
   __device__ __forceinline__ void f_load(C2 (&f)[2][8]) const {
 #if SPF_PBS_TMEM_F
+    if (fpark) {
+#pragma unroll
+      for (int c = 0; c < 16; c++) f[c >> 3][c & 7] = fpark[c * 2 * kTeam + h * kTeam + u];
+      return;
+    }
     uint32_t r[4][16];
 #pragma unroll
-    for (int c = 0; c < 4; c++) tmem_ld16(r[c], own_taddr + 192 + 16 * c);
+    for (int c = 0; c < 4; c++) tmem_ld16(r[c], f_taddr + 16 * c);
     tmem_wait_ld();
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -226,6 +274,35 @@ struct DevPairCx {
     for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
 #endif
   }
+  __device__ __forceinline__ void own_ld8(uint64_t (&o)[8], int c) const {
+    uint32_t r[16];
+    tmem_ld16(r, own_taddr + 16 * c);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = ((uint64_t)r[2 * i + 1] << 32) | r[2 * i];
+  }
+  __device__ __forceinline__ void own_ld4x2(uint64_t (&o)[8], int m4) const {
+    uint32_t a[8], b[8];
+    tmem_ld8(a, own_taddr + 2 * m4);
+    tmem_ld8(b, own_taddr + 2 * (m4 + 16));
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      o[i] = ((uint64_t)a[2 * i + 1] << 32) | a[2 * i];
+      o[4 + i] = ((uint64_t)b[2 * i + 1] << 32) | b[2 * i];
+    }
+  }
+  __device__ __forceinline__ void own_st4x2(const uint64_t (&o)[8], int m4) const {
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      a[2 * i] = (uint32_t)o[i]; a[2 * i + 1] = (uint32_t)(o[i] >> 32);
+      b[2 * i] = (uint32_t)o[4 + i]; b[2 * i + 1] = (uint32_t)(o[4 + i] >> 32);
+    }
+    tmem_st8(own_taddr + 2 * m4, a);
+    tmem_st8(own_taddr + 2 * (m4 + 16), b);
+  }
+  __device__ __forceinline__ void own_st_wait() const { tmem_wait_st(); }
   __device__ __forceinline__ void own_store(const uint64_t (&own)[32]) const {
 #if SPF_PBS_TMEM_OWN
 #pragma unroll
@@ -241,9 +318,9 @@ struct DevPairCx {
 };
 
 // Tensor-memory scratchpad of the pair / quad team kernels: one 512-column allocation per CTA.
-// Columns [0,64) pass-1 twiddles and [64,128) pass-2 twiddles of the thread (shared by the warps of
-// a lane quarter, which have the same thread-in-team index), [128 + 64 p, +64) and [320 + 64 p, +64)
-// private to the warps of pair p.  Returns this warp's lane-quarter base address.
+// Columns [0,64) pass-1 twiddles of the thread (shared by the warps of a lane quarter, which have the same
+// thread-in-team index), then the per-pair blocks of pbs_kernel (kPbsTmemOwn0, kPbsTmemF0); [448,512) pass-2
+// twiddles when SPF_PBS_TMEM_T2.  Returns this warp's lane-quarter base address.
 __device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2, uint32_t& alloc_base) {
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
@@ -265,12 +342,14 @@ __device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2,
       tmem_st4(t1_taddr + 4 * k1, (uint32_t)__double2loint(w.x), (uint32_t)__double2hiint(w.x),
                (uint32_t)__double2loint(w.y), (uint32_t)__double2hiint(w.y));
     }
+#if SPF_PBS_TMEM_T2
 #pragma unroll
     for (int k2 = 0; k2 < 16; k2++) {
       const C2 w = k2 ? sT2[(uu >> 4) * kT2Pad + k2] : C2{1.0, 0.0};
-      tmem_st4(t1_taddr + 64 + 4 * k2, (uint32_t)__double2loint(w.x), (uint32_t)__double2hiint(w.x),
+      tmem_st4(t1_taddr + 448 + 4 * k2, (uint32_t)__double2loint(w.x), (uint32_t)__double2hiint(w.x),
                (uint32_t)__double2loint(w.y), (uint32_t)__double2hiint(w.y));
     }
+#endif
     tmem_wait_st();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -307,9 +386,12 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   const int npairs = blockDim.x / (2 * kTeam);  // 1..kPbsPairs pairs per CTA (fewer for small batches)
   const int h = (threadIdx.x / kTeam) & 1;
   unsigned char* base = smem + kTableBytes + pair * kPbsPairBytes;
-  uint64_t* acc = reinterpret_cast<uint64_t*>(base);
-  C2* xb = reinterpret_cast<C2*>(base + 2 * kN * 8);
-  DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3, t1_taddr, t1_taddr + 128 + 64 * pair};
+  uint64_t* acc = reinterpret_cast<uint64_t*>(base);  // unused when SPF_PBS_TRANSIENT
+  C2* xb = reinterpret_cast<C2*>(base + (SPF_PBS_TRANSIENT ? 0 : 2 * kN * 8));
+  C2* fpark = pair < kPbsTmemFPairs ? nullptr
+                                    : reinterpret_cast<C2*>(smem + kTableBytes + kPbsPairs * kPbsPairBytes) + (pair - kPbsTmemFPairs) * 2 * kTeam * 16;
+  DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3, t1_taddr, t1_taddr + kPbsTmemOwn0 + 64 * pair,
+               t1_taddr + kPbsTmemF0 + 64 * (pair < kPbsTmemFPairs ? pair : 0), fpark};
   // Persistent pairs: slot (pair, CTA) takes ciphertexts slot, slot + slots, ...  Slots are numbered
   // pair-major so that a trailing partial round leaves at most one busy pair on as many SMs as
   // possible (a pair alone on an SM runs ~1.3x faster than one sharing it with two others).

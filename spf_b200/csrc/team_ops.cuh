@@ -351,8 +351,14 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
   const int n = A.lwe_n;
   const bool cbs = A.lut == nullptr;
   const int log2n = 12;  // log2(2N)
-  uint64_t* pa = acc + h * kN;  // the polynomial this half owns
   C2* xown = xb + h * kXBuf;
+  // Cx::kTransient: the accumulator polynomial of this half lives ONLY in the threads' own-coefficient copies
+  // (device: tensor memory); the shared-memory image the rotated gather reads is written into the half's exchange
+  // buffer at the end of a step and is dead once the digits have been taken, so a pair needs no persistent 32 KiB
+  // accumulator in shared memory (two more half-barriers per step: gather -> first exchange write, last exchange
+  // read -> image write).
+  constexpr bool kTr = Cx::kTransient;
+  uint64_t* pa = kTr ? reinterpret_cast<uint64_t*>(xown) : acc + h * kN;  // the polynomial this half owns
   // 1. acc = LUT * X^{-b~}   (programmable_bootstrapping.rs:378-390)
   {
     uint64_t b = ldg_u64(A.lwe_in + n);
@@ -377,10 +383,20 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
   uint64_t a_next = n > 0 ? ldg_u64(A.lwe_in) : 0;
   // own[i2] = pa[u + 64 i2]: the thread's own coefficients stay in registers from the accumulator
   // update of one step to the gather of the next (they are dead while the transforms run).
-  uint64_t own[32];
+  // Cx::kChunked (the 4-pairs-per-CTA build, 128 registers): they are instead fetched from the tensor-memory copy
+  // 8 (gather) or 4 + 4 (update) at a time, so neither phase holds all 32 next to a 16-point transform.
+  constexpr bool kCh = Cx::kChunked;
+  uint64_t own[kCh ? 8 : 32];
+  {
+    uint64_t o0[32];
 #pragma unroll
-  for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
-  cx.own_store(own);
+    for (int i2 = 0; i2 < 32; i2++) o0[i2] = pa[u + 64 * i2];
+    cx.own_store(o0);
+    if constexpr (!kCh) {
+#pragma unroll
+      for (int i2 = 0; i2 < 32; i2++) own[i2] = o0[i2];
+    }
+  }
 #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const int at = (int)modulus_switch(a_next, A.log_chi, A.log_v, log2n);
@@ -402,9 +418,12 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         const uint32_t bh9 = (uint32_t)(base >> 6) << 9;
 #pragma unroll
         for (int i2 = 0; i2 < 32; i2++) {
+          if constexpr (kCh) {
+            if ((i2 & 7) == 0) cx.own_ld8(own, i2 >> 3);  // own[0..7] = coefficients 8c .. 8c + 7
+          }
           const uint32_t t9 = bh9 + 512u * i2;  // bit 14 = negacyclic sign
           const uint64_t x = *reinterpret_cast<const uint64_t*>(col + (t9 & 0x3E00u));
-          const uint64_t diff = ((t9 & 0x4000u) ? 0 - x : x) - own[i2];
+          const uint64_t diff = ((t9 & 0x4000u) ? 0 - x : x) - own[kCh ? (i2 & 7) : i2];
           const uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
           const uint32_t w1 = w + 0x8000u;  // high half = second digit: (w >> 16) + carry of the first
           if (i2 < 16) { v[i2].x = digit_lo16_to_f64(w); pk[i2] = w1 >> 16; }
@@ -421,6 +440,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         fwd_pass1_core(v);
         cx.template t1_mul<false>(v, T1);  // v[k1] *= T1[k1][u]
         if (t == 1) cx.pair_sync();  // both halves have consumed the level-0 spectra
+        else if (kTr) cx.sync();     // every thread of the half has gathered from the accumulator image in xown
         fwd_x1_write(v, xown, u);
         cx.sync();
         fwd_x1_read(v, xown, u);
@@ -461,10 +481,11 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       inv_x1_write(w, xown, u);  // in place: no barrier after inv_x2_read
       cx.sync();
       inv_x1_read(w, xown, u);
+      if (kTr) cx.sync();  // xown becomes the accumulator image again
       cx.template t1_mul<true>(w, T1);  // w[k1] *= conj(T1[k1][u])
       double ws[16];
       inv_pass1_core_s(w, ws);  // true value ws[m] * w[m]: the untwist's real factor rides into the conversion
-      cx.own_load(own, pa);  // own[i2] = pa[u + 64 i2] (device: from the thread's tensor-memory copy)
+      if constexpr (!kCh) cx.own_load(own, pa);  // own[i2] = pa[u + 64 i2] (device: from the thread's tensor-memory copy)
       // The saturating-cast corner of the conversion (probability ~2^-53 per value) is tested once
       // per 8 values: the fast conversion only tracks the largest exponent word it saw.
 #pragma unroll
@@ -483,16 +504,30 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
             r[2 * i + 1] = f64_to_torus_s(w[m4 + i].y, ws[m4 + i]);
           }
         }
+        if constexpr (kCh) {
+          cx.own_ld4x2(own, m4);  // own[0..3] = coefficients m4 .. m4 + 3, own[4..7] = m4 + 16 .. m4 + 19
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int m = m4 + i, j = u + 64 * m;
-          own[m] += r[2 * i];
-          own[m + 16] += r[2 * i + 1];
-          pa[j] = own[m];
-          pa[j + kM] = own[m + 16];
+          for (int i = 0; i < 4; i++) {
+            const int j = u + 64 * (m4 + i);
+            own[i] += r[2 * i];
+            own[4 + i] += r[2 * i + 1];
+            pa[j] = own[i];
+            pa[j + kM] = own[4 + i];
+          }
+          cx.own_st4x2(own, m4);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int m = m4 + i, j = u + 64 * m;
+            own[m] += r[2 * i];
+            own[m + 16] += r[2 * i + 1];
+            pa[j] = own[m];
+            pa[j + kM] = own[m + 16];
+          }
         }
       }
-      cx.own_store(own);
+      if constexpr (kCh) cx.own_st_wait();
+      else cx.own_store(own);
     }
     cx.sync();  // next step gathers rotated coefficients written by other threads of this half
   }
@@ -501,6 +536,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     const int j = u + 64 * i;
     A.glwe_out[h * kN + j] = pa[j];
   }
+  if (kTr) cx.sync();  // the next ciphertext of this pair overwrites the image
 }
 
 // QUAD-TEAM blind rotation (latency mode, batches of at most one ciphertext per SM): one ciphertext

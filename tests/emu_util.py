@@ -27,6 +27,7 @@ def lib():
         l.emu_cmux_wide.argtypes = [_u64p, C.c_void_p, _u64p, _c64p, C.c_int, C.c_int]
         l.emu_pbs.argtypes = [_u64p, _u64p, C.c_void_p, _c64p] + [C.c_int] * 5
         l.emu_pbs_quad.argtypes = [_u64p, _u64p, C.c_void_p, _c64p] + [C.c_int] * 5
+        l.emu_pbs_variant.argtypes = [_u64p, _u64p, C.c_void_p, _c64p] + [C.c_int] * 7
         l.emu_trace_ss.argtypes = [_u64p, C.c_void_p, C.c_void_p, _c64p, _c64p] + [C.c_int] * 8
         l.emu_f64_to_torus.argtypes = [C.c_double]
         l.emu_f64_to_torus.restype = C.c_uint64
