@@ -138,12 +138,39 @@ class ClockSampler:
 # CPU baseline (the oracle port, all host threads) -- also the `--impl reference` arm
 # ---------------------------------------------------------------------------------------------
 def cpu_cbs_rate(keys, cts: np.ndarray, nthreads: int) -> tuple[float, float]:
+    """The timed CPU leg runs the FAST flavour of the oracle (oracle/libspf_oracle_fast.so: the same C restatement built
+    with -ffp-contract=fast and AVX2/FMA intrinsics for the FFT, the f64 -> torus conversion and the complex MAD), the
+    honest stand-in for the reference's +avx2,+fma build; the strict flavour stays the parity checker."""
     import oracle as O
 
     t0 = time.perf_counter()
-    O.circuit_bootstrap_batch(keys, cts, nthreads)
+    O.circuit_bootstrap_batch(keys, cts, nthreads, fast=True)
     dt = time.perf_counter() - t0
     return len(cts) / dt, dt
+
+
+CPU_KIND_NOTE = ("oracle/spf_oracle.c built -O3 -march=x86-64-v3 -ffp-contract=fast -DORC_FAST (AVX2/FMA radix-4 Stockham FFT, "
+                 "vectorised conversions and complex MADs): a C restatement of the reference CPU path with the reference's "
+                 "parallelisation model (one single-threaded op per task over all host threads); the Rust reference itself "
+                 "cannot be built in this image")
+
+
+def cpu_micro(keys, cts: np.ndarray) -> dict:
+    """Single-thread figures printed beside the CPU baseline so its class is visible: us per 1024-point (N = 2048)
+    forward transform and ms per circuit bootstrap on one core, fast and strict flavours."""
+    import oracle as O
+
+    out = {}
+    for name, fast in (("fast", True), ("strict", False)):
+        out[f"fft1024_us_{name}"] = 1e6 * O.lib(fast).orc_bench_fft_forward(2048, 20000)
+    O.circuit_bootstrap_batch(keys, cts[:1], 1, fast=True)
+    t0 = time.perf_counter()
+    O.circuit_bootstrap_batch(keys, cts[:2], 1, fast=True)
+    out["single_thread_ms_per_cbs_fast"] = 1e3 * (time.perf_counter() - t0) / 2
+    t0 = time.perf_counter()
+    O.circuit_bootstrap_batch(keys, cts[:1], 1, fast=False)
+    out["single_thread_ms_per_cbs_strict"] = 1e3 * (time.perf_counter() - t0)
+    return out
 
 
 def cpu_sample_size(rate: float, nt: int, batch: int, seconds: float = 10.0) -> int:
@@ -179,9 +206,7 @@ def run_reference(args):
         "config": {"workload": f"cbs_batch{args.batch}_default128 (bounded sample of {sample} CBS per step)",
                    "params": "DEFAULT_128", "batch_per_gpu": args.batch},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port",
-                         "sample": f"{sample} CBS per step x {args.steps} steps, oracle/spf_oracle.c (C restatement of "
-                                   "the reference CPU path; rustfft replaced by an in-tree radix-4 FFT), one op per "
-                                   "thread over all host threads"},
+                         "sample": f"{sample} CBS per step x {args.steps} steps; " + CPU_KIND_NOTE, **cpu_micro(keys, cts)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,7 +220,7 @@ def cpu_add_latency(keys, a_bits, b_bits, nthreads):
 
     import oracle as O
 
-    l = O.lib()
+    l = O.lib(fast=True)
     p = keys.params
     w = len(a_bits)
     t0 = time.perf_counter()
@@ -203,7 +228,7 @@ def cpu_add_latency(keys, a_bits, b_bits, nthreads):
     l1 = np.stack([O.sample_extract(keys, g, 0) for g in glwes])
     l0 = np.zeros((2 * w, keys.lwe0_len), dtype=np.uint64)
     l.orc_keyswitch_lwe_batch(l0, l1, 2 * w, keys.ksk, C.byref(p), nthreads)
-    ggsw = O.circuit_bootstrap_batch(keys, l0, nthreads)
+    ggsw = O.circuit_bootstrap_batch(keys, l0, nthreads, fast=True)
     sa, sb = ggsw[:w], ggsw[w:]
     zero = np.zeros(keys.glwe_len, dtype=np.uint64)
     one = zero.copy()
@@ -237,7 +262,7 @@ def cpu_run_graph(keys, circ, nthreads):
     import spf_b200
     from spf_b200 import OPS
 
-    l = O.lib()
+    l = O.lib(fast=True)
     p = keys.params
     level, _ = spf_b200.plan_graph(circ, 1)
     groups = {}
@@ -266,7 +291,7 @@ def cpu_run_graph(keys, circ, nthreads):
             for k, v in enumerate(ids):
                 val[v] = out[k]
         elif op == "CircuitBootstrap":
-            out = O.circuit_bootstrap_batch(keys, np.stack([val[i[0]] for i in ins]), min(nthreads, len(ids)))
+            out = O.circuit_bootstrap_batch(keys, np.stack([val[i[0]] for i in ins]), min(nthreads, len(ids)), fast=True)
             for k, v in enumerate(ids):
                 val[v] = out[k]
         elif op == "CMux":
@@ -603,9 +628,8 @@ def run_gpu(args):
             sample = args.cpu_sample or cpu_sample_size(rate0, nt, B)
             rate, dt = cpu_cbs_rate(keys, cts[: min(sample, B)], nt)
             cpu_baseline = {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
-                            "sample": f"{min(sample, B)} CBS of the same workload in {dt:.1f} s, oracle/spf_oracle.c "
-                                      "(C restatement of the reference CPU path), one single-threaded op per task over "
-                                      "all host threads"}
+                            "sample": f"{min(sample, B)} CBS of the same workload in {dt:.1f} s; " + CPU_KIND_NOTE,
+                            **cpu_micro(keys, cts)}
 
     # ---- Parasol add latency (the metric's second half): encrypted w-bit add through the graph
     #      executor (16/64 x SampleExtract -> Keyswitch -> CBS, then the ripple-carry MUX tree) ------

@@ -51,19 +51,31 @@ def build(force: bool = False) -> str:
     """Compile the oracle library if missing (or stale)."""
     src = os.path.join(_HERE, "spf_oracle.c")
     hdr = os.path.join(_HERE, "spf_oracle.h")
-    stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in (src, hdr)
-    )
+    fast = os.path.join(_HERE, "libspf_oracle_fast.so")
+    srcs = (src, hdr, os.path.join(_HERE, "fft_avx2.h"))
+    stale = any((not os.path.exists(l)) or any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(l) for f in srcs)
+                for l in (_LIB_PATH, fast))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 
 _lib = None
+_fast_lib = None
+_FAST_LIB_PATH = os.path.join(_HERE, "libspf_oracle_fast.so")
 
 
-def lib() -> C.CDLL:
-    global _lib
+def lib(fast: bool = False) -> C.CDLL:
+    """The oracle library.  fast=True: the AVX2/FMA build of the same source (-DORC_FAST, see spf_oracle.c header),
+    used ONLY as the timed CPU baseline of bench.py (cpu_baseline / --impl reference); every parity check uses the
+    strict build."""
+    global _lib, _fast_lib
+    if fast:
+        if _fast_lib is None:
+            build()
+            _fast_lib = C.CDLL(_FAST_LIB_PATH)
+            _declare(_fast_lib)
+        return _fast_lib
     if _lib is None:
         build()
         _lib = C.CDLL(_LIB_PATH)
@@ -142,6 +154,8 @@ def _declare(l):
     l.orc_ggsw_fft.argtypes = [_c64p, _u64p, _PP, Radix]
     l.orc_ggsw_ifft.argtypes = [_u64p, _c64p, _PP, Radix]
     l.orc_hw_threads.restype = C.c_int
+    l.orc_bench_fft_forward.argtypes = [C.c_uint32, C.c_int]
+    l.orc_bench_fft_forward.restype = C.c_double
 
 
 def default_128() -> Params:
@@ -386,11 +400,11 @@ def circuit_bootstrap(keys: Keys, lwe0: np.ndarray) -> np.ndarray:
     return out
 
 
-def circuit_bootstrap_batch(keys: Keys, lwe0: np.ndarray, nthreads: int | None = None) -> np.ndarray:
+def circuit_bootstrap_batch(keys: Keys, lwe0: np.ndarray, nthreads: int | None = None, fast: bool = False) -> np.ndarray:
     lwe0 = np.ascontiguousarray(lwe0, dtype=np.uint64)
     b = lwe0.shape[0]
     out = np.zeros((b, keys.ggsw_fft_len), dtype=np.complex128)
-    lib().orc_circuit_bootstrap_batch(out, lwe0, b, keys.bsk_fft, keys.ak_fft, keys.ssk_fft,
+    lib(fast).orc_circuit_bootstrap_batch(out, lwe0, b, keys.bsk_fft, keys.ak_fft, keys.ssk_fft,
                                       C.byref(keys.params), nthreads or hw_threads())
     return out
 

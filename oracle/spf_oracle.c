@@ -5,15 +5,27 @@
  *
  * Not a copy: the reference is Rust over flat "dst" arrays with iterator adaptors; this is
  * index arithmetic over the same flat layouts.  The complex FFT butterflies are this file's
- * own radix-2 (the reference calls the un-vendored crate rustfft 6.3.0), so FFT-domain
+ * own radix-4 Stockham (the reference calls the un-vendored crate rustfft 6.3.0), so FFT-domain
  * values agree with the reference to f64 rounding, not bit-for-bit.
+ *
+ * Two builds of this file (oracle/Makefile):
+ *   libspf_oracle.so       -ffp-contract=off, plain C: THE ORACLE (parity checker, keygen, decrypt).
+ *   libspf_oracle_fast.so  -DORC_FAST -ffp-contract=fast + AVX2/FMA intrinsics (fft_avx2.h) for the FFT, the
+ *                          f64 -> torus conversion and the complex MAD: the CPU BASELINE bench.py times, a stand-in
+ *                          for the reference's +avx2,+fma build (/root/reference/.cargo/config.toml) with rustfft and
+ *                          hand-vectorised MADs (math/simd/x86_64/avx512.rs:15-79).  Same algorithm, same call graph;
+ *                          tests/test_oracle_fast.py checks it against the strict build.
  */
 #include "spf_oracle.h"
+#ifdef ORC_FAST
+#include "fft_avx2.h"
+#endif
 
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 typedef uint64_t u64;
@@ -75,6 +87,11 @@ typedef struct {
   uint32_t m;       /* complex length N/2       */
   c64 *twist;       /* e^{2 pi i j / 2N}, j<m   (mod.rs:58-66) */
   double *wr, *wi;  /* e^{-2 pi i j / m}, j<m   (forward complex DFT twiddles, split) */
+#ifdef ORC_FAST
+  int fast;         /* m is a power of 4 >= 16: the AVX2 transform applies */
+  orc_fastplan fp;
+  double *twr, *twi; /* twist, split */
+#endif
 } orc_plan;
 
 static orc_plan g_plans[ORC_MAX_LOGN + 1];
@@ -95,6 +112,15 @@ static void build_plans(void) {
       long double a2 = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)m;
       pl->wr[j] = (double)cosl(a2); pl->wi[j] = (double)sinl(a2);
     }
+#ifdef ORC_FAST
+    pl->fast = orc_fast_ok(m);
+    if (pl->fast) {
+      orc_fastplan_build(&pl->fp, m, pl->wr, pl->wi);
+      pl->twr = (double *)aligned_alloc(64, sizeof(double) * m);
+      pl->twi = (double *)aligned_alloc(64, sizeof(double) * m);
+      for (uint32_t j = 0; j < m; j++) { pl->twr[j] = pl->twist[j].re; pl->twi[j] = pl->twist[j].im; }
+    }
+#endif
   }
 }
 
@@ -173,7 +199,16 @@ void orc_fft_forward(const double *x, c64 *out, uint32_t n) {
   const orc_plan *pl = get_plan(n);
   uint32_t m = pl->m;
   if (m == 0) return;
-  double xr[2048], xi[2048], yr[2048], yi[2048];
+  double xr[2048] __attribute__((aligned(64))), xi[2048] __attribute__((aligned(64))), yr[2048] __attribute__((aligned(64))),
+      yi[2048] __attribute__((aligned(64)));
+#ifdef ORC_FAST
+  if (pl->fast) {
+    orc_twist_avx2(x, pl->twr, pl->twi, xr, xi, m);
+    const int in_y = orc_cfft_avx2(xr, xi, yr, yi, &pl->fp);
+    orc_interleave_avx2(in_y ? yr : xr, in_y ? yi : xi, (double *)out, m);
+    return;
+  }
+#endif
   for (uint32_t j = 0; j < m; j++) {
     double re = x[j], im = x[j + m];
     c64 t = pl->twist[j];
@@ -190,10 +225,21 @@ void orc_fft_reverse(const c64 *in, double *out, uint32_t n) {
   const orc_plan *pl = get_plan(n);
   uint32_t m = pl->m;
   if (m == 0) return;
-  double xr[2048], xi[2048], yr[2048], yi[2048];
+  double xr[2048] __attribute__((aligned(64))), xi[2048] __attribute__((aligned(64))), yr[2048] __attribute__((aligned(64))),
+      yi[2048] __attribute__((aligned(64)));
+  double n_inv = 1.0 / (double)m;
+#ifdef ORC_FAST
+  if (pl->fast) {
+    orc_deinterleave_avx2((const double *)in, xr, xi, m);
+    /* inverse = forward on swapped re / im (the result comes back swapped again, i.e. in place) */
+    const int in_y = orc_cfft_avx2(xi, xr, yi, yr, &pl->fp);
+    const double *rr = in_y ? yr : xr, *ri = in_y ? yi : xi;
+    orc_untwist_round_avx2(rr, ri, pl->twr, pl->twi, n_inv, out, m);
+    return;
+  }
+#endif
   for (uint32_t j = 0; j < m; j++) { xr[j] = in[j].re; xi[j] = in[j].im; }
   cfft_split(xr, xi, yr, yi, pl, 1);
-  double n_inv = 1.0 / (double)m;
   for (uint32_t j = 0; j < m; j++) {
     /* tmp = x * n_inv * twist_inv[j]; twist_inv = twist^-1 = conj(twist) (unit modulus) */
     double ar = xr[j] * n_inv, ai = xi[j] * n_inv;
@@ -205,7 +251,11 @@ void orc_fft_reverse(const c64 *in, double *out, uint32_t n) {
 
 /* PolynomialRef::fft (entities/polynomial.rs:257-274): u64 -> i64 -> f64, then forward. */
 void orc_poly_fft(const u64 *p, c64 *out, uint32_t n) {
-  double stackx[4096];
+  double stackx[4096] __attribute__((aligned(64)));
+#ifdef ORC_FAST
+  if (n % 4 == 0) orc_i64_to_f64_avx2(stackx, p, n);
+  else
+#endif
   for (uint32_t j = 0; j < n; j++) stackx[j] = (double)(i64)p[j];
   orc_fft_forward(stackx, out, n);
 }
@@ -213,6 +263,9 @@ void orc_poly_fft(const u64 *p, c64 *out, uint32_t n) {
 /* simd/scalar.rs:75-119 vector_mod_pow2_q_f64 with log2_q = 64, and torus.rs:177-186
  * FromF64 (`x as i64` is a saturating cast in Rust). */
 void orc_mod_pow2_q_f64(u64 *c, const double *a, size_t len) {
+#ifdef ORC_FAST
+  if (len % 4 == 0 && orc_mod_pow2_64_avx2(c, a, len) == 0) return;  /* else: redo everything the reference way */
+#endif
   const double q = 18446744073709551616.0;       /* 2^64 */
   const double q_div_2 = 9223372036854775808.0;  /* 2^63 */
   for (size_t j = 0; j < len; j++) {
@@ -295,12 +348,14 @@ void orc_poly_mul_monomial(u64 *p, uint32_t n, i64 degree) {
   memcpy(tmp, p, sizeof(u64) * n);
   if (!negative) {
     /* rotate_right(shift); negate [0,degree) if degree<N else [shift,N) */
-    for (uint32_t j = 0; j < n; j++) p[j] = tmp[(j + n - shift) % n];
+    memcpy(p + shift, tmp, sizeof(u64) * (n - shift));
+    memcpy(p, tmp + (n - shift), sizeof(u64) * shift);
     uint32_t lo = deg < n ? 0 : shift, hi = deg < n ? (uint32_t)deg : n;
     for (uint32_t j = lo; j < hi; j++) p[j] = (u64)0 - p[j];
   } else {
     /* rotate_left(shift); negate [N-shift,N) if degree<N else [0,N-shift) */
-    for (uint32_t j = 0; j < n; j++) p[j] = tmp[(j + shift) % n];
+    memcpy(p, tmp + shift, sizeof(u64) * (n - shift));
+    memcpy(p + (n - shift), tmp, sizeof(u64) * shift);
     uint32_t lo = deg < n ? n - shift : 0, hi = deg < n ? n : n - shift;
     for (uint32_t j = lo; j < hi; j++) p[j] = (u64)0 - p[j];
   }
@@ -334,6 +389,9 @@ void orc_generate_lut(u64 *c, const u64 *table, uint32_t v, uint32_t n, uint32_t
 
 /* simd/scalar.rs:12-16 complex_mad: c += a*b */
 static void complex_mad(c64 *c, const c64 *a, const c64 *b, uint32_t len) {
+#ifdef ORC_FAST
+  if (len % 2 == 0) { orc_complex_mad_avx2((double *)c, (const double *)a, (const double *)b, len); return; }
+#endif
   for (uint32_t j = 0; j < len; j++) {
     c[j].re += a[j].re * b[j].re - a[j].im * b[j].im;
     c[j].im += a[j].re * b[j].im + a[j].im * b[j].re;
@@ -886,4 +944,18 @@ void orc_keygen_compute(orc_rng *g, const u64 *lwe0_sk, const u64 *glwe1_sk, c64
     }
     free(sk_k); free(ct); free(scaled);
   }
+}
+
+/* Seconds per forward negacyclic transform of degree n on this core (bench.py prints it next to the CPU baseline so the
+ * FFT class of the baseline is visible: rustfft-class is 2-4 us at n = 2048). */
+double orc_bench_fft_forward(uint32_t n, int iters) {
+  double x[4096] __attribute__((aligned(64)));
+  c64 f[2048];
+  for (uint32_t j = 0; j < n; j++) x[j] = (double)((j * 7919u) % 65536u) - 32768.0;
+  struct timespec t0, t1;
+  orc_fft_forward(x, f, n);
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int i = 0; i < iters; i++) { x[0] = (double)i; orc_fft_forward(x, f, n); }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return ((double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec)) / (double)iters + 0.0 * f[1].re;
 }

@@ -144,6 +144,7 @@ void orc_ggsw_fft(orc_c64 *out, const uint64_t *ggsw, const orc_params *p, orc_r
 void orc_ggsw_ifft(uint64_t *out, const orc_c64 *ggsw_fft, const orc_params *p, orc_radix r);
 
 int orc_hw_threads(void);
+double orc_bench_fft_forward(uint32_t n, int iters); /* seconds per forward transform on this core */
 
 #ifdef __cplusplus
 }

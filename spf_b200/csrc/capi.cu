@@ -175,7 +175,8 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
   }
   CUB(cudaFuncSetAttribute(pbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPbsSmem));
   CUB(cudaFuncSetAttribute(pbs_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadSmem));
-  CUB(cudaFuncSetAttribute(trace_ss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
+  CUB(cudaFuncSetAttribute(trace_ss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
+  CUB(cudaFuncSetAttribute(trace_ss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
   CUB(cudaFuncSetAttribute(cmux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCmuxSmem));
   CUB(cudaFuncSetAttribute(cmux_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideSmem));
   {
@@ -275,6 +276,26 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
     pbs_quad_kernel<<<(int)batch, 4 * kTeam, kQuadSmem, s>>>(P, tabs(ctx));
     return check_launch(ctx, "pbs_quad_kernel");
   }
+  // Tail wave: a batch is a whole number of waves (sm_count x kPbsPairs ciphertexts) plus a remainder.  A remainder of
+  // at most one ciphertext per SM would run as one pair per SM after everything else has finished (5.1 ms for e.g. the
+  // last 100 of 4096 ciphertexts); the four-team latency kernel does the same work in 3.5 ms, so the remainder goes
+  // there (same stream, right behind the full waves).  SPF_B200_PBS_TAIL=pair keeps everything on the pair kernel.
+  static const bool quad_tail = [] { const char* e = getenv("SPF_B200_PBS_TAIL"); return !(e && !strcmp(e, "pair")); }();
+  const size_t wave = (size_t)ctx->sm_count * kPbsPairs;
+  const size_t rem = batch % wave;
+  if (quad_tail && batch > wave && rem > 0 && rem <= (size_t)ctx->sm_count && !P.lut_stride) {
+    const size_t full = batch - rem;
+    P.batch = (int)full;
+    pbs_kernel<<<ctx->sm_count, kPbsPairs * 2 * kTeam, kPbsSmem, s>>>(P, tabs(ctx));
+    if (int rc = check_launch(ctx, "pbs_kernel")) return rc;
+    PbsBatch T = P;
+    T.batch = (int)rem;
+    T.glwe_out = d_glwe_out + full * 2 * kN;
+    if (ptrs) T.ptrs = ptrs + full;
+    else T.lwe_in = d_lwe_in + full * (size_t)(P.lwe_n + 1);
+    pbs_quad_kernel<<<(int)rem, 4 * kTeam, kQuadSmem, s>>>(T, tabs(ctx));
+    return check_launch(ctx, "pbs_quad_kernel");
+  }
   const int per = per_cta(ctx, batch, kPbsPairs);
   const int grid = (int)std::min<size_t>((batch + per - 1) / per, (size_t)ctx->sm_count);  // persistent pairs
   pbs_kernel<<<grid, per * 2 * kTeam, kPbsSmem, s>>>(P, tabs(ctx));
@@ -308,7 +329,8 @@ int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_gl
   const size_t items = batch * (size_t)levels;
   const int per = per_cta(ctx, items, kTrTeams);
   const int grid = (int)((items + per - 1) / per);
-  trace_ss_kernel<<<grid, per * kTeam, kTableBytes + per * kTrTeamBytes, s>>>(P, tabs(ctx));
+  if (P.peers.n > 0) trace_ss_kernel<true><<<grid, per * kTeam, kTableBytes + per * kTrTeamBytes, s>>>(P, tabs(ctx));
+  else trace_ss_kernel<false><<<grid, per * kTeam, kTableBytes + per * kTrTeamBytes, s>>>(P, tabs(ctx));
   return check_launch(ctx, "trace_ss_kernel");
 }
 

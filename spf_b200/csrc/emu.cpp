@@ -48,6 +48,28 @@ struct HostPairCxT {
     const int q = u >> 4;
     for (int k2 = 1; k2 < 16; k2++) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
   }
+  static constexpr bool kBskRing = false;   // the ring is device machinery: the host reads the key in place
+  const C2* bsk_acquire(int, const C2* g) { return g; }
+  void bsk_release(int) {}
+  void bsk_skip(int) {}
+  C2 bsk_load(const C2* p) { return *p; }
+  static constexpr bool kFusedStores = CH;  // exercised together with the chunked variant
+  void sts(C2* p, C2 v) { *p = v; }
+  template <bool CONJ>
+  void t1_mul_store(C2 (&v)[16], const C2* T1, C2* buf) {
+    for (int k1 = 0; k1 < 16; k1++) {
+      v[k1] = CONJ ? cmul_conj(v[k1], T1[k1 * 64 + u]) : cmul(v[k1], T1[k1 * 64 + u]);
+      buf[k1 * kXPad + u] = v[k1];
+    }
+  }
+  template <bool CONJ>
+  void t2_mul_store(C2 (&v)[16], const C2* T2, C2* buf) {
+    const int k1 = u & 15, q = u >> 4;
+    for (int k2 = 0; k2 < 16; k2++) {
+      if (k2) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
+      buf[k1 * kXPad + q + 4 * k2] = v[k2];
+    }
+  }
   // the device keeps a private copy of the thread's own accumulator coefficients in tensor memory
   uint64_t own_stash[32];
   void own_load(uint64_t (&own)[32], const uint64_t*) { memcpy(own, own_stash, sizeof(own_stash)); }
@@ -224,7 +246,10 @@ void emu_pbs_t(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, 
   std::vector<uint64_t> acc(2 * kN);
   PbsArgs A{lwe_in, lut, glwe_out, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count};
   using Cx = HostPairCxT<TR, CH>;
-  run_pair<Cx>([&](Cx& cx) { pbs_pair_team(cx, A, acc.data(), xbuf.data(), t.T1.data(), t.T2.data()); });
+  run_pair<Cx>([&](Cx& cx) {
+    int G = 0;
+    pbs_pair_team(cx, A, acc.data(), xbuf.data(), t.T1.data(), t.T2.data(), G);
+  });
 }
 }  // namespace
 

@@ -37,6 +37,25 @@ struct alignas(16) C2 {
   double x, y;
 };
 
+// SPF_ABL (experiment builds only, tools/ablate.sh): bit mask of kernel components replaced by no-ops to measure what the
+// blind-rotation kernel's time is sensitive to: 1 butterflies, 2 complex multiplies / MADs, 4 exchange-buffer traffic,
+// 8 barriers, 16 key loads, 32 accumulator gather, 64 f64 -> torus conversion.  Results are garbage by construction.
+#if defined(SPF_ABL) && defined(__CUDA_ARCH__)
+#define SPF_ABLATE(bit) ((SPF_ABL) & (bit))
+#else
+#define SPF_ABLATE(bit) 0
+#endif
+SPF_HD C2 abl_mix(C2 a, C2 b) {
+  C2 r;
+#if defined(__CUDA_ARCH__)
+  r.x = __longlong_as_double(__double_as_longlong(a.x) ^ __double_as_longlong(b.x));
+  r.y = __longlong_as_double(__double_as_longlong(a.y) ^ __double_as_longlong(b.y));
+#else
+  r = a; (void)b;
+#endif
+  return r;
+}
+
 constexpr int kN = 2048;        // polynomial degree (DEFAULT_128 l1_params)
 constexpr int kM = 1024;        // complex FFT length
 constexpr int kTeam = 64;       // threads per polynomial transform
@@ -68,11 +87,18 @@ SPF_HD double spf_fma(double a, double b, double c) {
 #endif
 }
 // a * (c + i s)
-SPF_HD C2 cmul_cs(C2 a, double c, double s) { return C2{spf_fma(a.x, c, -(a.y * s)), spf_fma(a.x, s, a.y * c)}; }
-SPF_HD C2 cmul(C2 a, C2 b) { return C2{spf_fma(a.x, b.x, -(a.y * b.y)), spf_fma(a.x, b.y, a.y * b.x)}; }
-SPF_HD C2 cmul_conj(C2 a, C2 b) { return C2{spf_fma(a.x, b.x, a.y * b.y), spf_fma(a.y, b.x, -(a.x * b.y))}; }  // a * conj(b)
+SPF_HD C2 cmul_cs(C2 a, double c, double s) {
+  if (SPF_ABLATE(2)) return abl_mix(a, C2{c, s});
+  return C2{spf_fma(a.x, c, -(a.y * s)), spf_fma(a.x, s, a.y * c)}; }
+SPF_HD C2 cmul(C2 a, C2 b) {
+  if (SPF_ABLATE(2)) return abl_mix(a, b);
+  return C2{spf_fma(a.x, b.x, -(a.y * b.y)), spf_fma(a.x, b.y, a.y * b.x)}; }
+SPF_HD C2 cmul_conj(C2 a, C2 b) {
+  if (SPF_ABLATE(2)) return abl_mix(a, b);
+  return C2{spf_fma(a.x, b.x, a.y * b.y), spf_fma(a.y, b.x, -(a.x * b.y))}; }  // a * conj(b)
 // acc += a * b as four chained FMAs
 SPF_HD void cmad(C2& acc, C2 a, C2 b) {
+  if (SPF_ABLATE(2)) { acc = abl_mix(acc, abl_mix(a, b)); return; }
   acc.x = spf_fma(-a.y, b.y, spf_fma(a.x, b.x, acc.x));
   acc.y = spf_fma(a.y, b.x, spf_fma(a.x, b.y, acc.y));
 }
@@ -80,6 +106,7 @@ SPF_HD void cmad(C2& acc, C2 a, C2 b) {
 // 4-point DFT in place: (a,b,c,d) -> (X0,X1,X2,X3); INV uses e^{+...}
 template <bool INV>
 SPF_HD void bfly4(C2& a, C2& b, C2& c, C2& d) {
+  if (SPF_ABLATE(1)) return;
   C2 apc = cadd(a, c), amc = csub(a, c), bpd = cadd(b, d), bmd = csub(b, d);
   a = cadd(apc, bpd);
   c = csub(apc, bpd);
@@ -105,6 +132,7 @@ SPF_HD void bfly4(C2& a, C2& b, C2& c, C2& d) {
 SPF_HD constexpr double spf_abs(double x) { return x < 0 ? -x : x; }
 // (v, s) *= e^{i pi e / 32}
 SPF_HD void rot_s(C2& v, double& s, int e) {
+  if (SPF_ABLATE(1)) return;
   e &= 63;
   if (e == 0) return;
   const double c = spf_cos32(e), sn = spf_sin32(e);
@@ -121,6 +149,7 @@ SPF_HD void rot_s(C2& v, double& s, int e) {
 // 4-point DFT of (a, sa) .. (d, sd); all four results carry scale sa.
 template <bool INV>
 SPF_HD void bfly4_s(C2& a, C2& b, C2& c, C2& d, double sa, double sb, double sc, double sd) {
+  if (SPF_ABLATE(1)) return;
   const double rc = sc / sa, rd = sd / sb, rb = sb / sa;
   const C2 apc{spf_fma(rc, c.x, a.x), spf_fma(rc, c.y, a.y)}, amc{spf_fma(-rc, c.x, a.x), spf_fma(-rc, c.y, a.y)};
   const C2 bpd{spf_fma(rd, d.x, b.x), spf_fma(rd, d.y, b.y)}, bmd{spf_fma(-rd, d.x, b.x), spf_fma(-rd, d.y, b.y)};
@@ -171,6 +200,34 @@ SPF_HD void dft16_s(C2 (&v)[16], double (&s)[16]) {
     for (int kh = 0; kh < 4; kh++) { v[kl + 4 * kh] = t[4 * kl + kh]; s[kl + 4 * kh] = ts[4 * kl + kh]; }
   }
 }
+// The same transform with unit input scales, handing every output to emit(k, X[k]) as soon as its last butterfly is
+// done (the caller stores it to the exchange buffer right there, so the stores interleave with the remaining
+// butterflies instead of queueing behind them); v is left in the internal order.
+template <bool INV, class Emit>
+SPF_HD void dft16_emit(C2 (&v)[16], Emit emit) {
+  double s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = 1.0;
+#pragma unroll
+  for (int m0 = 0; m0 < 4; m0++) {
+    bfly4_s<INV>(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12], s[m0], s[m0 + 4], s[m0 + 8], s[m0 + 12]);
+    s[m0 + 4] = s[m0 + 8] = s[m0 + 12] = s[m0];
+  }
+#pragma unroll
+  for (int m0 = 1; m0 < 4; m0++) {
+#pragma unroll
+    for (int kl = 1; kl < 4; kl++) {
+      const int e = 4 * m0 * kl;
+      rot_s(v[m0 + 4 * kl], s[m0 + 4 * kl], INV ? e : 64 - e);
+    }
+  }
+#pragma unroll
+  for (int kl = 0; kl < 4; kl++) {
+    bfly4_s<INV>(v[4 * kl], v[4 * kl + 1], v[4 * kl + 2], v[4 * kl + 3], s[4 * kl], s[4 * kl + 1], s[4 * kl + 2], s[4 * kl + 3]);
+#pragma unroll
+    for (int kh = 0; kh < 4; kh++) emit(kl + 4 * kh, v[4 * kl + kh]);  // scale s[4 kl] == 1
+  }
+}
 template <bool INV>
 SPF_HD void dft16(C2 (&v)[16]) {
   double s[16];
@@ -197,10 +254,12 @@ SPF_HD void fwd_pass1(C2 (&v)[16], int a, const C2* T1) {
   for (int k1 = 0; k1 < 16; k1++) v[k1] = cmul(v[k1], T1[k1 * 64 + a]);
 }
 SPF_HD void fwd_x1_write(const C2 (&v)[16], C2* buf, int a) {
+  if (SPF_ABLATE(4)) return;
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1++) buf[k1 * kXPad + a] = v[k1];
 }
 SPF_HD void fwd_x1_read(C2 (&v)[16], const C2* buf, int u) {
+  if (SPF_ABLATE(4)) return;
   const int k1 = u & 15, q = u >> 4;
 #pragma unroll
   for (int mp = 0; mp < 16; mp++) v[mp] = buf[k1 * kXPad + q + 4 * mp];
@@ -216,11 +275,13 @@ SPF_HD void fwd_pass2(C2 (&v)[16], int u, const C2* T2) {
 // write (each thread only overwrites what it alone consumed).  The reader of pass 3, thread
 // (k1, q), finds z of thread (k1, q') for k2 = q + 4 j at column q' + 4 q + 16 j of row k1.
 SPF_HD void fwd_x2_write(const C2 (&v)[16], C2* buf, int u) {
+  if (SPF_ABLATE(4)) return;
   const int k1 = u & 15, q = u >> 4;
 #pragma unroll
   for (int k2 = 0; k2 < 16; k2++) buf[k1 * kXPad + q + 4 * k2] = v[k2];
 }
 SPF_HD void fwd_x2_read(C2 (&v)[16], const C2* buf, int u) {
+  if (SPF_ABLATE(4)) return;
   const int k1 = u & 15, q = u >> 4;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -245,6 +306,7 @@ SPF_HD void inv_pass3(C2 (&v)[16]) {
 // Inverse direction, same in-place layout: inv_x2_read takes the 16 locations (row k1, column
 // q + 4 k2) that inv_x1_write of the same thread overwrites next, so no barrier separates them.
 SPF_HD void inv_x2_write(const C2 (&v)[16], C2* buf, int u) {
+  if (SPF_ABLATE(4)) return;
   const int k1 = u & 15, q = u >> 4;
 #pragma unroll
   for (int j = 0; j < 4; j++) {
@@ -253,6 +315,7 @@ SPF_HD void inv_x2_write(const C2 (&v)[16], C2* buf, int u) {
   }
 }
 SPF_HD void inv_x2_read(C2 (&v)[16], const C2* buf, int u) {
+  if (SPF_ABLATE(4)) return;
   const int k1 = u & 15, q = u >> 4;
 #pragma unroll
   for (int k2 = 0; k2 < 16; k2++) v[k2] = buf[k1 * kXPad + q + 4 * k2];
@@ -264,11 +327,13 @@ SPF_HD void inv_pass2(C2 (&v)[16], int u, const C2* T2) {
   dft16<true>(v);
 }
 SPF_HD void inv_x1_write(const C2 (&v)[16], C2* buf, int u) {
+  if (SPF_ABLATE(4)) return;
   const int k1 = u & 15, q = u >> 4;
 #pragma unroll
   for (int mp = 0; mp < 16; mp++) buf[k1 * kXPad + q + 4 * mp] = v[mp];
 }
 SPF_HD void inv_x1_read(C2 (&v)[16], const C2* buf, int a) {
+  if (SPF_ABLATE(4)) return;
 #pragma unroll
   for (int k1 = 0; k1 < 16; k1++) v[k1] = buf[k1 * kXPad + a];
 }
@@ -364,6 +429,7 @@ SPF_HD int64_t f64_to_i64_sat(double x) {
 constexpr uint32_t kTorusCornerMag = 0x43E00000u;  // high word of 2^63
 template <bool SCALED, bool CORNER>
 SPF_HD uint64_t f64_to_torus_impl(double xs, double sc, uint32_t* mag_max) {
+  if (SPF_ABLATE(64)) return f64_bits(xs);
   const double magic = 124615124604835863084731911901282304.0;  // 1.5 * 2^116
   const double hq = (SCALED ? spf_fma(sc, xs, magic) : xs + magic) - magic;
   const double lo = SCALED ? spf_fma(sc, xs, -hq) : xs - hq;

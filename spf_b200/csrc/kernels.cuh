@@ -88,13 +88,24 @@ constexpr int kPbsTmemOwn0 = 64;
 constexpr int kPbsTmemF0 = kPbsTmemOwn0 + 64 * kPbsPairs;
 constexpr int kPbsTmemFPairs = (512 - kPbsTmemF0) / 64 < kPbsPairs ? (512 - kPbsTmemF0) / 64 : kPbsPairs;
 constexpr int kPbsFParkBytes = (kPbsPairs - kPbsTmemFPairs) * 2 * kTeam * 16 * 16;  // 32 KiB per pair parked in smem
-constexpr int kPbsSmem = kTableBytes + kPbsPairs * kPbsPairBytes + kPbsFParkBytes;
+#ifndef SPF_PBS_RING
+#define SPF_PBS_RING 1  // bootstrapping key staged through a shared-memory ring by bulk copies, one copy per chunk and CTA
+#endif
+static_assert(!SPF_PBS_RING || SPF_PBS_TRANSIENT, "the BSK ring lives in the shared memory the transient accumulator frees");
+constexpr int kRingStages = 3;
+constexpr int kRingChunkElems = 2 * kM;                  // one (row, level) GLEV row of the BSK: [p][bin]
+constexpr int kRingChunkBytes = kRingChunkElems * 16;    // 32768
+constexpr int kPbsRingOff = kTableBytes + kPbsPairs * kPbsPairBytes + kPbsFParkBytes;
+constexpr int kPbsRingBytes = SPF_PBS_RING ? kRingStages * kRingChunkBytes + 64 : 0;  // + full barriers, release counters
+constexpr int kPbsSmem = kPbsRingOff + kPbsRingBytes;
+static_assert(kPbsSmem <= 232448, "pbs_kernel shared memory");
 
 #ifndef SPF_PBS_TMEM_T1
 #define SPF_PBS_TMEM_T1 1   // pass-1 twiddles (per thread) in tensor memory
 #endif
 #ifndef SPF_PBS_TMEM_T2
-#define SPF_PBS_TMEM_T2 0   // pass-2 twiddles in tensor memory (measured slower: 9.2 vs 8.6 ms per wave)
+#define SPF_PBS_TMEM_T2 1   // pass-2 twiddles in tensor memory: round 1 measured this slower (9.2 vs 8.6 ms per wave, 255-register
+                            // build); with the kernel bound by shared-memory wavefronts it is worth 2.6 % (7.39 -> 7.19 ms, r2)
 #endif
 #ifndef SPF_PBS_TMEM_F
 #define SPF_PBS_TMEM_F 1    // accumulators parked in tensor memory while the second digit level is transformed
@@ -138,21 +149,133 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// mbarrier wait that turns a lost wake-up into a trapped kernel instead of a hung GPU
+__device__ __forceinline__ void mbar_wait_trap(uint32_t bar, uint32_t parity) {
+  unsigned long long t_start = 0;
+  for (int spin = 0;; spin++) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    if ((spin & 1023) == 1023) {  // a chunk that has not landed after 2 s will never land
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t_start == 0) t_start = now;
+      else if (now - t_start > 2000000000ull) __trap();
+    }
+  }
+}
 static_assert(!SPF_PBS_TRANSIENT || SPF_PBS_TMEM_OWN, "the transient accumulator image needs the tensor-memory own copy");
 #ifndef SPF_PBS_CHUNKED
-#define SPF_PBS_CHUNKED (SPF_PBS_PAIRS > 3)  // 128-register build: own coefficients / twiddles fetched in small chunks
+#define SPF_PBS_CHUNKED 1  // own coefficients / twiddles fetched from tensor memory in small chunks (needed by the 128-register
+                           // 4-pair build; worth 2.7 % at 3 pairs too: shorter live ranges, better schedule)
+#endif
+#ifndef SPF_PBS_FUSED_ST
+#define SPF_PBS_FUSED_ST 0  // twiddle products stored to the exchange buffer one by one (interleaved STS)
 #endif
 struct DevPairCx {
   static constexpr bool kTransient = SPF_PBS_TRANSIENT != 0;
   static constexpr bool kChunked = SPF_PBS_CHUNKED != 0;
+  static constexpr bool kFusedStores = SPF_PBS_FUSED_ST != 0;
+  // ordered store: a volatile asm keeps its place among the twiddle multiplies
+  static __device__ __forceinline__ void sts_c2(C2* p, C2 v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "d"(v.x), "d"(v.y) : "memory");
+  }
+  __device__ __forceinline__ void sts(C2* p, C2 v) const { sts_c2(p, v); }
+  template <bool CONJ>
+  __device__ __forceinline__ void t1_mul_store(C2 (&v)[16], const C2* T1, C2* buf) const {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      uint32_t r[16];
+      tmem_ld16(r, t1_taddr + 16 * g);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const C2 w{__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2])};
+        const int k = 4 * g + i;
+        v[k] = CONJ ? cmul_conj(v[k], w) : cmul(v[k], w);
+        sts_c2(buf + k * kXPad + u, v[k]);
+      }
+    }
+  }
+  template <bool CONJ>
+  __device__ __forceinline__ void t2_mul_store(C2 (&v)[16], const C2* T2, C2* buf) const {
+    const int k1 = u & 15, q = u >> 4;
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) {
+      if (k2) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
+      sts_c2(buf + k1 * kXPad + q + 4 * k2, v[k2]);
+    }
+  }
   int u, h;
   int bar_half, bar_pair;
   uint32_t t1_taddr;   // this warp's lane quarter, column 0 of the T1 block
   uint32_t own_taddr;  // this warp's private 64 columns (own coefficients)
   uint32_t f_taddr;    // this warp's 64 columns for the parked accumulators (unused when fpark != nullptr)
   C2* fpark;           // shared-memory parking [16][128] of a pair whose accumulators do not fit in tensor memory
-  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar_half) : "memory"); }
-  __device__ __forceinline__ void pair_sync() const { asm volatile("bar.sync %0, 128;" ::"r"(bar_pair) : "memory"); }
+  // ---- BSK ring (SPF_PBS_RING; protocol in team_ops.cuh above pbs_pair_team) ----
+  static constexpr bool kBskRing = SPF_PBS_RING != 0;
+  uint32_t ring_s = 0, full_s = 0;  // shared addresses of stage 0 / of full[0]
+  unsigned* rel = nullptr;          // per-stage count of pairs that are done with the resident chunk
+  const C2* bsk = nullptr;
+  int lwe_n = 0, npairs = 0, total = 0;  // total: chunks this CTA consumes over the whole launch
+  bool elected = false;             // one thread per pair counts the pair off
+  // chunk G = 4 i + k: k = 2 t + row with digit level t <-> GLEV level 1 - t
+  __device__ __forceinline__ void ring_issue(int Gn) const {
+    const int i = (Gn >> 2) % lwe_n, k = Gn & 3, c = (k & 1) * 2 + (1 - (k >> 1)), st = Gn % kRingStages;
+    const C2* src = bsk + ((size_t)i * 4 + c) * kRingChunkElems;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_s + 8 * st), "r"((uint32_t)kRingChunkBytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ring_s + st * kRingChunkBytes), "l"(src), "r"((uint32_t)kRingChunkBytes), "r"(full_s + 8 * st) : "memory");
+  }
+  // returns the chunk's address: a shared-window address in a pointer's clothes when the ring is on (bsk_load)
+  __device__ __forceinline__ const C2* bsk_acquire(int G, const C2* g) const {
+#if SPF_PBS_RING
+    const int st = G % kRingStages;
+    mbar_wait_trap(full_s + 8 * st, (uint32_t)(G / kRingStages) & 1u);
+    return reinterpret_cast<const C2*>((size_t)(ring_s + st * kRingChunkBytes));
+#else
+    return g;
+#endif
+  }
+  __device__ __forceinline__ C2 bsk_load(const C2* p) const {
+#if SPF_PBS_RING
+    C2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"((uint32_t)(size_t)p) : "memory");
+    return r;
+#else
+    if (SPF_ABLATE(16)) return C2{1.5, (double)((size_t)p & 0xFF)};
+    return ldg_c2_pinned(p);
+#endif
+  }
+  __device__ __forceinline__ void bsk_release(int G) const {
+#if SPF_PBS_RING
+    if (elected) {
+      const int st = G % kRingStages;
+      __threadfence_block();
+      if (atomicAdd(rel + st, 1u) == (unsigned)npairs - 1u) {  // last pair out re-arms the stage
+        atomicExch(rel + st, 0u);
+        __threadfence_block();
+        if (G + kRingStages < total) ring_issue(G + kRingStages);
+      }
+    }
+#endif
+  }
+  __device__ __forceinline__ void bsk_skip(int G) const {  // a step whose rotation is the identity: count off unread chunks
+#if SPF_PBS_RING
+    if (elected) {
+#pragma unroll 1
+      for (int k = 0; k < 4; k++) {
+        mbar_wait_trap(full_s + 8 * ((G + k) % kRingStages), (uint32_t)((G + k) / kRingStages) & 1u);  // the copy has landed
+        bsk_release(G + k);
+      }
+    }
+#endif
+  }
+  __device__ __forceinline__ void sync() const { if (!SPF_ABLATE(8)) asm volatile("bar.sync %0, 64;" ::"r"(bar_half) : "memory"); }
+  __device__ __forceinline__ void pair_sync() const { if (!SPF_ABLATE(8)) asm volatile("bar.sync %0, 128;" ::"r"(bar_pair) : "memory"); }
   // v[k1] *= T1[k1][u] (or its conjugate).  The 16 twiddles of a thread never change, so they sit
   // in the thread's tensor-memory columns instead of a shared-memory table: 16 LDS.128 per
   // transform (12 % of the kernel's shared-memory wavefronts) become 4 tcgen05.ld on a path the
@@ -392,6 +515,32 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
                                     : reinterpret_cast<C2*>(smem + kTableBytes + kPbsPairs * kPbsPairBytes) + (pair - kPbsTmemFPairs) * 2 * kTeam * 16;
   DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3, t1_taddr, t1_taddr + kPbsTmemOwn0 + 64 * pair,
                t1_taddr + kPbsTmemF0 + 64 * (pair < kPbsTmemFPairs ? pair : 0), fpark};
+  int G = 0;        // chunk position of this pair in the CTA-wide BSK chunk sequence
+  int rounds = 0;   // ciphertexts the busiest pair (pair 0) of this CTA processes
+#if SPF_PBS_RING
+  {
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kPbsRingOff + kRingStages * kRingChunkBytes);
+    cx.ring_s = smem_u32(smem + kPbsRingOff);
+    cx.full_s = smem_u32(full);
+    cx.rel = reinterpret_cast<unsigned*>(full + kRingStages);
+    cx.bsk = P.bsk;
+    cx.lwe_n = P.lwe_n;
+    cx.npairs = npairs;
+    cx.elected = (threadIdx.x % (2 * kTeam)) == 0;
+    if ((int)blockIdx.x < P.batch) rounds = (P.batch - (int)blockIdx.x + (int)gridDim.x * npairs - 1) / ((int)gridDim.x * npairs);
+    cx.total = rounds * 4 * P.lwe_n;
+    if (threadIdx.x == 0) {
+      for (int st = 0; st < kRingStages; st++) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cx.full_s + 8 * st) : "memory");
+        cx.rel[st] = 0;
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int g0 = 0; g0 < kRingStages && g0 < cx.total; g0++) cx.ring_issue(g0);
+  }
+#endif
   // Persistent pairs: slot (pair, CTA) takes ciphertexts slot, slot + slots, ...  Slots are numbered
   // pair-major so that a trailing partial round leaves at most one busy pair on as many SMs as
   // possible (a pair alone on an SM runs ~1.3x faster than one sharing it with two others).
@@ -406,8 +555,16 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
     A.log_v = P.log_v;
     A.cbs_radix_log = P.cbs_radix_log;
     A.cbs_count = P.cbs_count;
-    pbs_pair_team(cx, A, acc, xb, sT1, sT2);
+    pbs_pair_team(cx, A, acc, xb, sT1, sT2, G);
   }
+#if SPF_PBS_RING
+  // a pair with fewer ciphertexts than pair 0 (the tail of the batch) still counts itself off the remaining chunks
+  if (cx.elected)
+    for (; G < cx.total; G++) {
+      mbar_wait_trap(cx.full_s + 8 * (G % kRingStages), (uint32_t)(G / kRingStages) & 1u);
+      cx.bsk_release(G);
+    }
+#endif
   pair_tmem_free(tmem_alloc);
 }
 
@@ -421,7 +578,6 @@ constexpr int kQuadT2Bytes = kT2Elems * 16;                                     
 constexpr int kQuadRowBytes = 8 * kM * 16;                                           // 131072: one GGSW of the BSK
 constexpr int kQuadSmem = kQuadT2Bytes + 2 * kN * 8 + 4 * kXBuf * 16 + kQuadRowBytes + 16;  // 231504
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 struct DevQuadCx {
   int u, h, t;
@@ -558,6 +714,7 @@ struct TraceSsBatch {
   PeerOffsets peers;       // n = 0: GGSWs are stored locally only
 };
 
+template <bool PEERS>
 __global__ void __launch_bounds__(kTrTeams * kTeam, SPF_TR_MIN_BLOCKS) trace_ss_kernel(const __grid_constant__ TraceSsBatch P, DevTables tabs) {
   extern __shared__ __align__(16) unsigned char smem[];
   C2* sT1 = reinterpret_cast<C2*>(smem);
@@ -604,7 +761,7 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, SPF_TR_MIN_BLOCKS) trace_ss_
     A.out_scale = P.out_scale;
     A.n_peers = P.peers.n;
     A.peer_off = P.peers.off;
-    trace_ss_team(cx, A, g, xbuf, sT1, sT2);
+    trace_ss_team<PEERS>(cx, A, g, xbuf, sT1, sT2);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -321,18 +321,18 @@ SPF_HD constexpr int split_bin(int u, int h, int s) { return u + 64 * (2 * h + (
 // xb[b]), then f[p] (+)= D * G[b][level][p] for both output polynomials p.  Written as two
 // independent 4-bin batches: the compiler hoists the second batch's BSK loads above the first
 // batch's arithmetic (measured: explicit earlier prefetching only costs registers and spills).
-template <bool INIT>
-SPF_HD void mad_split(C2 (&f)[2][8], const C2* xbb, const C2* g /* GGSW row b, level: [p][bin] */, int u, int h) {
+template <bool INIT, class Cx>
+SPF_HD void mad_split(Cx& cx, C2 (&f)[2][8], const C2* xbb, const C2* g /* GGSW row b, level: [p][bin] */, int u, int h) {
   const int k1 = u & 15, q = u >> 4;
 #pragma unroll
   for (int jj = 0; jj < 2; jj++) {
     C2 d[4], g0[4], g1[4];
 #pragma unroll
-    for (int qp = 0; qp < 4; qp++) d[qp] = xbb[k1 * kXPad + qp + 4 * q + 16 * (2 * h + jj)];
+    for (int qp = 0; qp < 4; qp++) d[qp] = SPF_ABLATE(4) ? C2{1.0 + qp, 2.0 + jj} : xbb[k1 * kXPad + qp + 4 * q + 16 * (2 * h + jj)];
 #pragma unroll
     for (int k3 = 0; k3 < 4; k3++) {
-      g0[k3] = ldg_c2_pinned(g + split_bin(u, h, 4 * jj + k3));
-      g1[k3] = ldg_c2_pinned(g + kM + split_bin(u, h, 4 * jj + k3));
+      g0[k3] = cx.bsk_load(g + split_bin(u, h, 4 * jj + k3));
+      g1[k3] = cx.bsk_load(g + kM + split_bin(u, h, 4 * jj + k3));
     }
     bfly4<false>(d[0], d[1], d[2], d[3]);
 #pragma unroll
@@ -344,8 +344,14 @@ SPF_HD void mad_split(C2 (&f)[2][8], const C2* xbb, const C2* g /* GGSW row b, l
   }
 }
 
+// BSK ring (Cx::kBskRing, device only): the key is consumed in CHUNKS of one (row, level) GLEV row [p][bin] = 32 KiB, four
+// per CMUX step in the order (row 0, level 1), (row 1, level 1), (row 0, level 0), (row 1, level 0).  All pairs of a
+// CTA walk the same chunk sequence G = 4 i + k (continuing over the ciphertexts they process: the key repeats), so
+// ONE bulk copy per chunk (cp.async.bulk -> mbarrier, kernels.cuh) serves all of them from a small shared-memory ring:
+// bsk_acquire waits until chunk G has landed, bsk_release (one thread per pair, after a pair barrier that follows the
+// last read) counts the pair off; the last pair to release a stage re-arms it with chunk G + stages.
 template <class Cx>
-SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const C2* T1, const C2* T2) {
+SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const C2* T1, const C2* T2, int& G) {
   const int u = cx.u, h = cx.h;
   const int k1 = u & 15, q = u >> 4;
   const int n = A.lwe_n;
@@ -401,7 +407,11 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
   for (int i = 0; i < n; i++) {
     const int at = (int)modulus_switch(a_next, A.log_chi, A.log_v, log2n);
     if (i + 1 < n) a_next = ldg_u64(A.lwe_in + i + 1);
-    if (at == 0) continue;  // rot == acc: the CMUX adds IFFT(0) = 0 exactly (uniform over the pair)
+    if (at == 0) {  // rot == acc: the CMUX adds IFFT(0) = 0 exactly (uniform over the pair)
+      cx.bsk_skip(G);  // the pair still counts itself off the four chunks of this step
+      G += 4;
+      continue;
+    }
     const C2* ggsw = A.bsk + (size_t)i * 8 * kM;
     C2 f[2][8];
     {
@@ -422,7 +432,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
             if ((i2 & 7) == 0) cx.own_ld8(own, i2 >> 3);  // own[0..7] = coefficients 8c .. 8c + 7
           }
           const uint32_t t9 = bh9 + 512u * i2;  // bit 14 = negacyclic sign
-          const uint64_t x = *reinterpret_cast<const uint64_t*>(col + (t9 & 0x3E00u));
+          const uint64_t x = SPF_ABLATE(32) ? (uint64_t)t9 * 0x9E3779B97F4A7C15ull : *reinterpret_cast<const uint64_t*>(col + (t9 & 0x3E00u));
           const uint64_t diff = ((t9 & 0x4000u) ? 0 - x : x) - own[kCh ? (i2 & 7) : i2];
           const uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
           const uint32_t w1 = w + 0x8000u;  // high half = second digit: (w >> 16) + carry of the first
@@ -438,20 +448,34 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
           for (int m = 0; m < 16; m++) { v[m].x = digit_lo16_to_f64(pk[m]); v[m].y = digit_hi16_to_f64(pk[m]); }
         }
         fwd_pass1_core(v);
-        cx.template t1_mul<false>(v, T1);  // v[k1] *= T1[k1][u]
-        if (t == 1) cx.pair_sync();  // both halves have consumed the level-0 spectra
-        else if (kTr) cx.sync();     // every thread of the half has gathered from the accumulator image in xown
-        fwd_x1_write(v, xown, u);
-        cx.sync();
-        fwd_x1_read(v, xown, u);
-        dft16<false>(v);
-        cx.template t2_mul<false>(v, T2);  // v[k2] *= W64^(q k2)
-        fwd_x2_write(v, xown, u);  // in place: no barrier after fwd_x1_read
+        if constexpr (Cx::kFusedStores) {
+          // every product goes to the exchange buffer as soon as it exists: the stores overlap the remaining
+          // multiplies instead of queueing up behind them in front of the barrier
+          if (t == 1) { cx.pair_sync(); cx.bsk_release(G); cx.bsk_release(G + 1); }
+          else if (kTr) cx.sync();
+          cx.template t1_mul_store<false>(v, T1, xown);  // v[k1] *= T1[k1][u]; xown[k1][u] = v[k1]
+          cx.sync();
+          fwd_x1_read(v, xown, u);
+          dft16<false>(v);
+          cx.template t2_mul_store<false>(v, T2, xown);  // v[k2] *= W64^(q k2); in-place second exchange
+        } else {
+          cx.template t1_mul<false>(v, T1);  // v[k1] *= T1[k1][u]
+          if (t == 1) { cx.pair_sync(); cx.bsk_release(G); cx.bsk_release(G + 1); }  // both halves have consumed the level-0 spectra (and the key chunks)
+          else if (kTr) cx.sync();     // every thread of the half has gathered from the accumulator image in xown
+          fwd_x1_write(v, xown, u);
+          cx.sync();
+          fwd_x1_read(v, xown, u);
+          dft16<false>(v);
+          cx.template t2_mul<false>(v, T2);  // v[k2] *= W64^(q k2)
+          fwd_x2_write(v, xown, u);  // in place: no barrier after fwd_x1_read
+        }
         if (t == 1) cx.f_load(f);
         cx.pair_sync();
-        if (t == 0) mad_split<true>(f, xb, ggsw + (size_t)((0 * 2 + level) * 2) * kM, u, h);
-        else mad_split<false>(f, xb, ggsw + (size_t)((0 * 2 + level) * 2) * kM, u, h);
-        mad_split<false>(f, xb + kXBuf, ggsw + (size_t)((1 * 2 + level) * 2) * kM, u, h);
+        const C2* g0 = cx.bsk_acquire(G + 2 * t, ggsw + (size_t)((0 * 2 + level) * 2) * kM);
+        if (t == 0) mad_split<true>(cx, f, xb, g0, u, h);
+        else mad_split<false>(cx, f, xb, g0, u, h);
+        const C2* g1 = cx.bsk_acquire(G + 2 * t + 1, ggsw + (size_t)((1 * 2 + level) * 2) * kM);
+        mad_split<false>(cx, f, xb + kXBuf, g1, u, h);
         if (t == 0) cx.f_store(f);  // device: parked in tensor memory while the second transform runs
       }
     }
@@ -468,17 +492,24 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       for (int jj = 0; jj < 2; jj++) {
 #pragma unroll
         for (int qp = 0; qp < 4; qp++)
-          xb[p * kXBuf + k1 * kXPad + qp + 4 * q + 16 * (2 * h + jj)] = f[p][4 * jj + qp];
+          if (!SPF_ABLATE(4)) xb[p * kXBuf + k1 * kXPad + qp + 4 * q + 16 * (2 * h + jj)] = f[p][4 * jj + qp];
       }
     }
     cx.pair_sync();
+    cx.bsk_release(G + 2);
+    cx.bsk_release(G + 3);
+    G += 4;
     // acc[h] += IFFT(output polynomial h)
     {
       C2 w[16];
       inv_x2_read(w, xown, u);
       cx.template t2_mul<true>(w, T2);
-      dft16<true>(w);
-      inv_x1_write(w, xown, u);  // in place: no barrier after inv_x2_read
+      if constexpr (Cx::kFusedStores) {
+        dft16_emit<true>(w, [&](int mp, C2 val) { cx.sts(xown + k1 * kXPad + q + 4 * mp, val); });  // = inv_x1_write
+      } else {
+        dft16<true>(w);
+        inv_x1_write(w, xown, u);  // in place: no barrier after inv_x2_read
+      }
       cx.sync();
       inv_x1_read(w, xown, u);
       if (kTr) cx.sync();  // xown becomes the accumulator image again
@@ -738,9 +769,16 @@ struct TraceSsArgs {
   const long long* peer_off;
 };
 
+// PEERS is a compile-time switch: the replica / single-GPU instantiation carries no peer loop at all (the loop was
+// unrolled for up to 7 peers behind predicates at each of the 64 store sites: 2 112 STG in a 19 k-instruction kernel
+// whose instruction fetch already showed up in the stall samples).
+template <bool PEERS>
 SPF_HD void ggsw_store(const TraceSsArgs& A, C2* p, C2 v) {
   *p = v;
-  for (int r = 0; r < A.n_peers; r++) *reinterpret_cast<C2*>(reinterpret_cast<char*>(p) + A.peer_off[r]) = v;
+  if (PEERS) {
+#pragma unroll 1
+    for (int r = 0; r < A.n_peers; r++) *reinterpret_cast<C2*>(reinterpret_cast<char*>(p) + A.peer_off[r]) = v;
+  }
 }
 
 // y[j] of sigma_k(p): polynomial_pow_k (ops/polynomial/mod.rs:62-87) as a gather.
@@ -749,7 +787,7 @@ SPF_HD uint64_t automorph_coeff(const uint64_t* p, int j, uint32_t kinv) {
   return i < (uint32_t)kN ? p[i] : 0 - p[i - kN];
 }
 
-template <class Cx>
+template <bool PEERS = true, class Cx>
 SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2048]*/, C2* xbuf, const C2* T1,
                           const C2* T2) {
   const int u = cx.u;
@@ -824,17 +862,17 @@ SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2
     // FFT(x.b): row 1 b-slot, and the a-slot of row 0 (update_encrypted_secret_key_component_fft)
     team_poly_fft(cx, f[0], [&](int j) { return g[kN + j]; }, xbuf, T1, T2);
 #pragma unroll
-    for (int s = 0; s < 16; s++) { ggsw_store(A, row1 + kM + bin_of(u, s), cscale(f[0][s], A.out_scale)); f[1][s] = C2{0.0, 0.0}; }
+    for (int s = 0; s < 16; s++) { ggsw_store<PEERS>(A, row1 + kM + bin_of(u, s), cscale(f[0][s], A.out_scale)); f[1][s] = C2{0.0, 0.0}; }
     gadget_mad_stateless(cx, f, [&](int j) { return g[j]; }, xbuf, T1, T2, A.ssk, A.ss_radix_log, A.ss_count);
 #pragma unroll
     for (int s = 0; s < 16; s++) {
-      ggsw_store(A, row0 + bin_of(u, s), cscale(f[0][s], A.out_scale));
-      ggsw_store(A, row0 + kM + bin_of(u, s), cscale(f[1][s], A.out_scale));
+      ggsw_store<PEERS>(A, row0 + bin_of(u, s), cscale(f[0][s], A.out_scale));
+      ggsw_store<PEERS>(A, row0 + kM + bin_of(u, s), cscale(f[1][s], A.out_scale));
     }
     // row 1 a-slot: FFT(x.a)
     team_poly_fft(cx, f[0], [&](int j) { return g[j]; }, xbuf, T1, T2);
 #pragma unroll
-    for (int s = 0; s < 16; s++) ggsw_store(A, row1 + bin_of(u, s), cscale(f[0][s], A.out_scale));
+    for (int s = 0; s < 16; s++) ggsw_store<PEERS>(A, row1 + bin_of(u, s), cscale(f[0][s], A.out_scale));
   }
 }
 

@@ -257,6 +257,25 @@ def test_kernel_selection_thresholds(oracle, keys, client, evaluation):
         assert client.decrypt_glwe_l1(wide[i])[:2].tolist() == ([1, 1] if bits[i] else [0, 1])
 
 
+@pytest.mark.parametrize("batch", [149, 297, 445, 494, 593, 889])
+def test_pbs_wave_and_tail_shapes(oracle, keys, client, evaluation, batch):
+    """Every way launch_pbs lays a batch out: 2 or 3 pairs per CTA sharing one BSK ring, a ragged last round (pairs with
+    fewer ciphertexts count themselves off the ring), full waves followed by the quad-kernel tail (445 = 444 + 1,
+    494 = 444 + 50, 889 = 2 x 444 + 1), and a remainder too large for the tail kernel (593 = 444 + 149).  Items at every
+    boundary must decrypt."""
+    p = keys.params
+    lut = oracle.generate_lut(p, [lambda x: (x + 1) % 8], 3)
+    rng = np.random.default_rng(batch)
+    msgs = rng.integers(0, 8, batch)
+    cts = np.zeros((batch, keys.lwe0_len), dtype=np.uint64)
+    for m in range(batch):
+        oracle.lib().orc_encrypt_lwe(C.byref(client.rng), cts[m], keys.lwe0_sk, p.lwe_n, p.lwe_std, int(msgs[m]) << 60)
+    out = evaluation.programmable_bootstrap(cts, lut)
+    idx = sorted({0, 1, 147, 148, 149, 295, 296, 443, 444, 445, 591, 592, 887, 888, batch - 2, batch - 1} & set(range(batch)))
+    for i in idx:
+        assert int(oracle.decode(client.decrypt_glwe_l1_raw(out[i])[:1], 3)[0]) == (msgs[i] + 1) % 8, (batch, i)
+
+
 def test_short_lwe_through_every_kernel():
     """tools/sanitizer_probe.py: DEFAULT_128 rings with a 16-step blind rotation through every kernel
     (quad and pair-team PBS, trace / scheme switch, wide and bulk CMUX, tensor-core and IMAD keyswitch);
