@@ -55,7 +55,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-add", action="store_true", help="skip the Parasol program latency measurements (8/32-bit add, mul32 + compare)")
-    ap.add_argument("--check", type=int, default=8, help="outputs decrypted with the oracle after the run (checker only)")
+    ap.add_argument("--check", type=int, default=512, help="outputs decrypted with the oracle after the run, spread over every PBS wave (checker only)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 3-point batch-size sweep (BASELINE config 5)")
+    ap.add_argument("--no-sharded-graph", action="store_true", help="N > 1: skip the sharded mul32+compare graph (BASELINE config 4)")
     return ap.parse_args()
 
 
@@ -421,6 +423,198 @@ def measure_add_latency(ev, keys, args):
 
 
 # ---------------------------------------------------------------------------------------------
+# end to end the way the reference uses the path: LWE in -> circuit bootstrap -> CMUX -> GLWE out
+# ---------------------------------------------------------------------------------------------
+class E2EGraphPipeline:
+    """The whole batch as a few FheCircuit graphs (InputLwe0 -> CircuitBootstrap -> CMux(sel, a, b) -> OutputGlwe1) on
+    the asynchronous executor (spf_b200_graph_spawn): host buffers are rows of page-locked slabs, every graph's H2D /
+    D2H copies are inside the timed region and overlap the neighbouring graphs' kernels.  The GGSWs never leave the
+    device -- as in the reference, where L1GgswCiphertext is not even serialisable (crypto/encryption.rs:94-98)."""
+
+    def __init__(self, ev, h_lwe: np.ndarray, glwe_len: int, wave: int):
+        import spf_b200
+
+        B = len(h_lwe)
+        self.B = B
+        self.h_lwe = h_lwe                                         # [B][n + 1], page-locked
+        self.h_out = spf_b200.pinned_zeros((B, glwe_len))          # [B][2N]
+        ab = spf_b200.pinned_zeros((2, glwe_len))
+        ab[1, glwe_len // 2] = np.uint64(1 << 63)                  # a = trivial 0, b = trivial 1: the output decrypts to the selector
+        self.ab = ab
+        # chunks: whole PBS waves (3 waves each) so that chunking costs no extra tail; the remainder is its own graph
+        per = 3 * wave
+        bounds = list(range(0, B, per)) + [B]
+        proc = spf_b200.CircuitProcessor(ev)
+        self.graphs = []
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            c = spf_b200.FheCircuit()
+            na, nb = c.add("InputGlwe1", io=ab[0]), c.add("InputGlwe1", io=ab[1])
+            ins = [c.add("InputLwe0", io=h_lwe[i]) for i in range(lo, hi)]
+            sels = [c.add("CircuitBootstrap", x) for x in ins]
+            mux = [c.add("CMux", sl, na, nb) for sl in sels]
+            for i, m in zip(range(lo, hi), mux):
+                c.add("OutputGlwe1", m, io=self.h_out[i])
+            self.graphs.append(proc.compile(c))
+        self.h2d = int(h_lwe.nbytes + len(self.graphs) * ab.nbytes)
+        self.d2h = int(self.h_out.nbytes)
+
+    def step(self):
+        for g in self.graphs:
+            g.spawn()
+        for g in self.graphs:
+            g.wait()
+
+    def close(self):
+        for g in self.graphs:
+            g.close()
+
+
+def measure_sweep(ev, lwe_sk, p, world, rank, dev, stream, flush, batches=(64, 1024, 16384)):
+    """BASELINE config 5 in three points: device-resident CBS throughput per batch size, every rank its own batch,
+    whole-job rate = world * B / max-over-ranks CUDA-event time."""
+    import torch
+    import torch.distributed as dist
+
+    rows = []
+    for B in batches:
+        bits = np.random.default_rng(0x5EE9 + rank).integers(0, 2, B)
+        d_in = torch.from_numpy(encrypt_lwe0_numpy(lwe_sk, bits, p.lwe_std, 0x5EE9 + rank).view(np.int64)).to(dev)
+        d_out = torch.empty(B * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
+        fn = lambda: ev.dev_circuit_bootstrap(d_out.data_ptr(), d_in.data_ptr(), B, reference_scale=False, stream=stream)
+        fn()
+        ms = []
+        for _ in range(3 if B <= 4096 else 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([min(ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rows.append({"batch_per_gpu": B, "ms": float(t.item()), "cbs_per_s": world * B / float(t.item()) * 1e3})
+        del d_in, d_out
+    return rows
+
+
+def measure_sharded_graph(ev, keys, args, world, rank, dev):
+    """BASELINE config 4 under the driver: `world` x (mul32 then greater-than) as ONE graph sharded over the ranks
+    (spf_b200_graph_run_sharded): bootstrap levels split evenly, every MUX tree on one rank, level exchange over peer
+    memory (NVLink P2P stores fused into the scheme-switch kernel + flag barriers) and, for comparison, NCCL all-gathers;
+    rank 0 then runs the same graph alone.  Inputs are encrypted on rank 0 and broadcast; outputs are collected on
+    rank 0 and decrypted."""
+    import torch
+    import torch.distributed as dist
+
+    import spf_b200
+    from spf_b200.circuits import multiply_then_greater_than
+    from spf_b200.multi import NcclExchange, open_peer_arenas
+
+    w, programs = 32, world
+    glwe_len = ev.len_glwe
+    n_in, n_out = programs * 3 * w, programs * (w + 1)
+    slab = spf_b200.pinned_zeros((n_in + n_out, glwe_len))
+    vals = None
+    if rank == 0:
+        import oracle as O
+
+        client = O.Client(keys)
+        rng = np.random.default_rng(2024)
+        vals = [(int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w)), int(rng.integers(0, 1 << w))) for _ in range(programs)]
+        k = 0
+        for v in vals:
+            for x in v:
+                for i in range(w):
+                    slab[k] = client.encrypt_glwe_l1([(x >> i) & 1])
+                    k += 1
+    t_in = torch.from_numpy(slab[:n_in].view(np.int64)).to(dev)
+    dist.broadcast(t_in, src=0)
+    slab[:n_in] = t_in.cpu().numpy().view(np.uint64)
+    rows = iter(slab)
+    a, b, c = [], [], []
+    for _ in range(programs):
+        a.append([next(rows) for _ in range(w)]); b.append([next(rows) for _ in range(w)]); c.append([next(rows) for _ in range(w)])
+    out_prod = [[next(rows) for _ in range(w)] for _ in range(programs)]
+    out_gt = [next(rows) for _ in range(programs)]
+    circ = multiply_then_greater_than(a, b, c, out_prod, out_gt, programs)
+    out_nodes = [i for i, nd in enumerate(circ.nodes) if nd[0] == spf_b200.OP["OutputGlwe1"]]
+    res = {"workload": f"{programs} x (mul32 low word then greater-than) as one graph, sharded over {world} GPUs",
+           "cmux": int((circ.ops == spf_b200.OP["CMux"]).sum()), "circuit_bootstraps": int((circ.ops == spf_b200.OP["CircuitBootstrap"]).sum())}
+
+    def timed(g, runs=3):
+        ts = []
+        for _ in range(runs + 1):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            g.run()
+            ts.append(1e3 * (time.perf_counter() - t0))
+        t = torch.tensor([min(ts[1:])], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def collect_and_check(g):
+        """every output lives on one rank (its tree's owner) or on all: sum the owners' copies on rank 0 and decrypt"""
+        for node in out_nodes:
+            r = g.output_rank(node)
+            if not (r == rank or (r < 0 and rank == 0)):
+                circ.nodes[node][3][:] = 0
+        t = torch.from_numpy(slab[n_in:].view(np.int64)).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ok = None
+        if rank == 0:
+            got = t.cpu().numpy().view(np.uint64).reshape(n_out, glwe_len)
+            ok, k = True, 0
+            dec = [int(client.decrypt_glwe_l1(g_)[0]) for g_ in got]
+            prods, gts = dec[:programs * w], dec[programs * w:]
+            for p_, (x, y, z) in enumerate(vals):
+                prod = sum(bit << i for i, bit in enumerate(prods[p_ * w:(p_ + 1) * w]))
+                ok &= prod == (x * y) % (1 << w) and gts[p_] == int(prod > z)
+        slab[n_in:] = 0
+        return ok
+
+    for mode in ("peer", "nccl"):
+        ex = NcclExchange(rank) if mode == "nccl" else None
+        g = spf_b200.CompiledGraph(ev, circ, world=world, rank=rank, exchange=ex)
+        if mode == "peer":
+            open_peer_arenas(g)
+        res[f"ms_{mode}"] = timed(g)
+        ok = collect_and_check(g)
+        if rank == 0:
+            res[f"correct_{mode}"] = bool(ok)
+        if ex is not None:
+            res["exchange_bytes_per_run"] = ex.bytes // 4
+            res["exchanges_per_run"] = ex.calls // 4
+        res["levels"], res["launches_per_rank"] = g.levels, g.launches
+        g.close()
+    # the same work on ONE GPU (rank 0; the other ranks wait), and one program alone: the latency floor
+    if rank == 0:
+        g = spf_b200.CompiledGraph(ev, circ)
+        g.run()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); g.run(); ts.append(1e3 * (time.perf_counter() - t0))
+        res["ms_same_work_1gpu"] = min(ts)
+        g.close()
+        one = multiply_then_greater_than(a[:1], b[:1], c[:1], out_prod[:1], out_gt[:1], 1)
+        g = spf_b200.CompiledGraph(ev, one)
+        g.run()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); g.run(); ts.append(1e3 * (time.perf_counter() - t0))
+        res["ms_one_program_1gpu"] = min(ts)
+        g.close()
+        best = min(res["ms_peer"], res["ms_nccl"])
+        res["speedup_vs_1gpu"] = res["ms_same_work_1gpu"] / best
+        res["correct"] = bool(res.get("correct_peer") and res.get("correct_nccl"))
+        res["limiter"] = ("per-program latency floor: one program is a chain of ~630 dependency levels (%.1f ms alone on one GPU), "
+                          "a sharded run cannot finish before its slowest tree; the level exchange costs %.1f ms (peer) / %.1f ms (nccl) on top"
+                          % (res["ms_one_program_1gpu"], res["ms_peer"] - res["ms_one_program_1gpu"], res["ms_nccl"] - res["ms_one_program_1gpu"]))
+    dist.barrier()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def run_gpu(args):
@@ -569,36 +763,56 @@ def run_gpu(args):
         }
         del d_rot, d_glwe, lut
 
-    # ---- end to end through the host-pointer C ABI call (pinned buffers, copies inside) ---------
-    e2e = None
+    # ---- end to end (headline): LWE in -> CBS -> CMUX -> GLWE out through the graph API on the asynchronous executor,
+    #      host buffers (page-locked slabs), H2D + D2H inside the timed region -----------------------------------------
+    e2e = e2e_ggsw = None
+    e2e_out = None
     if not args.no_e2e:
-        h_out = torch.empty(B * ev.len_ggsw * 2, dtype=torch.float64).pin_memory()
-        lib = spf_b200.lib()
-
-        def host_step():
-            rc = lib.spf_b200_circuit_bootstrap(ev.handle, h_out.data_ptr(), h_in.data_ptr(), B)
-            if rc != 0:
-                raise RuntimeError(lib.spf_b200_last_error(ev.handle))
-
-        host_step()
+        lwe_len = p.lwe_n + 1
+        h_lwe = h_in.numpy().view(np.uint64).reshape(B, lwe_len)
+        pipe = E2EGraphPipeline(ev, h_lwe, ev.len_glwe, 148 * 3)
+        pipe.step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        e2e_steps = max(1, min(args.steps, 5))
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 3))
         for _ in range(e2e_steps):
-            host_step()
+            pipe.step()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * 8),
-               "d2h_bytes_per_step": int(h_out.numel() * 8), "steps": e2e_steps,
-               "api": "spf_b200_circuit_bootstrap (host pointers, pinned)"}
-        result_host = h_out.numpy().view(np.complex128).reshape(B, ev.len_ggsw)
-    else:
-        result_host = None
+        e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d, "d2h_bytes_per_step": pipe.d2h,
+               "steps": e2e_steps, "graphs_per_step": len(pipe.graphs),
+               "api": "FheCircuit graphs (InputLwe0 -> CircuitBootstrap -> CMux -> OutputGlwe1) through spf_b200_graph_spawn / "
+                      "spf_b200_graph_wait, page-locked host buffers; the GGSWs stay in HBM as in the reference "
+                      "(L1GgswCiphertext is not serialisable, crypto/encryption.rs:94-98)"}
+        e2e_out = pipe.h_out.copy()
+        pipe.close()
+        del pipe
+        # the round-1 e2e for continuity (1 GPU only): GGSW results shipped to the host, 256 KiB per bootstrap -- a transfer the
+        # reference never makes; at 8 GPUs it measures the host's PCIe / memory system (SCALE_r01: 0.85 efficiency)
+        if world == 1:
+            h_out = torch.empty(B * ev.len_ggsw * 2, dtype=torch.float64).pin_memory()
+            lib = spf_b200.lib()
+
+            def host_step():
+                rc = lib.spf_b200_circuit_bootstrap(ev.handle, h_out.data_ptr(), h_in.data_ptr(), B)
+                if rc != 0:
+                    raise RuntimeError(lib.spf_b200_last_error(ev.handle))
+
+            host_step()
+            t0 = time.perf_counter()
+            n_h = max(1, min(args.steps, 3))
+            for _ in range(n_h):
+                host_step()
+            dt = time.perf_counter() - t0
+            e2e_ggsw = {"value": B * n_h / dt, "unit": UNIT, "h2d_bytes_per_step": int(h_in.numel() * 8),
+                        "d2h_bytes_per_step": int(h_out.numel() * 8), "steps": n_h,
+                        "api": "spf_b200_circuit_bootstrap (host pointers, pinned): GGSW-FFT outputs copied to the host"}
+            del h_out
 
     # ---- checker + CPU baseline (rank 0, N = 1 only for the baseline) --------------------------
     check = None
@@ -608,20 +822,25 @@ def run_gpu(args):
 
         client = O.Client(keys)
         if args.check > 0:
-            if result_host is None:
-                nchk = min(args.check, B)
-                tmp = torch.empty(nchk * ev.len_ggsw * 2, dtype=torch.float64, device=dev)
-                ev.dev_fft_rescale(tmp.data_ptr(), d_out.data_ptr(), nchk * ev.len_ggsw, to_device=False, stream=stream)
+            # outputs spread over every PBS wave (444 ciphertexts each) and both sides of every wave boundary
+            nchk = min(args.check, B)
+            idx = set(np.linspace(0, B - 1, nchk).astype(int).tolist())
+            idx |= {i for w0 in range(444, B, 444) for i in (w0 - 1, w0) if i < B}
+            idx = sorted(idx)
+            tmp = torch.empty(ev.len_ggsw * 2, dtype=torch.float64, device=dev)
+            bad = []
+            for i in idx:
+                ev.dev_fft_rescale(tmp.data_ptr(), d_out.data_ptr() + i * ev.len_ggsw * 16, ev.len_ggsw, to_device=False, stream=stream)
                 torch.cuda.synchronize()
-                sample_out = tmp.cpu().numpy().view(np.complex128).reshape(nchk, ev.len_ggsw)
-                idx = list(range(nchk))
-            else:
-                idx = np.linspace(0, B - 1, args.check).astype(int).tolist()
-                sample_out = result_host[idx]
-            ok = all(client.decrypt_ggsw_l1(g) == int(bits[i]) for g, i in zip(sample_out, idx))
-            check = {"decrypted": len(idx), "ok": bool(ok)}
-            if not ok:
-                raise SystemExit("bench.py: GPU outputs do not decrypt to the expected plaintexts")
+                if client.decrypt_ggsw_l1(tmp.cpu().numpy().view(np.complex128)) != int(bits[i]):
+                    bad.append(i)
+            check = {"decrypted": len(idx), "ok": not bad, "what": "GGSW outputs of the timed device-resident steps"}
+            if e2e_out is not None:
+                bad_e = [i for i in idx if int(client.decrypt_glwe_l1(e2e_out[i])[0]) != int(bits[i])]
+                check.update({"e2e_decrypted": len(idx), "e2e_ok": not bad_e})
+                bad += bad_e
+            if bad:
+                raise SystemExit(f"bench.py: GPU outputs do not decrypt to the expected plaintexts: {bad[:16]}")
         if world == 1 and not args.no_cpu_baseline:
             nt = O.hw_threads()
             rate0, _ = cpu_cbs_rate(keys, cts[: min(2 * nt, B)], nt)  # warm-up, also sizes the sample
@@ -630,6 +849,13 @@ def run_gpu(args):
             cpu_baseline = {"value": rate, "unit": UNIT, "cores": nt, "kind": "port",
                             "sample": f"{min(sample, B)} CBS of the same workload in {dt:.1f} s; " + CPU_KIND_NOTE,
                             **cpu_micro(keys, cts)}
+
+    # ---- BASELINE config 5 (3-point batch sweep) and config 4 (sharded program graph, N > 1) ----------------------
+    sweep = sharded = None
+    if not args.no_sweep:
+        sweep = measure_sweep(ev, lwe_sk, p, world, rank, dev, stream, flush)
+    if world > 1 and not args.no_sharded_graph:
+        sharded = measure_sharded_graph(ev, keys, args, world, rank, dev)
 
     # ---- Parasol add latency (the metric's second half): encrypted w-bit add through the graph
     #      executor (16/64 x SampleExtract -> Keyswitch -> CBS, then the ripple-carry MUX tree) ------
@@ -652,6 +878,7 @@ def run_gpu(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "check": check, "wall_s_timed_region": wall,
             "parasol_add_latency": add_latency, "parasol_mul32_cmp_latency": program_latency,
+            "e2e_ggsw_to_host": e2e_ggsw, "throughput_sweep": sweep, "sharded_graph": sharded,
         }
         print(json.dumps(line))
     ev.close()

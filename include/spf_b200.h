@@ -195,10 +195,43 @@ int spf_b200_graph_run(spf_b200_graph *graph);
 void spf_b200_graph_destroy(spf_b200_graph *graph);
 int spf_b200_graph_levels(const spf_b200_graph *graph);
 uint64_t spf_b200_graph_launches(const spf_b200_graph *graph); /* kernel launches of the last run */
-/* Re-points the host buffer of an Input* / Output* node of a built graph: one validated, levelised,
+/* Re-points the io buffer of an Input* / Output* node of a built graph: one validated, levelised,
  * device-resident graph then serves every invocation of the same instruction shape (the reference
- * rebuilds and re-levelises the MUX circuit per instruction dispatch, fhe_circuit.rs:473-494). */
+ * rebuilds and re-levelises the MUX circuit per instruction dispatch, fhe_circuit.rs:473-494).
+ *
+ * CIPHERTEXT HANDLES.  An io pointer (here and in spf_node.io) may be
+ *   - page-locked host memory (spf_b200_host_alloc, cudaHostAlloc, a caller's cudaHostRegister): plain DMA;
+ *   - pageable host memory: page-locked by spf_b200_graph_build, staged through the graph's own page-locked slab when it
+ *     arrives through spf_b200_graph_set_io (no per-call registration);
+ *   - DEVICE memory (cudaMalloc / a torch tensor / spf_b200_device_alloc): a ciphertext that never leaves HBM -- the
+ *     role of the reference's Arc<AtomicRefCell<Option<Ciphertext>>> task outputs shared between graphs
+ *     (circuit_processor/task.rs:10-16): the Output* node of graph k and the Input* node of graph k + 1 name the same
+ *     device buffer, the copies are device-to-device, GGSWs keep the device scale (2^-10) and, like the reference's
+ *     L1GgswCiphertext (encryption.rs:94-98), never reach the host.
+ * The kind is detected with cudaPointerGetAttributes. */
 int spf_b200_graph_set_io(spf_b200_graph *graph, size_t node, void *io);
+/* Device memory for ciphertext handles (cudaMalloc / cudaFree on the context's device). */
+int spf_b200_device_alloc(spf_b200_ctx *ctx, void **out, size_t bytes);
+int spf_b200_device_free(spf_b200_ctx *ctx, void *p);
+
+/* ---- asynchronous execution: CircuitProcessor::spawn_graph, CompletionHandler, flow control --------------------
+ * (parasol_runtime/src/circuit_processor/mod.rs:130-253,573-623; completion_handler.rs:14-56).
+ * spf_b200_graph_spawn enqueues one whole run of `graph` on the graph's own CUDA stream and returns; on_complete(user,
+ * status, message) fires exactly once when every op of the run has retired, with the FIRST error of the run (0 and
+ * NULL = none) -- CompletionHandler's callback with Option<RuntimeError>.  Outputs must not be read before it fires.
+ * `after`: graphs whose last spawned run must complete first (ordered on the device by events, the host does not wait);
+ * a run whose dependency failed retires as a no-op with the dependency's error, as tasks do once
+ * CompletionHandler::error is set.  At most spf_b200_set_max_in_flight (default 4) spawned runs are between dispatch and
+ * completion per context: further spawns block in the caller, as dispatch() blocks on the flow-control channel.
+ * The callback runs on a CUDA-internal thread and must not call CUDA or spf_b200 functions.  Sharded graphs
+ * (world > 1) are not spawned.  spf_b200_graph_wait blocks until the graph's last run (callback included) is over
+ * and returns its status. */
+typedef void (*spf_completion_fn)(void *user, int status, const char *message);
+int spf_b200_graph_spawn(spf_b200_graph *graph, spf_b200_graph *const *after, size_t n_after,
+                         spf_completion_fn on_complete, void *user);
+int spf_b200_graph_wait(spf_b200_graph *graph);
+const char *spf_b200_graph_status_message(const spf_b200_graph *graph); /* error message of the last spawned run, "" if none */
+int spf_b200_set_max_in_flight(spf_b200_ctx *ctx, int n);
 /* Page-locked host memory for ciphertext buffers.  Input and Output node buffers that are already page-locked (this
  * allocator, cudaHostAlloc, a cudaHostRegister done by the caller) are used as they are; any other buffer is registered
  * by the graph on first use, which is slow when there are hundreds of them (allocate ONE slab and slice it). */

@@ -223,6 +223,10 @@ class Evaluation:
     def synchronize(self):
         self._check(lib().spf_b200_synchronize(self._h))
 
+    def set_max_in_flight(self, n: int) -> None:
+        """Flow control of the asynchronous executor: at most n spawned graphs between dispatch and completion."""
+        self._check(lib().spf_b200_set_max_in_flight(self._h, int(n)))
+
     def fp64_peak_tflops(self) -> float:
         out = C.c_double()
         self._check(lib().spf_b200_fp64_peak(self._h, C.byref(out)))
@@ -403,7 +407,15 @@ ABI.update({
     "spf_b200_graph_open_peers": [_vp, C.c_int, C.c_int, _vp],
     "spf_b200_graph_set_peers": [_vp, C.c_int, C.c_int, C.POINTER(_vp)],
     "spf_b200_graph_plan": [C.POINTER(Params), C.POINTER(_Node), _sz, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "spf_b200_graph_spawn": [_vp, C.POINTER(_vp), _sz, _vp, _vp],
+    "spf_b200_graph_wait": [_vp],
+    "spf_b200_graph_status_message": [_vp],
+    "spf_b200_set_max_in_flight": [_vp, C.c_int],
+    "spf_b200_device_alloc": [_vp, C.POINTER(_vp), _sz],
+    "spf_b200_device_free": [_vp, _vp],
 })
+# spf_completion_fn(user, status, message)
+COMPLETION_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p)
 
 
 class _MuxNode(C.Structure):
@@ -418,7 +430,52 @@ ABI.update({
 _RESTYPES["spf_b200_mux_free"] = None
 # spf_exchange_fn(user, d_buf, chunk_bytes, world, stream) -> int
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
-_RESTYPES.update({"spf_b200_graph_destroy": None, "spf_b200_graph_launches": C.c_uint64, "spf_b200_graph_arena": _vp})
+_RESTYPES.update({"spf_b200_graph_destroy": None, "spf_b200_graph_launches": C.c_uint64, "spf_b200_graph_arena": _vp,
+                  "spf_b200_graph_status_message": C.c_char_p})
+
+
+class DeviceCiphertext:
+    """A ciphertext HANDLE: `nbytes` of device memory holding one ciphertext that never leaves HBM (the role of the
+    reference's Arc<AtomicRefCell<Option<Ciphertext>>> task outputs shared between graphs, circuit_processor/task.rs:10-16).
+    Pass it as the `io` of an Output* node of one graph and of an Input* node of the next.  GGSWs behind a handle are in
+    the device scale.  Wraps a raw pointer (`ptr`), a torch CUDA tensor, or allocates (`DeviceCiphertext.alloc`)."""
+
+    def __init__(self, ptr, nbytes: int | None = None, owner=None):
+        if hasattr(ptr, "data_ptr"):  # torch tensor
+            owner, nbytes, ptr = ptr, ptr.numel() * ptr.element_size(), ptr.data_ptr()
+        self.ptr, self.nbytes, self._owner = int(ptr), int(nbytes), owner
+
+    @classmethod
+    def alloc(cls, ev: "Evaluation", nbytes: int) -> "DeviceCiphertext":
+        import weakref
+
+        p = _vp()
+        ev._check(lib().spf_b200_device_alloc(ev.handle, C.byref(p), nbytes))
+        h = cls(p.value, nbytes, owner=ev)
+        weakref.finalize(h, lib().spf_b200_device_free, ev.handle, p.value)
+        return h
+
+
+def _io_ptr(io) -> int:
+    return io.ptr if isinstance(io, DeviceCiphertext) else io.ctypes.data
+
+
+def _io_nbytes(io) -> int:
+    return io.nbytes
+
+
+# bytes of the ciphertext behind an Input* / Output* node at DEFAULT_128-style params: op name -> length function, element size
+_IO_KIND = {"Lwe0": ("spf_b200_len_lwe_l0", 8), "Lwe1": ("spf_b200_len_lwe_l1", 8), "Glwe1": ("spf_b200_len_glwe_l1", 8),
+            "Ggsw1": ("spf_b200_len_ggsw_l1", 16), "Glev1": ("spf_b200_len_glev_l1", 8)}
+
+
+def io_bytes(op: str, params: "Params | None" = None) -> int:
+    """Size in bytes of the buffer an Input* / Output* node reads or writes (spf_node carries no length: the executor
+    DMAs exactly this many bytes through the raw pointer, so the host mirror checks it)."""
+    kind = op.replace("Input", "").replace("Output", "")
+    fn, elem = _IO_KIND[kind]
+    p = params or default_128()
+    return int(getattr(lib(), fn)(C.byref(p))) * elem
 
 
 class FheCircuit:
@@ -429,7 +486,8 @@ class FheCircuit:
 
     _DT = np.dtype([("op", "<u4"), ("arg", "<u4"), ("inp", "<i4", (3,)), ("pad", "<u4"), ("io", "<u8")])  # spf_node
 
-    def __init__(self):
+    def __init__(self, params: "Params | None" = None):
+        self.params = params      # io buffer sizes are checked against these (default: DEFAULT_128)
         self._n = 0
         self._buf = np.zeros(64, dtype=self._DT)   # node table in the C ABI's layout, grown geometrically
         self._buf["inp"] = -1
@@ -448,9 +506,26 @@ class FheCircuit:
     def add(self, op: str, *inputs: int, arg: int = 0, io: np.ndarray | None = None) -> int:
         return self._append(OP[op], int(arg), tuple(inputs) + (-1,) * (3 - len(inputs)), io)
 
+    def _check_io(self, opc: int, io) -> None:
+        """An io buffer must hold exactly one ciphertext of the node's kind: the executor copies that many bytes
+        through the raw pointer whatever the array's size (the reference is type-safe at this seam)."""
+        if not isinstance(io, DeviceCiphertext):
+            if not isinstance(io, np.ndarray) or not io.flags["C_CONTIGUOUS"]:
+                raise SpfError(-1, "io buffers must be C-contiguous numpy arrays or DeviceCiphertext handles")
+        name = OPS[opc]
+        if not (name.startswith("Input") or name.startswith("Output")):
+            raise SpfError(-1, f"{name} takes no io buffer")
+        want = io_bytes(name, self.params)
+        if _io_nbytes(io) != want:
+            raise SpfError(-1, f"{name}: io buffer has {_io_nbytes(io)} bytes, the ciphertext has {want}")
+        if isinstance(io, np.ndarray):
+            ok = io.dtype in (np.dtype(np.complex128), np.dtype(np.float64)) if name.endswith("Ggsw1") else io.dtype == np.dtype(np.uint64)
+            if not ok:
+                raise SpfError(-1, f"{name}: io buffer has dtype {io.dtype}")
+
     def _append(self, opc: int, arg: int, ins, io) -> int:
-        if io is not None and not io.flags["C_CONTIGUOUS"]:
-            raise SpfError(-1, "io buffers must be C-contiguous")
+        if io is not None:
+            self._check_io(opc, io)
         self._reserve(1)
         i = self._n
         row = self._buf[i]
@@ -488,7 +563,7 @@ class FheCircuit:
         arr = self._buf[:max(self._n, 1)].copy()
         arr["io"] = 0
         for i, io in self._io.items():
-            arr["io"][i] = io.ctypes.data
+            arr["io"][i] = _io_ptr(io)
         self._packed = arr  # keeps the memory alive for the duration of the call
         return arr.ctypes.data_as(C.POINTER(_Node))
 
@@ -572,6 +647,22 @@ class CircuitProcessor:
         finally:
             g.close()
 
+    def spawn_graph(self, circuit: FheCircuit, on_completion=None, after=()) -> "CompiledGraph":
+        """spawn_graph (mod.rs:573-623): dispatches the graph and returns; `on_completion(error)` is called once when all
+        of its ops have retired, with None or the first SpfError (CompletionHandler, completion_handler.rs:14-56) --
+        validation errors included, as in the reference.  Outputs must not be read before.  Returns the compiled graph:
+        pass it in `after` of a later spawn that consumes this one's DeviceCiphertext outputs, and close() it after
+        wait()."""
+        try:
+            g = self.compile(circuit)
+        except SpfError as e:
+            if on_completion is None:
+                raise
+            on_completion(e)
+            return None
+        g.spawn(after=after, on_complete=on_completion)
+        return g
+
 
 class CompiledGraph:
     """A levelised graph resident on one GPU.  With world > 1 the graph is laid out for a sharded
@@ -615,14 +706,42 @@ class CompiledGraph:
             raise self._cb_error
         self.ev._check(rc)
 
-    def set_io(self, node: int, buf: np.ndarray) -> None:
-        """Re-point an Input*/Output* node at another host buffer (same ciphertext kind): a compiled graph
-        is reusable across invocations of the same instruction shape."""
-        if not isinstance(buf, np.ndarray) or not buf.flags["C_CONTIGUOUS"]:
-            raise SpfError(-1, "io buffers must be C-contiguous numpy arrays")
-        self.ev._check(lib().spf_b200_graph_set_io(self._h, node, buf.ctypes.data))
+    def set_io(self, node: int, buf) -> None:
+        """Re-point an Input*/Output* node at another buffer of the same ciphertext kind (a numpy array -- page-locked
+        or pageable -- or a DeviceCiphertext handle): a compiled graph is reusable across invocations of the same
+        instruction shape."""
+        if not 0 <= node < len(self._keep):
+            raise SpfError(-1, f"set_io: node {node} out of range")
+        self._keep._check_io(int(self._keep.ops[node]), buf)
+        self.ev._check(lib().spf_b200_graph_set_io(self._h, node, _io_ptr(buf)))
         self._bound = getattr(self, "_bound", {})
         self._bound[node] = buf  # keep alive
+
+    def spawn(self, after=(), on_complete=None) -> None:
+        """One asynchronous run (spf_b200_graph_spawn): returns as soon as the work is enqueued (or blocks while the
+        context's flow-control limit of in-flight graphs is reached).  `after`: CompiledGraphs whose last spawned run must
+        finish first (ordered on the device).  on_complete(error) is called from a CUDA callback thread with None or
+        the first SpfError of the run; it must not call into spf_b200 or CUDA."""
+        if self.world != 1:
+            raise SpfError(-1, "sharded graphs are not spawned")
+        deps = [d for d in after if d is not None]
+        arr = (_vp * max(len(deps), 1))(*[d._h for d in deps])
+
+        def _done(user, status, message):
+            try:
+                if on_complete is not None:
+                    on_complete(None if status == 0 else SpfError(int(status), (message or b"").decode()))
+            except Exception:  # never let an exception cross the C ABI
+                pass
+
+        self._spawn_cb = COMPLETION_FN(_done)  # kept alive until the next spawn / close
+        self.ev._check(lib().spf_b200_graph_spawn(self._h, arr, len(deps), C.cast(self._spawn_cb, _vp), None))
+
+    def wait(self) -> None:
+        """Block until the last run (spawned or blocking) is over; raises its error, if any."""
+        rc = lib().spf_b200_graph_wait(self._h)
+        if rc:
+            raise SpfError(int(rc), (lib().spf_b200_graph_status_message(self._h) or b"").decode() or "the graph's last run failed")
 
     # ---- peer-memory exchange (no exchange callable): every rank maps every other rank's arena ----
     @property

@@ -9,8 +9,10 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -49,6 +51,13 @@ struct spf_b200_ctx {
   std::string err;
   std::atomic<uint64_t> launches{0};
   int sm_count = 148;
+  // lifetime: graphs built on this context keep it alive (spf_b200_destroy only drops the owner's reference)
+  std::atomic<int> refs{1};
+  // flow control of the asynchronous executor (graph.cuh: spf_b200_graph_spawn): at most max_in_flight spawned graphs
+  // between dispatch and completion, as the bounded channel of CircuitProcessor::new (circuit_processor/mod.rs:95-123)
+  std::mutex fc_mu;
+  std::condition_variable fc_cv;
+  int in_flight = 0, max_in_flight = 4;
   // device constants for the graph executor's Zero*/One* nodes (graph.cuh::ensure_constants)
   void* consts = nullptr;
   char *c_lwe0[2] = {nullptr, nullptr}, *c_glwe[2] = {nullptr, nullptr}, *c_glev[2] = {nullptr, nullptr},
@@ -382,7 +391,7 @@ int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const 
 }
 
 int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, size_t batch, cudaStream_t s,
-                     const void* const* ptrs = nullptr) {
+                     const void* const* ptrs = nullptr, DevBuf* states = nullptr /* caller-owned digit-state scratch */) {
   if (batch == 0) return 0;
   KsBatch P;
   P.out = d_out;
@@ -395,15 +404,16 @@ int launch_keyswitch(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_in, s
   P.n0 = (int)ctx->p.lwe_n;
   P.radix_log = (int)ctx->p.ks.radix_log;
   P.count = (int)ctx->p.ks.count;
-  if (ctx->ks_bfrag && !getenv("SPF_B200_KS_NO_TC")) {  // dense contraction on the int8 tensor cores (K4t)
+  static const bool ks_no_tc = getenv("SPF_B200_KS_NO_TC") != nullptr;  // environment knobs are read once, not per launch
+  static const bool ks_mma = [] { const char* e = getenv("SPF_B200_KS_IMPL"); return e && !strcmp(e, "mma"); }();
+  if (ctx->ks_bfrag && !ks_no_tc) {  // dense contraction on the int8 tensor cores (K4t)
     KsTcBatch T;
-    DevBuf& st16 = ctx->scratch[s == ctx->stream[1] ? 1 : 0][6];
+    DevBuf& st16 = states ? *states : ctx->scratch[s == ctx->stream[1] ? 1 : 0][6];
     if (int rc = ensure(ctx, st16, batch * (size_t)P.n1 * 2)) return rc;
     ks_tc_states_kernel<<<std::min<int>((int)((batch * (size_t)P.n1 + 255) / 256), ctx->sm_count * 8), 256, 0, s>>>(
         (uint16_t*)st16.p, d_in, ptrs, P.batch, P.n1, P.radix_log, P.count);
     if (int rc = check_launch(ctx, "ks_tc_states_kernel")) return rc;
-    const char* impl = getenv("SPF_B200_KS_IMPL");  // "mma": legacy mma.sync kernel (K4t), default: tcgen05 (K4u)
-    if (!(impl && !strcmp(impl, "mma"))) {
+    if (!ks_mma) {  // SPF_B200_KS_IMPL=mma: legacy mma.sync kernel (K4t); default: tcgen05 (K4u)
       KsUBatch U;
       U.out = d_out; U.in = d_in; U.ptrs = ptrs; U.st16 = (const uint16_t*)st16.p; U.btiles = ctx->ks_btiles; U.colsum = ctx->ks_tc_colsum;
       U.batch = P.batch; U.n1 = P.n1; U.n0 = P.n0; U.radix_log = P.radix_log; U.count = P.count;
@@ -602,6 +612,7 @@ int spf_b200_create_from_device(const spf_params* params, const double* d_bsk_ff
 
 void spf_b200_destroy(spf_b200_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->refs.fetch_sub(1) > 1) return;  // graphs built on this context are still alive: the last one frees it
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   cudaFree(ctx->bsk); cudaFree(ctx->ak); cudaFree(ctx->ssk); cudaFree(ctx->ksk); cudaFree(ctx->ksk_colsum); cudaFree(ctx->ks_bfrag); cudaFree(ctx->ks_tc_colsum); cudaFree(ctx->ks_btiles);

@@ -117,6 +117,32 @@ struct spf_b200_graph {
   unsigned long long epoch = 0;
   std::vector<void*> ipc_opened;
   std::vector<void*> pinned;  // io buffers page-locked by this graph (cudaHostRegister), so that their copies are true DMAs
+  // io kinds per node (Input* / Output* only): 0 = page-locked host memory (plain DMA), 1 = pageable host memory staged
+  // through the graph's own page-locked slab (set_io on an unpinned buffer: registering costs 0.4 ms per buffer and call),
+  // 2 = DEVICE memory: a ciphertext handle that never leaves HBM (another graph's output, a torch tensor, ...); GGSWs
+  // behind device handles keep the device scale (2^-10)
+  std::vector<char> io_kind;
+  std::vector<unsigned long long> io_alloc;  // allocation that holds the node's io buffer (alloc_base_of), 0 = do not merge copies
+  char* h_stage = nullptr;        // page-locked staging slab for kind-1 buffers
+  size_t h_stage_bytes = 0;
+  std::vector<size_t> stage_off;  // per node: offset of its ciphertext in h_stage (kind 1), (size_t)-1 otherwise
+  // asynchronous execution (spf_b200_graph_spawn): the graph's own stream, an event recorded behind every run, the first
+  // error latched by the current / last run, the digit-state scratch of its keyswitch levels
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  std::atomic<int> status{0};
+  std::string status_msg;
+  DevBuf ks_states;
+  bool poisoned = false;  // a failed peer-mode run leaves the ranks' barrier epochs out of step: rebuild the graphs
+};
+
+// one spawned run between dispatch and completion
+struct SpawnRecord {
+  spf_b200_graph* g;
+  spf_completion_fn cb;
+  void* user;
+  int status;
+  std::string msg;
 };
 
 namespace {
@@ -165,13 +191,44 @@ int graph_fail(spf_b200_ctx* ctx, const std::string& msg) { return fail(ctx, SPF
 // Buffers that are page-locked already (spf_b200_host_alloc, cudaHostAlloc, a caller's own registration) are left
 // alone: cudaHostRegister costs 0.4 ms per 32 KiB buffer and grows with the number of registrations (5 s for the 516
 // buffers of four mul32 programs), so hosts should carve their ciphertext buffers out of ONE pinned slab.
-void pin_io(spf_b200_graph* g, void* p, size_t bytes) {
-  if (!p || getenv("SPF_B200_NO_PIN")) return;
-  cudaPointerAttributes attr;
-  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return;
+// Base address of the allocation (cudaMalloc / cudaHostAlloc) that contains p, 0 when p is not inside ONE such
+// allocation known to the driver (pageable memory, a range registered piecemeal).  Copies are only ever merged between
+// buffers of the same allocation: a cudaMemcpyAsync that runs over the end of an allocation or registration is refused
+// by the driver, and two numpy rows or two 32 KiB cudaMallocs are routinely adjacent.
+unsigned long long alloc_base_of(const void* p) {
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  static range_fn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) f = nullptr;
+    cudaGetLastError();
+    return reinterpret_cast<range_fn>(f);
+  }();
+  if (!fn || !p) return 0;
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return 0;
+  return base;
+}
+
+// Returns the io kind (see spf_b200_graph::io_kind).  `may_register`: page-lock an unpinned host buffer (graph build);
+// otherwise (set_io on a built graph) unpinned buffers are staged through the graph's slab.
+int pin_io(spf_b200_graph* g, void* p, size_t bytes, bool may_register = true) {
+  static const bool no_pin = getenv("SPF_B200_NO_PIN") != nullptr;
+  if (!p) return 0;
+  // both ends: a buffer that merely shares its first page with a neighbour's registration is not page-locked
+  cudaPointerAttributes attr, attr_end;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess &&
+      cudaPointerGetAttributes(&attr_end, static_cast<char*>(p) + (bytes ? bytes - 1 : 0)) == cudaSuccess) {
+    if (attr.type == cudaMemoryTypeHost && attr_end.type == cudaMemoryTypeHost) return 0;
+    if ((attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) && attr_end.type == attr.type) return 2;
+  }
   cudaGetLastError();
-  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) g->pinned.push_back(p);
-  else cudaGetLastError();  // clear the sticky-free error
+  if (!may_register) return 1;
+  if (no_pin) return 0;  // plain pageable cudaMemcpyAsync (diagnostics)
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) { g->pinned.push_back(p); return 0; }
+  cudaGetLastError();  // clear the sticky-free error
+  return 1;
 }
 
 // Items per rank of a sharded CircuitBootstrap group: equal chunks (the last ones may be short or
@@ -194,7 +251,7 @@ int run_group_range(spf_b200_graph* g, const Group& G, cudaStream_t s, size_t st
     case SPF_OP_SAMPLE_EXTRACT:
       return launch_sample_extract(ctx, reinterpret_cast<uint64_t*>(out), nullptr, u32, 0, n, s, p1);
     case SPF_OP_KEYSWITCH_L1_TO_L0:
-      return launch_keyswitch(ctx, reinterpret_cast<uint64_t*>(out), nullptr, n, s, p1);
+      return launch_keyswitch(ctx, reinterpret_cast<uint64_t*>(out), nullptr, n, s, p1, &g->ks_states);
     case SPF_OP_NOT:
       return launch_elementwise(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, 1, 0, n, s, p2);
     case SPF_OP_GLWE_ADD:
@@ -255,10 +312,12 @@ int plan_graph(spf_b200_ctx* ectx, const spf_params* p, spf_b200_graph* g, int w
       if (e < oi.n_in) {
         if (src < 0 || (size_t)src >= n)
           return graph_fail(ectx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): missing ciphertext input on edge " + std::to_string(e));
-      } else if (src >= 0 && nd.op != SPF_OP_RETIRE && nd.op != SPF_OP_NOP) {
+      } else if (src >= 0) {  // also Nop / Retire: Task::validate_inputs rejects any edge on a 0-input op (task.rs:100-118)
         return graph_fail(ectx, std::string("node ") + std::to_string(i) + " (" + kOpNames[nd.op] + "): unexpected extra input edge");
       }
     }
+    if (nd.op == SPF_OP_RETIRE)  // user graphs never contain Retire (circuit_processor/mod.rs:606-611, illegal_retire_op)
+      return graph_fail(ectx, "node " + std::to_string(i) + ": illegal Retire op in a user graph");
     if (nd.op == SPF_OP_SAMPLE_EXTRACT && nd.arg >= p->glwe_n)
       return graph_fail(ectx, "illegal sample extract index " + std::to_string(nd.arg));
     const bool is_io = nd.op <= SPF_OP_OUTPUT_GLEV1;
@@ -417,9 +476,21 @@ extern "C" {
 
 void spf_b200_graph_destroy(spf_b200_graph* g);
 int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user);
+int spf_b200_graph_set_io(spf_b200_graph* g, size_t node, void* io);
 int spf_b200_graph_output_rank(const spf_b200_graph* g, size_t node);
 
+static int graph_build_sharded_impl(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, int world, spf_b200_graph** out);
+// C++ exceptions (std::bad_alloc / length_error on a huge graph) never cross the C ABI
 int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, int world, spf_b200_graph** out) {
+  try {
+    return graph_build_sharded_impl(ctx, nodes, n, world, out);
+  } catch (const std::exception& e) {
+    return fail(ctx, SPF_E_GRAPH, std::string("graph build: ") + e.what());
+  } catch (...) {
+    return fail(ctx, SPF_E_GRAPH, "graph build: unknown exception");
+  }
+}
+static int graph_build_sharded_impl(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, int world, spf_b200_graph** out) {
   if (!ctx) return SPF_E_INVALID;
   if (!out || (!nodes && n)) return fail(ctx, SPF_E_INVALID, "NULL argument");
   if (world < 1 || world > 1024) return fail(ctx, SPF_E_INVALID, "world must be in 1..1024");
@@ -427,8 +498,12 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
   const spf_params* p = &ctx->p;
   std::unique_ptr<spf_b200_graph, void (*)(spf_b200_graph*)> g(new spf_b200_graph(), spf_b200_graph_destroy);
   g->ctx = ctx;
+  ctx->refs.fetch_add(1);  // released by spf_b200_graph_destroy: a graph may outlive its owner's spf_b200_destroy
   g->world = world;
   g->nodes.assign(nodes, nodes + n);
+  g->io_kind.assign(n, 0);
+  g->io_alloc.assign(n, 0);
+  g->stage_off.assign(n, (size_t)-1);
   static const bool build_timing = getenv("SPF_B200_GRAPH_TIMING") != nullptr;
   auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_start = now_ms();
@@ -534,6 +609,8 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
     }
   }
   CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&g->done, cudaEventDisableTiming));
   const size_t pool_off = arena;
   arena = align(arena + g->pool_slots * ct_bytes(p, T_GLWE1));
   g->arena_bytes = std::max<size_t>(arena, 256);
@@ -566,10 +643,15 @@ int spf_b200_graph_build_sharded(spf_b200_ctx* ctx, const spf_node* nodes, size_
           if (G.slot_outputs) g->dptr[id] = g->arena + pool_off + (size_t)g->slot[id] * ct_bytes(p, T_GLWE1);
           else if (G.out_base) g->dptr[id] = G.out_base + k * ct_bytes(p, oi.out);
       }
-      if (G.op <= SPF_OP_INPUT_GLEV1) { g->inputs.push_back(id); pin_io(g.get(), g->nodes[id].io, ct_host_bytes(p, g->type[id])); }
+      if (G.op <= SPF_OP_INPUT_GLEV1) {
+        g->inputs.push_back(id);
+        g->io_kind[id] = (char)pin_io(g.get(), g->nodes[id].io, ct_host_bytes(p, g->type[id]));
+        g->io_alloc[id] = alloc_base_of(g->nodes[id].io);
+      }
       if (G.op >= SPF_OP_OUTPUT_LWE0 && G.op <= SPF_OP_OUTPUT_GLEV1) {
         g->outputs.push_back(id);
-        pin_io(g.get(), g->nodes[id].io, ct_host_bytes(p, g->type[g->nodes[id].in[0]]));
+        g->io_kind[id] = (char)pin_io(g.get(), g->nodes[id].io, ct_host_bytes(p, g->type[g->nodes[id].in[0]]));
+        g->io_alloc[id] = alloc_base_of(g->nodes[id].io);
       }
     }
   }
@@ -653,61 +735,79 @@ int spf_b200_graph_build(spf_b200_ctx* ctx, const spf_node* nodes, size_t n, spf
   return spf_b200_graph_build_sharded(ctx, nodes, n, 1, out);
 }
 
-// Executes the graph once: copies every Input* ciphertext from its io pointer, runs the levels,
-// copies every Output* ciphertext to its io pointer, and returns when the outputs are valid
-// (CircuitProcessor::run_graph_blocking, circuit_processor/mod.rs:641-655).
-// Sharded over `world` ranks (one process per GPU, every rank runs the same graph on the same
-// inputs): each CircuitBootstrap group -- the only expensive ops -- is split into `world` equal
-// chunks, rank r bootstraps chunk r, then `exchange` (an all-gather over NVLink, see
-// spf_b200/multi.py) completes the group's GGSWs on every rank; the cheap ops in between
-// (sample extract, keyswitch, the MUX tree) run replicated, so no other data moves.
-int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user) {
-  if (!g) return SPF_E_INVALID;
+}  // extern "C"
+
+namespace {
+
+// offset of node id's ciphertext in the page-locked staging slab (kind-1 io: pageable host memory), growing the slab
+int stage_slot(spf_b200_graph* g, int id, size_t bytes, char** out) {
   spf_b200_ctx* ctx = g->ctx;
-  if (world != g->world || rank < 0 || rank >= world)
-    return fail(ctx, SPF_E_INVALID, "rank/world do not match the graph's sharded layout");
-  const bool peer_mode = world > 1 && !exchange;
-  if (peer_mode && (!g->peers_set || g->peer_rank != rank))
-    return fail(ctx, SPF_E_INVALID, "a sharded run needs an exchange callback or opened peer arenas (spf_b200_graph_open_peers)");
+  if (g->stage_off[id] == (size_t)-1) {
+    size_t total = 0;
+    for (size_t v = 0; v < g->nodes.size(); v++)
+      if (g->io_kind[v] == 1 || (int)v == id) {
+        const uint32_t op = g->nodes[v].op;
+        const CtType t = op <= SPF_OP_INPUT_GLEV1 ? g->type[v] : g->type[g->nodes[v].in[0]];
+        g->stage_off[v] = total;
+        total += (ct_host_bytes(&ctx->p, t) + 255) & ~(size_t)255;
+      }
+    if (total > g->h_stage_bytes) {
+      CU(cudaStreamSynchronize(g->stream));
+      if (g->h_stage) CU(cudaFreeHost(g->h_stage));
+      g->h_stage = nullptr;
+      CU(cudaHostAlloc(reinterpret_cast<void**>(&g->h_stage), total, cudaHostAllocDefault));
+      g->h_stage_bytes = total;
+    }
+  }
+  (void)bytes;
+  *out = g->h_stage + g->stage_off[id];
+  return 0;
+}
+
+// Everything of one run that is ENQUEUED on stream s: input copies, all levels, exchanges, output copies.  Returns the
+// first error (message in ctx->err); work already enqueued keeps running -- the caller drains the stream.
+int enqueue_run(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user, cudaStream_t s,
+                std::vector<cudaEvent_t>* timing_events) {
+  spf_b200_ctx* ctx = g->ctx;
   const spf_params* p = &ctx->p;
-  CU(cudaSetDevice(ctx->device));
-  cudaStream_t s = ctx->stream[0];
-  const uint64_t l0 = ctx->launches.load();
+  const bool peer_mode = world > 1 && !exchange;
   // every rank has finished its previous run before anyone stores into its arena again
   if (peer_mode) if (int rc = peer_barrier(g, s)) return rc;
   // inputs whose host buffers AND device buffers are consecutive (rows of one host slab, in node order) go up as one copy
   for (size_t i = 0; i < g->inputs.size();) {
     const int id0 = g->inputs[i];
+    const int kind = g->io_kind[id0];
     size_t bytes = ct_host_bytes(p, g->type[id0]), j = i + 1;
-    while (j < g->inputs.size() && g->dptr[g->inputs[j]] == g->dptr[id0] + bytes &&
+    if (kind == 1) {  // pageable host buffer: through the page-locked slab
+      char* st = nullptr;
+      if (int rc = stage_slot(g, id0, bytes, &st)) return rc;
+      memcpy(st, g->nodes[id0].io, bytes);
+      CU(cudaMemcpyAsync(g->dptr[id0], st, bytes, cudaMemcpyHostToDevice, s));
+      i = j;
+      continue;
+    }
+    while (j < g->inputs.size() && g->io_kind[g->inputs[j]] == kind && g->io_alloc[id0] != 0 && g->io_alloc[g->inputs[j]] == g->io_alloc[id0] &&
+           g->dptr[g->inputs[j]] == g->dptr[id0] + bytes &&
            static_cast<char*>(g->nodes[g->inputs[j]].io) == static_cast<char*>(g->nodes[id0].io) + bytes) {
       bytes += ct_host_bytes(p, g->type[g->inputs[j]]);
       j++;
     }
-    CU(cudaMemcpyAsync(g->dptr[id0], g->nodes[id0].io, bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(g->dptr[id0], g->nodes[id0].io, bytes, kind == 2 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
     i = j;
   }
   for (int id : g->inputs) {
     const CtType t = g->type[id];
-    if (t == T_GGSW1)
+    if (t == T_GGSW1 && g->io_kind[id] != 2)  // device handles carry GGSWs in the device scale already
       if (int rc = launch_scale(ctx, reinterpret_cast<C2*>(g->dptr[id]), reinterpret_cast<const C2*>(g->dptr[id]),
                                 spf_b200_len_ggsw_l1(p), 1.0 / 1024.0, s))
         return rc;
   }
-  // SPF_B200_GRAPH_TIMING=1: CUDA events around every group, per-op totals on stderr (diagnostics only;
-  // the events serialise nothing but do defeat the programmatic overlap between CMUX levels)
-  static const bool timing = getenv("SPF_B200_GRAPH_TIMING") != nullptr;
-  std::vector<cudaEvent_t> ev;
-  if (timing) {
-    ev.resize(g->groups.size() + 1);
-    for (auto& e : ev) cudaEventCreate(&e);
-    cudaEventRecord(ev[0], s);
-  }
+  if (timing_events) cudaEventRecord((*timing_events)[0], s);
   size_t gi = 0;
   for (const Group& G : g->groups) {
     // peer mode: the scheme-switch kernel stores its GGSWs into every rank's arena while it computes them
     if (int rc = run_group(g, G, s, rank, peer_mode && G.op == SPF_OP_CIRCUIT_BOOTSTRAP ? &g->peers : nullptr)) return rc;
-    if (timing) cudaEventRecord(ev[++gi], s);
+    if (timing_events) cudaEventRecord((*timing_events)[++gi], s);
     if (world > 1 && G.gather_chunk > 0) {  // circuit-bootstrap outputs (GGSW) and keyswitch outputs (L0 LWE)
       const size_t item_bytes = ct_bytes(p, op_info(G.op).out);
       if (!peer_mode) {
@@ -742,13 +842,21 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
     const int id = g->outputs[k];
     const int src = g->nodes[id].in[0];
     const CtType t = g->type[src];
+    const int kind = g->io_kind[id];
+    char* dst = static_cast<char*>(g->nodes[id].io);
+    if (kind == 1 && mine(k))
+      if (int rc = stage_slot(g, id, ct_host_bytes(p, t), &dst)) return rc;
     if (t == T_GGSW1) {
       char* tmp = g->d_out_stage + stage;
       stage += ct_bytes(p, T_GGSW1);
       if (mine(k)) {
-        if (int rc = launch_scale(ctx, reinterpret_cast<C2*>(tmp), reinterpret_cast<const C2*>(g->dptr[src]), spf_b200_len_ggsw_l1(p), 1024.0, s))
-          return rc;
-        CU(cudaMemcpyAsync(g->nodes[id].io, tmp, ct_host_bytes(p, t), cudaMemcpyDeviceToHost, s));
+        if (kind == 2) {  // device handle: the GGSW stays in HBM in the device scale
+          CU(cudaMemcpyAsync(dst, g->dptr[src], ct_bytes(p, t), cudaMemcpyDeviceToDevice, s));
+        } else {
+          if (int rc = launch_scale(ctx, reinterpret_cast<C2*>(tmp), reinterpret_cast<const C2*>(g->dptr[src]), spf_b200_len_ggsw_l1(p), 1024.0, s))
+            return rc;
+          CU(cudaMemcpyAsync(dst, tmp, ct_host_bytes(p, t), cudaMemcpyDeviceToHost, s));
+        }
       }
       k++;
       continue;
@@ -756,24 +864,97 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
     if (!mine(k)) { k++; continue; }
     // consecutive outputs whose host buffers are consecutive too leave in one copy
     size_t bytes = ct_host_bytes(p, t), j = k + 1;
-    while (j < g->outputs.size() && g->gather_off[j] == g->gather_off[k] + bytes && mine(j) &&
+    while (kind != 1 && j < g->outputs.size() && g->io_kind[g->outputs[j]] == kind && g->io_alloc[id] != 0 &&
+           g->io_alloc[g->outputs[j]] == g->io_alloc[id] && g->gather_off[j] == g->gather_off[k] + bytes && mine(j) &&
            static_cast<char*>(g->nodes[g->outputs[j]].io) == static_cast<char*>(g->nodes[id].io) + bytes) {
       bytes += ct_host_bytes(p, g->type[g->nodes[g->outputs[j]].in[0]]);
       j++;
     }
-    CU(cudaMemcpyAsync(g->nodes[id].io, g->d_gather + g->gather_off[k], bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(dst, g->d_gather + g->gather_off[k], bytes, kind == 2 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
     k = j;
   }
-  CU(cudaStreamSynchronize(s));
-  if (peer_mode) {
+  return 0;
+}
+
+// After the stream has drained: staged (pageable) outputs go to their buffers.  Pure host work (also runs inside the
+// stream's host-function callback of a spawned run).
+void copy_out_staged(spf_b200_graph* g, int rank) {
+  const spf_params* p = &g->ctx->p;
+  for (size_t k = 0; k < g->outputs.size(); k++) {
+    const int id = g->outputs[k];
+    if (g->io_kind[id] != 1 || g->stage_off[id] == (size_t)-1) continue;
+    const int r = spf_b200_graph_output_rank(g, (size_t)id);
+    if (!(r < 0 || r == rank)) continue;
+    memcpy(g->nodes[id].io, g->h_stage + g->stage_off[id], ct_host_bytes(p, g->type[g->nodes[id].in[0]]));
+  }
+}
+
+void CUDART_CB spawn_done(void* arg) {
+  SpawnRecord* rec = static_cast<SpawnRecord*>(arg);
+  spf_b200_graph* g = rec->g;
+  if (rec->status == 0) copy_out_staged(g, 0);
+  spf_b200_ctx* ctx = g->ctx;
+  {
+    std::lock_guard<std::mutex> lk(ctx->fc_mu);
+    ctx->in_flight--;
+  }
+  ctx->fc_cv.notify_all();
+  if (rec->cb) rec->cb(rec->user, rec->status, rec->status ? rec->msg.c_str() : nullptr);
+  delete rec;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Executes the graph once: copies every Input* ciphertext from its io pointer, runs the levels,
+// copies every Output* ciphertext to its io pointer, and returns when the outputs are valid
+// (CircuitProcessor::run_graph_blocking, circuit_processor/mod.rs:641-655).
+// Sharded over `world` ranks (one process per GPU, every rank runs the same graph on the same
+// inputs): each CircuitBootstrap group -- the only expensive ops -- is split into `world` equal
+// chunks, rank r bootstraps chunk r, then `exchange` (an all-gather over NVLink, see
+// spf_b200/multi.py) or the peer-memory stores complete the group's GGSWs on every rank; MUX trees run on their
+// owner ranks.  A failure after the first enqueue drains the stream before returning (the caller's io buffers are
+// not touched afterwards); in peer mode it also leaves the ranks' barrier epochs out of step, so the graph is
+// marked poisoned and must be rebuilt.
+int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user) {
+  if (!g) return SPF_E_INVALID;
+  spf_b200_ctx* ctx = g->ctx;
+  if (world != g->world || rank < 0 || rank >= world)
+    return fail(ctx, SPF_E_INVALID, "rank/world do not match the graph's sharded layout");
+  const bool peer_mode = world > 1 && !exchange;
+  if (peer_mode && (!g->peers_set || g->peer_rank != rank))
+    return fail(ctx, SPF_E_INVALID, "a sharded run needs an exchange callback or opened peer arenas (spf_b200_graph_open_peers)");
+  if (g->poisoned)
+    return fail(ctx, SPF_E_GRAPH, "an earlier peer-memory run of this graph failed: the ranks' barrier epochs disagree, rebuild the graphs");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = g->stream;
+  const uint64_t l0 = ctx->launches.load();
+  // SPF_B200_GRAPH_TIMING=1: CUDA events around every group, per-op totals on stderr (diagnostics only;
+  // the events serialise nothing but do defeat the programmatic overlap between CMUX levels)
+  static const bool timing = getenv("SPF_B200_GRAPH_TIMING") != nullptr;
+  std::vector<cudaEvent_t> ev;
+  if (timing) {
+    ev.resize(g->groups.size() + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+  }
+  int rc = enqueue_run(g, rank, world, exchange, user, s, timing ? &ev : nullptr);
+  const std::string msg = rc ? ctx->err : std::string();
+  const cudaError_t se = cudaStreamSynchronize(s);  // also on failure: nothing of this run is in flight afterwards
+  cudaEventRecord(g->done, s);
+  if (rc == 0 && se != cudaSuccess) rc = fail(ctx, SPF_E_CUDA, std::string("graph run: ") + cudaGetErrorString(se));
+  else if (rc) ctx->err = msg;
+  if (rc == 0) copy_out_staged(g, rank);
+  if (rc == 0 && peer_mode) {
     int err = 0;
-    CU(cudaMemcpy(&err, g->arena + 2048, sizeof(int), cudaMemcpyDeviceToHost));
+    if (cudaMemcpy(&err, g->arena + 2048, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) err = 1;
     if (err) {
-      CU(cudaMemset(g->arena + 2048, 0, sizeof(int)));
-      return fail(ctx, SPF_E_GRAPH, "peer barrier timed out: a rank of the sharded run did not arrive");
+      cudaMemset(g->arena + 2048, 0, sizeof(int));
+      rc = fail(ctx, SPF_E_GRAPH, "peer barrier timed out: a rank of the sharded run did not arrive");
     }
   }
-  if (timing) {
+  if (rc && peer_mode) g->poisoned = true;
+  if (timing && rc == 0) {
     std::map<uint32_t, std::pair<double, size_t>> per_op;
     std::map<uint32_t, size_t> groups_of;
     for (size_t k = 0; k < g->groups.size(); k++) {
@@ -785,15 +966,96 @@ int spf_b200_graph_run_sharded(spf_b200_graph* g, int rank, int world, spf_excha
     }
     for (auto& kv : per_op)
       fprintf(stderr, "[spf_b200 graph] %-18s %6zu groups %8zu nodes %9.3f ms\n", kOpNames[kv.first], groups_of[kv.first], kv.second.second, kv.second.first);
-    for (auto& e : ev) cudaEventDestroy(e);
   }
+  for (auto& e : ev) cudaEventDestroy(e);
+  g->status.store(rc);
   g->launches_per_run = ctx->launches.load() - l0;
+  return rc;
+}
+
+// ---- asynchronous execution: CircuitProcessor::spawn_graph + CompletionHandler + flow control -------------------------
+// (circuit_processor/mod.rs:130-253,573-623; completion_handler.rs:14-56).  The whole run is enqueued on the graph's own
+// stream and the call returns; `on_complete(user, status, message)` fires exactly once when every op has retired, with
+// the FIRST error of the run (0 = none).  A run whose dependency failed retires as a no-op with that error, as tasks
+// do after CompletionHandler::error is set.  At most spf_b200_set_max_in_flight graphs are between dispatch and
+// completion: further spawns block in the caller, as dispatch() blocks on the flow-control channel.  `after`: graphs
+// whose LAST spawned run must complete first (stream-ordered on the device, no host wait) -- with device handles as
+// io buffers (see spf_b200_graph_set_io) graph k + 1 consumes graph k's outputs without leaving HBM.
+// The callback runs on a CUDA-internal thread: it must not call CUDA or spf_b200 functions.
+int spf_b200_graph_spawn(spf_b200_graph* g, spf_b200_graph* const* after, size_t n_after, spf_completion_fn on_complete, void* user) {
+  if (!g) return SPF_E_INVALID;
+  spf_b200_ctx* ctx = g->ctx;
+  if (g->world != 1) return fail(ctx, SPF_E_INVALID, "spawn: sharded graphs run through spf_b200_graph_run_sharded");
+  if (n_after && !after) return fail(ctx, SPF_E_INVALID, "spawn: NULL dependency list");
+  CU(cudaSetDevice(ctx->device));
+  {
+    std::unique_lock<std::mutex> lk(ctx->fc_mu);
+    ctx->fc_cv.wait(lk, [&] { return ctx->in_flight < ctx->max_in_flight; });
+    ctx->in_flight++;
+  }
+  // the staging slab of pageable io buffers is reused by the next run: wait for the previous one
+  bool staged = false;
+  for (char k : g->io_kind) staged |= k == 1;
+  if (staged) cudaEventSynchronize(g->done);
+  SpawnRecord* rec = new SpawnRecord{g, on_complete, user, 0, std::string()};
+  for (size_t i = 0; i < n_after && rec->status == 0; i++) {
+    spf_b200_graph* d = after[i];
+    if (!d || d == g) continue;
+    if (const int ds = d->status.load()) {
+      rec->status = ds;
+      rec->msg = "a dependency of this graph failed: " + d->status_msg;
+    } else if (cudaStreamWaitEvent(g->stream, d->done, 0) != cudaSuccess) {
+      rec->status = SPF_E_CUDA;
+      rec->msg = "cudaStreamWaitEvent on a dependency failed";
+    }
+  }
+  if (rec->status == 0) {
+    if (const int rc = enqueue_run(g, 0, 1, nullptr, nullptr, g->stream, nullptr)) {
+      rec->status = rc;
+      rec->msg = ctx->err;
+    }
+  }
+  g->status.store(rec->status);
+  g->status_msg = rec->msg;
+  const cudaError_t e = cudaLaunchHostFunc(g->stream, spawn_done, rec);
+  cudaEventRecord(g->done, g->stream);
+  if (e != cudaSuccess) {  // could not even enqueue the completion: deliver it here
+    cudaStreamSynchronize(g->stream);
+    rec->status = rec->status ? rec->status : SPF_E_CUDA;
+    if (rec->msg.empty()) rec->msg = std::string("cudaLaunchHostFunc: ") + cudaGetErrorString(e);
+    spawn_done(rec);
+  }
+  return 0;
+}
+
+// Blocks until the last run of the graph (spawned or blocking) has completed, callback included; returns its status.
+int spf_b200_graph_wait(spf_b200_graph* g) {
+  if (!g) return SPF_E_INVALID;
+  spf_b200_ctx* ctx = g->ctx;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(g->done));
+  return g->status.load();
+}
+
+// message of the error latched by the graph's last spawned run ("" when it succeeded)
+const char* spf_b200_graph_status_message(const spf_b200_graph* g) { return g ? g->status_msg.c_str() : ""; }
+
+int spf_b200_set_max_in_flight(spf_b200_ctx* ctx, int n) {
+  if (!ctx) return SPF_E_INVALID;
+  if (n < 1) return fail(ctx, SPF_E_INVALID, "max_in_flight must be at least 1");
+  {
+    std::lock_guard<std::mutex> lk(ctx->fc_mu);
+    ctx->max_in_flight = n;
+  }
+  ctx->fc_cv.notify_all();
   return 0;
 }
 
 void spf_b200_graph_destroy(spf_b200_graph* g) {
   if (!g) return;
-  cudaSetDevice(g->ctx->device);
+  spf_b200_ctx* ctx = g->ctx;
+  cudaSetDevice(ctx->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);  // a spawned run may still be in flight
   for (void* q : g->ipc_opened) cudaIpcCloseMemHandle(q);
   cudaFree(g->arena);
   cudaFree(g->d_ptrs);
@@ -801,8 +1063,13 @@ void spf_b200_graph_destroy(spf_b200_graph* g) {
   cudaFree(g->d_out_stage);
   cudaFree(g->d_gather);
   cudaFree(g->d_gather_tab);
+  cudaFree(g->ks_states.p);
+  if (g->h_stage) cudaFreeHost(g->h_stage);
   for (void* q : g->pinned) cudaHostUnregister(q);
+  if (g->done) cudaEventDestroy(g->done);
+  if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
+  spf_b200_destroy(ctx);  // drops the graph's reference; frees the context if its owner is gone already
 }
 
 int spf_b200_graph_run(spf_b200_graph* g) {
@@ -811,9 +1078,12 @@ int spf_b200_graph_run(spf_b200_graph* g) {
   return spf_b200_graph_run_sharded(g, 0, 1, nullptr, nullptr);
 }
 
-// Re-points the host buffer of an Input*/Output* node, so that one built (validated, levelised, device-
+// Re-points the io buffer of an Input*/Output* node, so that one built (validated, levelised, device-
 // resident) graph serves every invocation of the same instruction shape: the reference rebuilds the
 // MUX circuit and re-levelises on every instruction dispatch (fhe_circuit.rs:473-494).
+// The buffer may be page-locked host memory (plain DMA), pageable host memory (copied through the graph's own
+// page-locked slab: no cudaHostRegister per call) or DEVICE memory (a ciphertext handle: device-to-device copy, GGSWs
+// in the device scale) -- detected with cudaPointerGetAttributes.
 int spf_b200_graph_set_io(spf_b200_graph* g, size_t node, void* io) {
   if (!g) return SPF_E_INVALID;
   if (node >= g->nodes.size() || g->nodes[node].op > SPF_OP_OUTPUT_GLEV1)
@@ -821,12 +1091,18 @@ int spf_b200_graph_set_io(spf_b200_graph* g, size_t node, void* io) {
   if (!io) return fail(g->ctx, SPF_E_INVALID, "set_io: io pointer is NULL");
   void* old = g->nodes[node].io;
   if (old == io) return 0;
+  cudaSetDevice(g->ctx->device);
   auto it = std::find(g->pinned.begin(), g->pinned.end(), old);
-  if (it != g->pinned.end()) { cudaHostUnregister(old); g->pinned.erase(it); }
+  if (it != g->pinned.end()) {
+    bool shared = false;  // several nodes may read the same registered buffer
+    for (size_t v = 0; v < g->nodes.size(); v++) shared |= v != node && g->nodes[v].op <= SPF_OP_OUTPUT_GLEV1 && g->nodes[v].io == old;
+    if (!shared) { cudaStreamSynchronize(g->stream); cudaHostUnregister(old); g->pinned.erase(it); }
+  }
   g->nodes[node].io = io;
   const uint32_t op = g->nodes[node].op;
   const CtType t = op <= SPF_OP_INPUT_GLEV1 ? g->type[node] : g->type[g->nodes[node].in[0]];
-  pin_io(g, io, ct_host_bytes(&g->ctx->p, t));
+  g->io_kind[node] = (char)pin_io(g, io, ct_host_bytes(&g->ctx->p, t), /*may_register=*/false);
+  g->io_alloc[node] = alloc_base_of(io);
   return 0;
 }
 
@@ -848,6 +1124,21 @@ int spf_b200_host_alloc(void** out, size_t bytes) {
   *out = nullptr;
   const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
   if (e != cudaSuccess) return fail(nullptr, SPF_E_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return 0;
+}
+int spf_b200_device_alloc(spf_b200_ctx* ctx, void** out, size_t bytes) {
+  if (!ctx) return SPF_E_INVALID;
+  if (!out || !bytes) return fail(ctx, SPF_E_INVALID, "device_alloc: NULL / empty");
+  *out = nullptr;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMalloc(out, bytes));
+  return 0;
+}
+int spf_b200_device_free(spf_b200_ctx* ctx, void* p) {
+  if (!ctx) return SPF_E_INVALID;
+  if (!p) return 0;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaFree(p));
   return 0;
 }
 int spf_b200_host_free(void* p) {
@@ -913,7 +1204,17 @@ int spf_b200_graph_open_peers(spf_b200_graph* g, int rank, int world, const uint
 
 // Host-only planning (no GPU, no context): the validation, levelisation and ownership partition of
 // spf_b200_graph_build_sharded, for hosts that want to inspect or test a schedule.
+static int graph_plan_impl(const spf_params* params, const spf_node* nodes, size_t n, int world, int32_t* level_out, int32_t* owner_out);
 int spf_b200_graph_plan(const spf_params* params, const spf_node* nodes, size_t n, int world, int32_t* level_out, int32_t* owner_out) {
+  try {
+    return graph_plan_impl(params, nodes, n, world, level_out, owner_out);
+  } catch (const std::exception& e) {
+    return fail(nullptr, SPF_E_GRAPH, std::string("graph plan: ") + e.what());
+  } catch (...) {
+    return fail(nullptr, SPF_E_GRAPH, "graph plan: unknown exception");
+  }
+}
+static int graph_plan_impl(const spf_params* params, const spf_node* nodes, size_t n, int world, int32_t* level_out, int32_t* owner_out) {
   if (!params || (!nodes && n)) return fail(nullptr, SPF_E_INVALID, "NULL argument");
   if (world < 1 || world > 1024) return fail(nullptr, SPF_E_INVALID, "world must be in 1..1024");
   spf_b200_graph g;

@@ -406,7 +406,15 @@ int emit(BddManager& M, const Fns& outs, uint32_t n_inputs, const std::vector<ui
 
 extern "C" {
 
+static int mux_circuit_impl(uint32_t kind, uint32_t n, uint32_t m, uint32_t flags, spf_mux_node** out, size_t* count);
 int spf_b200_mux_circuit(uint32_t kind, uint32_t n, uint32_t m, uint32_t flags, spf_mux_node** out, size_t* count) {
+  try {  // C++ exceptions (std::bad_alloc on a huge BDD) never cross the C ABI
+    return mux_circuit_impl(kind, n, m, flags, out, count);
+  } catch (...) {
+    return SPF_E_INVALID;
+  }
+}
+static int mux_circuit_impl(uint32_t kind, uint32_t n, uint32_t m, uint32_t flags, spf_mux_node** out, size_t* count) {
   if (!out || !count) return SPF_E_INVALID;
   *out = nullptr;
   *count = 0;

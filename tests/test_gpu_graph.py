@@ -30,7 +30,7 @@ def test_copy_and_constants(keys, client, proc):
     c.add("OutputGlwe1", c.add("OneGlwe1"), io=o)
     c.add("OutputGgsw1", c.add("ZeroGgsw1"), io=gz)
     c.add("OutputGgsw1", c.add("OneGgsw1"), io=go)
-    c.add("Retire")
+    c.add("Nop")
     proc.run_graph_blocking(c)
     assert np.array_equal(g_out, g_in) and np.array_equal(l0_out, l0_in)
     assert client.decrypt_glwe_l1(z)[:2].tolist() == [0, 0] and client.decrypt_glwe_l1(o)[:2].tolist() == [1, 0]

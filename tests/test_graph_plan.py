@@ -113,6 +113,23 @@ def test_malformed_graphs_are_rejected_without_a_gpu():
     c = FheCircuit()
     c.nodes.append((99, 0, (-1, -1, -1), None))
     expect(c, "unknown op")
+    # faults.rs wrong_inputs_none_expected: an edge into ANY zero-input op is an error, Nop included (task.rs:100-118)
+    for op in ("Nop", "ZeroGlwe1", "OneGgsw1", "InputGlwe1"):
+        c = FheCircuit()
+        c.nodes.append((OP[op], 0, (c.add("ZeroLwe0"), -1, -1), glwe if op == "InputGlwe1" else None))
+        expect(c, "unexpected extra input edge")
+    # faults.rs illegal_retire_op: user graphs never contain Retire (mod.rs:606-611)
+    c = FheCircuit()
+    c.add("Retire")
+    expect(c, "illegal Retire")
+    # the host mirror refuses io buffers of the wrong size or element type before they reach the executor
+    c = FheCircuit()
+    with pytest.raises(SpfError):
+        c.add("InputGlwe1", io=np.zeros(4095, np.uint64))
+    with pytest.raises(SpfError):
+        c.add("OutputLwe0", c.add("ZeroLwe0"), io=np.zeros(638, np.float64))
+    with pytest.raises(SpfError):
+        c.add("Not", c.add("ZeroGlwe1"), io=glwe)
     with pytest.raises(SpfError):
         plan_graph(FheCircuit(), world=0)
 
