@@ -6,8 +6,10 @@ Bars (DESIGN.md "Parity contract"):
   * single-pass FFT ops on exact inputs (cmux, external product, scheme switch): max torus
     distance <= 2^-30 (f64 rounding of ~2^88-sized IFFT outputs), FFT-domain rel. error <= 1e-12;
   * multi-step ops whose later steps decompose values carrying FFT rounding noise (PBS, trace,
-    CBS): decryptions bit-exact, phase (b - a.s) distance <= 2^-18 -- ciphertext bytes are not
-    comparable between any two FFT implementations (see test_emu.test_pbs_first_steps...).
+    CBS): decryptions bit-exact, phase (b - a.s) distance <= 4 x the measured maximum (PBS 3.8e-6, CBS 2.4e-6,
+    trace 1.9e-7 of the torus; tests/test_gpu_distances.py) -- ciphertext bytes are not comparable between any
+    two FFT implementations (see test_emu.test_pbs_first_steps...); against the host emulator, which
+    rounds identically, every kernel is BIT-EXACT (tests/test_gpu_bitexact.py).
 """
 import ctypes as C
 
@@ -110,7 +112,7 @@ def test_trace_decrypts_like_oracle(oracle, keys, client, evaluation):
     dec = client.decrypt_glwe_l1(out, 4)
     assert dec[0] == 1 and not dec[1:].any()
     ph = oracle.torus_distance(client.decrypt_glwe_l1_raw(ref), client.decrypt_glwe_l1_raw(out))
-    assert ph.max() <= 2.0 ** -18
+    assert ph.max() <= 1.9e-7  # 4 x the measured maximum (tests/test_gpu_distances.py)
 
 
 def test_single_pbs_config2(oracle, keys, client, evaluation):
@@ -132,7 +134,7 @@ def test_single_pbs_config2(oracle, keys, client, evaluation):
             assert int(oracle.decode(client.decrypt_glwe_l1_raw(ref)[:1], 3)[0]) == fn(m)
             d = oracle.torus_distance(client.decrypt_glwe_l1_raw(ref)[:1], client.decrypt_glwe_l1_raw(out[m])[:1]).max()
             worst = max(worst, d)
-    assert worst <= 2.0 ** -18, worst
+    assert worst <= 3.8e-6, worst  # 4 x the measured maximum 9.5e-7 (tests/test_gpu_distances.py, profiles/r2_measured_distances.json)
 
 
 def test_multifunction_pbs_cbs_stage(oracle, keys, client, evaluation):

@@ -133,6 +133,21 @@ def test_monomial_rotation_goldens(oracle, name, sign):
         assert np.array_equal(p, arr(want)), (name, deg)
 
 
+def test_glwe_rotate_doc_kat(oracle):
+    """rotate_glwe_monomial_negacyclic's doc-test (ops/bootstrapping/blind_rotation.rs:60-78): message [1..8] at 4
+    plaintext bits rotated by +1 / -1 decodes to [8,1,..,7] / [2,..,8,15] (the wrapped element is negated: -1 = 15 mod 16).
+    The rotation is exactly what the blind rotation applies to the accumulator (orc_poly_mul_monomial on every GLWE
+    polynomial), checked here on the plaintext side of a trivial encryption."""
+    k = KATS["glwe_rotate_doc"]
+    pb = k["plaintext_bits"]
+    msg = np.array(k["input"], dtype=np.uint64) << np.uint64(64 - pb)
+    import oracle as O
+    for deg, want in ((1, k["plus1"]), (-1, k["minus1"])):
+        p = msg.copy()
+        oracle.lib().orc_poly_mul_monomial(p, len(p), deg)
+        assert O.decode(p, pb).tolist() == want
+
+
 def test_lut_matches_formula(oracle):
     """generate_lut + the multi-function layout (programmable_bootstrapping.rs:129-185): single
     identity map, p=8 on N=64: stride 8, first half-stride negated and rotated to the end."""
