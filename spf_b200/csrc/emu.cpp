@@ -19,6 +19,7 @@ using namespace spf;
 namespace {
 
 struct HostCx {
+  static constexpr bool kTmemTwiddles = false;
   int u;
   pthread_barrier_t* bar;
   void sync() { pthread_barrier_wait(bar); }

@@ -15,6 +15,7 @@ __device__ __forceinline__ void tmem_wait_ld();
 __device__ __forceinline__ void tmem_wait_st();
 
 struct DevCx {
+  static constexpr bool kTmemTwiddles = false;
   int u;
   int bar;
   uint32_t rp_taddr;  // 64 private tensor-memory columns of this warp (trace / scheme-switch kernel only)
@@ -687,6 +688,46 @@ __global__ void __launch_bounds__(4 * kTeam, 1) pbs_quad_kernel(PbsBatch P, DevT
 #ifndef SPF_TR_MIN_BLOCKS
 #define SPF_TR_MIN_BLOCKS 1
 #endif
+#ifndef SPF_TR_TMEM_TW
+#define SPF_TR_TMEM_TW 1  // trace / scheme-switch kernel: twiddles of both passes in tensor memory
+#endif
+// DevCx of the trace / scheme-switch kernel: tensor-memory columns [0,64) T1 | [64,128) T2 (per lane quarter, shared by the
+// two warps of the quarter: warps w and w + 4 have the same thread-in-team index) | 64 columns per warp of parked states
+struct DevTrCx : DevCx {
+  static constexpr bool kTmemTwiddles = SPF_TR_TMEM_TW != 0;
+  uint32_t tw_taddr;
+  template <bool CONJ>
+  __device__ __forceinline__ void t1_mul(C2 (&v)[16]) const {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      uint32_t r[16];
+      tmem_ld16(r, tw_taddr + 16 * g);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const C2 w{__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2])};
+        const int k = 4 * g + i;
+        v[k] = CONJ ? cmul_conj(v[k], w) : cmul(v[k], w);
+      }
+    }
+  }
+  template <bool CONJ>
+  __device__ __forceinline__ void t2_mul(C2 (&v)[16]) const {
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      uint32_t r[16];
+      tmem_ld16(r, tw_taddr + 64 + 16 * g);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const C2 w{__hiloint2double((int)r[4 * i + 1], (int)r[4 * i]), __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2])};
+        const int k = 4 * g + i;
+        if (k) v[k] = CONJ ? cmul_conj(v[k], w) : cmul(v[k], w);
+      }
+    }
+  }
+};
+constexpr int kTrTmemCols = SPF_TR_TMEM_TW ? 256 : 128;
 constexpr int kTrTeams = SPF_TR_TEAMS;
 constexpr int kTrTeamBytes = 2 * kN * 8 + kXBuf * 16;                 // g + xbuf = 49408 (digits are stateless)
 constexpr int kTrSmem = kTableBytes + kTrTeams * kTrTeamBytes;        // 215104
@@ -724,14 +765,33 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, SPF_TR_MIN_BLOCKS) trace_ss_
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(&tmem_base)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(&tmem_base)), "n"(kTrTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_alloc = tmem_base;
+  const uint32_t tw_taddr = tmem_alloc + ((uint32_t)((warp & 3) * 32) << 16);
+#if SPF_TR_TMEM_TW
+  if (warp < 4) {  // twiddles of thread-in-team index uu = 32 (warp & 1) + lane, for both warps of this lane quarter
+    const int uu = (warp & 1) * 32 + (threadIdx.x & 31);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const C2 w1 = sT1[k * 64 + uu];
+      tmem_st4(tw_taddr + 4 * k, (uint32_t)__double2loint(w1.x), (uint32_t)__double2hiint(w1.x), (uint32_t)__double2loint(w1.y),
+               (uint32_t)__double2hiint(w1.y));
+      const C2 w2 = k ? sT2[(uu >> 4) * kT2Pad + k] : C2{1.0, 0.0};
+      tmem_st4(tw_taddr + 64 + 4 * k, (uint32_t)__double2loint(w2.x), (uint32_t)__double2hiint(w2.x), (uint32_t)__double2loint(w2.y),
+               (uint32_t)__double2hiint(w2.y));
+    }
+    tmem_wait_st();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#endif
   const int team = threadIdx.x / kTeam;
   const int item = blockIdx.x * (blockDim.x / kTeam) + team;
   if (item < P.batch * P.levels) {  // no early return: every thread must reach the deallocation barrier
@@ -739,7 +799,11 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, SPF_TR_MIN_BLOCKS) trace_ss_
     unsigned char* base = smem + kTableBytes + team * kTrTeamBytes;
     uint64_t* g = reinterpret_cast<uint64_t*>(base);
     C2* xbuf = reinterpret_cast<C2*>(base + 2 * kN * 8);
-    DevCx cx{(int)(threadIdx.x % kTeam), team + 1, tmem_alloc + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(warp >> 2) * 64};
+    DevTrCx cx;
+    cx.u = (int)(threadIdx.x % kTeam);
+    cx.bar = team + 1;
+    cx.rp_taddr = tw_taddr + (SPF_TR_TMEM_TW ? 128u : 0u) + (uint32_t)(warp >> 2) * 64;
+    cx.tw_taddr = tw_taddr;
     TraceSsArgs A;
     const size_t glwe = 2 * kN;
     if (P.ptrs) A.glwe_in = static_cast<const uint64_t*>(P.ptrs[c]) + (P.mode == 2 ? (size_t)level * glwe : 0);
@@ -765,7 +829,7 @@ __global__ void __launch_bounds__(kTrTeams * kTeam, SPF_TR_MIN_BLOCKS) trace_ss_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_alloc) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_alloc), "n"(kTrTmemCols) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------

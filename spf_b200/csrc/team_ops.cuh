@@ -51,14 +51,27 @@ SPF_HD uint64_t ldg_u64(const uint64_t* p) {
 // ---- whole-polynomial transforms for a team ------------------------------------------------
 // xbuf must not be in use by any thread of the team on entry (the leading sync guarantees the
 // previous transform's reads are complete).
+// Cx::kTmemTwiddles: the thread's 16 pass-1 and 15 pass-2 twiddles come from its tensor-memory columns (cx.t1_mul / t2_mul,
+// same products in the same order) instead of the shared-memory tables: 31 LDS.128 per transform less on the pipe that
+// bounds these kernels.
 template <class Cx>
 SPF_HD void team_fft_fwd(Cx& cx, C2 (&v)[16], C2* xbuf, const C2* T1, const C2* T2) {
-  fwd_pass1(v, cx.u, T1);
+  if constexpr (Cx::kTmemTwiddles) {
+    fwd_pass1_core(v);
+    cx.template t1_mul<false>(v);
+  } else {
+    fwd_pass1(v, cx.u, T1);
+  }
   cx.sync();
   fwd_x1_write(v, xbuf, cx.u);
   cx.sync();
   fwd_x1_read(v, xbuf, cx.u);
-  fwd_pass2(v, cx.u, T2);
+  if constexpr (Cx::kTmemTwiddles) {
+    dft16<false>(v);
+    cx.template t2_mul<false>(v);
+  } else {
+    fwd_pass2(v, cx.u, T2);
+  }
   fwd_x2_write(v, xbuf, cx.u);  // in place: overwrites only what this thread has just read
   cx.sync();
   fwd_x2_read(v, xbuf, cx.u);
@@ -71,11 +84,21 @@ SPF_HD void team_fft_inv(Cx& cx, C2 (&v)[16], C2* xbuf, const C2* T1, const C2* 
   inv_x2_write(v, xbuf, cx.u);
   cx.sync();
   inv_x2_read(v, xbuf, cx.u);
-  inv_pass2(v, cx.u, T2);
+  if constexpr (Cx::kTmemTwiddles) {
+    cx.template t2_mul<true>(v);
+    dft16<true>(v);
+  } else {
+    inv_pass2(v, cx.u, T2);
+  }
   inv_x1_write(v, xbuf, cx.u);  // in place
   cx.sync();
   inv_x1_read(v, xbuf, cx.u);
-  inv_pass1(v, cx.u, T1);
+  if constexpr (Cx::kTmemTwiddles) {
+    cx.template t1_mul<true>(v);
+    inv_pass1_core(v);
+  } else {
+    inv_pass1(v, cx.u, T1);
+  }
 }
 
 // acc[p][s] += v[s] * G[p][s][u]   (glwe_polynomial_mad, ops/fft_ops.rs:107-124)
