@@ -133,6 +133,16 @@ int spf_b200_trace(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *glwe_i
 int spf_b200_not(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *glwe_in, size_t batch);
 int spf_b200_xor(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *a, const uint64_t *b, size_t batch);
 int spf_b200_mul_xn(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *glwe_in, uint32_t n, size_t batch);
+/* Encryption::encrypt_rlwe_l1 / encrypt_rlev_l1 (parasol_runtime/src/crypto/encryption.rs:205-249) =
+ * rlwe_encrypt_public (sunscreen_tfhe/src/ops/encryption/rlwe_encryption.rs:108-160), batched, with the randomness
+ * the reference draws inside (binary u, Gaussian e0 / e1; returned there as RlwePublicEncryptionRandomness) supplied
+ * by the caller, who owns the cryptographic RNG:  glwe_out[b] = (p0 * u[b] + e0[b], p1 * u[b] + e1[b] + encoded_msg[b])
+ * over Z_2^64[X]/(X^N + 1), exact integer arithmetic (polynomial_external_mad), for any u64 multiplier u.
+ * public_key: RlwePublicKey [2][N] (an encryption of zero, shared by the batch); encoded_msg, u, e0, e1: [batch][N];
+ * an RLEV encryption is cbs.count batch items with encoded_msg * q / B^(j+1).  k = 1, N = 2048 only. */
+int spf_b200_rlwe_encrypt_public(spf_b200_ctx *ctx, uint64_t *glwe_out, const uint64_t *public_key,
+                                 const uint64_t *encoded_msg, const uint64_t *u, const uint64_t *e0, const uint64_t *e1,
+                                 size_t batch);
 
 /* ---- device-pointer ops (asynchronous on `stream`) --------------------------------------- */
 
@@ -152,6 +162,9 @@ int spf_b200_dev_keyswitch_lwe_l1_lwe_l0(spf_b200_ctx *ctx, uint64_t *d_lwe0_out
                                          size_t batch, void *stream);
 int spf_b200_dev_sample_extract_l1(spf_b200_ctx *ctx, uint64_t *d_lwe1_out, const uint64_t *d_glwe_in,
                                    const uint32_t *d_idx, uint32_t idx_all, size_t batch, void *stream);
+int spf_b200_dev_rlwe_encrypt_public(spf_b200_ctx *ctx, uint64_t *d_glwe_out, const uint64_t *d_public_key,
+                                     const uint64_t *d_encoded_msg, const uint64_t *d_u, const uint64_t *d_e0,
+                                     const uint64_t *d_e1, size_t batch, void *stream);
 /* dst = src * 2^-10 (to_device != 0) or * 2^10: converts GGSW-FFT data between the reference
  * scale and the device scale; n complex elements. */
 int spf_b200_dev_fft_rescale(spf_b200_ctx *ctx, double *d_dst, const double *d_src, size_t n, int to_device,

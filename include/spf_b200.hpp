@@ -145,6 +145,16 @@ class Evaluation {
     check(spf_b200_mul_xn(ctx_, out.data(), in.data(), n, batch_of(in.size(), len_glwe_l1(), "mul_xn")), ctx_);
   }
 
+  // Encryption::encrypt_rlwe_l1 / rlwe_encrypt_public (encryption.rs:205-215, rlwe_encryption.rs:108-160), randomness given
+  void rlwe_encrypt_public(std::vector<Torus>& out, const std::vector<Torus>& public_key, const std::vector<Torus>& encoded_msg,
+                           const std::vector<Torus>& u, const std::vector<Torus>& e0, const std::vector<Torus>& e1) const {
+    const std::size_t n = len_glwe_l1() / 2, batch = batch_of(encoded_msg.size(), n, "rlwe_encrypt_public");
+    if (public_key.size() != 2 * n || u.size() != batch * n || e0.size() != batch * n || e1.size() != batch * n)
+      throw Error(SPF_E_INVALID, "rlwe_encrypt_public: operand sizes differ");
+    out.resize(batch * 2 * n);
+    check(spf_b200_rlwe_encrypt_public(ctx_, out.data(), public_key.data(), encoded_msg.data(), u.data(), e0.data(), e1.data(), batch), ctx_);
+  }
+
  private:
   explicit Evaluation(const spf_params& params) : p_(params) {}
   void reset() {

@@ -150,6 +150,9 @@ def _declare(l):
     l.orc_encrypt_glwe.argtypes = [C.POINTER(Rng), _u64p, _u64p, _u64p, _PP]
     l.orc_decrypt_glwe_raw.argtypes = [_u64p, _u64p, _u64p, _PP]
     l.orc_encrypt_glev.argtypes = [C.POINTER(Rng), _u64p, _u64p, _u64p, _PP, Radix]
+    l.orc_rlwe_generate_public_key.argtypes = [C.POINTER(Rng), _u64p, _u64p, _PP]
+    l.orc_rlwe_sample_randomness.argtypes = [C.POINTER(Rng), _u64p, _u64p, _u64p, _PP]
+    l.orc_rlwe_encrypt_public.argtypes = [_u64p, _u64p, _u64p, _u64p, _u64p, _u64p, _PP]
     l.orc_encrypt_ggsw.argtypes = [C.POINTER(Rng), _u64p, _u64p, _u64p, _PP, Radix]
     l.orc_ggsw_fft.argtypes = [_c64p, _u64p, _PP, Radix]
     l.orc_ggsw_ifft.argtypes = [_u64p, _c64p, _PP, Radix]
@@ -289,6 +292,28 @@ class Client:
     def decrypt_glwe_l1(self, ct: np.ndarray, plaintext_bits: int = 1) -> np.ndarray:
         return decode(self.decrypt_glwe_l1_raw(ct), plaintext_bits)
 
+    # RLWE public key (keys.rs:20-70, ops/encryption/rlwe_encryption.rs) -------------------------
+    def generate_public_key(self) -> np.ndarray:
+        """PublicKey::generate (keys.rs:60-69): an encryption of the zero polynomial under glwe_1."""
+        pk = np.zeros(self.k.glwe_len, dtype=np.uint64)
+        lib().orc_rlwe_generate_public_key(C.byref(self.rng), pk, self.k.glwe1_sk, C.byref(self.p))
+        return pk
+
+    def rlwe_randomness(self):
+        """(u, e0, e1) of rlwe_encrypt_public_impl (rlwe_encryption.rs:140-146) from the harness' seeded PRNG."""
+        n = self.p.glwe_n
+        u, e0, e1 = (np.zeros(n, dtype=np.uint64) for _ in range(3))
+        lib().orc_rlwe_sample_randomness(C.byref(self.rng), u, e0, e1, C.byref(self.p))
+        return u, e0, e1
+
+    def encrypt_rlwe_l1(self, bits, pk: np.ndarray, randomness=None, plaintext_bits: int = 1) -> np.ndarray:
+        """Encryption::encrypt_rlwe_l1 (encryption.rs:205-215) = rlwe_encode_encrypt_public with PlaintextBits(1)."""
+        msg = np.zeros(self.p.glwe_n, dtype=np.uint64)
+        bits = np.asarray(bits, dtype=np.uint64)
+        msg[: len(bits)] = bits << np.uint64(64 - plaintext_bits)
+        u, e0, e1 = randomness if randomness is not None else self.rlwe_randomness()
+        return rlwe_encrypt_public(self.p, msg, pk, u, e0, e1)
+
     def encrypt_glev_l1(self, bits) -> np.ndarray:
         msg = np.zeros(self.p.glwe_n, dtype=np.uint64)
         msg[: len(bits)] = np.asarray(bits, dtype=np.uint64)
@@ -370,6 +395,14 @@ def torus_distance(a: np.ndarray, b: np.ndarray) -> np.ndarray:
 
 
 # ---- thin functional wrappers used by the tests ---------------------------------------------
+
+def rlwe_encrypt_public(params: Params, encoded_msg, pk, u, e0, e1) -> np.ndarray:
+    """rlwe_encrypt_public_impl with given randomness (rlwe_encryption.rs:125-160)."""
+    ct = np.zeros((params.glwe_k + 1) * params.glwe_n, dtype=np.uint64)
+    a = [np.ascontiguousarray(x, dtype=np.uint64) for x in (encoded_msg, pk, u, e0, e1)]
+    lib().orc_rlwe_encrypt_public(ct, a[0], a[1], a[2], a[3], a[4], C.byref(params))
+    return ct
+
 
 def poly_fft(p: np.ndarray) -> np.ndarray:
     p = np.ascontiguousarray(p, dtype=np.uint64)

@@ -833,6 +833,32 @@ void orc_decrypt_glwe_raw(u64 *msg, const u64 *ct, const u64 *sk, const orc_para
   for (uint32_t i = 0; i < k; i++) poly_external_mad(tmp, ct + (size_t)i * n, sk + (size_t)i * n, n);
   for (uint32_t j = 0; j < n; j++) msg[j] = ct[(size_t)k * n + j] - tmp[j];
 }
+/* ops/encryption/rlwe_encryption.rs:47-61 rlwe_generate_public_key: the RLWE public key is a secret-key encryption of the
+ * zero polynomial (glwe.dim.size must be 1) */
+void orc_rlwe_generate_public_key(orc_rng *g, u64 *pk, const u64 *glwe_sk, const orc_params *p) {
+  u64 zero[4096];
+  memset(zero, 0, 8 * p->glwe_n);
+  orc_encrypt_glwe(g, pk, zero, glwe_sk, p);
+}
+/* rlwe_encryption.rs:140-146: u = binary_torus_polynomial, e0 / e1 = normal_torus_polynomial(glwe.std) (rand.rs:20-47) */
+void orc_rlwe_sample_randomness(orc_rng *g, u64 *u, u64 *e0, u64 *e1, const orc_params *p) {
+  for (uint32_t j = 0; j < p->glwe_n; j++) u[j] = orc_rng_u64(g) & 1;
+  for (uint32_t j = 0; j < p->glwe_n; j++) e0[j] = p->glwe_std == 0.0 ? 0 : orc_rng_normal_torus(g, p->glwe_std);
+  for (uint32_t j = 0; j < p->glwe_n; j++) e1[j] = p->glwe_std == 0.0 ? 0 : orc_rng_normal_torus(g, p->glwe_std);
+}
+/* rlwe_encryption.rs:125-160 rlwe_encrypt_public_impl for given randomness (the double-LWE trick):
+ * ct = (p0 * u + e0, p1 * u + e1 + m), every product the exact negacyclic one of polynomial_external_mad */
+void orc_rlwe_encrypt_public(u64 *ct, const u64 *encoded_msg, const u64 *pk, const u64 *u, const u64 *e0, const u64 *e1,
+                             const orc_params *p) {
+  uint32_t n = p->glwe_n;
+  u64 *a = ct, *b = ct + n;
+  memset(ct, 0, 16 * (size_t)n);                     /* ct.clear() */
+  poly_external_mad(a, pk, u, n);                    /* a = p0 * u */
+  for (uint32_t j = 0; j < n; j++) a[j] += e0[j];
+  poly_external_mad(b, pk + n, u, n);                /* b = p1 * u */
+  for (uint32_t j = 0; j < n; j++) b[j] += e1[j];
+  for (uint32_t j = 0; j < n; j++) b[j] += encoded_msg[j];
+}
 /* ops/encryption/glev_encryption.rs:23-79: GLWE_j encrypts msg * q/B^{j+1} */
 void orc_encrypt_glev(orc_rng *g, u64 *ct, const u64 *msg, const u64 *sk, const orc_params *p, orc_radix r) {
   uint32_t n = p->glwe_n;

@@ -136,6 +136,11 @@ void orc_encrypt_glwe(orc_rng *g, uint64_t *ct, const uint64_t *torus_msg, const
                       const orc_params *p);
 void orc_decrypt_glwe_raw(uint64_t *torus_msg, const uint64_t *ct, const uint64_t *sk,
                           const orc_params *p);
+/* RLWE public-key encryption (ops/encryption/rlwe_encryption.rs:47-160), k = 1 */
+void orc_rlwe_generate_public_key(orc_rng *g, uint64_t *pk /*2N*/, const uint64_t *glwe_sk, const orc_params *p);
+void orc_rlwe_sample_randomness(orc_rng *g, uint64_t *u, uint64_t *e0, uint64_t *e1, const orc_params *p);
+void orc_rlwe_encrypt_public(uint64_t *ct, const uint64_t *encoded_msg, const uint64_t *pk, const uint64_t *u,
+                             const uint64_t *e0, const uint64_t *e1, const orc_params *p);
 void orc_encrypt_glev(orc_rng *g, uint64_t *ct, const uint64_t *msg, const uint64_t *sk,
                       const orc_params *p, orc_radix r);
 void orc_encrypt_ggsw(orc_rng *g, uint64_t *ct, const uint64_t *msg, const uint64_t *sk,

@@ -176,6 +176,20 @@ impl Evaluation {
         self.expect("mul_xn output", output.len(), input.len())?;
         check!(self, unsafe { sys::spf_b200_mul_xn(self.raw(), output.as_mut_ptr(), input.as_ptr(), n as u32, batch) })
     }
+    /// `rlwe_encrypt_public` (`ops/encryption/rlwe_encryption.rs:108-160`) for a batch, randomness supplied by the caller
+    /// (the `RlwePublicEncryptionRandomness` the reference returns): `(p0 u + e0, p1 u + e1 + m)`, exact u64 arithmetic.
+    #[allow(clippy::too_many_arguments)]
+    pub fn rlwe_encrypt_public(&self, output: &mut [u64], public_key: &[u64], encoded_msg: &[u64], u: &[u64], e0: &[u64], e1: &[u64]) -> Result<()> {
+        let glwe = self.len(sys::spf_b200_len_glwe_l1);
+        let batch = output.len() / glwe;
+        self.expect("rlwe_encrypt_public public_key", public_key.len(), glwe)?;
+        for (name, x) in [("encoded_msg", encoded_msg), ("u", u), ("e0", e0), ("e1", e1)] {
+            self.expect(name, x.len(), batch * glwe / 2)?;
+        }
+        check!(self, unsafe {
+            sys::spf_b200_rlwe_encrypt_public(self.raw(), output.as_mut_ptr(), public_key.as_ptr(), encoded_msg.as_ptr(), u.as_ptr(), e0.as_ptr(), e1.as_ptr(), batch)
+        })
+    }
     /// Flow control of the asynchronous executor: the bound of `CircuitProcessor::new`'s channel (`mod.rs:95-123`).
     pub fn set_max_in_flight(&self, n: usize) -> Result<()> {
         check!(self, unsafe { sys::spf_b200_set_max_in_flight(self.raw(), n as c_int) })

@@ -85,6 +85,8 @@ ABI = {
     "spf_b200_not": [_vp, _vp, _vp, _sz],
     "spf_b200_xor": [_vp, _vp, _vp, _vp, _sz],
     "spf_b200_mul_xn": [_vp, _vp, _vp, C.c_uint32, _sz],
+    "spf_b200_rlwe_encrypt_public": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
+    "spf_b200_dev_rlwe_encrypt_public": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp],
     "spf_b200_dev_circuit_bootstrap": [_vp, _vp, _vp, _sz, C.c_int, _vp],
     "spf_b200_dev_programmable_bootstrap": [_vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, _sz, _vp],
     "spf_b200_dev_cmux": [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp],
@@ -350,6 +352,22 @@ class Evaluation:
         self._check(lib().spf_b200_mul_xn(self._h, out.ctypes.data, g.ctypes.data, int(n), g.shape[0]))
         return out
 
+    def rlwe_encrypt_public(self, public_key, encoded_msg, u, e0, e1) -> np.ndarray:
+        """Encryption::encrypt_rlwe_l1 / rlwe_encrypt_public (encryption.rs:205-215, rlwe_encryption.rs:108-160) with the
+        randomness (binary u, Gaussian e0 / e1) supplied by the caller: (p0 u + e0, p1 u + e1 + m), exact u64 arithmetic."""
+        n = self.params.glwe_n
+        pk = np.ascontiguousarray(public_key, dtype=np.uint64).reshape(-1)
+        if pk.shape[0] != self.len_glwe:
+            raise SpfError(-1, f"public_key: expected {self.len_glwe} u64, got {pk.shape[0]}")
+        m = self._in(encoded_msg, np.uint64, n, "encoded_msg")
+        uu, a0, a1 = (self._in(x, np.uint64, n, nm) for x, nm in ((u, "u"), (e0, "e0"), (e1, "e1")))
+        if not (m.shape == uu.shape == a0.shape == a1.shape):
+            raise SpfError(-1, "rlwe_encrypt_public: batch sizes differ")
+        out = np.empty((m.shape[0], self.len_glwe), dtype=np.uint64)
+        self._check(lib().spf_b200_rlwe_encrypt_public(self._h, out.ctypes.data, pk.ctypes.data, m.ctypes.data,
+                                                       uu.ctypes.data, a0.ctypes.data, a1.ctypes.data, m.shape[0]))
+        return out
+
     # -- device-pointer entry points (ints = CUdeviceptr), asynchronous on `stream` ----------
     def dev_circuit_bootstrap(self, d_ggsw_out: int, d_lwe0_in: int, batch: int, reference_scale: bool = False,
                               stream: int = 0):
@@ -370,6 +388,11 @@ class Evaluation:
     def dev_sample_extract_l1(self, d_out: int, d_glwe: int, d_idx: int, idx_all: int, batch: int, stream: int = 0):
         self._check(lib().spf_b200_dev_sample_extract_l1(self._h, d_out, d_glwe, d_idx or None, idx_all, batch,
                                                          stream or None))
+
+    def dev_rlwe_encrypt_public(self, d_out: int, d_pk: int, d_msg: int, d_u: int, d_e0: int, d_e1: int, batch: int,
+                                stream: int = 0):
+        self._check(lib().spf_b200_dev_rlwe_encrypt_public(self._h, d_out, d_pk, d_msg, d_u, d_e0, d_e1, batch,
+                                                           stream or None))
 
     def dev_fft_rescale(self, d_dst: int, d_src: int, n: int, to_device: bool, stream: int = 0):
         self._check(lib().spf_b200_dev_fft_rescale(self._h, d_dst, d_src, n, 1 if to_device else 0, stream or None))

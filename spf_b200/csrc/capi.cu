@@ -481,6 +481,24 @@ int launch_elementwise(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_a, 
   return check_launch(ctx, "glwe_elementwise_kernel");
 }
 
+int launch_rlwe_encrypt(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_pk, const uint64_t* d_msg, const uint64_t* d_u,
+                        const uint64_t* d_e0, const uint64_t* d_e1, size_t batch, cudaStream_t s) {
+  if (batch == 0) return 0;
+  if (ctx->p.glwe_k != 1 || ctx->p.glwe_n != (uint32_t)kN) return fail(ctx, SPF_E_UNSUPPORTED, "rlwe_encrypt_public: k = 1, N = 2048 only");
+  static const bool attr = [] {
+    return cudaFuncSetAttribute(rlwe_encrypt_public_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRlweSmem) == cudaSuccess;
+  }();
+  if (!attr) return fail(ctx, SPF_E_CUDA, "rlwe_encrypt_public_kernel: shared memory attribute");
+  for (size_t off = 0; off < batch; off += (size_t)1 << 30) {
+    const size_t n = std::min<size_t>((size_t)1 << 30, batch - off);
+    RlweBatch P{d_out + off * 2 * kN, d_pk, d_msg + off * kN, d_u + off * kN, d_e0 + off * kN, d_e1 + off * kN, (int)n};
+    const int blocks = (int)std::min<size_t>(n, (size_t)ctx->sm_count * 2);
+    rlwe_encrypt_public_kernel<<<blocks, kRlweThreads, kRlweSmem, s>>>(P);
+    if (int rc = check_launch(ctx, "rlwe_encrypt_public_kernel")) return rc;
+  }
+  return 0;
+}
+
 // Largest chunk of a host-pointer batch processed per pipeline slot: a whole number of PBS
 // waves (148 SMs x 3 ciphertexts) so chunking costs no tail.
 size_t cbs_chunk(const spf_b200_ctx* ctx) {
@@ -861,6 +879,43 @@ int spf_b200_xor(spf_b200_ctx* ctx, uint64_t* glwe_out, const uint64_t* a, const
 }
 int spf_b200_mul_xn(spf_b200_ctx* ctx, uint64_t* glwe_out, const uint64_t* glwe_in, uint32_t n, size_t batch) {
   return host_elementwise(ctx, glwe_out, glwe_in, nullptr, 2, n, batch);
+}
+
+int spf_b200_dev_rlwe_encrypt_public(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_public_key,
+                                     const uint64_t* d_encoded_msg, const uint64_t* d_u, const uint64_t* d_e0,
+                                     const uint64_t* d_e1, size_t batch, void* stream) {
+  if (!ctx) return SPF_E_INVALID;
+  if (batch == 0) return 0;
+  if (!d_glwe_out || !d_public_key || !d_encoded_msg || !d_u || !d_e0 || !d_e1) return fail(ctx, SPF_E_INVALID, "NULL buffer");
+  CU(cudaSetDevice(ctx->device));
+  return launch_rlwe_encrypt(ctx, d_glwe_out, d_public_key, d_encoded_msg, d_u, d_e0, d_e1, batch, pick(ctx, stream));
+}
+
+int spf_b200_rlwe_encrypt_public(spf_b200_ctx* ctx, uint64_t* glwe_out, const uint64_t* public_key,
+                                 const uint64_t* encoded_msg, const uint64_t* u, const uint64_t* e0, const uint64_t* e1,
+                                 size_t batch) {
+  if (!ctx) return SPF_E_INVALID;
+  if (batch == 0) return 0;
+  if (!glwe_out || !public_key || !encoded_msg || !u || !e0 || !e1) return fail(ctx, SPF_E_INVALID, "NULL buffer");
+  const size_t n = ctx->p.glwe_n, glwe = len_glwe(&ctx->p);
+  return run_chunks(ctx, batch, 4096, [&](int slot, size_t off, size_t cnt) -> int {
+    cudaStream_t s = ctx->stream[slot];
+    DevBuf* sc = ctx->scratch[slot];
+    for (int b = 0; b < 4; b++)
+      if (int rc = ensure(ctx, sc[b], cnt * n * 8)) return rc;
+    if (int rc = ensure(ctx, sc[4], cnt * glwe * 8)) return rc;
+    if (int rc = ensure(ctx, sc[5], glwe * 8)) return rc;
+    CU(cudaMemcpyAsync(sc[5].p, public_key, glwe * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(sc[0].p, encoded_msg + off * n, cnt * n * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(sc[1].p, u + off * n, cnt * n * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(sc[2].p, e0 + off * n, cnt * n * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(sc[3].p, e1 + off * n, cnt * n * 8, cudaMemcpyHostToDevice, s));
+    if (int rc = launch_rlwe_encrypt(ctx, (uint64_t*)sc[4].p, (const uint64_t*)sc[5].p, (const uint64_t*)sc[0].p,
+                                     (const uint64_t*)sc[1].p, (const uint64_t*)sc[2].p, (const uint64_t*)sc[3].p, cnt, s))
+      return rc;
+    CU(cudaMemcpyAsync(glwe_out + off * glwe, sc[4].p, cnt * glwe * 8, cudaMemcpyDeviceToHost, s));
+    return 0;
+  });
 }
 
 int spf_b200_fp64_peak(spf_b200_ctx* ctx, double* tflops_out) {

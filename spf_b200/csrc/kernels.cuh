@@ -1544,6 +1544,80 @@ __global__ void glwe_elementwise_kernel(uint64_t* out, const uint64_t* a, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// K8: RLWE public-key encryption, the "double-LWE trick" of rlwe_encrypt_public_impl
+// (ops/encryption/rlwe_encryption.rs:125-160; Encryption::encrypt_rlwe_l1 / encrypt_rlev_l1,
+// parasol_runtime/src/crypto/encryption.rs:205-249), with the randomness (u, e0, e1) supplied by the caller:
+//   ct = (p0 * u + e0, p1 * u + e1 + m)   over Z_2^64[X]/(X^N + 1), k = 1
+// Both products are the EXACT negacyclic ones of polynomial_external_mad (integer work, bit-exact against the oracle),
+// for any u64 multiplier -- not only the binary u the reference samples.  One CTA per ciphertext, 256 threads.
+// Shared memory: the public key with the negacyclic sign folded in, pe[p][i] = p[i], pe[p][i + N] = -p[i]
+// (so (p * u)[k] = sum_i u[i] * pe[(k - i) mod 2N], no sign logic in the loop), and u.  Thread t owns the outputs
+// k = t + 256 kk, kk = 0..7, and walks the multiplier in groups i = ib + 256 ii, ii = 0..7: then
+// k - i = (t - ib) + 256 (kk - ii) -- the 64 products of a group need only 15 key values per polynomial, 256 apart,
+// and consecutive threads read consecutive addresses (conflict-free): 38 shared loads per 128 multiply-adds.
+constexpr int kRlweThreads = 256;
+constexpr int kRlweSmem = (2 * 2 * kN + kN) * 8;  // 81920
+struct RlweBatch {
+  uint64_t* out;        // [B][2][N]
+  const uint64_t* pk;   // [2][N], shared by the batch
+  const uint64_t* msg;  // [B][N] encoded message (torus)
+  const uint64_t* u;    // [B][N]
+  const uint64_t* e0;   // [B][N]
+  const uint64_t* e1;   // [B][N]
+  int batch;
+};
+__global__ void __launch_bounds__(kRlweThreads, 2) rlwe_encrypt_public_kernel(RlweBatch P) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* pe = reinterpret_cast<uint64_t*>(smem);  // [2][2N]
+  uint64_t* su = pe + 2 * 2 * kN;                    // [N]
+  const int t = threadIdx.x;
+  for (int i = t; i < 2 * kN; i += kRlweThreads) {
+    const uint64_t v = P.pk[i];
+    const int p = i / kN, j = i % kN;
+    pe[p * 2 * kN + j] = v;
+    pe[p * 2 * kN + kN + j] = 0 - v;
+  }
+  for (int c = blockIdx.x; c < P.batch; c += gridDim.x) {
+    __syncthreads();  // the previous ciphertext's reads of su are done (and pe is complete)
+    for (int i = t; i < kN; i += kRlweThreads) su[i] = P.u[(size_t)c * kN + i];
+    __syncthreads();
+    uint64_t acc[2][8];
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) acc[p][kk] = 0;
+#pragma unroll 1
+    for (int ib = 0; ib < 256; ib++) {
+      uint64_t uu[8], w0[15], w1[15];
+#pragma unroll
+      for (int ii = 0; ii < 8; ii++) uu[ii] = su[ib + 256 * ii];
+      const int base = t - ib;  // in (-256, 256)
+#pragma unroll
+      for (int d = 0; d < 15; d++) {
+        const int idx = (base + 256 * (d - 7)) & (2 * kN - 1);
+        w0[d] = pe[idx];
+        w1[d] = pe[2 * kN + idx];
+      }
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++)
+#pragma unroll
+        for (int ii = 0; ii < 8; ii++) {
+          acc[0][kk] += w0[kk - ii + 7] * uu[ii];
+          acc[1][kk] += w1[kk - ii + 7] * uu[ii];
+        }
+    }
+    uint64_t* o = P.out + (size_t)c * 2 * kN;
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+      const int k = t + 256 * kk;
+      const size_t e = (size_t)c * kN + k;
+      o[k] = acc[0][kk] + P.e0[e];
+      o[kN + k] = acc[1][kk] + P.e1[e] + P.msg[e];
+    }
+  }
+}
+
 // FFT-domain polynomials: dst = src * scale (2^-10 to import reference-scale data, 2^10 to export)
 __global__ void fft_scale_kernel(C2* dst, const C2* src, size_t n, double scale) {
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {

@@ -290,3 +290,35 @@ def test_short_lwe_through_every_kernel():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitizer_probe.py")], capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0 and "sanitizer probe: ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_rlwe_encrypt_public_bit_exact(oracle, keys, evaluation):
+    """spf_b200_rlwe_encrypt_public vs the oracle's rlwe_encrypt_public_impl (rlwe_encryption.rs:125-160): integer work,
+    bit-exact, for the reference's binary u and for arbitrary u64 multipliers; ragged batches; decrypts like
+    can_rlwe_public_key_encrypt (:188-211)."""
+    c = oracle.Client(keys, seed=0xC0FFEE)
+    p = keys.params
+    n = p.glwe_n
+    pk = c.generate_public_key()
+    rng = np.random.default_rng(9)
+    for batch in (1, 3, 301):
+        bits = rng.integers(0, 2, (batch, n), dtype=np.uint64)
+        msg = bits << np.uint64(63)
+        rnd = [c.rlwe_randomness() for _ in range(batch)]
+        u, e0, e1 = (np.stack([r[i] for r in rnd]) for i in range(3))
+        got = evaluation.rlwe_encrypt_public(pk, msg, u, e0, e1)
+        for i in sorted({0, batch // 2, batch - 1}):
+            assert np.array_equal(got[i], oracle.rlwe_encrypt_public(p, msg[i], pk, u[i], e0[i], e1[i])), (batch, i)
+            assert np.array_equal(c.decrypt_glwe_l1(got[i]), bits[i])
+    # any u64 multiplier, any key material
+    pk2 = rng.integers(0, 1 << 64, 2 * n, dtype=np.uint64)
+    m, u, e0, e1 = (rng.integers(0, 1 << 64, (2, n), dtype=np.uint64) for _ in range(4))
+    got = evaluation.rlwe_encrypt_public(pk2, m, u, e0, e1)
+    for i in range(2):
+        assert np.array_equal(got[i], oracle.rlwe_encrypt_public(p, m[i], pk2, u[i], e0[i], e1[i]))
+    # empty batch and bad shapes
+    assert evaluation.rlwe_encrypt_public(pk, np.zeros((0, n), np.uint64), np.zeros((0, n), np.uint64),
+                                          np.zeros((0, n), np.uint64), np.zeros((0, n), np.uint64)).shape == (0, 2 * n)
+    import spf_b200
+    with pytest.raises(spf_b200.SpfError):
+        evaluation.rlwe_encrypt_public(pk[:n], m, u, e0, e1)

@@ -88,3 +88,52 @@ def test_scheme_switch_matches_fresh_ggsw(oracle, keys, client):
     for bit in (0, 1):
         g = oracle.scheme_switch(keys, client.encrypt_glev_l1([bit]))
         assert np.array_equal(client.ggsw_level_messages(g), client.ggsw_expected_messages(bit))
+
+
+def _negacyclic_mul_ref(a, u):
+    """Exact product in Z_2^64[X]/(X^n + 1) with Python integers (the definition polynomial_external_mad implements)."""
+    n = len(a)
+    out = [0] * n
+    for i, ui in enumerate(int(x) for x in u):
+        if ui == 0:
+            continue
+        for j, aj in enumerate(int(x) for x in a):
+            k = i + j
+            if k < n:
+                out[k] += aj * ui
+            else:
+                out[k - n] -= aj * ui
+    return np.array([x % (1 << 64) for x in out], dtype=np.uint64)
+
+
+def test_rlwe_encrypt_public_matches_definition(oracle, small_keys):
+    """rlwe_encrypt_public_impl (rlwe_encryption.rs:125-160): ct = (p0 u + e0, p1 u + e1 + m), checked against an
+    independent big-integer negacyclic product on the toy ring, with a non-binary multiplier too."""
+    p = small_keys.params
+    n = p.glwe_n
+    rng = np.random.default_rng(11)
+    pk = rng.integers(0, 1 << 64, 2 * n, dtype=np.uint64)
+    m, e0, e1 = (rng.integers(0, 1 << 64, n, dtype=np.uint64) for _ in range(3))
+    for u in (rng.integers(0, 2, n, dtype=np.uint64), rng.integers(0, 1 << 64, n, dtype=np.uint64)):
+        ct = oracle.rlwe_encrypt_public(p, m, pk, u, e0, e1)
+        assert np.array_equal(ct[:n], _negacyclic_mul_ref(pk[:n], u) + e0)
+        assert np.array_equal(ct[n:], _negacyclic_mul_ref(pk[n:], u) + e1 + m)
+
+
+def test_rlwe_public_key_encrypts_zero(oracle, keys, client):
+    """rlwe_public_key_encrypts_zero (rlwe_encryption.rs:170-186) at the L1 parameters of DEFAULT_128."""
+    c = oracle.Client(keys, seed=0xA11CE)
+    for _ in range(3):
+        pk = c.generate_public_key()
+        assert not c.decrypt_glwe_l1(pk).any()
+
+
+def test_can_rlwe_public_key_encrypt(oracle, keys):
+    """can_rlwe_public_key_encrypt (rlwe_encryption.rs:188-211): msg_i = i mod 2 over the whole polynomial."""
+    c = oracle.Client(keys, seed=0xB0B)
+    n = keys.params.glwe_n
+    msg = np.arange(n, dtype=np.uint64) % 2
+    for _ in range(3):
+        pk = c.generate_public_key()
+        ct = c.encrypt_rlwe_l1(msg, pk)
+        assert np.array_equal(c.decrypt_glwe_l1(ct), msg)
