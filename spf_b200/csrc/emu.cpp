@@ -37,6 +37,12 @@ struct HostPairCxT {
   int u, h;
   pthread_barrier_t* bar_half;
   pthread_barrier_t* bar_pair;
+  // the device runs the first exchange inside the warp through tensor memory (renumbering the threads in the time
+  // domain); the arithmetic per logical thread is the same, so the host keeps the plain numbering and shared buffers
+  static constexpr bool kTmemX1 = false;
+  int time_index() const { return u; }
+  void x1_fwd(C2 (&)[16]) {}
+  void x1_inv(C2 (&)[16]) {}
   void sync() { pthread_barrier_wait(bar_half); }
   void pair_sync() { pthread_barrier_wait(bar_pair); }
   // the device keeps the thread's 16 pass-1 twiddles in tensor memory; here they come from the table

@@ -264,6 +264,25 @@ SPF_HD void fwd_x1_read(C2 (&v)[16], const C2* buf, int u) {
 #pragma unroll
   for (int mp = 0; mp < 16; mp++) v[mp] = buf[k1 * kXPad + q + 4 * mp];
 }
+// ---- warp-local first exchange (pbs_kernel, Cx::kTmemX1) ------------------------------------------------------------
+// The first exchange moves data between the 16 threads a = q + 4 m', m' = 0..15, and the 16 threads (k1, q): with the
+// team's threads numbered so that each such group sits inside ONE warp it needs no shared memory at all (the device
+// transposes the 16 x 16 tile through tensor memory, kernels.cuh::DevPairCx::x1_fwd).  Physical thread p = 32 W + l
+// (warp W of the team, lane l) then plays two roles:
+//   time domain / pass 1:  a = x1_time_index(p) = 4 (l >> 1) + 2 W + (l & 1)      (group q = 2 W + (l & 1), member l >> 1)
+//   pass 2 and later:      u = p = k1 + 16 q,  k1 = l & 15,  q = 2 W + (l >> 4)   (unchanged)
+// Everything laid out per thread in shared memory (accumulator image, first-exchange buffer) is indexed by the
+// PHYSICAL thread, so consecutive lanes still touch consecutive addresses; x1_position maps a logical a to it.
+SPF_HD constexpr int x1_time_index(int p) { return 4 * ((p & 31) >> 1) + 2 * (p >> 5) + (p & 1); }
+SPF_HD constexpr int x1_position(int a) { return 32 * ((a >> 1) & 1) + 2 * (a >> 2) + (a & 1); }
+// fwd_x1_read for a buffer written at physical positions (buf[k1][p] = y_a[k1], a = x1_time_index(p)):
+// thread (k1, q) gathers a = q + 4 m' from position 32 (q >> 1) + (q & 1) + 2 m'.
+SPF_HD void fwd_x1_read_perm(C2 (&v)[16], const C2* buf, int u) {
+  if (SPF_ABLATE(4)) return;
+  const int k1 = u & 15, q = u >> 4;
+#pragma unroll
+  for (int mp = 0; mp < 16; mp++) v[mp] = buf[k1 * kXPad + 32 * (q >> 1) + (q & 1) + 2 * mp];
+}
 SPF_HD void fwd_pass2(C2 (&v)[16], int u, const C2* T2) {
   const int q = u >> 4;
   dft16<false>(v);

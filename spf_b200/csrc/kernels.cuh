@@ -168,6 +168,7 @@ __device__ __forceinline__ void mbar_wait_trap(uint32_t bar, uint32_t parity) {
   }
 }
 static_assert(!SPF_PBS_TRANSIENT || SPF_PBS_TMEM_OWN, "the transient accumulator image needs the tensor-memory own copy");
+
 #ifndef SPF_PBS_CHUNKED
 #define SPF_PBS_CHUNKED 1  // own coefficients / twiddles fetched from tensor memory in small chunks (needed by the 128-register
                            // 4-pair build; worth 2.7 % at 3 pairs too: shorter live ranges, better schedule)
@@ -175,6 +176,71 @@ static_assert(!SPF_PBS_TRANSIENT || SPF_PBS_TMEM_OWN, "the transient accumulator
 #ifndef SPF_PBS_FUSED_ST
 #define SPF_PBS_FUSED_ST 0  // twiddle products stored to the exchange buffer one by one (interleaved STS)
 #endif
+#ifndef SPF_PBS_TMEM_X1
+#define SPF_PBS_TMEM_X1 0  // first exchange of a transform inside the warp, through tensor memory (fft16.cuh: x1_time_index):
+                           // bit-exact, but measured SLOWER (7.36 vs 7.24 ms per 444-ciphertext wave, profiles/r2_j_x1_ab.txt): the
+                           // two store -> wait -> load -> wait round trips cost more exposed latency than the 50 pipe clocks
+                           // per warp they save (tcgen05.st runs at 256 B/clk/SM on the same pipe as ld/st.shared)
+#endif
+// 16x256b shape: thread t of a warp <-> lanes base + t/4 and base + 8 + t/4, the 64-bit unit (t % 4) + 4 cg of each
+// 256-bit column group cg; register w + 2 eh + 4 cg = word w of that unit in lane base + 8 eh + t/4 (cute: SM100_TMEM_LOAD_16dp256b4x;
+// checked in both directions by tools/probes/tmem_xchg_probe.cu).  "Store 32x32b, load 16x256b" therefore moves two lane-index bits
+// into the register index and two column-index bits into the lane index.
+__device__ __forceinline__ void tmem_ld256x4(uint32_t* r, uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st256x4(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16p(uint32_t* r, uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16p(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// Register / column bookkeeping of the two-round 16 x 16 transpose (all indices are compile-time after unrolling).
+// Round 1 (pass-1 thread, lane (i3 i2 i1 i0 g), doubles D(k, c), c = re / im):  32x32b unit = (k >> 2) + 4 (c + 2 (k & 3));
+//   its 16x256b read hands thread (i1 i0 g | k3 k2) the doubles E(e = (i3 i2), klo = k & 3, c);
+// round 2: 32x32b unit = klo + 4 (c + 2 e); its 16x256b read hands thread (g | k3 k2 k1 k0) = lane 16 g + k1 the doubles
+//   F(e, e' = (i1 i0), c) = y_{a}[k1].c of the group member m' = 4 e + e'.
+__device__ __forceinline__ constexpr int x1_unit1(int k, int c) { return (k >> 2) + 4 * (c + 2 * (k & 3)); }
+__device__ __forceinline__ constexpr int x1_unit2(int e, int klo, int c) { return klo + 4 * (c + 2 * e); }
+// register of word w in the four 16x256b.x4 accesses (block 2 b + ch: lane base 16 b, column offset 32 ch)
+__device__ __forceinline__ constexpr int x1_reg256(int b, int eh, int ch, int cg, int w) { return 16 * (2 * b + ch) + w + 2 * eh + 4 * cg; }
+__device__ __forceinline__ constexpr int x1_reg_r1(int e, int klo, int c, int w) {  // E(e, klo, c): j1 = c + 2 klo = cg + 4 ch
+  return x1_reg256(e >> 1, e & 1, klo >> 1, c + 2 * (klo & 1), w);
+}
+__device__ __forceinline__ constexpr int x1_reg_r2(int e, int ep, int c, int w) {   // F(e, e', c): j2 = c + 2 e = cg + 4 ch
+  return x1_reg256(ep >> 1, ep & 1, e >> 1, c + 2 * (e & 1), w);
+}
+__device__ __forceinline__ void x1_ld256(uint32_t (&r)[64], uint32_t ta) {
+  tmem_ld256x4(r, ta); tmem_ld256x4(r + 16, ta + 32); tmem_ld256x4(r + 32, ta + (16u << 16)); tmem_ld256x4(r + 48, ta + 32 + (16u << 16));
+}
+__device__ __forceinline__ void x1_st256(uint32_t ta, const uint32_t (&r)[64]) {
+  tmem_st256x4(ta, r); tmem_st256x4(ta + 32, r + 16); tmem_st256x4(ta + (16u << 16), r + 32); tmem_st256x4(ta + 32 + (16u << 16), r + 48);
+}
+__device__ __forceinline__ void x1_ld32(uint32_t (&r)[64], uint32_t ta) {
+  tmem_ld16p(r, ta); tmem_ld16p(r + 16, ta + 16); tmem_ld16p(r + 32, ta + 32); tmem_ld16p(r + 48, ta + 48);
+}
+__device__ __forceinline__ void x1_st32(uint32_t ta, const uint32_t (&r)[64]) {
+  tmem_st16p(ta, r); tmem_st16p(ta + 16, r + 16); tmem_st16p(ta + 32, r + 32); tmem_st16p(ta + 48, r + 48);
+}
 struct DevPairCx {
   static constexpr bool kTransient = SPF_PBS_TRANSIENT != 0;
   static constexpr bool kChunked = SPF_PBS_CHUNKED != 0;
@@ -207,6 +273,74 @@ struct DevPairCx {
     for (int k2 = 0; k2 < 16; k2++) {
       if (k2) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
       sts_c2(buf + k1 * kXPad + q + 4 * k2, v[k2]);
+    }
+  }
+  // ---- first exchange through tensor memory (SPF_PBS_TMEM_X1) ----
+  static constexpr bool kTmemX1 = SPF_PBS_TMEM_X1 != 0;
+  __device__ __forceinline__ int time_index() const { return kTmemX1 ? x1_time_index(u) : u; }
+  // forward: v[k1] of pass-1 thread a  ->  v[m'] = y_{q + 4 m'}[k1] of pass-2 thread (k1, q).  The 64 scratch columns are the
+  // warp's parking place of the accumulators (f_taddr), which is free whenever this is called (pbs_pair_team).
+  __device__ __forceinline__ void x1_fwd(C2 (&v)[16]) const {
+    uint32_t r[64], s[64];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      r[2 * x1_unit1(k, 0)] = (uint32_t)__double2loint(v[k].x); r[2 * x1_unit1(k, 0) + 1] = (uint32_t)__double2hiint(v[k].x);
+      r[2 * x1_unit1(k, 1)] = (uint32_t)__double2loint(v[k].y); r[2 * x1_unit1(k, 1) + 1] = (uint32_t)__double2hiint(v[k].y);
+    }
+    x1_st32(f_taddr, r);
+    tmem_wait_st();
+    x1_ld256(s, f_taddr);
+    tmem_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+#pragma unroll
+      for (int klo = 0; klo < 4; klo++)
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int w = 0; w < 2; w++) r[2 * x1_unit2(e, klo, c) + w] = s[x1_reg_r1(e, klo, c, w)];
+    x1_st32(f_taddr, r);
+    tmem_wait_st();
+    x1_ld256(s, f_taddr);
+    tmem_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+#pragma unroll
+      for (int ep = 0; ep < 4; ep++) {
+        v[4 * e + ep].x = __hiloint2double((int)s[x1_reg_r2(e, ep, 0, 1)], (int)s[x1_reg_r2(e, ep, 0, 0)]);
+        v[4 * e + ep].y = __hiloint2double((int)s[x1_reg_r2(e, ep, 1, 1)], (int)s[x1_reg_r2(e, ep, 1, 0)]);
+      }
+  }
+  // inverse: w[m'] of thread (k1, q)  ->  w[k1] of thread a = q + 4 m' (the same two rounds backwards, shapes swapped)
+  __device__ __forceinline__ void x1_inv(C2 (&v)[16]) const {
+    uint32_t r[64], s[64];
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+#pragma unroll
+      for (int ep = 0; ep < 4; ep++) {
+        s[x1_reg_r2(e, ep, 0, 0)] = (uint32_t)__double2loint(v[4 * e + ep].x); s[x1_reg_r2(e, ep, 0, 1)] = (uint32_t)__double2hiint(v[4 * e + ep].x);
+        s[x1_reg_r2(e, ep, 1, 0)] = (uint32_t)__double2loint(v[4 * e + ep].y); s[x1_reg_r2(e, ep, 1, 1)] = (uint32_t)__double2hiint(v[4 * e + ep].y);
+      }
+    x1_st256(f_taddr, s);
+    tmem_wait_st();
+    x1_ld32(r, f_taddr);
+    tmem_wait_ld();
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+#pragma unroll
+      for (int klo = 0; klo < 4; klo++)
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+          for (int w = 0; w < 2; w++) s[x1_reg_r1(e, klo, c, w)] = r[2 * x1_unit2(e, klo, c) + w];
+    x1_st256(f_taddr, s);
+    tmem_wait_st();
+    x1_ld32(r, f_taddr);
+    tmem_wait_ld();
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      v[k].x = __hiloint2double((int)r[2 * x1_unit1(k, 0) + 1], (int)r[2 * x1_unit1(k, 0)]);
+      v[k].y = __hiloint2double((int)r[2 * x1_unit1(k, 1) + 1], (int)r[2 * x1_unit1(k, 1)]);
     }
   }
   int u, h;
@@ -441,11 +575,14 @@ struct DevPairCx {
   }
 };
 
+static_assert(!SPF_PBS_TMEM_X1 || (SPF_PBS_TMEM_T1 && SPF_PBS_TMEM_F && !SPF_PBS_FUSED_ST && kPbsTmemFPairs == kPbsPairs),
+              "the tensor-memory first exchange needs the per-thread twiddles and a parking block per pair in tensor memory");
+
 // Tensor-memory scratchpad of the pair / quad team kernels: one 512-column allocation per CTA.
 // Columns [0,64) pass-1 twiddles of the thread (shared by the warps of a lane quarter, which have the same
 // thread-in-team index), then the per-pair blocks of pbs_kernel (kPbsTmemOwn0, kPbsTmemF0); [448,512) pass-2
 // twiddles when SPF_PBS_TMEM_T2.  Returns this warp's lane-quarter base address.
-__device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2, uint32_t& alloc_base) {
+__device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2, uint32_t& alloc_base, bool time_remap = false) {
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -460,9 +597,10 @@ __device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2,
   const uint32_t t1_taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   if (warp < 4) {  // every lane quarter is shared by warps w, w+4, w+8, which have the same u
     const int uu = (warp & 1) * 32 + (threadIdx.x & 31);
+    const int ua = time_remap ? x1_time_index(uu) : uu;  // pass-1 identity of this thread (SPF_PBS_TMEM_X1)
 #pragma unroll
     for (int k1 = 0; k1 < 16; k1++) {
-      const C2 w = sT1[k1 * 64 + uu];
+      const C2 w = sT1[k1 * 64 + ua];
       tmem_st4(t1_taddr + 4 * k1, (uint32_t)__double2loint(w.x), (uint32_t)__double2hiint(w.x),
                (uint32_t)__double2loint(w.y), (uint32_t)__double2hiint(w.y));
     }
@@ -505,7 +643,7 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
   uint32_t tmem_alloc;
-  const uint32_t t1_taddr = pair_tmem_init(sT1, sT2, tmem_alloc);
+  const uint32_t t1_taddr = pair_tmem_init(sT1, sT2, tmem_alloc, DevPairCx::kTmemX1);
   const int pair = threadIdx.x / (2 * kTeam);
   const int npairs = blockDim.x / (2 * kTeam);  // 1..kPbsPairs pairs per CTA (fewer for small batches)
   const int h = (threadIdx.x / kTeam) & 1;

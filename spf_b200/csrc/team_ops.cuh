@@ -381,6 +381,12 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
   const bool cbs = A.lut == nullptr;
   const int log2n = 12;  // log2(2N)
   C2* xown = xb + h * kXBuf;
+  // Cx::kTmemX1 (device): the first exchange of a transform stays inside the warp (fft16.cuh: x1_time_index).  The thread
+  // then owns the coefficients j = ua + 64 i of its polynomial in the time domain while everything it keeps per thread in
+  // shared memory (the accumulator image pa[u + 64 i]) stays indexed by the physical thread u; from pass 2 on it is
+  // thread (k1, q) = u as before.
+  constexpr bool kX1 = Cx::kTmemX1;
+  const int ua = cx.time_index();
   // Cx::kTransient: the accumulator polynomial of this half lives ONLY in the threads' own-coefficient copies
   // (device: tensor memory); the shared-memory image the rotated gather reads is written into the half's exchange
   // buffer at the end of a step and is dead once the digits have been taken, so a pair needs no persistent 32 KiB
@@ -396,7 +402,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     const int rot = (2 * kN - bt) & (2 * kN - 1);
     const int v = 1 << A.log_v;
     for (int i = 0; i < 32; i++) {
-      const int j = u + 64 * i;
+      const int j = ua + 64 * i;
       int idx = j - rot;
       bool neg = false;
       if (idx < 0) { idx += kN; neg = true; }
@@ -404,7 +410,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       uint64_t c;
       if (cbs) c = h ? cbs_lut_coeff(idx, A.cbs_radix_log, A.cbs_count, v) : 0;
       else c = ldg_u64(A.lut + h * kN + idx);
-      pa[j] = neg ? 0 - c : c;
+      pa[u + 64 * i] = neg ? 0 - c : c;
     }
   }
   cx.sync();
@@ -444,10 +450,10 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       // signed 16-bit digits, LSB first (math/radix.rs:81-113 for logB=16, l=2).  The source index
       // of coefficient j = u + 64 i2 is (u - a~ + 64 i2) mod 2N: bit 11 = negacyclic sign.
       {
-        const int base = (u - at) & (2 * kN - 1);
+        const int base = (ua - at) & (2 * kN - 1);
         // byte address of source row tt = (base >> 6) + i2 (mod 32) of this thread's column:
         // rows are 512 B apart, so the row index lives in bits 9..13 of the offset
-        const char* col = reinterpret_cast<const char*>(pa) + 8 * (base & 63);
+        const char* col = reinterpret_cast<const char*>(pa) + 8 * (kX1 ? x1_position(base & 63) : (base & 63));
         const uint32_t bh9 = (uint32_t)(base >> 6) << 9;
 #pragma unroll
         for (int i2 = 0; i2 < 32; i2++) {
@@ -482,7 +488,26 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
           dft16<false>(v);
           cx.template t2_mul_store<false>(v, T2, xown);  // v[k2] *= W64^(q k2); in-place second exchange
         } else {
-          cx.template t1_mul<false>(v, T1);  // v[k1] *= T1[k1][u]
+          cx.template t1_mul<false>(v, T1);  // v[k1] *= T1[k1][ua]
+          if constexpr (kX1) {
+            if (t == 0) {
+              // first digit level: the accumulators are not live, their tensor-memory columns carry the exchange
+              cx.x1_fwd(v);
+              dft16<false>(v);
+              cx.template t2_mul<false>(v, T2);
+              if (kTr) cx.sync();  // every thread of the half has gathered from the accumulator image in xown
+            } else {
+              // second digit level (the accumulators are parked in those columns): shared memory, per-thread slots
+              cx.pair_sync(); cx.bsk_release(G); cx.bsk_release(G + 1);
+              fwd_x1_write(v, xown, u);
+              cx.sync();
+              fwd_x1_read_perm(v, xown, u);
+              dft16<false>(v);
+              cx.template t2_mul<false>(v, T2);
+              cx.sync();  // the slots read above are not the ones fwd_x2_write overwrites: wait for the other readers of the row
+            }
+            fwd_x2_write(v, xown, u);
+          } else {
           if (t == 1) { cx.pair_sync(); cx.bsk_release(G); cx.bsk_release(G + 1); }  // both halves have consumed the level-0 spectra (and the key chunks)
           else if (kTr) cx.sync();     // every thread of the half has gathered from the accumulator image in xown
           fwd_x1_write(v, xown, u);
@@ -491,6 +516,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
           dft16<false>(v);
           cx.template t2_mul<false>(v, T2);  // v[k2] *= W64^(q k2)
           fwd_x2_write(v, xown, u);  // in place: no barrier after fwd_x1_read
+          }
         }
         if (t == 1) cx.f_load(f);
         cx.pair_sync();
@@ -529,13 +555,18 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       cx.template t2_mul<true>(w, T2);
       if constexpr (Cx::kFusedStores) {
         dft16_emit<true>(w, [&](int mp, C2 val) { cx.sts(xown + k1 * kXPad + q + 4 * mp, val); });  // = inv_x1_write
+      } else if constexpr (kX1) {
+        dft16<true>(w);
+        cx.x1_inv(w);  // w[k1] of thread ua; the accumulators' tensor-memory columns are free again
       } else {
         dft16<true>(w);
         inv_x1_write(w, xown, u);  // in place: no barrier after inv_x2_read
       }
-      cx.sync();
-      inv_x1_read(w, xown, u);
-      if (kTr) cx.sync();  // xown becomes the accumulator image again
+      if constexpr (!kX1) {
+        cx.sync();
+        inv_x1_read(w, xown, u);
+      }
+      if (kTr) cx.sync();  // xown becomes the accumulator image again (every thread has read its inverse-pass inputs)
       cx.template t1_mul<true>(w, T1);  // w[k1] *= conj(T1[k1][u])
       double ws[16];
       inv_pass1_core_s(w, ws);  // true value ws[m] * w[m]: the untwist's real factor rides into the conversion
@@ -586,10 +617,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     cx.sync();  // next step gathers rotated coefficients written by other threads of this half
   }
   // 3. result
-  for (int i = 0; i < 32; i++) {
-    const int j = u + 64 * i;
-    A.glwe_out[h * kN + j] = pa[j];
-  }
+  for (int i = 0; i < 32; i++) A.glwe_out[h * kN + ua + 64 * i] = pa[u + 64 * i];
   if (kTr) cx.sync();  // the next ciphertext of this pair overwrites the image
 }
 

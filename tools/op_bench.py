@@ -82,6 +82,16 @@ alg = B * (ev.len_glwe // 2 + ev.len_lwe_l1) * 8  # reads the a polynomial + one
 rows.append({"op": "sample_extract", "batch": B, "ms": ms, "ops_per_s": B / ms * 1e3, "algorithmic_gb_s": alg / ms / 1e6,
              "hbm_frac": alg / ms / 1e6 / hbm})
 del g, l1o, l1, l0
+# ---- RLWE public-key encryption (exact negacyclic u64 products; 4 194 304 u64 multiply-adds per polynomial, 2 per ciphertext) ----
+n = keys.params.glwe_n
+pk_d = rand_u64(2 * n)
+m_d, e0_d, e1_d = rand_u64(B, n), rand_u64(B, n), rand_u64(B, n)
+u_d = torch.from_numpy(rng.integers(0, 2, (B, n), dtype=np.int64)).to(dev)
+ct_d = torch.empty(B * 2 * n, dtype=torch.int64, device=dev)
+ms = timed(lambda: ev.dev_rlwe_encrypt_public(ct_d.data_ptr(), pk_d.data_ptr(), m_d.data_ptr(), u_d.data_ptr(), e0_d.data_ptr(),
+                                              e1_d.data_ptr(), B, stream=s))
+rows.append({"op": "rlwe_encrypt_public", "batch": B, "ms": ms, "ops_per_s": B / ms * 1e3, "u64_mad_per_s": B * 2 * n * n / ms * 1e3})
+del pk_d, m_d, e0_d, e1_d, u_d, ct_d
 # ---- CBS and PBS ----
 bits = rng.integers(0, 2, B)
 cts = torch.from_numpy(encrypt_lwe0_numpy(keys.lwe0_sk, bits, keys.params.lwe_std, 5).view(np.int64)).to(dev)
@@ -124,4 +134,7 @@ t0 = time.perf_counter(); O.cbs_pbs_stage(keys, l0c); cpu["programmable_bootstra
 ge = client.encrypt_glev_l1([1])
 t0 = time.perf_counter(); O.glev_cmux(keys, ge, ge, one); cpu["glev_cmux_ms"] = 1e3 * (time.perf_counter() - t0)
 t0 = time.perf_counter(); O.scheme_switch(keys, ge); cpu["scheme_switch_ms"] = 1e3 * (time.perf_counter() - t0)
+pkc = client.generate_public_key()
+rr = client.rlwe_randomness()
+t0 = time.perf_counter(); O.rlwe_encrypt_public(keys.params, g0[:keys.params.glwe_n], pkc, *rr); cpu["rlwe_encrypt_public_ms"] = 1e3 * (time.perf_counter() - t0)
 print(json.dumps({"cpu_port_single_thread": cpu}), flush=True)
