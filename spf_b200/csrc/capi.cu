@@ -47,6 +47,8 @@ struct spf_b200_ctx {
   cudaStream_t stream[2] = {nullptr, nullptr};
   cudaEvent_t ev[2] = {nullptr, nullptr};
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};  // host-pointer CBS pipeline: staging buffer of a slot is free again
+  cudaStream_t aux = nullptr;                      // launch_cbs: the partial last wave of the blind rotation (high priority)
+  cudaEvent_t ev_cbs_main = nullptr, ev_cbs_tail = nullptr;
   DevBuf scratch[2][7];  // per pipeline slot: grow-only device scratch ([6]: keyswitch digit states)
   std::string err;
   std::atomic<uint64_t> launches{0};
@@ -182,6 +184,13 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
     CUB(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
   }
+  {
+    int lo = 0, hi = 0;
+    CUB(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUB(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, hi));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_cbs_main, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&ctx->ev_cbs_tail, cudaEventDisableTiming));
+  }
   CUB(cudaFuncSetAttribute(pbs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPbsSmem));
   CUB(cudaFuncSetAttribute(pbs_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadSmem));
   CUB(cudaFuncSetAttribute(trace_ss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
@@ -263,7 +272,8 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
 // ---- kernel launch helpers (device pointers) ---------------------------------------------
 
 int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in, const uint64_t* d_lut, bool cbs,
-               uint32_t log_chi, uint32_t log_v, size_t batch, cudaStream_t s, const void* const* ptrs = nullptr) {
+               uint32_t log_chi, uint32_t log_v, size_t batch, cudaStream_t s, const void* const* ptrs = nullptr,
+               bool packed = false) {
   if (batch == 0) return 0;
   PbsBatch P;
   P.lwe_in = d_lwe_in;
@@ -281,6 +291,11 @@ int launch_pbs(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe_in
   // A pair (one ciphertext) is largely latency-bound: alone on an SM it takes ~7 ms per PBS, ~9 ms
   // when three share the SM; small batches get one ciphertext per SM so they do not queue behind
   // each other, large ones run as persistent pairs (see pbs_kernel).
+  if (packed) {  // launch_cbs: kPbsPairs ciphertexts per SM on as few SMs as possible, the rest of the GPU is busy elsewhere
+    const int grid = (int)std::min<size_t>((batch + kPbsPairs - 1) / kPbsPairs, (size_t)ctx->sm_count);
+    pbs_kernel<<<grid, kPbsPairs * 2 * kTeam, kPbsSmem, s>>>(P, tabs(ctx));
+    return check_launch(ctx, "pbs_kernel");
+  }
   if (batch <= (size_t)ctx->sm_count) {  // latency mode: one ciphertext per SM on four teams
     pbs_quad_kernel<<<(int)batch, 4 * kTeam, kQuadSmem, s>>>(P, tabs(ctx));
     return check_launch(ctx, "pbs_quad_kernel");
@@ -341,6 +356,38 @@ int launch_trace_ss(spf_b200_ctx* ctx, const uint64_t* d_glwe_in, uint64_t* d_gl
   if (P.peers.n > 0) trace_ss_kernel<true><<<grid, per * kTeam, kTableBytes + per * kTrTeamBytes, s>>>(P, tabs(ctx));
   else trace_ss_kernel<false><<<grid, per * kTeam, kTableBytes + per * kTrTeamBytes, s>>>(P, tabs(ctx));
   return check_launch(ctx, "trace_ss_kernel");
+}
+
+// Circuit bootstrap = blind rotation (pbs_kernel) then trace + scheme switch (trace_ss_kernel) per ciphertext.
+// The blind rotation runs in waves of sm_count x kPbsPairs ciphertexts; a batch such as 4096 = 9 x 444 + 100 ends in a
+// remainder that cannot fill the GPU.  Run alone, that remainder costs a whole extra pass of the latency kernel
+// (3.5 ms for 100 ciphertexts on 100 SMs while 48 idle, then 8.7 ms of trace kernels).  Here it is packed three to an SM
+// onto ceil(rem / 3) SMs (the throughput configuration: 2.4 instead of 3.5 SM-ms per ciphertext) on a high-priority
+// side stream and runs CONCURRENTLY with the trace / scheme-switch kernel of the full waves, whose thousands of short
+// CTAs fill the remaining SMs: the step ends after (all work) / (all SMs) instead of after the sum of three under-filled
+// phases.  Only scheduling depends on the first event (the remainder reads nothing the full waves write); the second one
+// orders the remainder's trace kernel behind its blind rotation.  SPF_B200_CBS_OVERLAP=0 restores the serial form.
+int launch_cbs(spf_b200_ctx* ctx, C2* d_ggsw_out, uint64_t* d_glwe, const uint64_t* d_lwe_in, const void* const* ptrs,
+               double out_scale, size_t batch, cudaStream_t s, const PeerOffsets* peers = nullptr) {
+  if (batch == 0) return 0;
+  static const bool overlap = [] { const char* e = getenv("SPF_B200_CBS_OVERLAP"); return !(e && !strcmp(e, "0")); }();
+  const int levels = (int)ctx->p.cbs.count;
+  const size_t wave = (size_t)ctx->sm_count * kPbsPairs, rem = batch % wave, full = batch - rem;
+  const size_t lwe = (size_t)ctx->p.lwe_n + 1, ggsw = len_ggsw(&ctx->p, ctx->p.cbs);
+  if (!overlap || full == 0 || rem == 0 || rem > wave / 2 || s == ctx->aux) {
+    if (int rc = launch_pbs(ctx, d_glwe, d_lwe_in, nullptr, true, 0, cbs_log_v(&ctx->p), batch, s, ptrs)) return rc;
+    return launch_trace_ss(ctx, d_glwe, nullptr, d_ggsw_out, 0, levels, out_scale, batch, s, nullptr, peers);
+  }
+  if (int rc = launch_pbs(ctx, d_glwe, d_lwe_in, nullptr, true, 0, cbs_log_v(&ctx->p), full, s, ptrs)) return rc;
+  CU(cudaEventRecord(ctx->ev_cbs_main, s));
+  CU(cudaStreamWaitEvent(ctx->aux, ctx->ev_cbs_main, 0));
+  if (int rc = launch_pbs(ctx, d_glwe + full * 2 * kN, ptrs ? nullptr : d_lwe_in + full * lwe, nullptr, true, 0, cbs_log_v(&ctx->p), rem,
+                          ctx->aux, ptrs ? ptrs + full : nullptr, /*packed=*/true))
+    return rc;
+  CU(cudaEventRecord(ctx->ev_cbs_tail, ctx->aux));
+  if (int rc = launch_trace_ss(ctx, d_glwe, nullptr, d_ggsw_out, 0, levels, out_scale, full, s, nullptr, peers)) return rc;
+  CU(cudaStreamWaitEvent(s, ctx->ev_cbs_tail, 0));
+  return launch_trace_ss(ctx, d_glwe + full * 2 * kN, nullptr, d_ggsw_out + full * ggsw, 0, levels, out_scale, rem, s, nullptr, peers);
 }
 
 int launch_cmux(spf_b200_ctx* ctx, uint64_t* d_out, const uint64_t* d_d0, const uint64_t* d_d1, const C2* d_ggsw,
@@ -641,6 +688,9 @@ void spf_b200_destroy(spf_b200_ctx* ctx) {
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
   }
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
+  if (ctx->ev_cbs_main) cudaEventDestroy(ctx->ev_cbs_main);
+  if (ctx->ev_cbs_tail) cudaEventDestroy(ctx->ev_cbs_tail);
   delete ctx;
 }
 
@@ -668,9 +718,7 @@ int spf_b200_dev_circuit_bootstrap(spf_b200_ctx* ctx, double* d_ggsw_out, const 
   // PBS output scratch: slot 0 when running on the caller's stream
   DevBuf& g = ctx->scratch[0][5];
   if (int rc = ensure(ctx, g, batch * len_glwe(&ctx->p) * 8)) return rc;
-  if (int rc = launch_pbs(ctx, (uint64_t*)g.p, d_lwe0_in, nullptr, true, 0, cbs_log_v(&ctx->p), batch, s)) return rc;
-  return launch_trace_ss(ctx, (const uint64_t*)g.p, nullptr, (C2*)d_ggsw_out, 0, (int)ctx->p.cbs.count,
-                         reference_scale ? 1024.0 : 1.0, batch, s);
+  return launch_cbs(ctx, (C2*)d_ggsw_out, (uint64_t*)g.p, d_lwe0_in, nullptr, reference_scale ? 1024.0 : 1.0, batch, s);
 }
 
 int spf_b200_dev_programmable_bootstrap(spf_b200_ctx* ctx, uint64_t* d_glwe_out, const uint64_t* d_lwe0_in,
@@ -743,9 +791,7 @@ int spf_b200_circuit_bootstrap(spf_b200_ctx* ctx, double* ggsw_out, const uint64
     DevBuf* sc = ctx->scratch[slot];
     if (k >= 2) CU(cudaStreamWaitEvent(comp, ctx->ev_copied[slot], 0));  // staging buffer drained
     CU(cudaMemcpyAsync(sc[0].p, lwe0_in + off * lwe, n * lwe * 8, cudaMemcpyHostToDevice, comp));
-    rc = launch_pbs(ctx, (uint64_t*)sc[1].p, (const uint64_t*)sc[0].p, nullptr, true, 0, cbs_log_v(&ctx->p), n, comp);
-    if (rc == 0)
-      rc = launch_trace_ss(ctx, (const uint64_t*)sc[1].p, nullptr, (C2*)sc[2].p, 0, (int)ctx->p.cbs.count, 1024.0, n, comp);
+    rc = launch_cbs(ctx, (C2*)sc[2].p, (uint64_t*)sc[1].p, (const uint64_t*)sc[0].p, nullptr, 1024.0, n, comp);
     if (rc) break;
     CU(cudaEventRecord(ctx->ev[slot], comp));
     CU(cudaStreamWaitEvent(copy, ctx->ev[slot], 0));

@@ -266,11 +266,8 @@ int run_group_range(spf_b200_graph* g, const Group& G, cudaStream_t s, size_t st
       return launch_cmux(ctx, reinterpret_cast<uint64_t*>(out), nullptr, nullptr, nullptr, 0, (int)p->cbs.count, n * p->cbs.count, s, p3);
     case SPF_OP_CIRCUIT_BOOTSTRAP: {
       const size_t glwe = ct_bytes(p, T_GLWE1);
-      if (int rc = launch_pbs(ctx, reinterpret_cast<uint64_t*>(G.scratch + start * glwe), nullptr, nullptr, true, 0,
-                              cbs_log_v(p), n, s, p1))
-        return rc;
-      return launch_trace_ss(ctx, reinterpret_cast<const uint64_t*>(G.scratch + start * glwe), nullptr,
-                             reinterpret_cast<C2*>(out), 0, (int)p->cbs.count, 1.0, n, s, nullptr, peers);
+      return launch_cbs(ctx, reinterpret_cast<C2*>(out), reinterpret_cast<uint64_t*>(G.scratch + start * glwe), nullptr, p1, 1.0, n, s,
+                        peers);
     }
     case SPF_OP_SCHEME_SWITCH:
       return launch_trace_ss(ctx, nullptr, nullptr, reinterpret_cast<C2*>(out), 2, (int)p->cbs.count, 1.0, n, s, p1);
