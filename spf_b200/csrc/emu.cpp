@@ -155,6 +155,9 @@ struct HostWideCx {
   pthread_barrier_t* bar_cta;
   void sync() { pthread_barrier_wait(bar_team); }
   void cta_sync() { pthread_barrier_wait(bar_cta); }
+  static constexpr bool kStageG = false;  // device: the selector GGSW is staged in tensor memory during the transforms
+  template <int I> void g_stage() {}
+  void g_read16(C2 (&)[4][4], int) {}
 };
 template <class Body>
 struct WideLaunch {

@@ -1076,10 +1076,57 @@ constexpr int kWideGlweBytes = 2 * kN * 8;
 constexpr int kWideSmem = kTableBytes + kWideTeams * kXBuf * 16 + 2 * kWideGlweBytes + 16;  // 216144
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity);
 
+#ifndef SPF_WIDE_STAGE_G
+#define SPF_WIDE_STAGE_G 0  // selector GGSW staged in tensor memory while the forward transforms run: bit-exact, the
+                            // multiply-accumulate phase drops from 5.6 k to 3.1 k clocks, but the transforms that now share the
+                            // SM's 45 B/clk L2 port with the 256 KiB transfer lose 3.3 k (profiles/r2_m_wide_phases.txt):
+                            // 19.78 vs 19.58 ms for the mul32 + compare program -- the port, not its placement, is the floor
+#endif
 struct DevWideCx {
   int u, team;
   __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(team + 1) : "memory"); }
   __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+  // ---- GGSW staging (team_ops.cuh::cmux_wide, g_stage) ----
+  // Tensor memory is exactly one GGSW: 512 columns x 128 lanes x 4 B = 256 KiB.  Thread (p, k1, k2) of the multiply-accumulate
+  // phase owns the bins k1 + 16 k2 + 256 k3 of output p over the 8 spectra j: 32 complex values = 128 columns of its lane;
+  // the four warps of a lane quarter take the four 128-column blocks.  Batch j = the four values of spectrum j (k3 = 0..3).
+  static constexpr bool kStageG = SPF_WIDE_STAGE_G != 0;
+  const C2* gbase = nullptr;  // ggsw + p * kM + k1 + 16 k2 of this thread
+  uint32_t g_taddr = 0;       // this warp's lane quarter and 128-column block
+  int count = 4;
+  C2 stg[4];
+  template <int I>
+  __device__ __forceinline__ void g_stage() {
+    if constexpr (kStageG) {
+      if constexpr (I > 0) {
+        uint32_t r[16];
+#pragma unroll
+        for (int k3 = 0; k3 < 4; k3++) {
+          r[4 * k3] = (uint32_t)__double2loint(stg[k3].x); r[4 * k3 + 1] = (uint32_t)__double2hiint(stg[k3].x);
+          r[4 * k3 + 2] = (uint32_t)__double2loint(stg[k3].y); r[4 * k3 + 3] = (uint32_t)__double2hiint(stg[k3].y);
+        }
+        tmem_st16(g_taddr + 16 * (I - 1), r);
+        if constexpr (I == 8) tmem_wait_st();
+      }
+      if constexpr (I < 8) {
+        const int rr = I / 4, tt = I % 4;  // spectrum j = I: digit tt of polynomial rr <-> GGSW level count - 1 - tt (count == 4)
+        const C2* grow = gbase + (size_t)(rr * 4 + (3 - tt)) * 2 * kM;
+#pragma unroll
+        for (int k3 = 0; k3 < 4; k3++) stg[k3] = ldg_c2_pinned(grow + 256 * k3);
+      }
+    }
+  }
+  __device__ __forceinline__ void g_read16(C2 (&g)[4][4], int jb) const {
+    uint32_t r[4][16];
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) tmem_ld16(r[jj], g_taddr + 16 * (jb + jj));
+    tmem_wait_ld();
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++)
+#pragma unroll
+      for (int k3 = 0; k3 < 4; k3++)
+        g[jj][k3] = C2{__hiloint2double((int)r[jj][4 * k3 + 1], (int)r[jj][4 * k3]), __hiloint2double((int)r[jj][4 * k3 + 3], (int)r[jj][4 * k3 + 2])};
+  }
 };
 
 __global__ void __launch_bounds__(kWideTeams * kTeam, 1) cmux_wide_kernel(CmuxBatch P, DevTables tabs) {
@@ -1102,6 +1149,20 @@ __global__ void __launch_bounds__(kWideTeams * kTeam, 1) cmux_wide_kernel(CmuxBa
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   load_tables(sT1, sT2, tabs);  // ends with a CTA barrier: the mbarrier is initialised for everyone
+#if SPF_WIDE_STAGE_G
+  uint32_t tmem_alloc;
+  {
+    __shared__ uint32_t tmem_base;
+    if ((threadIdx.x >> 5) == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&tmem_base)), "n"(kPbsTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_alloc = tmem_base;
+  }
+#endif
   const size_t glwe = 2 * kN;
   const int item = c / P.glwe_per_item;
   const size_t off = P.ptrs ? (size_t)(c % P.glwe_per_item) * glwe : (size_t)c * glwe;
@@ -1118,10 +1179,21 @@ __global__ void __launch_bounds__(kWideTeams * kTeam, 1) cmux_wide_kernel(CmuxBa
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(smem_u32(sd0)), "l"(d0 + off), "r"((uint32_t)kWideGlweBytes), "r"(smem_u32(mbar)) : "memory");
   }
-  mbar_wait(smem_u32(mbar), 0);
   DevWideCx cx{(int)(threadIdx.x % kTeam), (int)(threadIdx.x / kTeam)};
+#if SPF_WIDE_STAGE_G
+  {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    cx.gbase = ggsw + (size_t)(tid >> 8) * kM + (tid & 255);  // p * kM + k1 + 16 k2
+    cx.g_taddr = tmem_alloc + ((uint32_t)((warp & 3) * 32) << 16) + 128 * (warp >> 2);
+    cx.count = P.count;
+  }
+#endif
+  mbar_wait(smem_u32(mbar), 0);
   cmux_wide(cx, P.out_ptrs ? static_cast<uint64_t*>(P.out_ptrs[c]) : P.out + (size_t)c * glwe, d0 ? sd0 : nullptr, sd1, ggsw, xb, sT1, sT2,
             P.radix_log, P.count);
+#if SPF_WIDE_STAGE_G
+  pair_tmem_free(tmem_alloc);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -957,6 +957,7 @@ SPF_HD void cmux_wide(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t*
     const uint64_t off = radix_offset(radix_log, count);
     const uint64_t dmask = (1ull << radix_log) - 1;
     const int32_t half = 1 << (radix_log - 1);
+    cx.template g_stage<0>();
     C2 v[16];
     const int shift = 64 - radix_log * count;
     if (shift >= 33) {
@@ -966,6 +967,7 @@ SPF_HD void cmux_wide(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t*
       const int sh = shift - 32 + t * radix_log;
 #pragma unroll
       for (int m = 0; m < 16; m++) {
+        if (m == 8) cx.template g_stage<1>();
         const int j = r * kN + u + 64 * m;
         const uint64_t x0 = d0 ? d1[j] - d0[j] : d1[j];  // d0 / d1 may be shared-memory copies (cmux_wide_kernel)
         const uint64_t x1 = d0 ? d1[j + kM] - d0[j + kM] : d1[j + kM];
@@ -973,6 +975,7 @@ SPF_HD void cmux_wide(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t*
         v[m].y = i32_to_f64((int32_t)((((uint32_t)(x1 >> 32) + c1) >> sh) & (uint32_t)dmask) - half);
       }
     } else {
+      cx.template g_stage<1>();
 #pragma unroll
       for (int m = 0; m < 16; m++) {
         const int j = r * kN + u + 64 * m;
@@ -984,13 +987,31 @@ SPF_HD void cmux_wide(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t*
       }
     }
     SPF_WT(1);
-    fwd_pass1(v, u, T1);
+    // cx.g_stage<i>: device only -- the selector GGSW (256 KiB, each element used once, by one thread) is brought into the
+    // thread's tensor-memory columns in 8 batches WHILE the digits are taken and the forward transforms run (batch i is
+    // requested at point i and parked at point i + 1), so the multiply-accumulate phase below no longer waits for
+    // 256 KiB to come through one SM's L2 port (6.5 k of the kernel's 20 k clocks)
+    cx.template g_stage<2>();
+    fwd_pass1_core(v);
+    cx.template g_stage<3>();
+#pragma unroll
+    for (int k1i = 0; k1i < 16; k1i++) v[k1i] = cmul(v[k1i], T1[k1i * 64 + u]);
+    cx.template g_stage<4>();
     fwd_x1_write(v, xown, u);
     cx.sync();
     SPF_WT(2);
     fwd_x1_read(v, xown, u);
-    fwd_pass2(v, u, T2);
+    cx.template g_stage<5>();
+    dft16<false>(v);
+    cx.template g_stage<6>();
+    {
+      const int qq = u >> 4;
+#pragma unroll
+      for (int k2i = 1; k2i < 16; k2i++) v[k2i] = cmul(v[k2i], T2[qq * kT2Pad + k2i]);
+    }
+    cx.template g_stage<7>();
     fwd_x2_write(v, xown, u);  // in place
+    cx.template g_stage<8>();
   }
   cx.cta_sync();
   SPF_WT(3);
@@ -1001,12 +1022,15 @@ SPF_HD void cmux_wide(Cx& cx, uint64_t* out, const uint64_t* d0, const uint64_t*
 #pragma unroll
   for (int jb = 0; jb < 2 * 4; jb += 4) {  // 4 spectra per batch: their GGSW values are requested together
     C2 g[4][4], d[4][4];
+    if constexpr (Cx::kStageG) cx.g_read16(g, jb);  // parked by g_stage: the same sixteen values
 #pragma unroll
     for (int jj = 0; jj < 4; jj++) {
       const int j = jb + jj, rr = j / count, tt = j % count;  // digit tt <-> GGSW level count-1-tt (fft_ops.rs:92)
       const C2* grow = ggsw + ((size_t)(rr * count + (count - 1 - tt)) * 2 + p) * kM;
+      if constexpr (!Cx::kStageG) {
 #pragma unroll
-      for (int k3 = 0; k3 < 4; k3++) g[jj][k3] = ldg_c2(grow + k1 + 16 * k2 + 256 * k3);
+        for (int k3 = 0; k3 < 4; k3++) g[jj][k3] = ldg_c2(grow + k1 + 16 * k2 + 256 * k3);
+      }
 #pragma unroll
       for (int qp = 0; qp < 4; qp++) d[jj][qp] = xb[j * kXBuf + k1 * kXPad + qp + 4 * k2];
     }
