@@ -444,6 +444,8 @@ class E2EGraphPipeline:
         # chunks: whole PBS waves (3 waves each) so that chunking costs no extra tail; the remainder is its own graph
         per = 3 * wave
         bounds = list(range(0, B, per)) + [B]
+        if len(bounds) > 2 and bounds[-1] - bounds[-2] < wave:
+            del bounds[-2]  # a remainder below one wave rides with the last chunk: its blind rotation overlaps that chunk's trace kernels (launch_cbs)
         proc = spf_b200.CircuitProcessor(ev)
         self.graphs = []
         for lo, hi in zip(bounds[:-1], bounds[1:]):

@@ -374,7 +374,18 @@ int launch_cbs(spf_b200_ctx* ctx, C2* d_ggsw_out, uint64_t* d_glwe, const uint64
   const int levels = (int)ctx->p.cbs.count;
   const size_t wave = (size_t)ctx->sm_count * kPbsPairs, rem = batch % wave, full = batch - rem;
   const size_t lwe = (size_t)ctx->p.lwe_n + 1, ggsw = len_ggsw(&ctx->p, ctx->p.cbs);
-  if (!overlap || full == 0 || rem == 0 || rem > wave / 2 || s == ctx->aux) {
+  // Worth it only when the trace kernels of the full waves can keep the other SMs busy for the remainder's whole round;
+  // otherwise the packed remainder (one round, R) becomes the critical path and the latency kernel (0.49 R) followed by
+  // the trace kernels is shorter.  Measured ratios: trace + scheme switch of one ciphertext = 2.93e-4 R of the whole GPU.
+  bool pays = false;
+  if (full > 0 && rem > 0 && rem <= wave / 2) {
+    const double c = 2.93e-4, sm = (double)ctx->sm_count;
+    const double serial = (rem <= (size_t)ctx->sm_count ? 0.49 : 1.0) + (double)batch * c;
+    const double tail_sms = (double)((rem + kPbsPairs - 1) / kPbsPairs);
+    const double packed = std::max(1.0, ((double)full * c * sm + tail_sms) / sm) + (double)rem * c;
+    pays = packed < serial;
+  }
+  if (!overlap || !pays || s == ctx->aux) {
     if (int rc = launch_pbs(ctx, d_glwe, d_lwe_in, nullptr, true, 0, cbs_log_v(&ctx->p), batch, s, ptrs)) return rc;
     return launch_trace_ss(ctx, d_glwe, nullptr, d_ggsw_out, 0, levels, out_scale, batch, s, nullptr, peers);
   }
@@ -385,6 +396,12 @@ int launch_cbs(spf_b200_ctx* ctx, C2* d_ggsw_out, uint64_t* d_glwe, const uint64
                           ctx->aux, ptrs ? ptrs + full : nullptr, /*packed=*/true))
     return rc;
   CU(cudaEventRecord(ctx->ev_cbs_tail, ctx->aux));
+  // Both successors of the full waves become runnable at the same instant.  The remainder's few long CTAs must be placed
+  // first: if the trace kernel's 4 000 CTAs take every SM, the remainder trickles in behind them and the step gets LONGER
+  // than the serial form (seen on one box in four: 77.3 instead of 75.7 ms; stream priority alone did not prevent it).
+  // A 20 us single-thread pause in front of the trace kernel gives the block scheduler time to seat the remainder.
+  pause_kernel<<<1, 1, 0, s>>>(20000u);
+  if (int rc = check_launch(ctx, "pause_kernel")) return rc;
   if (int rc = launch_trace_ss(ctx, d_glwe, nullptr, d_ggsw_out, 0, levels, out_scale, full, s, nullptr, peers)) return rc;
   CU(cudaStreamWaitEvent(s, ctx->ev_cbs_tail, 0));
   return launch_trace_ss(ctx, d_glwe + full * 2 * kN, nullptr, d_ggsw_out + full * ggsw, 0, levels, out_scale, rem, s, nullptr, peers);

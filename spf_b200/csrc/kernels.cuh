@@ -1828,6 +1828,13 @@ __global__ void __launch_bounds__(kRlweThreads, 2) rlwe_encrypt_public_kernel(Rl
   }
 }
 
+// one thread waits `ns` nanoseconds (capi.cu::launch_cbs: lets a concurrently submitted kernel be seated first)
+__global__ void pause_kernel(unsigned ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); } while (t - t0 < ns);
+}
+
 // FFT-domain polynomials: dst = src * scale (2^-10 to import reference-scale data, 2^10 to export)
 __global__ void fft_scale_kernel(C2* dst, const C2* src, size_t n, double scale) {
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
