@@ -197,6 +197,7 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
   CUB(cudaFuncSetAttribute(trace_ss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
   CUB(cudaFuncSetAttribute(cmux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCmuxSmem));
   CUB(cudaFuncSetAttribute(cmux_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideSmem));
+  CUB(cudaFuncSetAttribute(cmux_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideSmem));
   {
     const int ks_smem = kKsBatch * (int)(params->glwe_k * params->glwe_n + kKsBlock) * 4;
     switch (params->ks.count) {

@@ -133,6 +133,13 @@ struct spf_b200_graph {
   std::atomic<int> status{0};
   std::string status_msg;
   DevBuf ks_states;
+  // runs of consecutive narrow CMux levels executed by ONE cooperative launch each (cmux_chain_kernel): planned at the
+  // first run of a rank, the stage lists live in d_chain
+  struct Chain { size_t first, last; size_t stage_off; int n_stages; int grid; };
+  std::vector<Chain> chains;
+  int chain_rank = -1;          // rank the plan was made for (-1: not planned yet)
+  ChainStage* d_chain = nullptr;
+  unsigned long long* d_chain_bar = nullptr;
   bool poisoned = false;  // a failed peer-mode run leaves the ranks' barrier epochs out of step: rebuild the graphs
 };
 
@@ -761,6 +768,77 @@ int stage_slot(spf_b200_graph* g, int id, size_t bytes, char** out) {
   return 0;
 }
 
+// Runs of consecutive MUX-tree levels for cmux_chain_kernel.  Eligible: CMux / MultiplyGgswGlwe groups whose share for this
+// rank fits the wide kernel's regime (at most two outputs per SM); groups that launch nothing (inputs, outputs, constants)
+// are transparent; anything else ends the run.  A run needs at least two levels to be worth a cooperative launch.
+int plan_chains(spf_b200_graph* g, int rank) {
+  spf_b200_ctx* ctx = g->ctx;
+  g->chains.clear();
+  g->chain_rank = rank;
+  if (ctx->p.cbs.count != 4) return 0;
+  const size_t wide_max = 2 * (size_t)ctx->sm_count;
+  auto launches_nothing = [](uint32_t op) {
+    return op <= SPF_OP_INPUT_GLEV1 || (op >= SPF_OP_ZERO_LWE0 && op <= SPF_OP_ONE_GLEV1) || (op >= SPF_OP_OUTPUT_LWE0 && op <= SPF_OP_OUTPUT_GLEV1) ||
+           op == SPF_OP_RETIRE || op == SPF_OP_NOP;
+  };
+  std::vector<ChainStage> stages;
+  std::vector<int> stage_level;
+  size_t i = 0;
+  const size_t ng = g->groups.size();
+  while (i < ng) {
+    const size_t stage0 = stages.size();
+    size_t first = ng, last = 0, widest = 0;
+    int levels = 0, prev_level = -1;
+    size_t j = i;
+    for (; j < ng; j++) {
+      const Group& G = g->groups[j];
+      if (launches_nothing(G.op)) continue;
+      if (!(G.op == SPF_OP_CMUX || G.op == SPF_OP_MULTIPLY_GGSW_GLWE) || !G.slot_outputs) break;
+      const size_t mine = G.all_cnt + G.r_cnt[rank];
+      if (mine > wide_max) break;
+      const void* const* base = reinterpret_cast<const void* const*>(g->d_ptrs + G.ptr_off);
+      void* const* outs = reinterpret_cast<void* const*>(g->d_ptrs + G.ptr_off + 3 * G.ids.size());
+      const size_t starts[2] = {G.all_start, G.r_start[rank]}, cnts[2] = {G.all_cnt, G.r_cnt[rank]};
+      for (int k = 0; k < 2; k++) {
+        if (cnts[k] == 0) continue;
+        if (G.level != prev_level) { levels++; prev_level = G.level; }
+        stages.push_back(ChainStage{base + 3 * starts[k], outs + starts[k], (int)cnts[k], 0});
+        stage_level.push_back(G.level);
+        widest = std::max(widest, cnts[k]);
+        first = std::min(first, j);
+        last = j;
+      }
+    }
+    if (levels >= 2) {
+      for (size_t k = stage0; k + 1 < stages.size(); k++) stages[k].barrier_after = stage_level[k + 1] != stage_level[k];
+      g->chains.push_back({first, last, stage0, (int)(stages.size() - stage0), (int)std::min<size_t>(widest, (size_t)ctx->sm_count)});
+    } else {
+      stages.resize(stage0);
+      stage_level.resize(stage0);
+    }
+    i = std::max(j, i) + 1;  // j stopped at a group that breaks the run (or at the end)
+  }
+  if (g->chains.empty()) return 0;
+  CU(cudaSetDevice(ctx->device));
+  if (g->d_chain) { cudaFree(g->d_chain); g->d_chain = nullptr; }
+  CU(cudaMalloc(&g->d_chain, stages.size() * sizeof(ChainStage)));
+  CU(cudaMemcpy(g->d_chain, stages.data(), stages.size() * sizeof(ChainStage), cudaMemcpyHostToDevice));
+  if (!g->d_chain_bar) CU(cudaMalloc(&g->d_chain_bar, sizeof(unsigned long long)));
+  return 0;
+}
+
+int launch_chain(spf_b200_graph* g, const spf_b200_graph::Chain& c, cudaStream_t s) {
+  spf_b200_ctx* ctx = g->ctx;
+  CU(cudaMemsetAsync(g->d_chain_bar, 0, sizeof(unsigned long long), s));
+  ChainBatch P{g->d_chain + c.stage_off, c.n_stages, g->d_chain_bar, (int)ctx->p.cbs.radix_log, (int)ctx->p.cbs.count};
+  DevTables T = tabs(ctx);
+  void* args[] = {&P, &T};
+  const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cmux_chain_kernel), dim3((unsigned)c.grid), dim3(kWideTeams * kTeam), args,
+                                                    (size_t)kWideSmem, s);
+  if (e != cudaSuccess) return fail(ctx, SPF_E_CUDA, std::string("cmux_chain_kernel: ") + cudaGetErrorString(e));
+  return check_launch(ctx, "cmux_chain_kernel");
+}
+
 // Everything of one run that is ENQUEUED on stream s: input copies, all levels, exchanges, output copies.  Returns the
 // first error (message in ctx->err); work already enqueued keeps running -- the caller drains the stream.
 int enqueue_run(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange, void* user, cudaStream_t s,
@@ -800,8 +878,22 @@ int enqueue_run(spf_b200_graph* g, int rank, int world, spf_exchange_fn exchange
         return rc;
   }
   if (timing_events) cudaEventRecord((*timing_events)[0], s);
+  // SPF_B200_CHAIN=1: runs of narrow CMux levels as one cooperative launch each (cmux_chain_kernel; measured slower than
+  // programmatic dependent launches, so opt-in)
+  const char* chain_env = getenv("SPF_B200_CHAIN");
+  const bool use_chains = !timing_events && chain_env && chain_env[0] == '1';
+  if (use_chains && g->chain_rank != rank)
+    if (int rc = plan_chains(g, rank)) return rc;
+  size_t next_chain = 0;
   size_t gi = 0;
-  for (const Group& G : g->groups) {
+  for (size_t gidx = 0; gidx < g->groups.size(); gidx++) {
+    const Group& G = g->groups[gidx];
+    if (use_chains && next_chain < g->chains.size() && gidx == g->chains[next_chain].first) {
+      const spf_b200_graph::Chain& c = g->chains[next_chain++];
+      if (int rc = launch_chain(g, c, s)) return rc;
+      gidx = c.last;  // the groups in between launch nothing or were part of the run
+      continue;
+    }
     // peer mode: the scheme-switch kernel stores its GGSWs into every rank's arena while it computes them
     if (int rc = run_group(g, G, s, rank, peer_mode && G.op == SPF_OP_CIRCUIT_BOOTSTRAP ? &g->peers : nullptr)) return rc;
     if (timing_events) cudaEventRecord((*timing_events)[++gi], s);
@@ -1061,6 +1153,8 @@ void spf_b200_graph_destroy(spf_b200_graph* g) {
   cudaFree(g->d_gather);
   cudaFree(g->d_gather_tab);
   cudaFree(g->ks_states.p);
+  cudaFree(g->d_chain);
+  cudaFree(g->d_chain_bar);
   if (g->h_stage) cudaFreeHost(g->h_stage);
   for (void* q : g->pinned) cudaHostUnregister(q);
   if (g->done) cudaEventDestroy(g->done);

@@ -718,6 +718,9 @@ constexpr int kQuadRowBytes = 8 * kM * 16;                                      
 constexpr int kQuadSmem = kQuadT2Bytes + 2 * kN * 8 + 4 * kXBuf * 16 + kQuadRowBytes + 16;  // 231504
 
 
+#ifndef SPF_QUAD_TMEM_T2
+#define SPF_QUAD_TMEM_T2 1
+#endif
 struct DevQuadCx {
   int u, h, t;
   uint32_t t1_taddr;
@@ -772,9 +775,29 @@ struct DevQuadCx {
   }
   template <bool CONJ>
   __device__ __forceinline__ void t2_mul(C2 (&v)[16], const C2* T2) const {
+#if SPF_PBS_TMEM_T2 && SPF_QUAD_TMEM_T2
+    // the thread's 15 pass-2 twiddles from its tensor-memory columns [448, 512) (filled by pair_tmem_init): tcgen05.ld
+    // costs next to nothing on the load / store pipe, the 15 broadcast LDS.128 it replaces sat on the critical path
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      uint32_t r0[16], r1[16];
+      tmem_ld16(r0, t1_taddr + 448 + 32 * half);
+      tmem_ld16(r1, t1_taddr + 448 + 32 * half + 16);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const C2 w0{__hiloint2double((int)r0[4 * i + 1], (int)r0[4 * i]), __hiloint2double((int)r0[4 * i + 3], (int)r0[4 * i + 2])};
+        const C2 w1{__hiloint2double((int)r1[4 * i + 1], (int)r1[4 * i]), __hiloint2double((int)r1[4 * i + 3], (int)r1[4 * i + 2])};
+        const int ka = 8 * half + i, kb = 8 * half + 4 + i;
+        if (ka != 0) v[ka] = CONJ ? cmul_conj(v[ka], w0) : cmul(v[ka], w0);
+        v[kb] = CONJ ? cmul_conj(v[kb], w1) : cmul(v[kb], w1);
+      }
+    }
+#else
     const int q = u >> 4;
 #pragma unroll
     for (int k2 = 1; k2 < 16; k2++) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
+#endif
   }
 };
 
@@ -1194,6 +1217,117 @@ __global__ void __launch_bounds__(kWideTeams * kTeam, 1) cmux_wide_kernel(CmuxBa
 #if SPF_WIDE_STAGE_G
   pair_tmem_free(tmem_alloc);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------
+// K2c `cmux_chain_kernel`: a RUN of consecutive MUX-tree levels in ONE cooperative launch.
+// A MUX tree is a chain of narrow levels (the 32-bit multiplier: 621 levels, mean width 73): launched one kernel per
+// level, every level pays the dependent-launch gap (~4 us even with programmatic launch) on top of the 9.7 us the wide
+// CMUX kernel works.  Here the CTAs stay resident, walk the levels of the run from a device-side list (the graph
+// executor's own per-group pointer tables) and separate two levels by a grid-wide barrier -- a release / acquire counter
+// in global memory -- instead of a kernel boundary; twiddle tables and the mbarrier are set up once.  The per-item body is
+// cmux_wide, unchanged (bit-identical results).  Cooperative launch guarantees that all CTAs are co-resident (other
+// graphs of the asynchronous executor may be in flight on other streams), so the spin barrier cannot deadlock.
+// MEASURED (profiles/r2_r_chain_ab.txt): 637 -> 19 launches for the mul32 + compare program, and 19.96 instead of
+// 19.44 ms -- the release / acquire round trips through L2 cost ~4.2 us per level where a programmatic dependent launch,
+// whose successor has its tables loaded and its selector on the way before the predecessor ends, costs ~3.3 us.  Kept
+// as an opt-in (SPF_B200_CHAIN=1): the executor stays on one launch per level.
+// ------------------------------------------------------------------------------------------
+struct ChainStage {
+  const void* const* ptrs;  // {selector GGSW, d0 (may be null), d1} per item
+  void* const* out_ptrs;    // output GLWE per item
+  int n;                    // items of this stage
+  int barrier_after;        // the next stage belongs to a later level
+};
+struct ChainBatch {
+  const ChainStage* stages;
+  int n_stages;
+  unsigned long long* bar;  // zeroed before the launch
+  int radix_log, count;
+};
+struct DevChainCx {
+  static constexpr bool kStageG = false;
+  int u, team;
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(team + 1) : "memory"); }
+  __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+  template <int I> __device__ __forceinline__ void g_stage() const {}
+  __device__ __forceinline__ void g_read16(C2 (&)[4][4], int) const {}
+};
+__global__ void __launch_bounds__(kWideTeams * kTeam, 1) cmux_chain_kernel(ChainBatch P, DevTables tabs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  C2* sT1 = reinterpret_cast<C2*>(smem);
+  C2* sT2 = sT1 + kT1Elems;
+  C2* xb = reinterpret_cast<C2*>(smem + kTableBytes);
+  uint64_t* sd1 = reinterpret_cast<uint64_t*>(smem + kTableBytes + kWideTeams * kXBuf * 16);
+  uint64_t* sd0 = sd1 + 2 * kN;
+  uint64_t* mbar = sd0 + 2 * kN;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  load_tables(sT1, sT2, tabs);  // ends with a CTA barrier
+  DevChainCx cx{(int)(threadIdx.x % kTeam), (int)(threadIdx.x / kTeam)};
+  unsigned long long target = 0;
+  uint32_t phase = 0;
+  // the stage list and the pointer tables are written before the launch: the next stage's descriptor and this CTA's first
+  // item of it are fetched BEFORE the grid barrier, so the two dependent global round trips are off the path between levels
+  ChainStage S = P.n_stages > 0 ? P.stages[0] : ChainStage{nullptr, nullptr, 0, 0};
+  const void* nx[4] = {nullptr, nullptr, nullptr, nullptr};
+  auto fetch_first = [&](const ChainStage& T) {
+    if ((int)blockIdx.x < T.n) {
+      nx[0] = T.ptrs[3 * blockIdx.x]; nx[1] = T.ptrs[3 * blockIdx.x + 1]; nx[2] = T.ptrs[3 * blockIdx.x + 2]; nx[3] = T.out_ptrs[blockIdx.x];
+    }
+  };
+  fetch_first(S);
+  for (int st = 0; st < P.n_stages; st++) {
+    ChainStage Snext = st + 1 < P.n_stages ? P.stages[st + 1] : ChainStage{nullptr, nullptr, 0, 0};
+    for (int c = blockIdx.x; c < S.n; c += gridDim.x) {
+      const bool firsti = c == (int)blockIdx.x;
+      const C2* ggsw = static_cast<const C2*>(firsti ? nx[0] : S.ptrs[3 * c]);
+      const uint64_t* d0 = static_cast<const uint64_t*>(firsti ? nx[1] : S.ptrs[3 * c + 1]);
+      const uint64_t* d1 = static_cast<const uint64_t*>(firsti ? nx[2] : S.ptrs[3 * c + 2]);
+      uint64_t* outp = static_cast<uint64_t*>(firsti ? const_cast<void*>(nx[3]) : S.out_ptrs[c]);
+      if (threadIdx.x == 0) {
+        // the inputs may have been written by other CTAs of this launch (generic proxy, before the grid barrier): order
+        // this thread's acquire of the barrier before the bulk copies' reads (async proxy)
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const uint32_t bytes = d0 ? 2 * kWideGlweBytes : kWideGlweBytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sd1)), "l"(d1), "r"((uint32_t)kWideGlweBytes), "r"(smem_u32(mbar)) : "memory");
+        if (d0)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(sd0)), "l"(d0), "r"((uint32_t)kWideGlweBytes), "r"(smem_u32(mbar)) : "memory");
+      }
+      mbar_wait_trap(smem_u32(mbar), phase);
+      phase ^= 1u;
+      cmux_wide(cx, outp, d0 ? sd0 : nullptr, sd1, ggsw, xb, sT1, sT2, P.radix_log, P.count);
+      __syncthreads();  // the staged inputs and the exchange buffers are free for the next item
+    }
+    fetch_first(Snext);
+    if (S.barrier_after) {
+      __syncthreads();  // every thread's output stores precede thread 0's release
+      if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(P.bar, 1ull);
+        unsigned long long seen;
+        unsigned long long t_start = 0;
+        for (int spin = 0;; spin++) {
+          asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.bar) : "memory");
+          if (seen >= target) break;
+          if ((spin & 4095) == 4095) {  // a CTA that never arrives: trap instead of hanging the GPU
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > 2000000000ull) __trap();
+          }
+        }
+      }
+      __syncthreads();
+    }
+    S = Snext;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
