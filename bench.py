@@ -757,6 +757,9 @@ def run_gpu(args):
                            "MEASURED_PEAKS.json carries no FP64 figure",
             "flop_per_launch": FLOP_PER_PBS * B, "ms_per_launch": pbs_ms,
             "share_of_step": pbs_ms / (dev_ms / args.steps) if dev_ms else None,
+            "note": "timed alone (whole waves on pbs_kernel, a sub-wave remainder on the latency kernel); inside a step the remainder "
+                    "runs packed three to an SM concurrently with the trace / scheme-switch kernels (capi.cu::launch_cbs), so the "
+                    "step is shorter than this plus the trace kernels",
             "hbm": {"achieved": alg_bytes / (pbs_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes / (pbs_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
                     "peak_source": hbm_src},
