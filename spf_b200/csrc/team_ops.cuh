@@ -769,13 +769,32 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       cx.template t1_mul<true>(w, T1);
       inv_pass1_core_s(w, ws);
       SPF_QT(8);
+      // as in pbs_pair_team: the saturating-cast corner of the conversion (probability ~2^-53 per value) is tested once
+      // per 8 values, the fast conversion only tracks the largest exponent word it saw
 #pragma unroll
-      for (int m = 0; m < 16; m++) {
-        const int j = u + 64 * m;
-        own[m] += f64_to_torus_s(w[m].x, ws[m]);
-        own[m + 16] += f64_to_torus_s(w[m].y, ws[m]);
-        pa[j] = own[m];
-        pa[j + kM] = own[m + 16];
+      for (int m4 = 0; m4 < 16; m4 += 4) {
+        uint32_t mag_max = 0;
+        uint64_t r[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          r[2 * i] = f64_to_torus_s_fast(w[m4 + i].x, ws[m4 + i], mag_max);
+          r[2 * i + 1] = f64_to_torus_s_fast(w[m4 + i].y, ws[m4 + i], mag_max);
+        }
+        if (__builtin_expect(mag_max == kTorusCornerMag, 0)) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            r[2 * i] = f64_to_torus_s(w[m4 + i].x, ws[m4 + i]);
+            r[2 * i + 1] = f64_to_torus_s(w[m4 + i].y, ws[m4 + i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int m = m4 + i, j = u + 64 * m;
+          own[m] += r[2 * i];
+          own[m + 16] += r[2 * i + 1];
+          pa[j] = own[m];
+          pa[j + kM] = own[m + 16];
+        }
       }
     }
     SPF_QT(9);
