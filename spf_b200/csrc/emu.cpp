@@ -192,6 +192,15 @@ struct HostQuadCx {
   int u, h, t;
   pthread_barrier_t* bar_team;
   pthread_barrier_t* bar_quad;
+  // split gather: the two teams of a polynomial swap 16 packed digits per thread (device: through tensor memory)
+  static constexpr bool kSplitGather = true;
+  pthread_barrier_t* bar_poly = nullptr;  // the 128 threads of teams (h, 0) and (h, 1)
+  uint32_t* xchg = nullptr;               // [h][t][u][8]
+  void digit_xchg(uint32_t (&pk)[8]) {
+    memcpy(xchg + ((size_t)(h * 2 + t) * kTeam + u) * 8, pk, sizeof(pk));
+    pthread_barrier_wait(bar_poly);
+    memcpy(pk, xchg + ((size_t)(h * 2 + (1 - t)) * kTeam + u) * 8, sizeof(pk));
+  }
   void sync() { pthread_barrier_wait(bar_team); }
   void quad_sync() { pthread_barrier_wait(bar_quad); }
   // the device stages the next BSK row in shared memory with a bulk copy; the host reads the key directly
@@ -221,19 +230,22 @@ struct QuadLaunch {
 template <class Body>
 void run_quad(Body body) {
   const int nt = 4 * kTeam;
-  pthread_barrier_t team[4], quad;
+  pthread_barrier_t team[4], quad, poly[2];
   for (int i = 0; i < 4; i++) pthread_barrier_init(&team[i], nullptr, kTeam);
+  for (int i = 0; i < 2; i++) pthread_barrier_init(&poly[i], nullptr, 2 * kTeam);
   pthread_barrier_init(&quad, nullptr, nt);
+  std::vector<uint32_t> xchg(4 * kTeam * 8);
   std::vector<QuadLaunch<Body>> ls(nt);
   std::vector<pthread_t> th(nt);
   for (int t = 0; t < nt; t++) {
     const int tm = t / kTeam;
     ls[t].body = &body;
-    ls[t].cx = HostQuadCx{t % kTeam, tm >> 1, tm & 1, &team[tm], &quad};
+    ls[t].cx = HostQuadCx{t % kTeam, tm >> 1, tm & 1, &team[tm], &quad, &poly[tm >> 1], xchg.data()};
     pthread_create(&th[t], nullptr, QuadLaunch<Body>::run, &ls[t]);
   }
   for (int t = 0; t < nt; t++) pthread_join(th[t], nullptr);
   for (int i = 0; i < 4; i++) pthread_barrier_destroy(&team[i]);
+  for (int i = 0; i < 2; i++) pthread_barrier_destroy(&poly[i]);
   pthread_barrier_destroy(&quad);
 }
 

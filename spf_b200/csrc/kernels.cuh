@@ -721,7 +721,21 @@ constexpr int kQuadSmem = kQuadT2Bytes + 2 * kN * 8 + 4 * kXBuf * 16 + kQuadRowB
 #ifndef SPF_QUAD_TMEM_T2
 #define SPF_QUAD_TMEM_T2 1
 #endif
+#ifndef SPF_QUAD_SPLIT_GATHER
+#define SPF_QUAD_SPLIT_GATHER 1  // the two teams of a polynomial gather half of the rounded differences each and swap digits
+#endif
 struct DevQuadCx {
+  static constexpr bool kSplitGather = SPF_QUAD_SPLIT_GATHER != 0;
+  // Teams (h, 0) and (h, 1) are warps {2h, 2h+1} and {4 + 2h, 5 + 2h}: thread u of both sits on the same tensor-memory lane,
+  // so 16 packed digits change hands through eight columns of that lane (columns [64, 72) written by t = 0, [72, 80) by
+  // t = 1) and one 128-thread barrier -- no shared memory (the kernel has none left) and no second gather.
+  __device__ __forceinline__ void digit_xchg(uint32_t (&pk)[8]) const {
+    tmem_st8(t1_taddr + 64 + 8 * t, pk);
+    tmem_wait_st();
+    asm volatile("bar.sync %0, 128;" ::"r"(5 + h) : "memory");
+    tmem_ld8(pk, t1_taddr + 64 + 8 * (1 - t));
+    tmem_wait_ld();
+  }
   int u, h, t;
   uint32_t t1_taddr;
   C2* row;          // staged BSK row

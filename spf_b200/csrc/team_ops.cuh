@@ -12,6 +12,8 @@
 //    normalisation of complex_untwist, simd/scalar.rs:27); scaling by a power of two is exact
 //    so results are bit-identical to normalising after the inverse transform.
 #pragma once
+#include <type_traits>
+
 #include "fft16.cuh"
 
 namespace spf {
@@ -695,6 +697,36 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       const int base = (u - at) & (2 * kN - 1);
       const char* col = reinterpret_cast<const char*>(pa) + 8 * (base & 63);
       const uint32_t bh9 = (uint32_t)(base >> 6) << 9;
+      if constexpr (Cx::kSplitGather) {
+        // The two teams of a polynomial need the same 32 rounded differences, one digit level each.  Each gathers HALF of
+        // them (team t the coefficients 16 t .. 16 t + 15 of its column), keeps its own digit and hands the other level's
+        // 16 digits, packed two to a word, to the partner thread (same u, other t) -- on the device through eight
+        // tensor-memory columns of the lane the two threads share.  Same bits as before: a 16-bit digit d is converted
+        // by digit_lo16_to_f64(d), which equals digit_hi16_to_f64(d << 16).
+        uint32_t pk[8];
+        auto gather_half = [&](auto tt) {  // the half is a compile-time constant: own[] stays in registers
+          constexpr int T = decltype(tt)::value;
+#pragma unroll
+          for (int k = 0; k < 16; k++) {
+            const int i2 = 16 * T + k;
+            const uint32_t t9 = bh9 + 512u * i2;
+            const uint64_t x = *reinterpret_cast<const uint64_t*>(col + (t9 & 0x3E00u));
+            const uint64_t diff = ((t9 & 0x4000u) ? 0 - x : x) - own[i2];
+            const uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
+            const uint32_t w1 = w + 0x8000u;
+            const uint32_t other = T ? (w & 0xFFFFu) : (w1 >> 16);  // the digit of level 1 - T
+            if (T) v[k].y = digit_hi16_to_f64(w1); else v[k].x = digit_lo16_to_f64(w);
+            if (k & 1) pk[k >> 1] |= other << 16; else pk[k >> 1] = other;
+          }
+        };
+        if (t) gather_half(std::integral_constant<int, 1>{}); else gather_half(std::integral_constant<int, 0>{});
+        cx.digit_xchg(pk);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const double d = digit_lo16_to_f64(pk[k >> 1] >> (16 * (k & 1)));
+          if (t) v[k].x = d; else v[k].y = d;  // team 1 lacked the first half (real parts), team 0 the second
+        }
+      } else {
 #pragma unroll
       for (int i2 = 0; i2 < 32; i2++) {
         const uint32_t t9 = bh9 + 512u * i2;
@@ -704,6 +736,7 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         // digit 0: low half of w; digit 1: high half of w + 0x8000 (math/radix.rs:81-113, logB = 16, l = 2)
         const double d = t ? digit_hi16_to_f64(w + 0x8000u) : digit_lo16_to_f64(w);
         if (i2 < 16) v[i2].x = d; else v[i2 - 16].y = d;
+      }
       }
       SPF_QT(0);
       fwd_pass1_core(v);
@@ -801,7 +834,7 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     cx.quad_sync();
     if (t == 1) {
 #pragma unroll
-      for (int i2 = 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
+      for (int i2 = Cx::kSplitGather ? 16 : 0; i2 < 32; i2++) own[i2] = pa[u + 64 * i2];
     }
   }
 #if defined(SPF_QUAD_TRACE) && defined(__CUDA_ARCH__)
