@@ -431,38 +431,75 @@ class E2EGraphPipeline:
     D2H copies are inside the timed region and overlap the neighbouring graphs' kernels.  The GGSWs never leave the
     device -- as in the reference, where L1GgswCiphertext is not even serialisable (crypto/encryption.rs:94-98)."""
 
-    def __init__(self, ev, h_lwe: np.ndarray, glwe_len: int, wave: int):
+    def __init__(self, ev, h_lwe: np.ndarray, glwe_len: int, wave: int, mode: str = "double", depth: int = 4):
         import spf_b200
 
         B = len(h_lwe)
         self.B = B
+        self.mode = mode
         self.h_lwe = h_lwe                                         # [B][n + 1], page-locked
-        self.h_out = spf_b200.pinned_zeros((B, glwe_len))          # [B][2N]
         ab = spf_b200.pinned_zeros((2, glwe_len))
         ab[1, glwe_len // 2] = np.uint64(1 << 63)                  # a = trivial 0, b = trivial 1: the output decrypts to the selector
         self.ab = ab
-        # chunks: whole PBS waves (3 waves each) so that chunking costs no extra tail; the remainder is its own graph
-        per = 3 * wave
-        bounds = list(range(0, B, per)) + [B]
-        if len(bounds) > 2 and bounds[-1] - bounds[-2] < wave:
-            del bounds[-2]  # a remainder below one wave rides with the last chunk: its blind rotation overlaps that chunk's trace kernels (launch_cbs)
         proc = spf_b200.CircuitProcessor(ev)
-        self.graphs = []
-        for lo, hi in zip(bounds[:-1], bounds[1:]):
+
+        def build(lo, hi, out):
             c = spf_b200.FheCircuit()
             na, nb = c.add("InputGlwe1", io=ab[0]), c.add("InputGlwe1", io=ab[1])
             ins = [c.add("InputLwe0", io=h_lwe[i]) for i in range(lo, hi)]
             sels = [c.add("CircuitBootstrap", x) for x in ins]
             mux = [c.add("CMux", sl, na, nb) for sl in sels]
             for i, m in zip(range(lo, hi), mux):
-                c.add("OutputGlwe1", m, io=self.h_out[i])
-            self.graphs.append(proc.compile(c))
-        self.h2d = int(h_lwe.nbytes + len(self.graphs) * ab.nbytes)
+                c.add("OutputGlwe1", m, io=out[i])
+            return proc.compile(c)
+
+        if mode == "double":
+            # One graph = one whole step (the executor's own step schedule applies: capi.cu::launch_cbs packs the sub-wave
+            # remainder of the blind rotation next to the trace kernels); `depth` such graphs with their own host result
+            # buffers take turns: steps k + 1 .. k + depth - 1 are already spawned while step k's results travel to the host,
+            # so a blind rotation is always queued when the previous step's trace kernels drain.
+            self.depth = max(2, depth)
+            self.h_outs = [spf_b200.pinned_zeros((B, glwe_len)) for _ in range(self.depth)]
+            self.graphs = [build(0, B, o) for o in self.h_outs]
+            self.h_out = self.h_outs[0]
+            self.h2d = int(h_lwe.nbytes + ab.nbytes)
+        else:
+            self.h_out = spf_b200.pinned_zeros((B, glwe_len))      # [B][2N]
+            # chunks: whole PBS waves (3 waves each) so that chunking costs no extra tail; the remainder is its own graph
+            per = 3 * wave
+            bounds = list(range(0, B, per)) + [B]
+            if len(bounds) > 2 and bounds[-1] - bounds[-2] < wave:
+                del bounds[-2]  # a remainder below one wave rides with the last chunk
+            self.graphs = [build(lo, hi, self.h_out) for lo, hi in zip(bounds[:-1], bounds[1:])]
+            self.h2d = int(h_lwe.nbytes + len(self.graphs) * ab.nbytes)
         self.d2h = int(self.h_out.nbytes)
 
     def step(self):
+        for g in self.graphs:  # "double": both whole-step graphs once (warm-up)
+            g.spawn()
+        for g in self.graphs:
+            g.wait()
+
+    def run(self, steps: int):
+        """`steps` steps as a stream.  "double": the two whole-step graphs alternate, step k + 1 is spawned before step
+        k's results are awaited.  "chunks": a chunk graph is spawned again for the next step as soon as its results of
+        this step have arrived on the host.  Either way every step pays all of its H2D and D2H copies."""
+        if self.mode == "double":
+            d = self.depth
+            for k in range(steps):
+                if k >= d:
+                    self.graphs[k % d].wait()     # step k - d is complete on the host: its consumer may read h_outs[k % d]
+                self.graphs[k % d].spawn()
+            for k in range(max(0, steps - d), steps):
+                self.graphs[k % d].wait()
+            self.h_out = self.h_outs[(steps - 1) % d]
+            return
         for g in self.graphs:
             g.spawn()
+        for _ in range(steps - 1):
+            for g in self.graphs:
+                g.wait()
+                g.spawn()
         for g in self.graphs:
             g.wait()
 
@@ -775,22 +812,25 @@ def run_gpu(args):
     if not args.no_e2e:
         lwe_len = p.lwe_n + 1
         h_lwe = h_in.numpy().view(np.uint64).reshape(B, lwe_len)
-        pipe = E2EGraphPipeline(ev, h_lwe, ev.len_glwe, 148 * 3)
+        pipe = E2EGraphPipeline(ev, h_lwe, ev.len_glwe, 148 * 3, os.environ.get("SPF_B200_E2E_MODE", "double"),
+                                int(os.environ.get("SPF_B200_E2E_DEPTH", "4")))
         pipe.step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e2e_steps = max(1, min(args.steps, 5))
+        e2e_steps = max(1, min(args.steps, 16))
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            pipe.step()
+        pipe.run(e2e_steps)
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d, "d2h_bytes_per_step": pipe.d2h,
-               "steps": e2e_steps, "graphs_per_step": len(pipe.graphs),
+               "steps": e2e_steps, "graphs_per_step": 1 if pipe.mode == "double" else len(pipe.graphs),
+               "pipelining": ("%d whole-step graphs with their own page-locked result buffers take turns: the next steps are "
+                              "spawned before step k's results are awaited" % pipe.depth if pipe.mode == "double" else
+                              "chunk graphs, each re-spawned for step k + 1 once its step-k outputs are on the host"),
                "api": "FheCircuit graphs (InputLwe0 -> CircuitBootstrap -> CMux -> OutputGlwe1) through spf_b200_graph_spawn / "
                       "spf_b200_graph_wait, page-locked host buffers; the GGSWs stay in HBM as in the reference "
                       "(L1GgswCiphertext is not serialisable, crypto/encryption.rs:94-98)"}
