@@ -173,6 +173,9 @@ static_assert(!SPF_PBS_TRANSIENT || SPF_PBS_TMEM_OWN, "the transient accumulator
 #define SPF_PBS_CHUNKED 1  // own coefficients / twiddles fetched from tensor memory in small chunks (needed by the 128-register
                            // 4-pair build; worth 2.7 % at 3 pairs too: shorter live ranges, better schedule)
 #endif
+#ifndef SPF_PBS_TW_PIPE
+#define SPF_PBS_TW_PIPE 0  // twiddle chunks software-pipelined: the tensor-memory load of chunk g + 1 overlaps the products of chunk g
+#endif
 #ifndef SPF_PBS_FUSED_ST
 #define SPF_PBS_FUSED_ST 0  // twiddle products stored to the exchange buffer one by one (interleaved STS)
 #endif
@@ -417,7 +420,24 @@ struct DevPairCx {
   // LSU pipe does not see.
   template <bool CONJ>
   __device__ __forceinline__ void t1_mul(C2 (&v)[16], const C2* T1) const {
-#if SPF_PBS_TMEM_T1 && SPF_PBS_CHUNKED
+#if SPF_PBS_TMEM_T1 && SPF_PBS_CHUNKED && SPF_PBS_TW_PIPE
+    // the load of chunk g + 1 is in flight while chunk g is multiplied: one exposed tensor-memory round trip per call, not four
+    uint32_t r[2][16];
+    tmem_ld16(r[0], t1_taddr);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      if (g < 3) tmem_ld16(r[(g + 1) & 1], t1_taddr + 16 * (g + 1));
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t* rr = r[g & 1];
+        const C2 w{__hiloint2double((int)rr[4 * i + 1], (int)rr[4 * i]), __hiloint2double((int)rr[4 * i + 3], (int)rr[4 * i + 2])};
+        const int k = 4 * g + i;
+        v[k] = CONJ ? cmul_conj(v[k], w) : cmul(v[k], w);
+      }
+      if (g < 3) tmem_wait_ld();
+    }
+#elif SPF_PBS_TMEM_T1 && SPF_PBS_CHUNKED
 #pragma unroll
     for (int g = 0; g < 4; g++) {  // 4 twiddles (16 registers) at a time
       uint32_t r[16];
@@ -454,7 +474,23 @@ struct DevPairCx {
   // v[k2] *= T2[q][k2], k2 = 1..15
   template <bool CONJ>
   __device__ __forceinline__ void t2_mul(C2 (&v)[16], const C2* T2) const {
-#if SPF_PBS_TMEM_T2
+#if SPF_PBS_TMEM_T2 && SPF_PBS_TW_PIPE
+    uint32_t r[2][16];
+    tmem_ld16(r[0], t1_taddr + 448);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      if (g < 3) tmem_ld16(r[(g + 1) & 1], t1_taddr + 448 + 16 * (g + 1));
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t* rr = r[g & 1];
+        const C2 w{__hiloint2double((int)rr[4 * i + 1], (int)rr[4 * i]), __hiloint2double((int)rr[4 * i + 3], (int)rr[4 * i + 2])};
+        const int k = 4 * g + i;
+        if (k != 0) v[k] = CONJ ? cmul_conj(v[k], w) : cmul(v[k], w);
+      }
+      if (g < 3) tmem_wait_ld();
+    }
+#elif SPF_PBS_TMEM_T2
 #pragma unroll
     for (int half = 0; half < 2; half++) {
       uint32_t r0[16], r1[16];
