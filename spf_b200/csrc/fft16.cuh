@@ -135,6 +135,11 @@ SPF_HD void rot_s(C2& v, double& s, int e) {
   if (SPF_ABLATE(1)) return;
   e &= 63;
   if (e == 0) return;
+  // quarter turns are sign changes and swaps (they fold into the operand modifiers of the next FMA); the tan / cot form
+  // below would spend two FMAs with a zero factor on them (the compiler may not drop fma(0, x, y): x could be NaN)
+  if (e == 16) { v = C2{-v.y, v.x}; return; }
+  if (e == 32) { v = C2{-v.x, -v.y}; return; }
+  if (e == 48) { v = C2{v.y, -v.x}; return; }
   const double c = spf_cos32(e), sn = spf_sin32(e);
   if (spf_abs(c) >= spf_abs(sn)) {
     const double t = sn / c;
