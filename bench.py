@@ -818,7 +818,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e2e_steps = min(max(args.steps, 8), 16)  # a stream of whole-step graphs: at least 8 steps, so that the ramp (first H2D, last D2H) does not dominate
+        e2e_steps = 16  # a stream of whole-step graphs: long enough that the ramp (first H2D, last D2H) does not dominate
         t0 = time.perf_counter()
         pipe.run(e2e_steps)
         dt = time.perf_counter() - t0
