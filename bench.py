@@ -95,6 +95,13 @@ def ncu_traffic(batch: int):
         return None
 
 
+def ncu_pipes():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "pbs_kernel_dram_traffic.json"))).get("pipes")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -802,6 +809,8 @@ def run_gpu(args):
                     "peak_source": hbm_src},
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch (bytes), from the committed ncu capture
             "traffic": (ncu_traffic(B) or {}).get("bytes_per_launch"), "traffic_detail": ncu_traffic(B),
+            # pipe utilisation of the same kernel from the committed ncu capture (what binds it: DESIGN.md K3)
+            "ncu_pipes": ncu_pipes(),
         }
         del d_rot, d_glwe, lut
 
