@@ -156,6 +156,47 @@ def test_multifunction_pbs_cbs_stage(oracle, keys, client, evaluation):
             assert abs(int(np.int64(pr[i])) - want) < mag // 8
 
 
+def _cbs_preprocess(glwe: np.ndarray, level: int, params) -> np.ndarray:
+    """mod_switch_trace_and_rotate up to (not including) the trace, for cbs level `level` (circuit_bootstrapping.rs:
+    260-298): b[i'] += encode(1, 4 (i' + 1) + 1) for i' <= level (the reference adds them cumulatively on one buffer),
+    every polynomial times X^-level (entities/polynomial.rs:211-236), then glwe_mod_switch_and_expand_pow_2 by log2 N
+    (glwe_ciphertext_ops.rs:268-281, vector_shr_round scalar.rs:134-143).  Exact integer arithmetic in numpy."""
+    n, k = params.glwe_n, params.glwe_k
+    x = glwe.astype(np.uint64).reshape(k + 1, n).copy()
+    for i in range(level + 1):
+        x[k, i] += np.uint64(1 << (64 - (params.cbs.radix_log * (i + 1) + 1)))
+    j = np.arange(n) + level
+    y = np.where(j < n, x[:, j % n], (~x[:, j % n]) + np.uint64(1))      # (p X^-level)[j] = p[j + level], negated past N
+    shift = n.bit_length() - 1
+    return ((y >> np.uint64(shift)) + ((y >> np.uint64(shift - 1)) & np.uint64(1))).reshape(-1)
+
+
+def test_cbs_preprocessing_stage_bit_exact(oracle, keys, client, evaluation):
+    """SURVEY 8(a) row a10 on its own: the integer pre-processing that trace_ss_kernel fuses in front of the trace (level
+    offsets on b, X^-level, rounded shift by log2 N) against an exact numpy restatement -- blind rotation on the GPU,
+    pre-processing on the CPU, trace and scheme switch through their own entry points, and the result must equal the
+    one-call circuit bootstrap BIT FOR BIT (the floating-point stages are the same device code on the same inputs)."""
+    p = keys.params
+    bits = [0, 1, 1]
+    cts = client.encrypt_lwe_l0_batch(bits)
+    rot = cts.copy()
+    rot[:, -1] += np.uint64(1 << 62)                                     # lwe_rotate by encode(1, 2 bits), :403-408
+    lut = np.zeros(keys.glwe_len, dtype=np.uint64)
+    oracle.lib().orc_cbs_lut(lut, C.byref(p))
+    x = evaluation.programmable_bootstrap(rot, lut, 0, 2)                # hi_noise_lwe_to_lo_noise_glwe
+    # the numpy pre-processing agrees with the oracle's C restatement of the whole stage (trace included) on level 0 ..
+    pre = np.stack([[_cbs_preprocess(x[c], i, p) for i in range(p.cbs.count)] for c in range(len(bits))])
+    ref0 = oracle.cbs_trace_stage(keys, x[0]).reshape(p.cbs.count, -1)
+    assert np.array_equal(oracle.trace(keys, pre[0, 0]), ref0[0]) and np.array_equal(oracle.trace(keys, pre[0, 3]), ref0[3])
+    # .. and the GPU's fused form equals trace + scheme switch applied to it
+    glev = evaluation.trace(pre.reshape(-1, keys.glwe_len)).reshape(len(bits), -1)
+    staged = evaluation.scheme_switch(glev)
+    fused = evaluation.circuit_bootstrap(cts)
+    assert np.array_equal(staged.view(np.uint64), fused.view(np.uint64))
+    for i, bit in enumerate(bits):
+        assert np.array_equal(client.ggsw_level_messages(fused[i]), client.ggsw_expected_messages(bit))
+
+
 def test_circuit_bootstrap_all_levels(oracle, keys, client, evaluation):
     """can_circuit_bootstrap_via_trace_ss (circuit_bootstrapping.rs:721-805) through the C ABI:
     every (row, level) GLWE of the output GGSW decrypts like a fresh GGSW encryption."""
