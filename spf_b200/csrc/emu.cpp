@@ -55,6 +55,10 @@ struct HostPairCxT {
     const int q = u >> 4;
     for (int k2 = 1; k2 < 16; k2++) v[k2] = CONJ ? cmul_conj(v[k2], T2[q * kT2Pad + k2]) : cmul(v[k2], T2[q * kT2Pad + k2]);
   }
+  // reader-side pass-2 twiddles (device: the thread's constants sit in tensor memory; here they are recomputed, same arithmetic)
+  static constexpr bool kReaderT2 = true;
+  void rt2_fwd(double (&tw)[12], const C2* T2) { rt2_fwd_consts(T2, u >> 4, h, tw); }
+  void rt2_inv(C2 (&w)[6], const C2* T2) { rt2_inv_consts(T2, u >> 4, h, w); }
   static constexpr bool kBskRing = false;   // the ring is device machinery: the host reads the key in place
   const C2* bsk_acquire(int, const C2* g) { return g; }
   void bsk_release(int) {}

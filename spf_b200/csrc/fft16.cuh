@@ -169,6 +169,24 @@ SPF_HD void bfly4_s(C2& a, C2& b, C2& c, C2& d, double sa, double sb, double sc,
   }
 }
 
+// The same butterfly with the three scale ratios given at RUN time (rb = sb / sa, rc = sc / sa, rd = sd / sb; results carry
+// scale sa): the reader-side pass-2 twiddles of the pair kernel (team_ops.cuh: rt2_fwd_consts) arrive as per-thread constants.
+template <bool INV>
+SPF_HD void bfly4_r(C2& a, C2& b, C2& c, C2& d, double rb, double rc, double rd) {
+  if (SPF_ABLATE(1)) return;
+  const C2 apc{spf_fma(rc, c.x, a.x), spf_fma(rc, c.y, a.y)}, amc{spf_fma(-rc, c.x, a.x), spf_fma(-rc, c.y, a.y)};
+  const C2 bpd{spf_fma(rd, d.x, b.x), spf_fma(rd, d.y, b.y)}, bmd{spf_fma(-rd, d.x, b.x), spf_fma(-rd, d.y, b.y)};
+  a = C2{spf_fma(rb, bpd.x, apc.x), spf_fma(rb, bpd.y, apc.y)};
+  c = C2{spf_fma(-rb, bpd.x, apc.x), spf_fma(-rb, bpd.y, apc.y)};
+  if (!INV) {
+    b = C2{spf_fma(rb, bmd.y, amc.x), spf_fma(-rb, bmd.x, amc.y)};
+    d = C2{spf_fma(-rb, bmd.y, amc.x), spf_fma(rb, bmd.x, amc.y)};
+  } else {
+    b = C2{spf_fma(-rb, bmd.y, amc.x), spf_fma(rb, bmd.x, amc.y)};
+    d = C2{spf_fma(rb, bmd.y, amc.x), spf_fma(-rb, bmd.x, amc.y)};
+  }
+}
+
 // 16-point DFT, natural order in -> natural order out, all twiddles compile-time constants.
 // Inputs (v[i], s[i]); every output carries the INPUT scale s[0] (each butterfly group takes the
 // scale of its first element, and the first element of every second-layer group descends from

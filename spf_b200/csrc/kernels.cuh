@@ -173,6 +173,9 @@ static_assert(!SPF_PBS_TRANSIENT || SPF_PBS_TMEM_OWN, "the transient accumulator
 #define SPF_PBS_CHUNKED 1  // own coefficients / twiddles fetched from tensor memory in small chunks (needed by the 128-register
                            // 4-pair build; worth 2.7 % at 3 pairs too: shorter live ranges, better schedule)
 #endif
+#ifndef SPF_PBS_READER_T2
+#define SPF_PBS_READER_T2 1  // pass-2 twiddles applied by the consumers of the second exchange (team_ops.cuh: rt2_fwd_consts)
+#endif
 #ifndef SPF_PBS_TW_PIPE
 #define SPF_PBS_TW_PIPE 0  // twiddle chunks software-pipelined: the tensor-memory load of chunk g + 1 overlaps the products of chunk g
 #endif
@@ -345,6 +348,28 @@ struct DevPairCx {
       v[k].x = __hiloint2double((int)r[2 * x1_unit1(k, 0) + 1], (int)r[2 * x1_unit1(k, 0)]);
       v[k].y = __hiloint2double((int)r[2 * x1_unit1(k, 1) + 1], (int)r[2 * x1_unit1(k, 1)]);
     }
+  }
+  // ---- reader-side pass-2 twiddles: 12 + 12 doubles of this thread in the columns [448, 496) (pair_tmem_init) ----
+  static constexpr bool kReaderT2 = SPF_PBS_READER_T2 != 0;
+  __device__ __forceinline__ void rt2_fwd(double (&tw)[12], const C2*) const {
+    uint32_t a[16], b[8];
+    tmem_ld16(a, t1_taddr + 448);
+    tmem_ld8(b, t1_taddr + 448 + 16);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; i++) tw[i] = __hiloint2double((int)a[2 * i + 1], (int)a[2 * i]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) tw[8 + i] = __hiloint2double((int)b[2 * i + 1], (int)b[2 * i]);
+  }
+  __device__ __forceinline__ void rt2_inv(C2 (&w)[6], const C2*) const {
+    uint32_t a[16], b[8];
+    tmem_ld16(a, t1_taddr + 448 + 24);
+    tmem_ld8(b, t1_taddr + 448 + 24 + 16);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = C2{__hiloint2double((int)a[4 * i + 1], (int)a[4 * i]), __hiloint2double((int)a[4 * i + 3], (int)a[4 * i + 2])};
+#pragma unroll
+    for (int i = 0; i < 2; i++) w[4 + i] = C2{__hiloint2double((int)b[4 * i + 1], (int)b[4 * i]), __hiloint2double((int)b[4 * i + 3], (int)b[4 * i + 2])};
   }
   int u, h;
   int bar_half, bar_pair;
@@ -618,7 +643,8 @@ static_assert(!SPF_PBS_TMEM_X1 || (SPF_PBS_TMEM_T1 && SPF_PBS_TMEM_F && !SPF_PBS
 // Columns [0,64) pass-1 twiddles of the thread (shared by the warps of a lane quarter, which have the same
 // thread-in-team index), then the per-pair blocks of pbs_kernel (kPbsTmemOwn0, kPbsTmemF0); [448,512) pass-2
 // twiddles when SPF_PBS_TMEM_T2.  Returns this warp's lane-quarter base address.
-__device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2, uint32_t& alloc_base, bool time_remap = false) {
+__device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2, uint32_t& alloc_base, bool time_remap = false,
+                                                   bool reader_t2 = false) {
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -640,6 +666,21 @@ __device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2,
       tmem_st4(t1_taddr + 4 * k1, (uint32_t)__double2loint(w.x), (uint32_t)__double2hiint(w.x),
                (uint32_t)__double2loint(w.y), (uint32_t)__double2hiint(w.y));
     }
+    if (reader_t2) {
+      // pbs_kernel: the thread's reader-side pass-2 constants (warps 0..3 of a pair: half h = warp >> 1) instead of the table row
+      double tw[12];
+      C2 wi[6];
+      rt2_fwd_consts(sT2, uu >> 4, (warp >> 1) & 1, tw);
+      rt2_inv_consts(sT2, uu >> 4, (warp >> 1) & 1, wi);
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+        tmem_st4(t1_taddr + 448 + 4 * i, (uint32_t)__double2loint(tw[2 * i]), (uint32_t)__double2hiint(tw[2 * i]),
+                 (uint32_t)__double2loint(tw[2 * i + 1]), (uint32_t)__double2hiint(tw[2 * i + 1]));
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+        tmem_st4(t1_taddr + 448 + 24 + 4 * i, (uint32_t)__double2loint(wi[i].x), (uint32_t)__double2hiint(wi[i].x),
+                 (uint32_t)__double2loint(wi[i].y), (uint32_t)__double2hiint(wi[i].y));
+    } else {
 #if SPF_PBS_TMEM_T2
 #pragma unroll
     for (int k2 = 0; k2 < 16; k2++) {
@@ -648,6 +689,7 @@ __device__ __forceinline__ uint32_t pair_tmem_init(const C2* sT1, const C2* sT2,
                (uint32_t)__double2loint(w.y), (uint32_t)__double2hiint(w.y));
     }
 #endif
+    }
     tmem_wait_st();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -679,7 +721,7 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
   uint32_t tmem_alloc;
-  const uint32_t t1_taddr = pair_tmem_init(sT1, sT2, tmem_alloc, DevPairCx::kTmemX1);
+  const uint32_t t1_taddr = pair_tmem_init(sT1, sT2, tmem_alloc, DevPairCx::kTmemX1, DevPairCx::kReaderT2);
   const int pair = threadIdx.x / (2 * kTeam);
   const int npairs = blockDim.x / (2 * kTeam);  // 1..kPbsPairs pairs per CTA (fewer for small batches)
   const int h = (threadIdx.x / kTeam) & 1;

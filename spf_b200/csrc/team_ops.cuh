@@ -369,6 +369,64 @@ SPF_HD void mad_split(Cx& cx, C2 (&f)[2][8], const C2* xbb, const C2* g /* GGSW 
   }
 }
 
+// ---- reader-side pass-2 twiddles (Cx::kReaderT2) --------------------------------------------------------------------
+// The pass-2 -> pass-3 twiddle W64^(q' k2) of a forward transform does not have to be applied by the thread that produced
+// z[k2] (15 complex multiplies per transform): the thread that CONSUMES the value in mad_split knows q' (its loop index)
+// and k2 = q + 4 (2 h + jj) (its own bins), needs only 3 twiddles per radix-4 group -- the same 6 for all four spectra of a
+// step -- and can apply them in the tan form  w = c (1 + i t):  two FMAs per value, the factored-out c riding into the
+// butterfly as scale ratios (bfly4_r; the same instruction count as the plain butterfly).  4 x 2 x 3 x 2 = 48 FP64
+// instructions per thread and step instead of 2 x 15 x 4 = 120.  In the inverse direction the bin owner multiplies by the
+// conjugates before it hands the values back (12 complex multiplies instead of 15 on the receiving side).
+// Constants of thread (q = u >> 4, half h), group jj: o[6 jj + 0..2] = t_1..t_3, o[6 jj + 3..5] = c_1, c_2, c_3 / c_1.
+// cos(pi/2) in the table is ~1e-20, not 0 (tables.h rounds a long double): the quarter turn q' = 2, k2 = 8 comes out as
+// t ~ 1e19, c ~ 1e-20, exact to 2^-64; an exact zero is replaced so that no infinity can arise.
+SPF_HD void rt2_fwd_consts(const C2* T2, int q, int h, double (&o)[12]) {
+  for (int jj = 0; jj < 2; jj++) {
+    const int k2 = q + 4 * (2 * h + jj);
+    double c[4];
+    for (int qp = 1; qp < 4; qp++) {
+      const C2 w = T2[qp * kT2Pad + k2];
+      c[qp] = w.x == 0.0 ? 8.470329472543003e-22 /* 2^-70 */ : w.x;
+      o[6 * jj + qp - 1] = w.y / c[qp];
+    }
+    o[6 * jj + 3] = c[1];
+    o[6 * jj + 4] = c[2];
+    o[6 * jj + 5] = c[3] / c[1];
+  }
+}
+SPF_HD void rt2_inv_consts(const C2* T2, int q, int h, C2 (&o)[6]) {
+  for (int jj = 0; jj < 2; jj++)
+    for (int qp = 1; qp < 4; qp++) o[3 * jj + qp - 1] = T2[qp * kT2Pad + q + 4 * (2 * h + jj)];
+}
+// mad_split for spectra whose pass-2 twiddles have NOT been applied yet (tw from rt2_fwd_consts)
+template <bool INIT, class Cx>
+SPF_HD void mad_split_rt(Cx& cx, C2 (&f)[2][8], const C2* xbb, const C2* g, int u, int h, const double (&tw)[12]) {
+  const int k1 = u & 15, q = u >> 4;
+#pragma unroll
+  for (int jj = 0; jj < 2; jj++) {
+    C2 d[4], g0[4], g1[4];
+#pragma unroll
+    for (int qp = 0; qp < 4; qp++) d[qp] = SPF_ABLATE(4) ? C2{1.0 + qp, 2.0 + jj} : xbb[k1 * kXPad + qp + 4 * q + 16 * (2 * h + jj)];
+#pragma unroll
+    for (int k3 = 0; k3 < 4; k3++) {
+      g0[k3] = cx.bsk_load(g + split_bin(u, h, 4 * jj + k3));
+      g1[k3] = cx.bsk_load(g + kM + split_bin(u, h, 4 * jj + k3));
+    }
+#pragma unroll
+    for (int qp = 1; qp < 4; qp++) {
+      const double t = tw[6 * jj + qp - 1];
+      d[qp] = C2{spf_fma(-t, d[qp].y, d[qp].x), spf_fma(t, d[qp].x, d[qp].y)};  // d (1 + i t); the factor c rides in the ratios
+    }
+    bfly4_r<false>(d[0], d[1], d[2], d[3], tw[6 * jj + 3], tw[6 * jj + 4], tw[6 * jj + 5]);
+#pragma unroll
+    for (int k3 = 0; k3 < 4; k3++) {
+      const int s = 4 * jj + k3;
+      if (INIT) { f[0][s] = cmul(d[k3], g0[k3]); f[1][s] = cmul(d[k3], g1[k3]); }
+      else { cmad(f[0][s], d[k3], g0[k3]); cmad(f[1][s], d[k3], g1[k3]); }
+    }
+  }
+}
+
 // BSK ring (Cx::kBskRing, device only): the key is consumed in CHUNKS of one (row, level) GLEV row [p][bin] = 32 KiB, four
 // per CMUX step in the order (row 0, level 1), (row 1, level 1), (row 0, level 0), (row 1, level 0).  All pairs of a
 // CTA walk the same chunk sequence G = 4 i + k (continuing over the ciphertexts they process: the key repeats), so
@@ -488,7 +546,8 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
           cx.sync();
           fwd_x1_read(v, xown, u);
           dft16<false>(v);
-          cx.template t2_mul_store<false>(v, T2, xown);  // v[k2] *= W64^(q k2); in-place second exchange
+          if constexpr (Cx::kReaderT2) fwd_x2_write(v, xown, u);  // the twiddles are applied by the readers (mad_split_rt)
+          else cx.template t2_mul_store<false>(v, T2, xown);  // v[k2] *= W64^(q k2); in-place second exchange
         } else {
           cx.template t1_mul<false>(v, T1);  // v[k1] *= T1[k1][ua]
           if constexpr (kX1) {
@@ -496,7 +555,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
               // first digit level: the accumulators are not live, their tensor-memory columns carry the exchange
               cx.x1_fwd(v);
               dft16<false>(v);
-              cx.template t2_mul<false>(v, T2);
+              if constexpr (!Cx::kReaderT2) cx.template t2_mul<false>(v, T2);
               if (kTr) cx.sync();  // every thread of the half has gathered from the accumulator image in xown
             } else {
               // second digit level (the accumulators are parked in those columns): shared memory, per-thread slots
@@ -505,7 +564,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
               cx.sync();
               fwd_x1_read_perm(v, xown, u);
               dft16<false>(v);
-              cx.template t2_mul<false>(v, T2);
+              if constexpr (!Cx::kReaderT2) cx.template t2_mul<false>(v, T2);
               cx.sync();  // the slots read above are not the ones fwd_x2_write overwrites: wait for the other readers of the row
             }
             fwd_x2_write(v, xown, u);
@@ -516,17 +575,26 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
           cx.sync();
           fwd_x1_read(v, xown, u);
           dft16<false>(v);
-          cx.template t2_mul<false>(v, T2);  // v[k2] *= W64^(q k2)
+          if constexpr (!Cx::kReaderT2) cx.template t2_mul<false>(v, T2);  // v[k2] *= W64^(q k2) (else: by the readers, mad_split_rt)
           fwd_x2_write(v, xown, u);  // in place: no barrier after fwd_x1_read
           }
         }
         if (t == 1) cx.f_load(f);
         cx.pair_sync();
         const C2* g0 = cx.bsk_acquire(G + 2 * t, ggsw + (size_t)((0 * 2 + level) * 2) * kM);
+        if constexpr (Cx::kReaderT2) {
+          double tw[12];
+          cx.rt2_fwd(tw, T2);
+          if (t == 0) mad_split_rt<true>(cx, f, xb, g0, u, h, tw);
+          else mad_split_rt<false>(cx, f, xb, g0, u, h, tw);
+          const C2* g1 = cx.bsk_acquire(G + 2 * t + 1, ggsw + (size_t)((1 * 2 + level) * 2) * kM);
+          mad_split_rt<false>(cx, f, xb + kXBuf, g1, u, h, tw);
+        } else {
         if (t == 0) mad_split<true>(cx, f, xb, g0, u, h);
         else mad_split<false>(cx, f, xb, g0, u, h);
         const C2* g1 = cx.bsk_acquire(G + 2 * t + 1, ggsw + (size_t)((1 * 2 + level) * 2) * kM);
         mad_split<false>(cx, f, xb + kXBuf, g1, u, h);
+        }
         if (t == 0) cx.f_store(f);  // device: parked in tensor memory while the second transform runs
       }
     }
@@ -535,6 +603,16 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     for (int p = 0; p < 2; p++) {
       bfly4<true>(f[p][0], f[p][1], f[p][2], f[p][3]);
       bfly4<true>(f[p][4], f[p][5], f[p][6], f[p][7]);
+    }
+    if constexpr (Cx::kReaderT2) {  // the conjugate pass-2 twiddles of the inverse transform, applied by the bin owner
+      C2 wi[6];
+      cx.rt2_inv(wi, T2);
+#pragma unroll
+      for (int p = 0; p < 2; p++)
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+          for (int qp = 1; qp < 4; qp++) f[p][4 * jj + qp] = cmul_conj(f[p][4 * jj + qp], wi[3 * jj + qp - 1]);
     }
     // in place: every thread overwrites exactly the 8 locations per buffer it read in mad_split
 #pragma unroll
@@ -554,7 +632,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     {
       C2 w[16];
       inv_x2_read(w, xown, u);
-      cx.template t2_mul<true>(w, T2);
+      if constexpr (!Cx::kReaderT2) cx.template t2_mul<true>(w, T2);
       if constexpr (Cx::kFusedStores) {
         dft16_emit<true>(w, [&](int mp, C2 val) { cx.sts(xown + k1 * kXPad + q + 4 * mp, val); });  // = inv_x1_write
       } else if constexpr (kX1) {
