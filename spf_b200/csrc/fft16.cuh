@@ -404,8 +404,13 @@ SPF_HD void inv_pass1(C2 (&v)[16], int a, const C2* T1) {
 // scalar conversions
 // ------------------------------------------------------------------------------------------
 
-// int32 -> f64 without the conversion pipe: 2^52 + 2^31 + x is exact, subtract the bias.
+// int32 -> f64.  Host (and -DSPF_NO_I2F): without a conversion, 2^52 + 2^31 + x is exact, subtract the bias.
 SPF_HD double i32_to_f64(int32_t x) {
+#if defined(__CUDA_ARCH__) && !defined(SPF_NO_I2F)
+  // the conversion pipe is idle in these kernels while the FP64 pipe and the issue slots are not: one I2F.F64.S32 instead of
+  // an integer op, a move and a DADD (same value)
+  return __int2double_rn(x);
+#endif
   uint64_t bits = 0x4330000000000000ull | (uint64_t)((uint32_t)x ^ 0x80000000u);
   double d;
 #if defined(__CUDA_ARCH__)
@@ -502,6 +507,24 @@ SPF_HD uint64_t f64_to_torus(double x) { return f64_to_torus_impl<false, true>(x
 SPF_HD uint64_t f64_to_torus_s(double xs, double sc) { return f64_to_torus_impl<true, true>(xs, sc, nullptr); }
 SPF_HD uint64_t f64_to_torus_s_fast(double xs, double sc, uint32_t& mag_max) {
   return f64_to_torus_impl<true, false>(xs, sc, &mag_max);
+}
+
+// f64 -> torus of y = fl(sc * xs) with INTEGER arithmetic: a double of magnitude >= 2^52 is an integer M * 2^s (M the 53-bit
+// significand, s >= 0), so round() is the identity and the reduction mod 2^64 is a shift of M -- one FP64 instruction (the product)
+// instead of four plus a conversion.  Smaller magnitudes (probability ~2^-33 per coefficient of a blind rotation) and the
+// saturating-cast corner (|y| = 2^63 mod 2^64, see f64_to_torus_impl) only raise `slow`: the caller redoes its values with
+// f64_to_torus(sc * xs), which has the same semantics for every double.
+SPF_HD uint64_t f64_to_torus_int(double xs, double sc, uint32_t& slow) {
+  if (SPF_ABLATE(64)) return f64_bits(xs);
+  const double y = sc * xs;
+  const uint64_t b = f64_bits(y);
+  const uint32_t hi = (uint32_t)(b >> 32);
+  const int s = (int)((hi >> 20) & 0x7FFu) - 1075;
+  const uint64_t M = (b & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+  const uint64_t m = (uint32_t)s < 64u ? M << (s & 63) : 0ull;                    // s >= 64: a multiple of 2^64 (s < 0: redone)
+  const uint64_t neg = (uint64_t)((int64_t)b >> 63);
+  slow |= (uint32_t)(s < 0) | (uint32_t)(m == 0x8000000000000000ull);
+  return (m ^ neg) - neg;
 }
 
 // ------------------------------------------------------------------------------------------

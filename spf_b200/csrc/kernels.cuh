@@ -128,6 +128,9 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
 }
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -175,6 +178,12 @@ static_assert(!SPF_PBS_TRANSIENT || SPF_PBS_TMEM_OWN, "the transient accumulator
 #endif
 #ifndef SPF_PBS_READER_T2
 #define SPF_PBS_READER_T2 1  // pass-2 twiddles applied by the consumers of the second exchange (team_ops.cuh: rt2_fwd_consts)
+#endif
+#ifndef SPF_PBS_INT_CONV
+#define SPF_PBS_INT_CONV 0  // accumulator update: f64 -> torus by integer arithmetic on the rounded product (fft16.cuh: f64_to_torus_int)
+#endif
+#ifndef SPF_PBS_FST2
+#define SPF_PBS_FST2 1  // accumulators parked with one tcgen05.st per double instead of four 16-register stores
 #endif
 #ifndef SPF_PBS_TW_PIPE
 #define SPF_PBS_TW_PIPE 0  // twiddle chunks software-pipelined: the tensor-memory load of chunk g + 1 overlaps the products of chunk g
@@ -351,6 +360,7 @@ struct DevPairCx {
   }
   // ---- reader-side pass-2 twiddles: 12 + 12 doubles of this thread in the columns [448, 496) (pair_tmem_init) ----
   static constexpr bool kReaderT2 = SPF_PBS_READER_T2 != 0;
+  static constexpr bool kIntConv = SPF_PBS_INT_CONV != 0;
   __device__ __forceinline__ void rt2_fwd(double (&tw)[12], const C2*) const {
     uint32_t a[16], b[8];
     tmem_ld16(a, t1_taddr + 448);
@@ -544,6 +554,21 @@ struct DevPairCx {
       for (int c = 0; c < 16; c++) fpark[c * 2 * kTeam + h * kTeam + u] = f[c >> 3][c & 7];
       return;
     }
+#if SPF_PBS_FST2 == 2
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+      const C2 x = f[c >> 3][c & 7];
+      tmem_st4(f_taddr + 4 * c, (uint32_t)__double2loint(x.x), (uint32_t)__double2hiint(x.x), (uint32_t)__double2loint(x.y), (uint32_t)__double2hiint(x.y));
+    }
+#elif SPF_PBS_FST2
+    // one double per store: a 16-register store makes ptxas gather the 64 words into consecutive registers first (64 moves)
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+      const C2 x = f[c >> 3][c & 7];
+      tmem_st2(f_taddr + 4 * c, (uint32_t)__double2loint(x.x), (uint32_t)__double2hiint(x.x));
+      tmem_st2(f_taddr + 4 * c + 2, (uint32_t)__double2loint(x.y), (uint32_t)__double2hiint(x.y));
+    }
+#else
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       uint32_t r[16];
@@ -555,6 +580,7 @@ struct DevPairCx {
       }
       tmem_st16(f_taddr + 16 * c, r);
     }
+#endif
     tmem_wait_st();
 #endif
   }
