@@ -219,6 +219,13 @@ int create_common(const spf_params* params, const double* bsk, size_t bsk_len, c
     CUB(cudaMemcpy(ctx->T1, T1.data(), sizeof(C2) * kT1Elems, cudaMemcpyHostToDevice));
     CUB(cudaMemcpy(ctx->T2, T2.data(), sizeof(C2) * kT2Elems, cudaMemcpyHostToDevice));
     CUB(cudaMemcpy(ctx->kinv, kinv, sizeof(kinv), cudaMemcpyHostToDevice));
+    // constants of the in-register transforms, in the order the kernels consume them (fft16.cuh: constant pools)
+    static double pools[kPools][kPoolLen];
+    if (!fill_kpools(pools)) {
+      spf_b200_destroy(ctx);
+      return SPF_E_INVALID;
+    }
+    CUB(cudaMemcpyToSymbol(spf_kpool, pools, sizeof(pools)));
   }
   // keys: FFT-domain keys are rescaled by 2^-10 in place on the device (exact)
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;

@@ -119,6 +119,44 @@ SPF_HD void bfly4(C2& a, C2& b, C2& c, C2& d) {
   }
 }
 
+// ---- constant pools --------------------------------------------------------------------------------------------------
+// The deferred-scale transforms below use ~40 distinct double constants per pass (tangents, scale ratios).  As literals every
+// one of them costs two UMOV instructions (32-bit immediates into a uniform register pair) each time it is materialised:
+// ~230 of the ~3 700 instructions of a blind-rotation step, in a kernel whose time follows its instruction count.  A constant
+// PROVIDER hands them out instead: KLit returns the literal (host emulator, -DSPF_KPOOL=0), KDev<P> reads pool P of a
+// __constant__ array in call order -- after unrolling every index is a compile-time constant and ptxas fetches two constants
+// per LDCU.128 -- and KRec (host, tables.h: fill_kpools) records the same call sequence once to fill the array.  Factors of
+// exactly 1 stay literals so that the compiler still folds fma(1, x, y) into an add; the sequence is data-independent.
+struct KLit {
+  SPF_HD double operator()(double v) { return v; }
+};
+constexpr int kPoolLen = 80;
+constexpr int kPools = 4;  // 0 forward pass 1, 1 inverse pass 1 (+ output scales), 2 / 3 forward / inverse unit-scale 16-point transform
+struct KRec {
+  double* out;
+  int i;
+  SPF_HD double operator()(double v) {
+    if (v == 1.0) return 1.0;
+    if (i < kPoolLen) out[i] = v;
+    i++;
+    return v;
+  }
+};
+#ifndef SPF_KPOOL
+#define SPF_KPOOL 0  // measured: no gain in pbs_kernel (UMOV pairs become LDCU.64 + R2UR, 6.75 vs 6.73 ms per wave) and 255-register kernels spill (trace_ss_kernel 7.4 -> 9.0 ms): off
+#endif
+#if defined(__CUDACC__)
+__constant__ double spf_kpool[kPools][kPoolLen];
+template <int P>
+struct KDev {
+  int i = 0;
+  __device__ __forceinline__ double operator()(double v) {
+    if (v == 1.0) return 1.0;
+    return spf_kpool[P][i++];
+  }
+};
+#endif
+
 // ---- deferred-scale arithmetic --------------------------------------------------------------
 // Inside the in-register transforms a value is a pair (v, s): the true value is s * v, where s is a
 // real constant that is known at compile time once the loops are unrolled (on the device every s
@@ -131,7 +169,8 @@ SPF_HD void bfly4(C2& a, C2& b, C2& c, C2& d) {
 // pass 1 30 instead of 60 (Linzer-Feig style FMA butterflies).
 SPF_HD constexpr double spf_abs(double x) { return x < 0 ? -x : x; }
 // (v, s) *= e^{i pi e / 32}
-SPF_HD void rot_s(C2& v, double& s, int e) {
+template <class KP>
+SPF_HD void rot_s(C2& v, double& s, int e, KP& kp) {
   if (SPF_ABLATE(1)) return;
   e &= 63;
   if (e == 0) return;
@@ -142,20 +181,24 @@ SPF_HD void rot_s(C2& v, double& s, int e) {
   if (e == 48) { v = C2{v.y, -v.x}; return; }
   const double c = spf_cos32(e), sn = spf_sin32(e);
   if (spf_abs(c) >= spf_abs(sn)) {
-    const double t = sn / c;
+    const double t = kp(sn / c);
     v = C2{spf_fma(-t, v.y, v.x), spf_fma(t, v.x, v.y)};
     s *= c;
   } else {
-    const double t = c / sn;
+    const double t = kp(c / sn);
     v = C2{spf_fma(t, v.x, -v.y), spf_fma(t, v.y, v.x)};
     s *= sn;
   }
 }
+SPF_HD void rot_s(C2& v, double& s, int e) {
+  KLit kp;
+  rot_s(v, s, e, kp);
+}
 // 4-point DFT of (a, sa) .. (d, sd); all four results carry scale sa.
-template <bool INV>
-SPF_HD void bfly4_s(C2& a, C2& b, C2& c, C2& d, double sa, double sb, double sc, double sd) {
+template <bool INV, class KP>
+SPF_HD void bfly4_s(C2& a, C2& b, C2& c, C2& d, double sa, double sb, double sc, double sd, KP& kp) {
   if (SPF_ABLATE(1)) return;
-  const double rc = sc / sa, rd = sd / sb, rb = sb / sa;
+  const double rc = kp(sc / sa), rd = kp(sd / sb), rb = kp(sb / sa);
   const C2 apc{spf_fma(rc, c.x, a.x), spf_fma(rc, c.y, a.y)}, amc{spf_fma(-rc, c.x, a.x), spf_fma(-rc, c.y, a.y)};
   const C2 bpd{spf_fma(rd, d.x, b.x), spf_fma(rd, d.y, b.y)}, bmd{spf_fma(-rd, d.x, b.x), spf_fma(-rd, d.y, b.y)};
   a = C2{spf_fma(rb, bpd.x, apc.x), spf_fma(rb, bpd.y, apc.y)};
@@ -169,6 +212,11 @@ SPF_HD void bfly4_s(C2& a, C2& b, C2& c, C2& d, double sa, double sb, double sc,
   }
 }
 
+template <bool INV>
+SPF_HD void bfly4_s(C2& a, C2& b, C2& c, C2& d, double sa, double sb, double sc, double sd) {
+  KLit kp;
+  bfly4_s<INV>(a, b, c, d, sa, sb, sc, sd, kp);
+}
 // The same butterfly with the three scale ratios given at RUN time (rb = sb / sa, rc = sc / sa, rd = sd / sb; results carry
 // scale sa): the reader-side pass-2 twiddles of the pair kernel (team_ops.cuh: rt2_fwd_consts) arrive as per-thread constants.
 template <bool INV>
@@ -191,11 +239,11 @@ SPF_HD void bfly4_r(C2& a, C2& b, C2& c, C2& d, double rb, double rc, double rd)
 // Inputs (v[i], s[i]); every output carries the INPUT scale s[0] (each butterfly group takes the
 // scale of its first element, and the first element of every second-layer group descends from
 // v[0] without a twiddle), so the results are plain values whenever s[0] == 1.
-template <bool INV>
-SPF_HD void dft16_s(C2 (&v)[16], double (&s)[16]) {
+template <bool INV, class KP>
+SPF_HD void dft16_s(C2 (&v)[16], double (&s)[16], KP& kp) {
 #pragma unroll
   for (int m0 = 0; m0 < 4; m0++) {
-    bfly4_s<INV>(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12], s[m0], s[m0 + 4], s[m0 + 8], s[m0 + 12]);
+    bfly4_s<INV>(v[m0], v[m0 + 4], v[m0 + 8], v[m0 + 12], s[m0], s[m0 + 4], s[m0 + 8], s[m0 + 12], kp);
     s[m0 + 4] = s[m0 + 8] = s[m0 + 12] = s[m0];
   }
   // v[m0 + 4 kl] = Y[m0][kl];  twiddle W16^{m0 kl}
@@ -204,12 +252,12 @@ SPF_HD void dft16_s(C2 (&v)[16], double (&s)[16]) {
 #pragma unroll
     for (int kl = 1; kl < 4; kl++) {
       const int e = 4 * m0 * kl;  // angle pi*e/32 = 2 pi m0 kl / 16
-      rot_s(v[m0 + 4 * kl], s[m0 + 4 * kl], INV ? e : 64 - e);
+      rot_s(v[m0 + 4 * kl], s[m0 + 4 * kl], INV ? e : 64 - e, kp);
     }
   }
 #pragma unroll
   for (int kl = 0; kl < 4; kl++) {
-    bfly4_s<INV>(v[4 * kl], v[4 * kl + 1], v[4 * kl + 2], v[4 * kl + 3], s[4 * kl], s[4 * kl + 1], s[4 * kl + 2], s[4 * kl + 3]);
+    bfly4_s<INV>(v[4 * kl], v[4 * kl + 1], v[4 * kl + 2], v[4 * kl + 3], s[4 * kl], s[4 * kl + 1], s[4 * kl + 2], s[4 * kl + 3], kp);
     s[4 * kl + 1] = s[4 * kl + 2] = s[4 * kl + 3] = s[4 * kl];
   }
   // v[4 kl + kh] = X[kl + 4 kh] -> natural order
@@ -252,11 +300,25 @@ SPF_HD void dft16_emit(C2 (&v)[16], Emit emit) {
   }
 }
 template <bool INV>
-SPF_HD void dft16(C2 (&v)[16]) {
+SPF_HD void dft16_s(C2 (&v)[16], double (&s)[16]) {
+  KLit kp;
+  dft16_s<INV>(v, s, kp);
+}
+template <bool INV, class KP>
+SPF_HD void dft16_k(C2 (&v)[16], KP& kp) {
   double s[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) s[i] = 1.0;
-  dft16_s<INV>(v, s);  // unit input scales -> unit output scales
+  dft16_s<INV>(v, s, kp);  // unit input scales -> unit output scales
+}
+template <bool INV>
+SPF_HD void dft16(C2 (&v)[16]) {
+#if defined(__CUDA_ARCH__) && SPF_KPOOL
+  KDev<INV ? 3 : 2> kp;
+#else
+  KLit kp;
+#endif
+  dft16_k<INV>(v, kp);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -264,12 +326,21 @@ SPF_HD void dft16(C2 (&v)[16]) {
 // ------------------------------------------------------------------------------------------
 // pass 1 without its thread-dependent twiddle (applied by the caller: table in shared memory
 // below, or the thread's tensor-memory columns in the blind-rotation kernel)
-SPF_HD void fwd_pass1_core(C2 (&v)[16]) {
+template <class KP>
+SPF_HD void fwd_pass1_core_k(C2 (&v)[16], KP& kp) {
   double s[16];
   s[0] = 1.0;
 #pragma unroll
-  for (int m = 1; m < 16; m++) { s[m] = 1.0; rot_s(v[m], s[m], m); }
-  dft16_s<false>(v, s);  // the twist factors fold into the butterflies; outputs carry s[0] = 1
+  for (int m = 1; m < 16; m++) { s[m] = 1.0; rot_s(v[m], s[m], m, kp); }
+  dft16_s<false>(v, s, kp);  // the twist factors fold into the butterflies; outputs carry s[0] = 1
+}
+SPF_HD void fwd_pass1_core(C2 (&v)[16]) {
+#if defined(__CUDA_ARCH__) && SPF_KPOOL
+  KDev<0> kp;
+#else
+  KLit kp;
+#endif
+  fwd_pass1_core_k(v, kp);
 }
 SPF_HD void fwd_pass1(C2 (&v)[16], int a, const C2* T1) {
   fwd_pass1_core(v);
@@ -381,12 +452,23 @@ SPF_HD void inv_x1_read(C2 (&v)[16], const C2* buf, int a) {
 }
 // Inverse pass 1 with the untwist left as a deferred scale: true outputs are s[m] * v[m]
 // (consumed by f64_to_torus_s, whose first two operations absorb the factor as FMAs).
-SPF_HD void inv_pass1_core_s(C2 (&v)[16], double (&s)[16]) {
+template <class KP>
+SPF_HD void inv_pass1_core_s_k(C2 (&v)[16], double (&s)[16], KP& kp) {
 #pragma unroll
   for (int i = 0; i < 16; i++) s[i] = 1.0;
-  dft16_s<true>(v, s);
+  dft16_s<true>(v, s, kp);
 #pragma unroll
-  for (int m = 1; m < 16; m++) rot_s(v[m], s[m], 64 - m);
+  for (int m = 1; m < 16; m++) rot_s(v[m], s[m], 64 - m, kp);
+#pragma unroll
+  for (int m = 1; m < 16; m++) s[m] = kp(s[m]);  // the output scales are constants of the pool too (consumed as FMA factors)
+}
+SPF_HD void inv_pass1_core_s(C2 (&v)[16], double (&s)[16]) {
+#if defined(__CUDA_ARCH__) && SPF_KPOOL
+  KDev<1> kp;
+#else
+  KLit kp;
+#endif
+  inv_pass1_core_s_k(v, s, kp);
 }
 SPF_HD void inv_pass1_core(C2 (&v)[16]) {
   double s[16];

@@ -317,6 +317,9 @@ SPF_HD double digit16_to_f64(uint32_t d) {
 // 2^36 + 2^15 + sext16(d).
 // SPF_DIGIT_I2F (device): one conversion instruction (I2F.F64.S16 on the conversion pipe, which selects the half word itself)
 // instead of an integer op, a move for the exponent word and a DADD on the FP64 pipe; the values are identical.
+#ifndef SPF_GATHER_SEL
+#define SPF_GATHER_SEL 0  // pbs_pair_team: rotated gather with two base pointers / sign masks chosen by one comparison per coefficient
+#endif
 #ifndef SPF_DIGIT_I2F
 #define SPF_DIGIT_I2F 1  // measured: 6.96 -> 6.73 ms per 444-ciphertext wave of pbs_kernel (profiles/r2_zz_i2f_ab.txt)
 #endif
@@ -532,14 +535,32 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         // rows are 512 B apart, so the row index lives in bits 9..13 of the offset
         const char* col = reinterpret_cast<const char*>(pa) + 8 * (kX1 ? x1_position(base & 63) : (base & 63));
         const uint32_t bh9 = (uint32_t)(base >> 6) << 9;
+#if SPF_GATHER_SEL
+        // The row index (base >> 6) + i2 wraps past row 31 exactly once over i2 = 0..31, and the negacyclic sign flips at the
+        // same place: two base pointers and two sign masks per thread, chosen by ONE comparison per coefficient -- the row offset
+        // 512 i2 is then an immediate of the load and the conditional negation is (x ^ m) - m with m = 0 / ~0.
+        const int rb = (base >> 6) & 31;
+        const int wrap = 32 - rb;                                 // i2 >= wrap: wrapped
+        const char* pU = col + 512 * rb;
+        const char* pW = pU - 32 * 512;
+        const uint32_t mU = 0u - (uint32_t)(base >> 11), mW = ~mU;  // base bit 11: the sign before the wrap
+#endif
 #pragma unroll
         for (int i2 = 0; i2 < 32; i2++) {
           if constexpr (kCh) {
             if ((i2 & 7) == 0) cx.own_ld8(own, i2 >> 3);  // own[0..7] = coefficients 8c .. 8c + 7
           }
+#if SPF_GATHER_SEL
+          const bool wr = i2 >= wrap;
+          const uint64_t xr = *reinterpret_cast<const uint64_t*>((wr ? pW : pU) + 512 * i2);
+          const uint32_t m = wr ? mW : mU;
+          const uint64_t mm = ((uint64_t)m << 32) | m;
+          const uint64_t diff = ((xr ^ mm) - mm) - own[kCh ? (i2 & 7) : i2];
+#else
           const uint32_t t9 = bh9 + 512u * i2;  // bit 14 = negacyclic sign
           const uint64_t x = SPF_ABLATE(32) ? (uint64_t)t9 * 0x9E3779B97F4A7C15ull : *reinterpret_cast<const uint64_t*>(col + (t9 & 0x3E00u));
           const uint64_t diff = ((t9 & 0x4000u) ? 0 - x : x) - own[kCh ? (i2 & 7) : i2];
+#endif
           const uint32_t w = (uint32_t)(diff >> 32) + ((uint32_t)diff >> 31);
           const uint32_t w1 = w + 0x8000u;  // high half = second digit: (w >> 16) + carry of the first
           if (i2 < 16) { v[i2].x = digit_lo16_to_f64(w); pk[i2] = w1 >> 16; }
@@ -960,6 +981,28 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
   }
 }
 
+// The 32 coefficients a thread holds after an inverse transform -> torus.  The saturating-cast corner of the conversion
+// (|x| = 2^63 modulo 2^64, probability ~2^-53 per value) is tested once per 8 values: the fast conversion only tracks the
+// largest exponent word it saw, and a group that hit the corner is redone with the complete conversion (same results).
+SPF_HD void poly_to_torus(uint64_t (&r)[32], const C2 (&w)[16]) {
+#pragma unroll
+  for (int m4 = 0; m4 < 16; m4 += 4) {
+    uint32_t mag_max = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      r[m4 + i] = f64_to_torus_impl<false, false>(w[m4 + i].x, 1.0, &mag_max);
+      r[m4 + i + 16] = f64_to_torus_impl<false, false>(w[m4 + i].y, 1.0, &mag_max);
+    }
+    if (__builtin_expect(mag_max == kTorusCornerMag, 0)) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        r[m4 + i] = f64_to_torus(w[m4 + i].x);
+        r[m4 + i + 16] = f64_to_torus(w[m4 + i].y);
+      }
+    }
+  }
+}
+
 // ---- trace + scheme switch ---------------------------------------------------------------------
 // One team = one (ciphertext, cbs level) pair: mod_switch_trace_and_rotate for that level
 // (circuit_bootstrapping.rs:260-298), trace (ops/automorphisms/mod.rs:53-85) and that level's
@@ -1041,21 +1084,26 @@ SPF_HD void trace_ss_team(Cx& cx, const TraceSsArgs& A, uint64_t* g /*smem [2][2
       // keyswitch_glwe_to_glwe (fft_ops.rs:457-495): ks = (0, y_b) - IFFT(sum); out += ks
       team_fft_inv(cx, f[1], xbuf, T1, T2);
       uint64_t db[32];
+      poly_to_torus(db, f[1]);  // db[m] / db[m + 16]: coefficients u + 64 m and u + 64 m + 1024
 #pragma unroll
       for (int m = 0; m < 16; m++) {
         const int j = u + 64 * m;
-        db[m] = automorph_coeff(g + kN, j, kinv) - f64_to_torus(f[1][m].x);
-        db[m + 16] = automorph_coeff(g + kN, j + kM, kinv) - f64_to_torus(f[1][m].y);
+        db[m] = automorph_coeff(g + kN, j, kinv) - db[m];
+        db[m + 16] = automorph_coeff(g + kN, j + kM, kinv) - db[m + 16];
       }
       team_fft_inv(cx, f[0], xbuf, T1, T2);
       cx.sync();  // every gather of this round is done
+      {
+        uint64_t da[32];
+        poly_to_torus(da, f[0]);
 #pragma unroll
-      for (int m = 0; m < 16; m++) {
-        const int j = u + 64 * m;
-        g[j] -= f64_to_torus(f[0][m].x);
-        g[j + kM] -= f64_to_torus(f[0][m].y);
-        g[kN + j] += db[m];
-        g[kN + j + kM] += db[m + 16];
+        for (int m = 0; m < 16; m++) {
+          const int j = u + 64 * m;
+          g[j] -= da[m];
+          g[j + kM] -= da[m + 16];
+          g[kN + j] += db[m];
+          g[kN + j + kM] += db[m + 16];
+        }
       }
       cx.sync();
     }
