@@ -972,9 +972,36 @@ __global__ void __launch_bounds__(4 * kTeam, 1) pbs_quad_kernel(PbsBatch P, DevT
 #endif
 // DevCx of the trace / scheme-switch kernel: tensor-memory columns [0,64) T1 | [64,128) T2 (per lane quarter, shared by the
 // two warps of the quarter: warps w and w + 4 have the same thread-in-team index) | 64 columns per warp of parked states
+#ifndef SPF_TR_TW_PIPE
+#define SPF_TR_TW_PIPE 0  // twiddle chunks software-pipelined (the tensor-memory load of chunk g + 1 overlaps the products of chunk g)
+#endif
 struct DevTrCx : DevCx {
   static constexpr bool kTmemTwiddles = SPF_TR_TMEM_TW != 0;
   uint32_t tw_taddr;
+#if SPF_TR_TW_PIPE
+  template <bool CONJ, bool SKIP0>
+  __device__ __forceinline__ void tw_mul(C2 (&v)[16], uint32_t base) const {
+    uint32_t r[2][16];
+    tmem_ld16(r[0], base);
+    tmem_wait_ld();
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      if (g < 3) tmem_ld16(r[(g + 1) & 1], base + 16 * (g + 1));
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t* rr = r[g & 1];
+        const C2 w{__hiloint2double((int)rr[4 * i + 1], (int)rr[4 * i]), __hiloint2double((int)rr[4 * i + 3], (int)rr[4 * i + 2])};
+        const int k = 4 * g + i;
+        if (!SKIP0 || k) v[k] = CONJ ? cmul_conj(v[k], w) : cmul(v[k], w);
+      }
+      if (g < 3) tmem_wait_ld();
+    }
+  }
+  template <bool CONJ>
+  __device__ __forceinline__ void t1_mul(C2 (&v)[16]) const { tw_mul<CONJ, false>(v, tw_taddr); }
+  template <bool CONJ>
+  __device__ __forceinline__ void t2_mul(C2 (&v)[16]) const { tw_mul<CONJ, true>(v, tw_taddr + 64); }
+#else
   template <bool CONJ>
   __device__ __forceinline__ void t1_mul(C2 (&v)[16]) const {
 #pragma unroll
@@ -1005,6 +1032,7 @@ struct DevTrCx : DevCx {
       }
     }
   }
+#endif
 };
 constexpr int kTrTmemCols = SPF_TR_TMEM_TW ? 256 : 128;
 constexpr int kTrTeams = SPF_TR_TEAMS;
