@@ -57,6 +57,10 @@ struct HostPairCxT {
   }
   // reader-side pass-2 twiddles (device: the thread's constants sit in tensor memory; here they are recomputed, same arithmetic)
   static constexpr bool kReaderT2 = true;
+#ifndef SPF_PBS_TWOBUF
+#define SPF_PBS_TWOBUF 0
+#endif
+  static constexpr bool kTwoBuf = SPF_PBS_TWOBUF != 0 && !CH;  // the fused-store variant keeps the one-buffer form
 #ifndef SPF_PBS_INT_CONV
 #define SPF_PBS_INT_CONV 0
 #endif
@@ -272,7 +276,7 @@ template <bool TR, bool CH>
 void emu_pbs_t(uint64_t* glwe_out, const uint64_t* lwe_in, const uint64_t* lut, const C2* bsk_dev, int lwe_n,
                       int log_chi, int log_v, int cbs_radix_log, int cbs_count) {
   const Tables& t = tables();
-  std::vector<C2> xbuf(2 * kXBuf);
+  std::vector<C2> xbuf(4 * kXBuf);  // two exchange buffers per half when Cx::kTwoBuf
   std::vector<uint64_t> acc(2 * kN);
   PbsArgs A{lwe_in, lut, glwe_out, bsk_dev, lwe_n, log_chi, log_v, cbs_radix_log, cbs_count};
   using Cx = HostPairCxT<TR, CH>;

@@ -81,8 +81,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #ifndef SPF_PBS_TRANSIENT
 #define SPF_PBS_TRANSIENT 1  // accumulator image in the exchange buffer (pbs_pair_team, Cx::kTransient): 33 KB per pair
 #endif
+#ifndef SPF_PBS_TWOBUF
+#define SPF_PBS_TWOBUF 0  // two exchange buffers per half: both digit levels' transforms in flight together (team_ops.cuh, Cx::kTwoBuf); needs SPF_PBS_RING=0
+#endif
 constexpr int kPbsPairs = SPF_PBS_PAIRS;
-constexpr int kPbsPairBytes = (SPF_PBS_TRANSIENT ? 0 : 2 * kN * 8) + 2 * kXBuf * 16;  // [acc +] 2 exchange buffers
+constexpr int kPbsPairBytes = (SPF_PBS_TRANSIENT ? 0 : 2 * kN * 8) + (SPF_PBS_TWOBUF ? 4 : 2) * kXBuf * 16;  // [acc +] 2 (4) exchange buffers
 // tensor-memory columns: [0,64) T1 | own coefficients 64 per pair | parked accumulators 64 per pair while they fit
 // in the 512 columns (| T2 block when SPF_PBS_TMEM_T2); pairs beyond that park their accumulators in shared memory
 constexpr int kPbsTmemOwn0 = 64;
@@ -90,7 +93,7 @@ constexpr int kPbsTmemF0 = kPbsTmemOwn0 + 64 * kPbsPairs;
 constexpr int kPbsTmemFPairs = (512 - kPbsTmemF0) / 64 < kPbsPairs ? (512 - kPbsTmemF0) / 64 : kPbsPairs;
 constexpr int kPbsFParkBytes = (kPbsPairs - kPbsTmemFPairs) * 2 * kTeam * 16 * 16;  // 32 KiB per pair parked in smem
 #ifndef SPF_PBS_RING
-#define SPF_PBS_RING 1  // bootstrapping key staged through a shared-memory ring by bulk copies, one copy per chunk and CTA
+#define SPF_PBS_RING (!SPF_PBS_TWOBUF)  // bootstrapping key staged through a shared-memory ring by bulk copies, one copy per chunk and CTA
 #endif
 static_assert(!SPF_PBS_RING || SPF_PBS_TRANSIENT, "the BSK ring lives in the shared memory the transient accumulator frees");
 constexpr int kRingStages = 3;
@@ -360,6 +363,7 @@ struct DevPairCx {
   }
   // ---- reader-side pass-2 twiddles: 12 + 12 doubles of this thread in the columns [448, 496) (pair_tmem_init) ----
   static constexpr bool kReaderT2 = SPF_PBS_READER_T2 != 0;
+  static constexpr bool kTwoBuf = SPF_PBS_TWOBUF != 0;
   static constexpr bool kIntConv = SPF_PBS_INT_CONV != 0;
   __device__ __forceinline__ void rt2_fwd(double (&tw)[12], const C2*) const {
     uint32_t a[16], b[8];
@@ -415,6 +419,7 @@ struct DevPairCx {
   }
   __device__ __forceinline__ C2 bsk_load(const C2* p) const {
 #if SPF_PBS_RING
+    if (SPF_ABLATE(16)) return C2{1.5, (double)((size_t)p & 0xFF)};
     C2 r;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"((uint32_t)(size_t)p) : "memory");
     return r;

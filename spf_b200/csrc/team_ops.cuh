@@ -435,7 +435,8 @@ SPF_HD void mad_split_rt(Cx& cx, C2 (&f)[2][8], const C2* xbb, const C2* g, int 
 #pragma unroll
     for (int qp = 1; qp < 4; qp++) {
       const double t = tw[6 * jj + qp - 1];
-      d[qp] = C2{spf_fma(-t, d[qp].y, d[qp].x), spf_fma(t, d[qp].x, d[qp].y)};  // d (1 + i t); the factor c rides in the ratios
+      if (SPF_ABLATE(2)) d[qp] = abl_mix(d[qp], C2{t, t});
+      else d[qp] = C2{spf_fma(-t, d[qp].y, d[qp].x), spf_fma(t, d[qp].x, d[qp].y)};  // d (1 + i t); the factor c rides in the ratios
     }
     bfly4_r<false>(d[0], d[1], d[2], d[3], tw[6 * jj + 3], tw[6 * jj + 4], tw[6 * jj + 5]);
 #pragma unroll
@@ -567,6 +568,39 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
           else { v[i2 - 16].y = digit_lo16_to_f64(w); pk[i2 - 16] |= w1 & 0xFFFF0000u; }
         }
       }
+      if constexpr (Cx::kTwoBuf) {
+        // Two exchange buffers per half (Cx::kTwoBuf: xb + h kXBuf for digit level 0, xb + (2 + h) kXBuf for digit level 1): both
+        // forward transforms of the half are in flight together -- pass 1 of the second level is computed while the first
+        // level's products sit in shared memory, ONE half-barrier covers both first exchanges and ONE pair-barrier both
+        // second exchanges, and the multiply-accumulate of all four spectra follows in one piece: the accumulators are never
+        // parked, three barriers per step disappear.
+        static_assert(!Cx::kBskRing && !Cx::kTmemX1 && !Cx::kFusedStores && Cx::kReaderT2, "two-buffer form: LDG key, reader-side pass-2 twiddles");
+        C2* xown2 = xb + (2 + h) * kXBuf;
+        fwd_pass1_core(v);
+        cx.template t1_mul<false>(v, T1);
+        if (kTr) cx.sync();  // every thread of the half has gathered from the accumulator image in xown
+        fwd_x1_write(v, xown, u);
+#pragma unroll
+        for (int m = 0; m < 16; m++) { v[m].x = digit_lo16_to_f64(pk[m]); v[m].y = digit_hi16_to_f64(pk[m]); }
+        fwd_pass1_core(v);
+        cx.template t1_mul<false>(v, T1);
+        fwd_x1_write(v, xown2, u);
+        cx.sync();
+        fwd_x1_read(v, xown, u);
+        dft16<false>(v);
+        fwd_x2_write(v, xown, u);  // in place
+        fwd_x1_read(v, xown2, u);
+        dft16<false>(v);
+        fwd_x2_write(v, xown2, u);
+        cx.pair_sync();
+        double tw[12];
+        cx.rt2_fwd(tw, T2);
+        // the same accumulation order as the one-buffer form: (row 0, level 1), (row 1, level 1), (row 0, level 0), (row 1, level 0)
+        mad_split_rt<true>(cx, f, xb, ggsw + (size_t)((0 * 2 + 1) * 2) * kM, u, h, tw);
+        mad_split_rt<false>(cx, f, xb + kXBuf, ggsw + (size_t)((1 * 2 + 1) * 2) * kM, u, h, tw);
+        mad_split_rt<false>(cx, f, xb + 2 * kXBuf, ggsw + (size_t)((0 * 2 + 0) * 2) * kM, u, h, tw);
+        mad_split_rt<false>(cx, f, xb + 3 * kXBuf, ggsw + (size_t)((1 * 2 + 0) * 2) * kM, u, h, tw);
+      } else {
 #pragma unroll
       for (int t = 0; t < 2; t++) {
         const int level = 1 - t;  // LSB digit <-> last GLEV level (fft_ops.rs:92)
@@ -634,6 +668,7 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         mad_split<false>(cx, f, xb + kXBuf, g1, u, h);
         }
         if (t == 0) cx.f_store(f);  // device: parked in tensor memory while the second transform runs
+      }
       }
     }
     // first inverse pass on this half's bins of both output polynomials, hand them to their owners
