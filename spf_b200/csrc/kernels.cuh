@@ -96,10 +96,18 @@ constexpr int kPbsFParkBytes = (kPbsPairs - kPbsTmemFPairs) * 2 * kTeam * 16 * 1
 #define SPF_PBS_RING (!SPF_PBS_TWOBUF)  // bootstrapping key staged through a shared-memory ring by bulk copies, one copy per chunk and CTA
 #endif
 static_assert(!SPF_PBS_RING || SPF_PBS_TRANSIENT, "the BSK ring lives in the shared memory the transient accumulator frees");
-constexpr int kRingStages = 3;
+#ifndef SPF_PBS_RING_STAGES
+#define SPF_PBS_RING_STAGES 3
+#endif
+constexpr int kRingStages = SPF_PBS_RING_STAGES;
 constexpr int kRingChunkElems = 2 * kM;                  // one (row, level) GLEV row of the BSK: [p][bin]
 constexpr int kRingChunkBytes = kRingChunkElems * 16;    // 32768
-constexpr int kPbsRingOff = kTableBytes + kPbsPairs * kPbsPairBytes + kPbsFParkBytes;
+// Four stages: the twiddle tables are only read while tensor memory is filled, so they are loaded into the LAST stage's
+// place (behind the other three) and that stage joins the ring afterwards; with three stages they sit in front as before.
+constexpr bool kPbsTablesInRing = SPF_PBS_RING && kRingStages == 4;
+constexpr int kPbsPairOff = kPbsTablesInRing ? 0 : kTableBytes;
+constexpr int kPbsRingOff = kPbsPairOff + kPbsPairs * kPbsPairBytes + kPbsFParkBytes;
+constexpr int kPbsTablesOff = kPbsTablesInRing ? kPbsRingOff + 3 * kRingChunkBytes : 0;
 constexpr int kPbsRingBytes = SPF_PBS_RING ? kRingStages * kRingChunkBytes + 64 : 0;  // + full barriers, release counters
 constexpr int kPbsSmem = kPbsRingOff + kPbsRingBytes;
 static_assert(kPbsSmem <= 232448, "pbs_kernel shared memory");
@@ -174,6 +182,7 @@ __device__ __forceinline__ void mbar_wait_trap(uint32_t bar, uint32_t parity) {
   }
 }
 static_assert(!SPF_PBS_TRANSIENT || SPF_PBS_TMEM_OWN, "the transient accumulator image needs the tensor-memory own copy");
+static_assert(!kPbsTablesInRing || SPF_PBS_TMEM_T1, "four ring stages overlay the twiddle tables: the twiddles must live in tensor memory");
 
 #ifndef SPF_PBS_CHUNKED
 #define SPF_PBS_CHUNKED 1  // own coefficients / twiddles fetched from tensor memory in small chunks (needed by the 128-register
@@ -748,7 +757,7 @@ struct PbsBatch {
 
 __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch P, DevTables tabs) {
   extern __shared__ __align__(16) unsigned char smem[];
-  C2* sT1 = reinterpret_cast<C2*>(smem);
+  C2* sT1 = reinterpret_cast<C2*>(smem + kPbsTablesOff);
   C2* sT2 = sT1 + kT1Elems;
   load_tables(sT1, sT2, tabs);
   uint32_t tmem_alloc;
@@ -756,11 +765,11 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   const int pair = threadIdx.x / (2 * kTeam);
   const int npairs = blockDim.x / (2 * kTeam);  // 1..kPbsPairs pairs per CTA (fewer for small batches)
   const int h = (threadIdx.x / kTeam) & 1;
-  unsigned char* base = smem + kTableBytes + pair * kPbsPairBytes;
+  unsigned char* base = smem + kPbsPairOff + pair * kPbsPairBytes;
   uint64_t* acc = reinterpret_cast<uint64_t*>(base);  // unused when SPF_PBS_TRANSIENT
   C2* xb = reinterpret_cast<C2*>(base + (SPF_PBS_TRANSIENT ? 0 : 2 * kN * 8));
   C2* fpark = pair < kPbsTmemFPairs ? nullptr
-                                    : reinterpret_cast<C2*>(smem + kTableBytes + kPbsPairs * kPbsPairBytes) + (pair - kPbsTmemFPairs) * 2 * kTeam * 16;
+                                    : reinterpret_cast<C2*>(smem + kPbsPairOff + kPbsPairs * kPbsPairBytes) + (pair - kPbsTmemFPairs) * 2 * kTeam * 16;
   DevPairCx cx{(int)(threadIdx.x % kTeam), h, 1 + pair * 3 + h, 3 + pair * 3, t1_taddr, t1_taddr + kPbsTmemOwn0 + 64 * pair,
                t1_taddr + kPbsTmemF0 + 64 * (pair < kPbsTmemFPairs ? pair : 0), fpark};
   int G = 0;        // chunk position of this pair in the CTA-wide BSK chunk sequence
