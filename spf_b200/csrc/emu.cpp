@@ -70,6 +70,7 @@ struct HostPairCxT {
   static constexpr bool kBskRing = false;   // the ring is device machinery: the host reads the key in place
   const C2* bsk_acquire(int, const C2* g) { return g; }
   void bsk_release(int) {}
+  void bsk_release_early(int) {}
   void bsk_skip(int) {}
   C2 bsk_load(const C2* p) { return *p; }
   static constexpr bool kFusedStores = CH;  // exercised together with the chunked variant

@@ -105,7 +105,10 @@ constexpr int kRingChunkBytes = kRingChunkElems * 16;    // 32768
 // Four stages: the twiddle tables are only read while tensor memory is filled, so they are loaded into the LAST stage's
 // place (behind the other three) and that stage joins the ring afterwards; with three stages they sit in front as before.
 constexpr bool kPbsTablesInRing = SPF_PBS_RING && kRingStages == 4;
-constexpr int kPbsPairOff = kPbsTablesInRing ? 0 : kTableBytes;
+#ifndef SPF_PBS_PAIR_SHIFT
+#define SPF_PBS_PAIR_SHIFT 0  // experiment: extra byte offset of the pairs' exchange buffers
+#endif
+constexpr int kPbsPairOff = (kPbsTablesInRing ? 0 : kTableBytes) + SPF_PBS_PAIR_SHIFT;
 constexpr int kPbsRingOff = kPbsPairOff + kPbsPairs * kPbsPairBytes + kPbsFParkBytes;
 constexpr int kPbsTablesOff = kPbsTablesInRing ? kPbsRingOff + 3 * kRingChunkBytes : 0;
 constexpr int kPbsRingBytes = SPF_PBS_RING ? kRingStages * kRingChunkBytes + 64 : 0;  // + full barriers, release counters
@@ -196,6 +199,9 @@ static_assert(!kPbsTablesInRing || SPF_PBS_TMEM_T1, "four ring stages overlay th
 #endif
 #ifndef SPF_PBS_FST2
 #define SPF_PBS_FST2 1  // accumulators parked with one tcgen05.st per double instead of four 16-register stores
+#endif
+#ifndef SPF_PBS_EARLY_REL
+#define SPF_PBS_EARLY_REL 0  // BSK ring: per-warp release right behind the last read of a chunk
 #endif
 #ifndef SPF_PBS_TW_PIPE
 #define SPF_PBS_TW_PIPE 0  // twiddle chunks software-pipelined: the tensor-memory load of chunk g + 1 overlaps the products of chunk g
@@ -437,12 +443,27 @@ struct DevPairCx {
     return ldg_c2_pinned(p);
 #endif
   }
+  // SPF_PBS_EARLY_REL: every WARP counts itself off a chunk right after its last read of it (bsk_release_early, called behind the
+  // multiply-accumulate that consumed the chunk) instead of one thread per pair at the next pair barrier, which can be thousands of
+  // clocks later: the refill of the stage starts as soon as the twelfth warp is done, the pairs wait less for the next chunk.
+  static constexpr bool kEarlyRel = SPF_PBS_EARLY_REL != 0;
+  __device__ __forceinline__ void bsk_release_early(int G) const {
+#if SPF_PBS_RING && SPF_PBS_EARLY_REL
+    __syncwarp();
+    release_one(G);
+#endif
+  }
   __device__ __forceinline__ void bsk_release(int G) const {
+#if SPF_PBS_RING && !SPF_PBS_EARLY_REL
+    release_one(G);
+#endif
+  }
+  __device__ __forceinline__ void release_one(int G) const {
 #if SPF_PBS_RING
     if (elected) {
       const int st = G % kRingStages;
       __threadfence_block();
-      if (atomicAdd(rel + st, 1u) == (unsigned)npairs - 1u) {  // last pair out re-arms the stage
+      if (atomicAdd(rel + st, 1u) == (unsigned)npairs - 1u) {  // last pair (warp) out re-arms the stage
         atomicExch(rel + st, 0u);
         __threadfence_block();
         if (G + kRingStages < total) ring_issue(G + kRingStages);
@@ -456,7 +477,7 @@ struct DevPairCx {
 #pragma unroll 1
       for (int k = 0; k < 4; k++) {
         mbar_wait_trap(full_s + 8 * ((G + k) % kRingStages), (uint32_t)((G + k) / kRingStages) & 1u);  // the copy has landed
-        bsk_release(G + k);
+        release_one(G + k);
       }
     }
 #endif
@@ -782,8 +803,8 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
     cx.rel = reinterpret_cast<unsigned*>(full + kRingStages);
     cx.bsk = P.bsk;
     cx.lwe_n = P.lwe_n;
-    cx.npairs = npairs;
-    cx.elected = (threadIdx.x % (2 * kTeam)) == 0;
+    cx.npairs = DevPairCx::kEarlyRel ? 4 * npairs : npairs;                       // participants that count themselves off a chunk
+    cx.elected = (threadIdx.x % (DevPairCx::kEarlyRel ? 32 : 2 * kTeam)) == 0;  // one thread per warp / per pair
     if ((int)blockIdx.x < P.batch) rounds = (P.batch - (int)blockIdx.x + (int)gridDim.x * npairs - 1) / ((int)gridDim.x * npairs);
     cx.total = rounds * 4 * P.lwe_n;
     if (threadIdx.x == 0) {
@@ -819,7 +840,7 @@ __global__ void __launch_bounds__(kPbsPairs * 2 * kTeam, 1) pbs_kernel(PbsBatch 
   if (cx.elected)
     for (; G < cx.total; G++) {
       mbar_wait_trap(cx.full_s + 8 * (G % kRingStages), (uint32_t)(G / kRingStages) & 1u);
-      cx.bsk_release(G);
+      cx.release_one(G);
     }
 #endif
   pair_tmem_free(tmem_alloc);

@@ -659,8 +659,10 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
           cx.rt2_fwd(tw, T2);
           if (t == 0) mad_split_rt<true>(cx, f, xb, g0, u, h, tw);
           else mad_split_rt<false>(cx, f, xb, g0, u, h, tw);
+          cx.bsk_release_early(G + 2 * t);
           const C2* g1 = cx.bsk_acquire(G + 2 * t + 1, ggsw + (size_t)((1 * 2 + level) * 2) * kM);
           mad_split_rt<false>(cx, f, xb + kXBuf, g1, u, h, tw);
+          cx.bsk_release_early(G + 2 * t + 1);
         } else {
         if (t == 0) mad_split<true>(cx, f, xb, g0, u, h);
         else mad_split<false>(cx, f, xb, g0, u, h);
