@@ -203,6 +203,9 @@ static_assert(!kPbsTablesInRing || SPF_PBS_TMEM_T1, "four ring stages overlay th
 #ifndef SPF_PBS_EARLY_REL
 #define SPF_PBS_EARLY_REL 0  // BSK ring: per-warp release right behind the last read of a chunk
 #endif
+#ifndef SPF_PBS_RING_FENCE
+#define SPF_PBS_RING_FENCE 1  // fence.proxy.async in front of every refill of a ring stage
+#endif
 #ifndef SPF_PBS_TW_PIPE
 #define SPF_PBS_TW_PIPE 0  // twiddle chunks software-pipelined: the tensor-memory load of chunk g + 1 overlaps the products of chunk g
 #endif
@@ -417,7 +420,9 @@ struct DevPairCx {
   __device__ __forceinline__ void ring_issue(int Gn) const {
     const int i = (Gn >> 2) % lwe_n, k = Gn & 3, c = (k & 1) * 2 + (1 - (k >> 1)), st = Gn % kRingStages;
     const C2* src = bsk + ((size_t)i * 4 + c) * kRingChunkElems;
+#if SPF_PBS_RING_FENCE
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_s + 8 * st), "r"((uint32_t)kRingChunkBytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(ring_s + st * kRingChunkBytes), "l"(src), "r"((uint32_t)kRingChunkBytes), "r"(full_s + 8 * st) : "memory");
