@@ -173,8 +173,13 @@ __device__ __forceinline__ void mbar_wait_trap(uint32_t bar, uint32_t parity) {
   unsigned long long t_start = 0;
   for (int spin = 0;; spin++) {
     uint32_t ok;
+#if SPF_MBAR_HINT
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)SPF_MBAR_HINT) : "memory");
+#else
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     if (ok) return;
     if ((spin & 1023) == 1023) {  // a chunk that has not landed after 2 s will never land
       unsigned long long now;
@@ -205,6 +210,9 @@ static_assert(!kPbsTablesInRing || SPF_PBS_TMEM_T1, "four ring stages overlay th
 #endif
 #ifndef SPF_PBS_RING_FENCE
 #define SPF_PBS_RING_FENCE 1  // fence.proxy.async in front of every refill of a ring stage
+#endif
+#ifndef SPF_MBAR_HINT
+#define SPF_MBAR_HINT 0  // suspend-time hint (ns) of the mbarrier waits; 0: the hardware default
 #endif
 #ifndef SPF_PBS_TW_PIPE
 #define SPF_PBS_TW_PIPE 0  // twiddle chunks software-pipelined: the tensor-memory load of chunk g + 1 overlaps the products of chunk g
