@@ -214,6 +214,11 @@ struct HostQuadCx {
     pthread_barrier_wait(bar_poly);
     memcpy(pk, xchg + ((size_t)(h * 2 + (1 - t)) * kTeam + u) * 8, sizeof(pk));
   }
+#ifndef SPF_QUAD_READER_T2
+#define SPF_QUAD_READER_T2 1
+#endif
+  static constexpr bool kReaderT2 = SPF_QUAD_READER_T2 != 0;
+  void rt2(double (&tw)[6], C2 (&wi)[3], const C2* T2) { rt2_group_consts(T2, u >> 4, 2 * h + t, tw, wi); }
   void sync() { pthread_barrier_wait(bar_team); }
   void quad_sync() { pthread_barrier_wait(bar_quad); }
   // the device stages the next BSK row in shared memory with a bulk copy; the host reads the key directly

@@ -876,6 +876,9 @@ constexpr int kQuadSmem = kQuadT2Bytes + 2 * kN * 8 + 4 * kXBuf * 16 + kQuadRowB
 #ifndef SPF_QUAD_SPLIT_GATHER
 #define SPF_QUAD_SPLIT_GATHER 1  // the two teams of a polynomial gather half of the rounded differences each and swap digits
 #endif
+#ifndef SPF_QUAD_READER_T2
+#define SPF_QUAD_READER_T2 1  // pass-2 twiddles applied by the consumers of the second exchange, as in pbs_kernel (3.52 -> 3.36 ms at batch 1, 3.39 -> 3.31 at 64)
+#endif
 struct DevQuadCx {
   static constexpr bool kSplitGather = SPF_QUAD_SPLIT_GATHER != 0;
   // Teams (h, 0) and (h, 1) are warps {2h, 2h+1} and {4 + 2h, 5 + 2h}: thread u of both sits on the same tensor-memory lane,
@@ -887,6 +890,20 @@ struct DevQuadCx {
     asm volatile("bar.sync %0, 128;" ::"r"(5 + h) : "memory");
     tmem_ld8(pk, t1_taddr + 64 + 8 * (1 - t));
     tmem_wait_ld();
+  }
+  // reader-side pass-2 twiddles (team_ops.cuh: rt2_group_consts): 12 doubles per thread in the columns [448 + 24 t, 472 + 24 t)
+  // of its lane (warps w and w + 4 share a lane quarter and differ in t)
+  static constexpr bool kReaderT2 = SPF_QUAD_READER_T2 != 0;
+  __device__ __forceinline__ void rt2(double (&tw)[6], C2 (&wi)[3], const C2*) const {
+    uint32_t a[16], b[8];
+    tmem_ld16(a, t1_taddr + 448 + 24 * t);
+    tmem_ld8(b, t1_taddr + 448 + 24 * t + 16);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 6; i++) tw[i] = __hiloint2double((int)a[2 * i + 1], (int)a[2 * i]);
+    wi[0] = C2{__hiloint2double((int)a[13], (int)a[12]), __hiloint2double((int)a[15], (int)a[14])};
+    wi[1] = C2{__hiloint2double((int)b[1], (int)b[0]), __hiloint2double((int)b[3], (int)b[2])};
+    wi[2] = C2{__hiloint2double((int)b[5], (int)b[4]), __hiloint2double((int)b[7], (int)b[6])};
   }
   int u, h, t;
   uint32_t t1_taddr;
@@ -983,6 +1000,27 @@ __global__ void __launch_bounds__(4 * kTeam, 1) pbs_quad_kernel(PbsBatch P, DevT
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+#if SPF_QUAD_READER_T2
+  {  // every thread's reader-side pass-2 constants over the table row pair_tmem_init left in [448, 512)
+    const int tm = threadIdx.x / kTeam, uu = threadIdx.x % kTeam;
+    double tw[6];
+    C2 wi[3];
+    rt2_group_consts(sT2, uu >> 4, 2 * (tm & 1) + (tm >> 1), tw, wi);
+    const uint32_t base = t1_taddr + 448 + 24 * (tm >> 1);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      tmem_st4(base + 4 * i, (uint32_t)__double2loint(tw[2 * i]), (uint32_t)__double2hiint(tw[2 * i]), (uint32_t)__double2loint(tw[2 * i + 1]),
+               (uint32_t)__double2hiint(tw[2 * i + 1]));
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      tmem_st4(base + 12 + 4 * i, (uint32_t)__double2loint(wi[i].x), (uint32_t)__double2hiint(wi[i].x), (uint32_t)__double2loint(wi[i].y),
+               (uint32_t)__double2hiint(wi[i].y));
+    tmem_wait_st();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+#endif
   const int team = threadIdx.x / kTeam;
   // team w = (h, t) with h = w & 1, t = w >> 1: the two teams that run the inverse transforms (t = 0) are warps
   // 0..3, one per SM sub-partition (warp % 4) -- with h = w >> 1 they were warps 0,1,4,5, i.e. the FP64-issue-bound

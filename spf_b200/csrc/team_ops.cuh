@@ -418,6 +418,21 @@ SPF_HD void rt2_inv_consts(const C2* T2, int q, int h, C2 (&o)[6]) {
   for (int jj = 0; jj < 2; jj++)
     for (int qp = 1; qp < 4; qp++) o[3 * jj + qp - 1] = T2[qp * kT2Pad + q + 4 * (2 * h + jj)];
 }
+// the same constants for ONE radix-4 group k2 = q + 4 grp (the quad kernel: team g owns group g): tw[0..2] = t_1..t_3,
+// tw[3..5] = c_1, c_2, c_3 / c_1; wi[0..2] = W64^(q' k2), q' = 1..3 (conjugated by the consumer)
+SPF_HD void rt2_group_consts(const C2* T2, int q, int grp, double (&tw)[6], C2 (&wi)[3]) {
+  const int k2 = q + 4 * grp;
+  double c[4];
+  for (int qp = 1; qp < 4; qp++) {
+    const C2 w = T2[qp * kT2Pad + k2];
+    wi[qp - 1] = w;
+    c[qp] = w.x == 0.0 ? 8.470329472543003e-22 /* 2^-70 */ : w.x;
+    tw[qp - 1] = w.y / c[qp];
+  }
+  tw[3] = c[1];
+  tw[4] = c[2];
+  tw[5] = c[3] / c[1];
+}
 // mad_split for spectra whose pass-2 twiddles have NOT been applied yet (tw from rt2_fwd_consts)
 template <bool INIT, class Cx>
 SPF_HD void mad_split_rt(Cx& cx, C2 (&f)[2][8], const C2* xbb, const C2* g, int u, int h, const double (&tw)[12]) {
@@ -915,7 +930,7 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       SPF_QT(1);
       fwd_x1_read(v, xown, u);
       dft16<false>(v);
-      cx.template t2_mul<false>(v, T2);
+      if constexpr (!Cx::kReaderT2) cx.template t2_mul<false>(v, T2);  // else: applied by the readers below (as in pbs_pair_team)
       fwd_x2_write(v, xown, u);  // in place
       SPF_QT(2);
     }
@@ -926,6 +941,9 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
     executed++;
     SPF_QT(4);
     C2 f[2][4];
+    double rtw[6];
+    C2 rwi[3];
+    if constexpr (Cx::kReaderT2) cx.rt2(rtw, rwi, T2);  // this thread's pass-2 twiddles in the tan form (rt2_group_consts)
 #pragma unroll
     for (int b = 0; b < 4; b++) {  // spectrum of team b = (hb, tb): digit tb <-> GLEV level 1 - tb
       const C2* grow = staged + (size_t)(((b >> 1) * 2 + (1 - (b & 1))) * 2) * kM;
@@ -937,7 +955,13 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
         g0[k3] = cx.row_load(grow + u + 64 * (g + 4 * k3));
         g1[k3] = cx.row_load(grow + kM + u + 64 * (g + 4 * k3));
       }
-      bfly4<false>(d[0], d[1], d[2], d[3]);
+      if constexpr (Cx::kReaderT2) {
+#pragma unroll
+        for (int qp = 1; qp < 4; qp++) d[qp] = C2{spf_fma(-rtw[qp - 1], d[qp].y, d[qp].x), spf_fma(rtw[qp - 1], d[qp].x, d[qp].y)};
+        bfly4_r<false>(d[0], d[1], d[2], d[3], rtw[3], rtw[4], rtw[5]);
+      } else {
+        bfly4<false>(d[0], d[1], d[2], d[3]);
+      }
 #pragma unroll
       for (int k3 = 0; k3 < 4; k3++) {
         if (b == 0) { f[0][k3] = cmul(d[k3], g0[k3]); f[1][k3] = cmul(d[k3], g1[k3]); }
@@ -948,6 +972,10 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
 #pragma unroll
     for (int p = 0; p < 2; p++) {
       bfly4<true>(f[p][0], f[p][1], f[p][2], f[p][3]);
+      if constexpr (Cx::kReaderT2) {  // the inverse transform's conjugate pass-2 twiddles, applied by the bin owner
+#pragma unroll
+        for (int qp = 1; qp < 4; qp++) f[p][qp] = cmul_conj(f[p][qp], rwi[qp - 1]);
+      }
 #pragma unroll
       for (int qp = 0; qp < 4; qp++) xb[2 * p * kXBuf + k1 * kXPad + qp + 4 * q + 16 * g] = f[p][qp];
     }
@@ -962,7 +990,7 @@ SPF_HD void pbs_quad_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       C2 w[16];
       double ws[16];
       inv_x2_read(w, xown, u);
-      cx.template t2_mul<true>(w, T2);
+      if constexpr (!Cx::kReaderT2) cx.template t2_mul<true>(w, T2);
       dft16<true>(w);
       inv_x1_write(w, xown, u);  // in place
       cx.sync();
