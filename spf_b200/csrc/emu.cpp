@@ -65,6 +65,10 @@ struct HostPairCxT {
 #define SPF_PBS_INT_CONV 0
 #endif
   static constexpr bool kIntConv = SPF_PBS_INT_CONV != 0;
+#ifndef SPF_PBS_FRND_CONV
+#define SPF_PBS_FRND_CONV 0
+#endif
+  static constexpr bool kFrndConv = SPF_PBS_FRND_CONV != 0;
   void rt2_fwd(double (&tw)[12], const C2* T2) { rt2_fwd_consts(T2, u >> 4, h, tw); }
   void rt2_inv(C2 (&w)[6], const C2* T2) { rt2_inv_consts(T2, u >> 4, h, w); }
   static constexpr bool kBskRing = false;   // the ring is device machinery: the host reads the key in place

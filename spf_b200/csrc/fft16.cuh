@@ -591,6 +591,33 @@ SPF_HD uint64_t f64_to_torus_s_fast(double xs, double sc, uint32_t& mag_max) {
   return f64_to_torus_impl<true, false>(xs, sc, &mag_max);
 }
 
+// f64 -> torus of y = fl(sc * xs) with the ROUND-TO-INTEGRAL conversion instruction: t = y / 2^64 (the factor is folded into the
+// compile-time scale, so t is one DMUL), r = rint(t) on the conversion pipe, frac = t - r exactly (|frac| <= 1/2), and
+// lo = frac * 2^64 (an exponent-field add) is y reduced modulo 2^64 into [-2^63, 2^63]: an integer whenever |y| >= 2^52, so the
+// final F2I is exact.  Two FP64 instructions per value instead of four; the conversion pipe is idle in these kernels.
+// `small` tracks the minimum exponent word of t (|y| < 2^52 may carry a fraction: round-half-away needed) and `corner` the
+// maximum of frac (|frac| = 1/2 is the saturating-cast corner of f64_to_torus_impl): the caller redoes such (rare) groups with
+// f64_to_torus(sc * xs), which has the same semantics for every double.
+constexpr uint32_t kTorusSmallMag = 0x3F300000u;   // high word of 2^-12: |t| below it <=> |y| < 2^52
+constexpr uint32_t kTorusHalfMag = 0x3FE00000u;    // high word of 1/2
+SPF_HD uint64_t f64_to_torus_frnd(double xs, double sc, uint32_t& small_min, uint32_t& corner_max) {
+  if (SPF_ABLATE(64)) return f64_bits(xs);
+  const double t = (sc * 5.421010862427522e-20 /* 2^-64 */) * xs;
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("cvt.rni.f64.f64 %0, %1;" : "=d"(r) : "d"(t));
+#else
+  const double r = __builtin_nearbyint(t);  // round to nearest even, the default mode
+#endif
+  const double frac = t - r;
+  const uint64_t fb = f64_bits(frac);
+  const uint32_t th = (uint32_t)(f64_bits(t) >> 32) & 0x7FFFFFFFu, fh = (uint32_t)(fb >> 32) & 0x7FFFFFFFu;
+  small_min = th < small_min ? th : small_min;
+  corner_max = fh > corner_max ? fh : corner_max;
+  const double lo = bits_f64(fb + (64ull << 52));  // frac * 2^64 (frac = +-0 becomes +-2^-959: converts to 0)
+  return (uint64_t)f64_to_i64_sat(lo);
+}
+
 // f64 -> torus of y = fl(sc * xs) with INTEGER arithmetic: a double of magnitude >= 2^52 is an integer M * 2^s (M the 53-bit
 // significand, s >= 0), so round() is the identity and the reduction mod 2^64 is a shift of M -- one FP64 instruction (the product)
 // instead of four plus a conversion.  Smaller magnitudes (probability ~2^-33 per coefficient of a blind rotation) and the

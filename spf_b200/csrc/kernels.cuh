@@ -214,6 +214,9 @@ static_assert(!kPbsTablesInRing || SPF_PBS_TMEM_T1, "four ring stages overlay th
 #ifndef SPF_MBAR_HINT
 #define SPF_MBAR_HINT 0  // suspend-time hint (ns) of the mbarrier waits; 0: the hardware default
 #endif
+#ifndef SPF_PBS_FRND_CONV
+#define SPF_PBS_FRND_CONV 0  // accumulator update: f64 -> torus through the round-to-integral conversion (fft16.cuh: f64_to_torus_frnd)
+#endif
 #ifndef SPF_PBS_TW_PIPE
 #define SPF_PBS_TW_PIPE 0  // twiddle chunks software-pipelined: the tensor-memory load of chunk g + 1 overlaps the products of chunk g
 #endif
@@ -391,6 +394,7 @@ struct DevPairCx {
   static constexpr bool kReaderT2 = SPF_PBS_READER_T2 != 0;
   static constexpr bool kTwoBuf = SPF_PBS_TWOBUF != 0;
   static constexpr bool kIntConv = SPF_PBS_INT_CONV != 0;
+  static constexpr bool kFrndConv = SPF_PBS_FRND_CONV != 0;
   __device__ __forceinline__ void rt2_fwd(double (&tw)[12], const C2*) const {
     uint32_t a[16], b[8];
     tmem_ld16(a, t1_taddr + 448);

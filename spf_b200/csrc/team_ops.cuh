@@ -747,7 +747,22 @@ SPF_HD void pbs_pair_team(Cx& cx, const PbsArgs& A, uint64_t* acc, C2* xb, const
       for (int m4 = 0; m4 < 16; m4 += 4) {
         uint32_t mag_max = 0;
         uint64_t r[8];
-        if constexpr (Cx::kIntConv) {
+        if constexpr (Cx::kFrndConv) {
+          // round-to-integral conversion of fl(ws * w): two FP64 instructions per value instead of four (fft16.cuh: f64_to_torus_frnd)
+          uint32_t small_min = 0x7FFFFFFFu;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            r[2 * i] = f64_to_torus_frnd(w[m4 + i].x, ws[m4 + i], small_min, mag_max);
+            r[2 * i + 1] = f64_to_torus_frnd(w[m4 + i].y, ws[m4 + i], small_min, mag_max);
+          }
+          if (__builtin_expect(small_min < kTorusSmallMag || mag_max >= kTorusHalfMag, 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              r[2 * i] = f64_to_torus(ws[m4 + i] * w[m4 + i].x);
+              r[2 * i + 1] = f64_to_torus(ws[m4 + i] * w[m4 + i].y);
+            }
+          }
+        } else if constexpr (Cx::kIntConv) {
           // integer conversion of fl(ws * w): one FP64 instruction per value instead of four (fft16.cuh: f64_to_torus_int)
 #pragma unroll
           for (int i = 0; i < 4; i++) {
