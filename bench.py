@@ -466,6 +466,8 @@ class E2EGraphPipeline:
             # buffers take turns: steps k + 1 .. k + depth - 1 are already spawned while step k's results travel to the host,
             # so a blind rotation is always queued when the previous step's trace kernels drain.
             self.depth = max(2, depth)
+            if self.depth > 4:
+                ev.set_max_in_flight(self.depth)  # the executor's flow control admits 4 spawned graphs by default
             self.h_outs = [spf_b200.pinned_zeros((B, glwe_len)) for _ in range(self.depth)]
             self.graphs = [build(0, B, o) for o in self.h_outs]
             self.h_out = self.h_outs[0]
